@@ -1,0 +1,119 @@
+"""ctypes binding of librt_b200.so (include/rt_b200.h).  Product code: there is NO fallback --
+if the shared library (hand-written sm_100a kernels) is missing or does not load, importing the
+GPU entry points raises; nothing here ever routes to a CPU implementation."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+
+FP64_EXACT, FP32_FAST = 0, 1
+LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0x0, 0x1
+QUANT_RGB255, QUANT_RGBA16_SHR8 = 0x0, 0x2
+FLAG_COUNT, FLAG_BRUTE_FORCE, FLAG_SIMPLE = 0x4, 0x8, 0x10
+
+RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_STATE, RT_ERR_CANCELLED = 0, -1, -2, -3, -4, -5
+
+# every symbol include/rt_b200.h declares
+ABI_SYMBOLS = (
+    "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set",
+    "rt_render_region", "rt_bulk_trace", "rt_render_region_debug", "rt_render_region_device", "rt_render_tiles_device",
+    "rt_untile_device", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free",
+)
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("verts", C.c_void_p), ("n_verts", C.c_uint32),
+                ("normals", C.c_void_p), ("n_normals", C.c_uint32),
+                ("faces", C.c_void_p), ("n_faces", C.c_uint32),
+                ("materials", C.c_void_p), ("n_materials", C.c_uint32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("meshes", C.POINTER(MeshDesc)), ("n_meshes", C.c_uint32),
+                ("obj_pos", C.c_void_p), ("obj_mesh", C.c_void_p), ("n_objects", C.c_uint32),
+                ("device", C.c_int32), ("precision", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("forward", C.c_double * 3), ("left", C.c_double * 3), ("up", C.c_double * 3),
+                ("fov", C.c_double), ("tan_half_fov", C.c_double)]
+
+
+class Light(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("col", C.c_double * 3)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("hit_pixels", C.c_uint64),
+                ("nodes_fetched", C.c_uint64), ("tris_fetched", C.c_uint64), ("node_bytes", C.c_uint64),
+                ("tri_bytes", C.c_uint64), ("ms_primary", C.c_float), ("ms_shade", C.c_float), ("ms_write", C.c_float),
+                ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class BvhInfo(C.Structure):
+    _fields_ = [("n_faces", C.c_uint64), ("n_nodes", C.c_uint64), ("n_leaves", C.c_uint64), ("max_depth", C.c_uint32),
+                ("max_leaf", C.c_uint32), ("ms_build", C.c_float), ("sah_cost", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rt_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_LIB = None
+
+
+def load():
+    """Loads librt_b200.so; raises (loudly) if it is missing -- there is no CPU fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not found: build it with `python __graft_entry__.py build` (nvcc, sm_100a); "
+                          "this backend has no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    u32, vp = C.c_uint32, C.c_void_p
+    L.rt_scene_create.restype = C.c_int
+    L.rt_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp)]
+    L.rt_scene_destroy.restype = None
+    L.rt_scene_destroy.argtypes = [vp]
+    L.rt_last_error.restype = C.c_char_p
+    L.rt_last_error.argtypes = [vp]
+    L.rt_abi_version.restype = C.c_int
+    L.rt_device_count.restype = C.c_int
+    L.rt_frame_set.restype = C.c_int
+    L.rt_frame_set.argtypes = [vp, C.POINTER(Camera), vp, u32, vp]
+    L.rt_render_region.restype = C.c_int
+    L.rt_render_region.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, u32]
+    L.rt_bulk_trace.restype = C.c_int
+    L.rt_bulk_trace.argtypes = [vp, C.POINTER(Camera), vp, u32, vp, u32, u32, u32, u32, u32, u32, vp, u32]
+    L.rt_render_region_debug.restype = C.c_int
+    L.rt_render_region_debug.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp, u32]
+    L.rt_render_region_device.restype = C.c_int
+    L.rt_render_region_device.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, vp, u32]
+    L.rt_render_tiles_device.restype = C.c_int
+    L.rt_render_tiles_device.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, vp, u32]
+    L.rt_untile_device.restype = C.c_int
+    L.rt_untile_device.argtypes = [vp, u32, u32, u32, u32, u32, vp, vp, vp, u32]
+    L.rt_get_stats.restype = C.c_int
+    L.rt_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.rt_get_bvh_info.restype = C.c_int
+    L.rt_get_bvh_info.argtypes = [vp, u32, C.POINTER(BvhInfo)]
+    L.rt_synchronize.restype = C.c_int
+    L.rt_synchronize.argtypes = [vp]
+    L.rt_cancel.restype = C.c_int
+    L.rt_cancel.argtypes = [vp]
+    L.rt_host_alloc.restype = vp
+    L.rt_host_alloc.argtypes = [C.c_size_t]
+    L.rt_host_free.restype = None
+    L.rt_host_free.argtypes = [vp]
+    _LIB = L
+    return L

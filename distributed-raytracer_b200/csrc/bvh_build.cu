@@ -1,0 +1,258 @@
+// bvh_build.cu -- K1: on-GPU LBVH build (sm_100a).
+//
+// Replaces rtreego.NewTree(3,2,5) + one serial Insert per face
+// (/root/reference/shared/state/mesh.go:139,208).  Pipeline, all on the device:
+//   k_mesh_bounds   face vertices -> mesh bounds (warp-reduced ordered-int atomics)
+//   k_leaf_morton   per face: padded fp32 leaf box + 63-bit Morton key of the box centroid
+//   cub radix sort  (key, face) pairs                                  [library plumbing]
+//   k_karras        binary radix tree over the sorted keys (Karras 2012), parent links
+//   k_refit_sah     bottom-up boxes + SAH cost, collapse subtrees of <= max_leaf faces into leaves
+//   k_emit_count / scan / k_emit_write   BFS re-emission into 64 B traversal nodes (top of tree = prefix)
+//   k_gather_tris   triangle records in leaf order: 48 B fp32 and/or 80 B fp64
+#include "rt_internal.h"
+#include <cub/cub.cuh>
+
+namespace {
+
+__device__ __forceinline__ unsigned int f2ord(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned int u) {
+    unsigned int v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(v);
+#else
+    float f; memcpy(&f, &v, 4); return f;
+#endif
+}
+
+// bounds[0..2] = min (ordered uint), bounds[3..5] = max
+__global__ void k_mesh_bounds(const double *__restrict__ fverts, uint32_t n, unsigned int *bounds) {
+    float lo[3] = { HUGE_VALF, HUGE_VALF, HUGE_VALF }, hi[3] = { -HUGE_VALF, -HUGE_VALF, -HUGE_VALF };
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+        const double *p = fverts + 9 * (size_t)f;
+        for (int v = 0; v < 3; v++)
+            for (int k = 0; k < 3; k++) {
+                double c = p[3 * v + k];
+                lo[k] = fminf(lo[k], f32_down(c));
+                hi[k] = fmaxf(hi[k], f32_up(c));
+            }
+    }
+    for (int k = 0; k < 3; k++) {
+        unsigned int l = f2ord(lo[k]), h = f2ord(hi[k]);
+        l = __reduce_min_sync(0xffffffffu, l);
+        h = __reduce_max_sync(0xffffffffu, h);
+        if ((threadIdx.x & 31) == 0) { atomicMin(&bounds[k], l); atomicMax(&bounds[3 + k], h); }
+    }
+}
+
+__global__ void k_leaf_morton(const double *__restrict__ fverts, uint32_t n, BuildParams bp, BoxF *__restrict__ leafbox,
+                              unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals) {
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n) leaf_morton_thread(f, fverts, bp, leafbox, keys, vals);
+}
+
+__global__ void k_karras(const unsigned long long *__restrict__ keys, int n, KarrasNode *__restrict__ kn,
+                         int *__restrict__ parent_int, int *__restrict__ parent_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) karras_thread(i, keys, n, kn, parent_int, parent_leaf);
+}
+
+__global__ void k_refit_sah(int n, const uint32_t *__restrict__ vals, const BoxF *__restrict__ leafbox,
+                            const KarrasNode *__restrict__ kn, const int *__restrict__ parent_int,
+                            const int *__restrict__ parent_leaf, BoxF *ibox, float *icost, unsigned char *collapsed,
+                            unsigned int *flags, int max_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) refit_sah_thread(i, vals, leafbox, kn, parent_int, parent_leaf, ibox, icost, collapsed, flags, max_leaf);
+}
+
+__global__ void k_emit_count(const int *__restrict__ frontier, int fsize, const KarrasNode *__restrict__ kn,
+                             const unsigned char *__restrict__ collapsed, int *__restrict__ cnt) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < fsize) emit_count_thread(p, frontier, kn, collapsed, cnt);
+}
+
+__global__ void k_emit_write(const int *__restrict__ frontier, int fsize, int level_base, const KarrasNode *__restrict__ kn,
+                             const unsigned char *__restrict__ collapsed, const int *__restrict__ off,
+                             const uint32_t *__restrict__ vals, const BoxF *__restrict__ leafbox,
+                             const BoxF *__restrict__ ibox, RtNode *__restrict__ nodes, int *__restrict__ next_frontier,
+                             unsigned int *__restrict__ leaf_counter) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fsize) return;
+    unsigned int nleaf = emit_write_thread(p, frontier, fsize, level_base, kn, collapsed, off, vals, leafbox, ibox, nodes, next_frontier);
+    if (nleaf) atomicAdd(leaf_counter, nleaf);
+}
+
+__global__ void k_gather_tris(const double *__restrict__ fverts, const uint32_t *__restrict__ vals, uint32_t n,
+                              rt_f4 *__restrict__ tri32, double *__restrict__ tri64) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gather_tri_thread(i, fverts, vals, tri32, tri64);
+}
+
+// scratch allocations of one build, released on scope exit
+struct Scratch {
+    std::vector<void *> ptrs;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    MeshDevice *m = nullptr;
+    bool ok = false;
+    template <class T> cudaError_t alloc(T **p, size_t bytes) {
+        cudaError_t e = cudaMalloc((void **)p, bytes ? bytes : 16);
+        if (e == cudaSuccess) ptrs.push_back((void *)*p);
+        return e;
+    }
+    ~Scratch() {
+        for (void *p : ptrs) cudaFree(p);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (!ok && m) {
+            cudaFree(m->nodes); cudaFree(m->tri32); cudaFree(m->tri64);
+            m->nodes = nullptr; m->tri32 = nullptr; m->tri64 = nullptr;
+        }
+    }
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+}  // namespace
+
+// Builds nodes / tri32 / tri64 of `m` from m.fverts (device, 9 doubles per face).  Returns false + err.
+bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStream_t st, std::string &err) {
+    const uint32_t n = m.n_faces;
+    m.nodes = nullptr; m.tri32 = nullptr; m.tri64 = nullptr; m.n_nodes = 0; m.root_ref = 0;
+    memset(&m.info, 0, sizeof m.info);
+    m.info.n_faces = n; m.info.max_leaf = (uint32_t)max_leaf;
+    for (int k = 0; k < 3; k++) { m.lo[k] = 0.f; m.hi[k] = 0.f; }
+    if (n == 0) return true;
+    if (n > RT_LEAF_FIRST_MASK) { err = "mesh has too many faces for the 27-bit leaf encoding"; return false; }
+    if (max_leaf < 1) max_leaf = 1;
+    if (max_leaf > RT_MAX_LEAF) max_leaf = RT_MAX_LEAF;
+
+    unsigned int *d_bounds = nullptr; BoxF *d_leafbox = nullptr, *d_ibox = nullptr;
+    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
+    KarrasNode *d_kn = nullptr; int *d_pint = nullptr, *d_pleaf = nullptr; float *d_icost = nullptr;
+    unsigned char *d_coll = nullptr; unsigned int *d_flags = nullptr, *d_leafcnt = nullptr;
+    int *d_front[2] = { nullptr, nullptr }, *d_cnt = nullptr, *d_off = nullptr;
+    void *d_tmp = nullptr; size_t tmp_bytes = 0, tmp_scan = 0;
+    Scratch sc; sc.m = &m;
+    const int TB = 256;
+    const unsigned int nb = (n + TB - 1) / TB;
+    unsigned int hb[6];
+    BuildParams bp;
+    uint32_t *sorted_vals = nullptr;
+    unsigned long long *sorted_keys = nullptr;
+
+    CK(cudaEventCreate(&sc.ev0)); CK(cudaEventCreate(&sc.ev1));
+    CK(cudaEventRecord(sc.ev0, st));
+    CK(sc.alloc(&d_bounds, 6 * sizeof(unsigned int)));
+    {
+        unsigned int init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
+        CK(cudaMemcpyAsync(d_bounds, init, sizeof init, cudaMemcpyHostToDevice, st));
+    }
+    k_mesh_bounds<<<min(nb, 148u * 8u), TB, 0, st>>>(m.fverts, n, d_bounds);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(hb, d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    {
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; k++) { lo[k] = ord2f(hb[k]); hi[k] = ord2f(hb[3 + k]); }
+        bp = make_build_params(lo, hi, m.lo, m.hi);
+    }
+    CK(sc.alloc(&d_leafbox, sizeof(BoxF) * (size_t)n));
+    CK(sc.alloc(&d_keys, sizeof(unsigned long long) * (size_t)n));
+    CK(sc.alloc(&d_keys2, sizeof(unsigned long long) * (size_t)n));
+    CK(sc.alloc(&d_vals, sizeof(uint32_t) * (size_t)n));
+    CK(sc.alloc(&d_vals2, sizeof(uint32_t) * (size_t)n));
+    k_leaf_morton<<<nb, TB, 0, st>>>(m.fverts, n, bp, d_leafbox, d_keys, d_vals);
+    CK(cudaGetLastError());
+    {
+        cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys2);
+        cub::DoubleBuffer<uint32_t> vb(d_vals, d_vals2);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, (int)n, 0, 63, st));
+        CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (int *)nullptr, (int *)nullptr, (int)n, st));
+        if (tmp_scan > tmp_bytes) tmp_bytes = tmp_scan;
+        CK(sc.alloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
+        size_t tb = tmp_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(d_tmp, tb, kb, vb, (int)n, 0, 63, st));
+        sorted_keys = kb.Current(); sorted_vals = vb.Current();
+    }
+    if (want32) CK(cudaMalloc(&m.tri32, sizeof(rt_f4) * 3 * (size_t)n));
+    if (want64) CK(cudaMalloc(&m.tri64, sizeof(double) * 10 * (size_t)n));
+    k_gather_tris<<<nb, TB, 0, st>>>(m.fverts, sorted_vals, n, m.tri32, m.tri64);
+    CK(cudaGetLastError());
+
+    if (n == 1) {
+        m.root_ref = rt_leaf_ref(0, 1);
+        m.info.n_leaves = 1; m.info.max_depth = 0;
+    } else {
+        const int ni = (int)n - 1;
+        const unsigned int nbi = (ni + TB - 1) / TB;
+        CK(sc.alloc(&d_kn, sizeof(KarrasNode) * (size_t)ni));
+        CK(sc.alloc(&d_pint, sizeof(int) * (size_t)ni));
+        CK(sc.alloc(&d_pleaf, sizeof(int) * (size_t)n));
+        CK(sc.alloc(&d_ibox, sizeof(BoxF) * (size_t)ni));
+        CK(sc.alloc(&d_icost, sizeof(float) * (size_t)ni));
+        CK(sc.alloc(&d_coll, (size_t)ni));
+        CK(sc.alloc(&d_flags, sizeof(unsigned int) * (size_t)ni));
+        CK(sc.alloc(&d_leafcnt, sizeof(unsigned int)));
+        CK(cudaMemsetAsync(d_flags, 0, sizeof(unsigned int) * (size_t)ni, st));
+        CK(cudaMemsetAsync(d_leafcnt, 0, sizeof(unsigned int), st));
+        k_karras<<<nbi, TB, 0, st>>>(sorted_keys, (int)n, d_kn, d_pint, d_pleaf);
+        CK(cudaGetLastError());
+        k_refit_sah<<<nb, TB, 0, st>>>((int)n, sorted_vals, d_leafbox, d_kn, d_pint, d_pleaf, d_ibox, d_icost, d_coll,
+                                       d_flags, max_leaf);
+        CK(cudaGetLastError());
+        // root
+        unsigned char root_coll = 0; float root_cost = 0.f; BoxF root_box;
+        CK(cudaMemcpyAsync(&root_coll, d_coll, 1, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&root_cost, d_icost, sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&root_box, d_ibox, sizeof(BoxF), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        { float a = box_half_area(root_box); m.info.sah_cost = a > 0.f ? root_cost / a : 0.f; }
+        if (root_coll) {
+            m.root_ref = rt_leaf_ref(0, n);
+            m.info.n_leaves = 1;
+        } else {
+            CK(cudaMalloc(&m.nodes, sizeof(RtNode) * (size_t)ni));
+            CK(sc.alloc(&d_front[0], sizeof(int) * (size_t)ni));
+            CK(sc.alloc(&d_front[1], sizeof(int) * (size_t)ni));
+            CK(sc.alloc(&d_cnt, sizeof(int) * (size_t)(ni + 1)));
+            CK(sc.alloc(&d_off, sizeof(int) * (size_t)(ni + 1)));
+            int zero = 0;
+            CK(cudaMemcpyAsync(d_front[0], &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+            int fsize = 1, base = 0, cur = 0, depth = 0;
+            while (fsize > 0) {
+                unsigned int fb = (fsize + TB - 1) / TB;
+                k_emit_count<<<fb, TB, 0, st>>>(d_front[cur], fsize, d_kn, d_coll, d_cnt);
+                CK(cudaGetLastError());
+                size_t tb = tmp_bytes;
+                CK(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_off, fsize, st));
+                k_emit_write<<<fb, TB, 0, st>>>(d_front[cur], fsize, base, d_kn, d_coll, d_off, sorted_vals, d_leafbox, d_ibox,
+                                                m.nodes, d_front[cur ^ 1], d_leafcnt);
+                CK(cudaGetLastError());
+                int last_off = 0, last_cnt = 0;
+                CK(cudaMemcpyAsync(&last_off, d_off + (fsize - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(&last_cnt, d_cnt + (fsize - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                base += fsize;
+                fsize = last_off + last_cnt;
+                cur ^= 1;
+                depth++;
+                if (depth > RT_STACK_SIZE - 2) { err = "BVH deeper than the traversal stack"; return false; }
+            }
+            m.n_nodes = (uint32_t)base;
+            m.root_ref = 0;
+            m.info.max_depth = (uint32_t)depth;
+            unsigned int nl = 0;
+            CK(cudaMemcpyAsync(&nl, d_leafcnt, sizeof nl, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            m.info.n_leaves = nl;
+        }
+    }
+    m.info.n_nodes = m.n_nodes;
+    CK(cudaEventRecord(sc.ev1, st));
+    CK(cudaEventSynchronize(sc.ev1));
+    CK(cudaEventElapsedTime(&m.info.ms_build, sc.ev0, sc.ev1));
+    sc.ok = true;
+    return true;
+}

@@ -1,0 +1,376 @@
+// render.cu -- the render kernels (sm_100a):
+//   K2  k_primary_*        primary-ray generation + nearest-hit BVH traversal, appends compact HitRecs
+//   K3  Moller-Trumbore    device functions tri_test32 / tri_intersection_exact inlined in K2 and K4
+//   K4  k_shade            fused shadow rays + Phong shading per primary hit (fp64, reference order)
+//   K5  k_write            8-bit framebuffer writer (+ optional dense debug outputs)
+//       k_untile           multi-GPU: interleaved-tile buffers -> framebuffer
+//
+// They replace the per-pixel double loop of worker/distributed/main.go:67-88 and
+// worker/sequential/main.go:21-28 (each iteration = tracer.Trace, worker/shared/tracer/tracer.go:81-91).
+#include "rt_internal.h"
+#include "rt_traverse.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ void flush_counters(Counters *g, const Counters &c) {
+    if (g) {
+        unsigned long long n = c.nodes, t = c.tris;
+        // warp-aggregate
+        for (int o = 16; o > 0; o >>= 1) { n += __shfl_down_sync(FULL, n, o); t += __shfl_down_sync(FULL, t, o); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&g->nodes, n); atomicAdd(&g->tris, t); }
+    }
+}
+
+// append this lane's hit (if any) to the compact hit list; all 32 lanes must call
+__device__ __forceinline__ void append_hit(bool hit, uint32_t ray, int obj, int face, float t, HitRec *hits,
+                                           unsigned int *hit_count) {
+    unsigned m = __ballot_sync(FULL, hit);
+    if (m == 0) return;
+    unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(hit_count, (unsigned)__popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (hit) {
+        HitRec h; h.pix = ray; h.obj = obj; h.face = face; h.t = t;
+        hits[base + __popc(m & ((1u << lane) - 1u))] = h;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2, FP64_EXACT: one thread per ray, 8x4 pixel block per warp
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_primary_exact(FrameParams fp, SceneView sc, bool brute, HitRec *hits,
+                                                        unsigned int *counters, Counters *gstats) {
+    uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nrays = ray_count(fp);
+    Counters c; c.nodes = 0; c.tris = 0;
+    bool hit = false;
+    TraceExact tr; tr.face = -1; tr.obj = -1;
+    if (ray < nrays) {
+        PixMap pm = map_ray(ray, fp, false);
+        if (pm.valid) {
+            dv d = primary_dir_exact(pm.i, pm.j, fp);
+            hit = trace_exact(sc, fp, dv_ld(fp.cam_pos), d, brute, tr, COUNT ? &c : nullptr);
+        }
+    }
+    append_hit(hit, ray, tr.obj, tr.face, 0.0f, hits, &counters[1]);
+    if (COUNT) flush_counters(gstats, c);
+}
+
+// fp32 primary ray (direction normalised in fp32); shading recomputes the fp64 ray exactly
+__device__ __forceinline__ void primary_dir32(int i, int j, const FrameParams &fp, float &dx, float &dy, float &dz) {
+    int hw = fp.W / 2, hh = fp.H / 2;
+    float phw = (float)fp.tan_half;
+    float phh = phw * (float)fp.H / (float)fp.W;
+    float si = phw * ((float)(hw - i) - 0.5f) / (float)hw;
+    float sj = phh * ((float)(hh - j) - 0.5f) / (float)hh;
+    float x = (float)fp.fwd[0] + (float)fp.left[0] * si + (float)fp.up[0] * sj;
+    float y = (float)fp.fwd[1] + (float)fp.left[1] * si + (float)fp.up[1] * sj;
+    float z = (float)fp.fwd[2] + (float)fp.left[2] * si + (float)fp.up[2] * sj;
+    float inv = rsqrtf(x * x + y * y + z * z);
+    dx = x * inv; dy = y * inv; dz = z * inv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2, FP32_FAST, simple variant: one thread per ray (any number of objects)
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_primary_fast_simple(FrameParams fp, SceneView sc, HitRec *hits,
+                                                              unsigned int *counters, Counters *gstats) {
+    uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nrays = ray_count(fp);
+    Counters c; c.nodes = 0; c.tris = 0;
+    bool hit = false;
+    TraceFast tr; tr.face = -1; tr.obj = -1; tr.t = 0.f;
+    if (ray < nrays) {
+        PixMap pm = map_ray(ray, fp, false);
+        if (pm.valid) {
+            float dx, dy, dz;
+            primary_dir32(pm.i, pm.j, fp, dx, dy, dz);
+            dv d = dv_make((double)dx, (double)dy, (double)dz);
+            hit = trace_fast_nearest(sc, fp, dv_ld(fp.cam_pos), d, true, tr, COUNT ? &c : nullptr);
+        }
+    }
+    append_hit(hit, ray, tr.obj, tr.face, tr.t, hits, &counters[1]);
+    if (COUNT) flush_counters(gstats, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2, FP32_FAST, persistent warp-cooperative variant (single object / single mesh).
+//
+//  * persistent threads: grid = SMs x resident CTAs; every warp pulls rays from one global counter
+//  * refill: idle lanes are found with a ballot, ONE atomicAdd per warp claims popc(idle) rays, the base
+//    is shuffled to all lanes and each idle lane takes base + its rank among the idle lanes
+//  * traversal: per-lane while-while loop (internal nodes, then the postponed leaf); a lane that found
+//    a leaf keeps descending speculatively until every lane of the warp has one (__any_sync)
+//  * a warp whose live-lane count drops below REFILL_BELOW leaves the loop and refills
+//  * the first TOPN nodes (BFS order => the top levels of the tree) are served from shared memory
+//  * node = 4 x LDG.128, triangle = 3 x LDG.128 through the read-only path
+// ---------------------------------------------------------------------------------------------
+constexpr int SENTINEL = 0x7fffffff;
+
+template <bool COUNT, int TOPN, int REFILL_BELOW>
+__global__ void __launch_bounds__(128, 4)
+k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, float olz, HitRec *hits, unsigned int *counters,
+                          Counters *gstats) {
+    __shared__ RtNode s_top[TOPN > 0 ? TOPN : 1];
+    const int ntop = TOPN < (int)m.n_nodes ? TOPN : (int)m.n_nodes;
+    if (TOPN > 0) {
+        // cooperative 16-byte copy of the top of the tree
+        const float4 *src = reinterpret_cast<const float4 *>(m.nodes);
+        float4 *dst = reinterpret_cast<float4 *>(s_top);
+        for (int k = threadIdx.x; k < ntop * 4; k += blockDim.x) dst[k] = __ldg(src + k);
+        __syncthreads();
+    }
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t nrays = ray_count(fp);
+    Counters c; c.nodes = 0; c.tris = 0;
+
+    int stack[RT_STACK_SIZE];
+    int sp = 0;
+    int ref = SENTINEL;       // SENTINEL => lane has no ray in flight
+    int leaf = 0;             // postponed leaf (negative ref) or 0
+    bool have = false;        // lane holds a ray whose result is not stored yet
+    uint32_t ray = 0;
+    RayF r = make_rayf(0, 0, 0, 0, 0, 1);
+    float tbest = 0.f;
+    int face = -1;
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- store finished rays (warp-converged point) ----
+        bool finished = have && ref == SENTINEL && leaf == 0;
+        append_hit(finished && face >= 0, ray, 0, face, tbest, hits, &counters[1]);
+        if (finished) have = false;
+
+        // ---- refill idle lanes: ballot + one atomicAdd per warp + shuffle ----
+        unsigned idle = __ballot_sync(FULL, !have);
+        if (idle && !exhausted) {
+            unsigned n = __popc(idle);
+            unsigned base = 0;
+            if (lane == (unsigned)(__ffs(idle) - 1)) base = atomicAdd(&counters[0], n);
+            base = __shfl_sync(FULL, base, __ffs(idle) - 1);
+            if (base + n >= nrays) exhausted = true;      // warp-uniform
+            if (!have) {
+                uint32_t my = base + __popc(idle & lt_mask);
+                if (my < nrays) {
+                    PixMap pm = map_ray(my, fp, false);
+                    if (pm.valid) {
+                        float dx, dy, dz;
+                        primary_dir32(pm.i, pm.j, fp, dx, dy, dz);
+                        r = make_rayf(olx, oly, olz, dx, dy, dz);
+                        tbest = 3.0e38f; face = -1;
+                        float tin;
+                        // root box; a miss needs no store at all (the framebuffer is pre-cleared)
+                        if (slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, tbest, tin)) {
+                            have = true; ray = my; sp = 0; leaf = 0; ref = m.root_ref;
+                            if (ref < 0) { leaf = ref; ref = SENTINEL; }   // the whole mesh is one leaf
+                        }
+                    }
+                }
+            }
+        }
+        unsigned live = __ballot_sync(FULL, have);
+        if (live == 0) { if (exhausted) break; else continue; }
+        // most rays of a frame miss the root box: keep claiming rays until enough lanes are live
+        if (!exhausted && __popc(live) < REFILL_BELOW) continue;
+
+        // ---- traversal ----
+        while (ref != SENTINEL || leaf < 0) {
+            // internal nodes
+            while (ref >= 0 && ref != SENTINEL) {
+                rt_f4 a, b, cc; rt_i4 ch;
+                if (TOPN > 0 && ref < ntop) { a = s_top[ref].a; b = s_top[ref].b; cc = s_top[ref].c; ch = s_top[ref].d; }
+                else { const RtNode *n = m.nodes + ref; a = ld_f4(&n->a); b = ld_f4(&n->b); cc = ld_f4(&n->c); ch = ld_i4(&n->d); }
+                if (COUNT) c.nodes++;
+                float t0, t1;
+                bool h0 = slab32(a.x, a.y, a.z, a.w, cc.x, cc.y, r, tbest, t0);
+                bool h1 = slab32(b.x, b.y, b.z, b.w, cc.z, cc.w, r, tbest, t1);
+                if (h0 && h1) {
+                    int nearc = ch.x, farc = ch.y;
+                    if (t1 < t0) { nearc = ch.y; farc = ch.x; }
+                    stack[sp++] = farc;
+                    ref = nearc;
+                } else if (h0) ref = ch.x;
+                else if (h1) ref = ch.y;
+                else ref = sp ? stack[--sp] : SENTINEL;
+                // postpone the first leaf found and keep descending (speculative traversal)
+                if (ref < 0 && leaf == 0) { leaf = ref; ref = sp ? stack[--sp] : SENTINEL; }
+                // every lane of the converged group holds a leaf -> go intersect
+                if (!__any_sync(__activemask(), leaf == 0)) break;
+            }
+            // leaves
+            while (leaf < 0) {
+                uint32_t first = rt_leaf_first(leaf), count = rt_leaf_count(leaf);
+                if (COUNT) c.tris += count;
+                for (uint32_t k = first; k < first + count; k++) {
+                    const rt_f4 *p = m.tri32 + 3 * (size_t)k;
+                    rt_f4 v0 = ld_f4(p), v1 = ld_f4(p + 1), v2 = ld_f4(p + 2);
+                    float t, u, v;
+                    if (tri_test32(v0, v1, v2, r, t, u, v)) {
+                        int f = __float_as_int(v0.w);
+                        if (t < tbest || (t == tbest && (face < 0 || f < face))) { tbest = t; face = f; }
+                    }
+                }
+                // the node reached after the postponed leaf may itself be a leaf
+                leaf = 0;
+                if (ref < 0) { leaf = ref; ref = sp ? stack[--sp] : SENTINEL; }
+            }
+            // too few live lanes in this warp -> go back and refill
+            if (!exhausted && __popc(__activemask()) < REFILL_BELOW) break;
+        }
+    }
+    if (COUNT) flush_counters(gstats, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: fused shadow rays + Phong shading, one thread per primary hit; warps claim 32 hits at a time
+// ---------------------------------------------------------------------------------------------
+template <bool EXACT, bool COUNT>
+__global__ void __launch_bounds__(128) k_shade(FrameParams fp, SceneView sc, bool brute, const HitRec *__restrict__ hits,
+                                                unsigned int *counters, double *__restrict__ hit_colour,
+                                                uint32_t *__restrict__ hit_lit, Counters *gstats) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned int nhits = counters[1];
+    Counters c; c.nodes = 0; c.tris = 0;
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&counters[2], 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= nhits) break;
+        unsigned h = base + lane;
+        if (h < nhits) {
+            HitRec hr = hits[h];
+            PixMap pm = map_ray(hr.pix, fp, false);
+            double col[3];
+            uint32_t lit = shade_hit<EXACT>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, COUNT ? &c : nullptr);
+            hit_colour[3 * (size_t)h] = col[0]; hit_colour[3 * (size_t)h + 1] = col[1]; hit_colour[3 * (size_t)h + 2] = col[2];
+            hit_lit[h] = lit;
+        }
+    }
+    if (COUNT) flush_counters(gstats, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: 8-bit framebuffer writer.  Misses were pre-cleared (sequential/main.go:17 FillRect(nil,0);
+// distributed/main.go:70 default 0,0,0).  Quantisers: colour.go:59-61 and colour.go:54-56 (+ SDL >>8).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_write(FrameParams fp, const HitRec *__restrict__ hits, const unsigned int *counters,
+                        const double *__restrict__ hit_colour, const uint32_t *__restrict__ hit_lit, bool rowmajor, bool sdl,
+                        uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour, int32_t *__restrict__ out_face,
+                        int32_t *__restrict__ out_obj, uint32_t *__restrict__ out_lit) {
+    const unsigned int nhits = counters[1];
+    for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < nhits; h += gridDim.x * blockDim.x) {
+        HitRec hr = hits[h];
+        PixMap pm = map_ray(hr.pix, fp, rowmajor);
+        size_t o = pm.out;
+        double cr = hit_colour[3 * (size_t)h], cg = hit_colour[3 * (size_t)h + 1], cb = hit_colour[3 * (size_t)h + 2];
+        if (out_rgb) {
+            out_rgb[3 * o] = quantise_exact(cr, sdl);
+            out_rgb[3 * o + 1] = quantise_exact(cg, sdl);
+            out_rgb[3 * o + 2] = quantise_exact(cb, sdl);
+        }
+        if (out_colour) { out_colour[3 * o] = cr; out_colour[3 * o + 1] = cg; out_colour[3 * o + 2] = cb; }
+        if (out_face) out_face[o] = hr.face;
+        if (out_obj) out_obj[o] = hr.obj;
+        if (out_lit) out_lit[o] = hit_lit[h];
+    }
+}
+
+// multi-GPU: gathered interleaved-tile buffers -> framebuffer (one thread per pixel)
+__global__ void k_untile(const uint8_t *__restrict__ tiles, uint8_t *__restrict__ out, int W, int H, int tw, int th,
+                         int n_ranks, int tiles_per_rank_max, bool rowmajor) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= W || j >= H) return;
+    int tiles_x = (W + tw - 1) / tw;
+    int t = (j / th) * tiles_x + (i / tw);
+    int rank = t % n_ranks, lt = t / n_ranks;
+    size_t src = ((size_t)(rank * tiles_per_rank_max + lt) * (size_t)(tw * th) + (size_t)((j % th) * tw + (i % tw))) * 3;
+    size_t dst = (rowmajor ? (size_t)j * W + i : (size_t)i * H + j) * 3;
+    out[dst] = tiles[src]; out[dst + 1] = tiles[src + 1]; out[dst + 2] = tiles[src + 2];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
+    const FrameParams &fp = job.fp;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights;
+    const uint32_t nrays = ray_count(fp);
+    if (nrays == 0) return cudaSuccess;
+    const bool count = (job.flags & RT_FLAG_COUNT) != 0;
+    const unsigned nblk = (nrays + 127) / 128;
+    if (job.precision == RT_FP64_EXACT) {
+        const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
+        if (count) k_primary_exact<true><<<nblk, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_stats);
+        else k_primary_exact<false><<<nblk, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_stats);
+        return cudaGetLastError();
+    }
+    const bool simple = (job.flags & RT_FLAG_SIMPLE) != 0 || fp.n_obj != 1 || !job.single_mesh;
+    if (simple) {
+        if (count) k_primary_fast_simple<true><<<nblk, 128, 0, st>>>(fp, sc, job.d_hits, job.d_counters, job.d_stats);
+        else k_primary_fast_simple<false><<<nblk, 128, 0, st>>>(fp, sc, job.d_hits, job.d_counters, job.d_stats);
+        return cudaGetLastError();
+    }
+    // persistent: one object; its mesh view and the object-space ray origin are passed by value
+    const MeshView &m = job.h_mesh0;
+    const float olx = (float)(fp.cam_pos[0] - job.h_obj0_pos[0]), oly = (float)(fp.cam_pos[1] - job.h_obj0_pos[1]),
+                olz = (float)(fp.cam_pos[2] - job.h_obj0_pos[2]);
+    int per_sm = 0;
+    cudaError_t e;
+#define LAUNCH_PERSISTENT(COUNTF, TOPN)                                                                                  \
+    do {                                                                                                                 \
+        auto kern = k_primary_fast_persistent<COUNTF, TOPN, 20>;                                                         \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);                                        \
+        if (e != cudaSuccess) return e;                                                                                  \
+        if (per_sm < 1) per_sm = 1;                                                                                      \
+        unsigned g = (unsigned)(job.sm_count * per_sm);                                                                  \
+        unsigned need = (nrays + 127) / 128;                                                                             \
+        if (g > need) g = need;                                                                                          \
+        kern<<<g, 128, 0, st>>>(fp, m, olx, oly, olz, job.d_hits, job.d_counters, job.d_stats);                          \
+    } while (0)
+    if (job.top_in_smem) { if (count) LAUNCH_PERSISTENT(true, 256); else LAUNCH_PERSISTENT(false, 256); }
+    else { if (count) LAUNCH_PERSISTENT(true, 0); else LAUNCH_PERSISTENT(false, 0); }
+#undef LAUNCH_PERSISTENT
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
+    const FrameParams &fp = job.fp;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights;
+    if (ray_count(fp) == 0) return cudaSuccess;
+    const bool count = (job.flags & RT_FLAG_COUNT) != 0;
+    const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
+    const unsigned g = (unsigned)job.sm_count * 8u;
+    if (job.precision == RT_FP64_EXACT) {
+        if (count) k_shade<true, true><<<g, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
+        else k_shade<true, false><<<g, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
+    } else {
+        if (count) k_shade<false, true><<<g, 128, 0, st>>>(fp, sc, false, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
+        else k_shade<false, false><<<g, 128, 0, st>>>(fp, sc, false, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_write(const RenderJob &job, cudaStream_t st) {
+    if (ray_count(job.fp) == 0) return cudaSuccess;
+    const bool rowmajor = (job.flags & RT_LAYOUT_ROWMAJOR) != 0, sdl = (job.flags & RT_QUANT_RGBA16_SHR8) != 0;
+    k_write<<<(unsigned)job.sm_count * 8u, 256, 0, st>>>(job.fp, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit,
+                                                        rowmajor, sdl, job.d_out_rgb, job.d_out_colour, job.d_out_face,
+                                                        job.d_out_obj, job.d_out_lit);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_untile(const uint8_t *d_tiles, uint8_t *d_out, int W, int H, int tile_w, int tile_h, int n_ranks,
+                             int tiles_per_rank_max, bool rowmajor, cudaStream_t st) {
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    k_untile<<<g, b, 0, st>>>(d_tiles, d_out, W, H, tile_w, tile_h, n_ranks, tiles_per_rank_max, rowmajor);
+    return cudaGetLastError();
+}

@@ -1,0 +1,63 @@
+// rt_internal.h -- declarations shared by the translation units of librt_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rt_types.h"
+#include "rt_bvh.cuh"
+
+// Device-resident mesh (owned by rt_scene)
+struct MeshDevice {
+    RtNode   *nodes = nullptr;
+    rt_f4    *tri32 = nullptr;
+    double   *tri64 = nullptr;
+    double   *fverts = nullptr;
+    double   *fnormals = nullptr;
+    uint32_t *fmat = nullptr;
+    double   *materials = nullptr;
+    uint32_t  n_faces = 0, n_nodes = 0, n_materials = 0;
+    int       root_ref = 0;
+    float     lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+    rt_bvh_info info;
+};
+
+bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStream_t st, std::string &err);
+
+// Per-render device scratch + launch description
+struct RenderJob {
+    FrameParams fp;
+    const MeshView *d_meshes;
+    const ObjRec   *d_objs;
+    const LightRec *d_lights;
+    uint32_t precision;
+    uint32_t flags;
+    // scratch (device)
+    HitRec   *d_hits;         // capacity = ray_count
+    double   *d_hit_colour;   // 3 per hit
+    uint32_t *d_hit_lit;      // per hit
+    unsigned int *d_counters; // [0]=next ray (primary), [1]=hit count, [2]=next hit (shade), [3]=next hit (write)
+    Counters *d_stats;        // nodes/tris (RT_FLAG_COUNT) or nullptr
+    // outputs (device)
+    uint8_t  *d_out_rgb;
+    double   *d_out_colour;   // optional dense debug outputs
+    int32_t  *d_out_face;
+    int32_t  *d_out_obj;
+    uint32_t *d_out_lit;
+    int       sm_count;
+    bool      single_mesh;    // exactly one object => the persistent kernel takes its mesh by value
+    MeshView  h_mesh0;        // host copy of object 0's mesh view
+    double    h_obj0_pos[3];
+    bool      top_in_smem;    // keep the first levels of the BVH in shared memory (single-mesh scenes)
+};
+
+// render.cu : enqueue K2 (primary) / K4 (shadow+shade) / K5 (framebuffer) on `st`
+cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st);
+cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st);
+cudaError_t rt_launch_write(const RenderJob &job, cudaStream_t st);
+cudaError_t rt_launch_untile(const uint8_t *d_tiles, uint8_t *d_out, int W, int H, int tile_w, int tile_h, int n_ranks,
+                             int tiles_per_rank_max, bool rowmajor, cudaStream_t st);

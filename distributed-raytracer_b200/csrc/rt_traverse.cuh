@@ -1,0 +1,349 @@
+// rt_traverse.cuh -- per-ray BVH traversal + scene-level trace/shade device functions.
+//
+// Everything here is RT_HD (host+device) and free of warp intrinsics so that tests/emul can run
+// the identical code on the CPU; the persistent warp-cooperative primary kernel in render.cu
+// re-uses the node/triangle primitives below inside its own restructured loop.
+//
+// Reference semantics implemented (paths under /root/reference/):
+//   shared/state/object.go:63-110   per-object nearest hit, metric Len(o_local - ip), strict '<'
+//   worker/shared/tracer/tracer.go:27-50  world nearest, metric Len(ip_world - Cam.Pos), strict '<'
+//   worker/shared/tracer/tracer.go:53-77  phong with full nearest-hit shadow queries
+// The R-tree candidate search (object.go:76, box.go:29-69) is replaced by a BVH that may only CULL:
+// in FP64_EXACT mode boxes are padded and the cull bound is inflated so that every face the
+// reference's Moller-Trumbore test accepts and that could win is still tested, and the winner is
+// the lexicographic (distance, face index) minimum == "first in enumeration order, strict <".
+#pragma once
+#include "rt_exact.cuh"
+
+struct alignas(16) rt_d2 { double x, y; };
+
+struct SceneView {
+    const MeshView *meshes;
+    const ObjRec   *objs;
+    const LightRec *lights;
+};
+
+#if defined(__CUDA_ARCH__)
+#define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); } while (0)
+#else
+#define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); } while (0)
+#endif
+
+RT_HD rt_f4 ld_f4(const rt_f4 *p) {
+#if defined(__CUDA_ARCH__)
+    float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+    rt_f4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    return *p;
+#endif
+}
+RT_HD rt_i4 ld_i4(const rt_i4 *p) {
+#if defined(__CUDA_ARCH__)
+    int4 v = __ldg(reinterpret_cast<const int4 *>(p));
+    rt_i4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    return *p;
+#endif
+}
+RT_HD rt_d2 ld_d2(const double *p) {
+#if defined(__CUDA_ARCH__)
+    double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+    rt_d2 r; r.x = v.x; r.y = v.y; return r;
+#else
+    rt_d2 r; r.x = p[0]; r.y = p[1]; return r;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64_EXACT
+// ------------------------------------------------------------------------------------------------
+struct BestExact { bool has; double dist; TriHit h; int face; };
+
+// object.go:88-105 for one candidate face
+RT_HD void consider_exact(dv P1, dv P2, dv P3, int face, dv o, dv d, BestExact &b) {
+    TriHit h;
+    if (tri_intersection_exact(P1, P2, P3, o, d, h)) {                      // object.go:88
+        double dist = dv_len(dv_sub(o, h.ip));                              // object.go:97
+        if (!b.has || dist < b.dist || (dist == b.dist && face < b.face)) { // object.go:98 (+ lowest index on ties)
+            b.has = true; b.dist = dist; b.h = h; b.face = face;
+        }
+    }
+}
+
+// conservative fp64 slab test of a padded fp32 box
+RT_HD bool slab64(float lox, float hix, float loy, float hiy, float loz, float hiz, dv o, dv idir, double cull,
+                  double &tin) {
+    double t1 = ((double)lox - o.x) * idir.x, t2 = ((double)hix - o.x) * idir.x;
+    double tmin = fmin(t1, t2), tmax = fmax(t1, t2);
+    t1 = ((double)loy - o.y) * idir.y; t2 = ((double)hiy - o.y) * idir.y;
+    tmin = fmax(tmin, fmin(t1, t2)); tmax = fmin(tmax, fmax(t1, t2));
+    t1 = ((double)loz - o.z) * idir.z; t2 = ((double)hiz - o.z) * idir.z;
+    tmin = fmax(tmin, fmin(t1, t2)); tmax = fmin(tmax, fmax(t1, t2));
+    tin = tmin;
+    return tmin <= tmax && tmax >= 0.0 && tmin <= cull;
+}
+
+RT_HD double cull_bound(const BestExact &b) { return b.has ? b.dist * (1.0 + 1e-9) + 1e-300 : HUGE_VAL; }
+
+// Nearest hit of one mesh in object space.  brute => every face in index order (no BVH).
+RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bool brute, Counters *cnt) {
+    if (m.n_faces == 0) return;
+    if (brute) {
+        for (uint32_t f = 0; f < m.n_faces; f++) {
+            const double *p = m.fverts + 9 * (size_t)f;
+            consider_exact(dv_ld(p), dv_ld(p + 3), dv_ld(p + 6), (int)f, o, d, best);
+        }
+        RT_COUNT(cnt, tris, m.n_faces);
+        return;
+    }
+    dv idir = dv_make(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    double tin;
+    if (!slab64(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], o, idir, cull_bound(best), tin)) return;
+    int stack[RT_STACK_SIZE];
+    int sp = 0;
+    int ref = m.root_ref;
+    for (;;) {
+        if (ref >= 0) {
+            const RtNode *n = m.nodes + ref;
+            rt_f4 a = ld_f4(&n->a), b = ld_f4(&n->b), c = ld_f4(&n->c);
+            rt_i4 ch = ld_i4(&n->d);
+            RT_COUNT(cnt, nodes, 1);
+            double cull = cull_bound(best);
+            double t0, t1;
+            bool h0 = slab64(a.x, a.y, a.z, a.w, c.x, c.y, o, idir, cull, t0);
+            bool h1 = slab64(b.x, b.y, b.z, b.w, c.z, c.w, o, idir, cull, t1);
+            if (h0 && h1) {
+                int nearc = ch.x, farc = ch.y;
+                if (t1 < t0) { nearc = ch.y; farc = ch.x; }
+                stack[sp++] = farc;
+                ref = nearc;
+                continue;
+            } else if (h0) { ref = ch.x; continue; }
+            else if (h1) { ref = ch.y; continue; }
+        } else {
+            uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
+            RT_COUNT(cnt, tris, count);
+            for (uint32_t k = first; k < first + count; k++) {
+                const double *p = m.tri64 + 10 * (size_t)k;
+                rt_d2 q0 = ld_d2(p), q1 = ld_d2(p + 2), q2 = ld_d2(p + 4), q3 = ld_d2(p + 6), q4 = ld_d2(p + 8);
+                consider_exact(dv_make(q0.x, q0.y, q1.x), dv_make(q1.y, q2.x, q2.y), dv_make(q3.x, q3.y, q4.x),
+                               (int)q4.y, o, d, best);
+            }
+        }
+        if (sp == 0) break;
+        ref = stack[--sp];
+    }
+}
+
+struct TraceExact { dv ip; int face, obj; double r1, r2, r3; };
+
+// tracer.go:27-50 (objects visited in scene order; ties of the camera distance keep the first)
+RT_HD bool trace_exact(const SceneView &sc, const FrameParams &fp, dv o, dv d, bool brute, TraceExact &out,
+                       Counters *cnt) {
+    bool exists = false;
+    double nd = 0.0;
+    dv cam = dv_ld(fp.cam_pos);
+    for (int k = 0; k < fp.n_obj; k++) {
+        const ObjRec &ob = sc.objs[k];
+        dv pos = dv_ld(ob.pos);
+        BestExact b; b.has = false; b.dist = 0.0; b.face = -1;
+        mesh_nearest_exact(sc.meshes[ob.mesh], dv_sub(o, pos), d, b, brute, cnt);       // object.go:71
+        if (b.has) {
+            dv ipw = dv_add(b.h.ip, pos);                                                // object.go:109
+            double dist = dv_len(dv_sub(ipw, cam));                                      // tracer.go:38
+            if (!exists || dist < nd) {                                                  // tracer.go:39
+                exists = true; nd = dist;
+                out.ip = ipw; out.face = b.face; out.obj = k; out.r1 = b.h.r1; out.r2 = b.h.r2; out.r3 = b.h.r3;
+            }
+        }
+    }
+    return exists;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32_FAST
+// ------------------------------------------------------------------------------------------------
+struct RayF { float ox, oy, oz, dx, dy, dz, ix, iy, iz, ax, ay, az; };   // i = 1/d, a = o/d
+
+RT_HD float safe_rcp(float d) {
+    const float eps = 8.2718061e-25f;   // 2^-80
+    float ad = fabsf(d) > eps ? d : copysignf(eps, d);
+    return 1.0f / ad;
+}
+RT_HD RayF make_rayf(float ox, float oy, float oz, float dx, float dy, float dz) {
+    RayF r;
+    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+    r.ix = safe_rcp(dx); r.iy = safe_rcp(dy); r.iz = safe_rcp(dz);
+    r.ax = ox * r.ix; r.ay = oy * r.iy; r.az = oz * r.iz;
+    return r;
+}
+
+// slab test of one child box; returns entry distance in tin
+RT_HD bool slab32(float lox, float hix, float loy, float hiy, float loz, float hiz, const RayF &r, float tbest,
+                  float &tin) {
+    float x0 = fmaf(lox, r.ix, -r.ax), x1 = fmaf(hix, r.ix, -r.ax);
+    float y0 = fmaf(loy, r.iy, -r.ay), y1 = fmaf(hiy, r.iy, -r.ay);
+    float z0 = fmaf(loz, r.iz, -r.az), z1 = fmaf(hiz, r.iz, -r.az);
+    float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tbest));
+    tin = tmin;
+    return tmin <= tmax;
+}
+
+// fp32 Moller-Trumbore, same acceptance rules as triangle.go:37-77 (two-sided, inclusive, t >= 0)
+RT_HD bool tri_test32(rt_f4 v0, rt_f4 v1, rt_f4 v2, const RayF &r, float &t, float &u, float &v) {
+    float e1x = v1.x - v0.x, e1y = v1.y - v0.y, e1z = v1.z - v0.z;
+    float e2x = v2.x - v0.x, e2y = v2.y - v0.y, e2z = v2.z - v0.z;
+    float px = fmaf(r.dy, e2z, -(r.dz * e2y)), py = fmaf(r.dz, e2x, -(r.dx * e2z)), pz = fmaf(r.dx, e2y, -(r.dy * e2x));
+    float det = fmaf(e1x, px, fmaf(e1y, py, e1z * pz));
+    if (det == 0.0f) return false;
+    float inv = 1.0f / det;
+    float tx = r.ox - v0.x, ty = r.oy - v0.y, tz = r.oz - v0.z;
+    u = fmaf(tx, px, fmaf(ty, py, tz * pz)) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    float qx = fmaf(ty, e1z, -(tz * e1y)), qy = fmaf(tz, e1x, -(tx * e1z)), qz = fmaf(tx, e1y, -(ty * e1x));
+    v = fmaf(r.dx, qx, fmaf(r.dy, qy, r.dz * qz)) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    t = fmaf(e2x, qx, fmaf(e2y, qy, e2z * qz)) * inv;
+    return t >= 0.0f;
+}
+
+// Simple per-ray traversal of one mesh (object space).  ANY: stop at the first hit with t <= tbest.
+// Nearest: winner = min t, ties -> lowest face index.  Returns true if something was accepted.
+template <bool ANY>
+RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &face, Counters *cnt) {
+    if (m.n_faces == 0) return false;
+    float tin;
+    if (!slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, tbest, tin)) return false;
+    bool found = false;
+    int stack[RT_STACK_SIZE];
+    int sp = 0;
+    int ref = m.root_ref;
+    for (;;) {
+        if (ref >= 0) {
+            const RtNode *n = m.nodes + ref;
+            rt_f4 a = ld_f4(&n->a), b = ld_f4(&n->b), c = ld_f4(&n->c);
+            rt_i4 ch = ld_i4(&n->d);
+            RT_COUNT(cnt, nodes, 1);
+            float t0, t1;
+            bool h0 = slab32(a.x, a.y, a.z, a.w, c.x, c.y, r, tbest, t0);
+            bool h1 = slab32(b.x, b.y, b.z, b.w, c.z, c.w, r, tbest, t1);
+            if (h0 && h1) {
+                int nearc = ch.x, farc = ch.y;
+                if (t1 < t0) { nearc = ch.y; farc = ch.x; }
+                stack[sp++] = farc;
+                ref = nearc;
+                continue;
+            } else if (h0) { ref = ch.x; continue; }
+            else if (h1) { ref = ch.y; continue; }
+        } else {
+            uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
+            RT_COUNT(cnt, tris, count);
+            for (uint32_t k = first; k < first + count; k++) {
+                const rt_f4 *p = m.tri32 + 3 * (size_t)k;
+                rt_f4 v0 = ld_f4(p), v1 = ld_f4(p + 1), v2 = ld_f4(p + 2);
+                float t, u, v;
+                if (tri_test32(v0, v1, v2, r, t, u, v)) {
+#if defined(__CUDA_ARCH__)
+                    int f = __float_as_int(v0.w);
+#else
+                    int f; { float w = v0.w; memcpy(&f, &w, 4); }
+#endif
+                    if (ANY) { if (t <= tbest) { face = f; tbest = t; return true; } }
+                    else if (t < tbest || (t == tbest && found && f < face) || (t == tbest && !found)) {
+                        tbest = t; face = f; found = true;
+                    }
+                }
+            }
+        }
+        if (sp == 0) break;
+        ref = stack[--sp];
+    }
+    return found;
+}
+
+struct TraceFast { int face, obj; float t; };
+
+// World-level nearest hit in fp32.  from_camera: primary ray (metric == t); otherwise (shadow ray in a
+// multi-object scene) objects are ranked by the hit's distance to the camera, tracer.go:38.
+RT_HD bool trace_fast_nearest(const SceneView &sc, const FrameParams &fp, dv o, dv d, bool from_camera, TraceFast &out,
+                              Counters *cnt) {
+    bool exists = false;
+    float best_metric = 0.0f;
+    for (int k = 0; k < fp.n_obj; k++) {
+        const ObjRec &ob = sc.objs[k];
+        RayF r = make_rayf((float)(o.x - ob.pos[0]), (float)(o.y - ob.pos[1]), (float)(o.z - ob.pos[2]), (float)d.x,
+                           (float)d.y, (float)d.z);
+        float t = 3.0e38f;
+        int face = -1;
+        if (mesh_trace_fast<false>(sc.meshes[ob.mesh], r, t, face, cnt)) {
+            float metric = t;
+            if (!from_camera) {
+                float px = (float)(o.x + d.x * t - fp.cam_pos[0]), py = (float)(o.y + d.y * t - fp.cam_pos[1]),
+                      pz = (float)(o.z + d.z * t - fp.cam_pos[2]);
+                metric = sqrtf(px * px + py * py + pz * pz);
+            }
+            if (!exists || metric < best_metric) { exists = true; best_metric = metric; out.face = face; out.obj = k; out.t = t; }
+        }
+    }
+    return exists;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shading of one primary hit (both modes): tracer.go:53-77.  Returns the lit mask.
+// ------------------------------------------------------------------------------------------------
+template <bool EXACT>
+RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int j, int obj, int face, float t32,
+                         bool brute, double col[3], Counters *cnt) {
+    dv cam = dv_ld(fp.cam_pos);
+    dv d = primary_dir_exact(i, j, fp);                                         // tracer.go:86
+    const ObjRec &ob = sc.objs[obj];
+    const MeshView &m = sc.meshes[ob.mesh];
+    dv pos = dv_ld(ob.pos);
+    const double *pv = m.fverts + 9 * (size_t)face;
+    dv ol = dv_sub(cam, pos);                                                    // object.go:71
+    TriHit h;
+    if (!tri_intersection_exact(dv_ld(pv), dv_ld(pv + 3), dv_ld(pv + 6), ol, d, h)) {
+        // FP32_FAST only: the fp32 winner is rejected by the fp64 test by a hair -> evaluate it anyway
+        if (!tri_intersection_exact(dv_ld(pv), dv_ld(pv + 3), dv_ld(pv + 6), ol, d, h, true)) {
+            h.t = (double)t32; h.ip = dv_add(ol, dv_scale(d, h.t)); h.r1 = 1.0; h.r2 = 0.0; h.r3 = 0.0;
+        }
+    }
+    dv P = dv_add(h.ip, pos);                                                    // object.go:109
+    dv N = hit_normal_exact(m, face, h.r1, h.r2, h.r3);                          // object.go:90-95
+    const double *mat = m.materials + 10 * (size_t)m.fmat[face];
+    double c[3] = { mat[0], mat[1], mat[2] };                                    // tracer.go:56
+    uint32_t lit_mask = 0;
+    for (int l = 0; l < fp.n_lights; l++) {
+        const LightRec &L = sc.lights[l];
+        dv Lv = dv_sub(dv_ld(L.pos), P);
+        dv Ld = dv_norm(Lv);                                                     // tracer.go:61
+        dv so = dv_add(P, dv_scale(Ld, RT_SHADOW_BIAS));                         // tracer.go:64
+        double lightLen = dv_len(Lv);
+        bool lit;
+        if (EXACT) {
+            TraceExact s;
+            bool shaded = trace_exact(sc, fp, so, Ld, brute, s, cnt);
+            lit = !shaded || lightLen < dv_len(dv_sub(s.ip, P));                 // tracer.go:64
+        } else if (fp.n_obj == 1) {
+            // one object: "nearest hit, then compare with the light distance" == any hit with
+            // t + bias <= lightLen  
+            RayF r = make_rayf((float)(so.x - pos.x), (float)(so.y - pos.y), (float)(so.z - pos.z), (float)Ld.x,
+                               (float)Ld.y, (float)Ld.z);
+            float tmax = (float)(lightLen - RT_SHADOW_BIAS);
+            int f = -1;
+            lit = !mesh_trace_fast<true>(m, r, tmax, f, cnt);
+        } else {
+            TraceFast s;
+            bool shaded = trace_fast_nearest(sc, fp, so, Ld, false, s, cnt);
+            lit = !shaded || lightLen < (double)s.t + RT_SHADOW_BIAS;
+        }
+        if (lit) {
+            lit_mask |= 1u << (l & 31);
+            phong_light_exact(c, mat, N, Ld, cam, P, L.col);                     // tracer.go:65-72
+        }
+    }
+    col[0] = c[0]; col[1] = c[1]; col[2] = c[2];
+    return lit_mask;
+}
+

@@ -1,0 +1,109 @@
+// rt_types.h -- records shared by the host code and the sm_100a kernels.
+//
+// HBM layout (per mesh, all built once at rt_scene_create; see DESIGN.md "Data layout"):
+//   nodes     : BVH2 node records, 64 B each (4 x 16 B), BFS order so the top of the tree is a prefix
+//   tri32     : FP32_FAST triangle records, 48 B (3 x float4), Morton/leaf order
+//   tri64     : FP64_EXACT triangle records, 80 B (5 x double2), Morton/leaf order
+//   fverts    : 9 doubles per face, ORIGINAL face order (winner re-intersection + flat normals)
+//   fnormals  : 9 doubles per face, ORIGINAL face order (Phong normals), absent if the mesh has no vn
+//   fmat      : material index per face; materials: 10 doubles each
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RT_HD __host__ __device__ __forceinline__
+#else
+#define RT_HD inline
+#endif
+
+#define RT_STACK_SIZE 96          // >= 63 Morton bits + 27 index bits (Karras tree depth bound)
+#define RT_LEAF_FIRST_BITS 27     // child ref < 0: ~ref = first | (count-1) << 27
+#define RT_LEAF_FIRST_MASK ((1u << RT_LEAF_FIRST_BITS) - 1u)
+#define RT_MAX_LEAF 16
+#define RT_NODE_BYTES 64
+#define RT_TRI32_BYTES 48
+#define RT_TRI64_BYTES 80
+#define RT_SHADOW_BIAS 0.0001     // tracer.go:64
+
+struct alignas(16) rt_f4 { float x, y, z, w; };
+struct alignas(16) rt_i4 { int x, y, z, w; };
+
+// One BVH2 node = both children's boxes + both child refs (Aila-Laine style packing).
+//   a = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
+//   b = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//   c = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+//   d = (ref0, ref1, 0, 0) as int bits; ref >= 0: node index, ref < 0: leaf (see above)
+struct RtNode { rt_f4 a, b, c; rt_i4 d; };
+
+RT_HD int rt_leaf_ref(uint32_t first, uint32_t count) { return ~(int)(first | ((count - 1u) << RT_LEAF_FIRST_BITS)); }
+RT_HD uint32_t rt_leaf_first(int ref) { return ((uint32_t)~ref) & RT_LEAF_FIRST_MASK; }
+RT_HD uint32_t rt_leaf_count(int ref) { return (((uint32_t)~ref) >> RT_LEAF_FIRST_BITS) + 1u; }
+
+struct MeshView {
+    const RtNode  *nodes;
+    const rt_f4   *tri32;      // 3 per triangle: (P1,faceidx) (P2,-) (P3,-)
+    const double  *tri64;      // 10 per triangle: P1 P2 P3, [9] = face index (as double, exact)
+    const double  *fverts;     // 9 per face
+    const double  *fnormals;   // 9 per face or nullptr
+    const uint32_t *fmat;
+    const double  *materials;  // 10 per material
+    uint32_t n_faces, n_nodes;
+    int      root_ref;         // ref encoding; meaningful iff n_faces > 0
+    float    lo[3], hi[3];     // padded mesh bounds (object space)
+};
+
+struct ObjRec { double pos[3]; uint32_t mesh; uint32_t pad; };
+struct LightRec { double pos[3]; double col[3]; };
+
+struct FrameParams {
+    double cam_pos[3], fwd[3], left[3], up[3];
+    double tan_half;
+    int W, H;            // full screen (tracer.go:81)
+    int x, y, w, h;      // region     (distributed/main.go:50-51)
+    int n_lights, n_obj;
+    // tile mode (multi-GPU): if tile_w > 0 the region-linear pixel index maps through interleaved tiles
+    int tile_w, tile_h, tiles_x, rank, n_ranks, n_local_tiles;
+};
+
+// primary-hit record appended by the primary kernel, consumed by the shade kernel (16 B)
+struct HitRec { uint32_t pix; int32_t obj; int32_t face; float t; };
+
+struct Counters { unsigned long long nodes, tris; };
+
+// ------------------------------------------------------------------------------------------------
+// ray index <-> pixel mapping.  Rays are numbered so that 32 consecutive indices form an 8x4 pixel
+// block (coherent warps).  Region mode: blocks row-major over the region.  Tile mode (multi-GPU):
+// tiles t = lt*n_ranks + rank, each tile_w x tile_h (multiples of 8 x 4), blocks row-major in a tile.
+// ------------------------------------------------------------------------------------------------
+struct PixMap { int i, j; uint32_t out; bool valid; };   // i,j = absolute screen pixel; out = index in the output buffer
+
+RT_HD uint32_t ray_count(const FrameParams &fp) {
+    if (fp.tile_w > 0) return (uint32_t)fp.n_local_tiles * (uint32_t)(fp.tile_w * fp.tile_h);
+    uint32_t nbx = (uint32_t)(fp.w + 7) / 8, nby = (uint32_t)(fp.h + 3) / 4;
+    return nbx * nby * 32u;
+}
+
+RT_HD PixMap map_ray(uint32_t r, const FrameParams &fp, bool rowmajor) {
+    PixMap p;
+    uint32_t lane = r & 31u, blk = r >> 5;
+    int lx = (int)(lane & 7u), ly = (int)(lane >> 3);
+    if (fp.tile_w > 0) {
+        uint32_t bpt = (uint32_t)(fp.tile_w * fp.tile_h) / 32u;       // blocks per tile
+        uint32_t lt = blk / bpt, b = blk % bpt;
+        uint32_t bx = b % (uint32_t)(fp.tile_w / 8), by = b / (uint32_t)(fp.tile_w / 8);
+        int tx = (int)bx * 8 + lx, ty = (int)by * 4 + ly;
+        uint32_t t = lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
+        p.i = (int)(t % (uint32_t)fp.tiles_x) * fp.tile_w + tx;
+        p.j = (int)(t / (uint32_t)fp.tiles_x) * fp.tile_h + ty;
+        p.out = lt * (uint32_t)(fp.tile_w * fp.tile_h) + (uint32_t)(ty * fp.tile_w + tx);
+        p.valid = p.i < fp.W && p.j < fp.H;
+        return p;
+    }
+    uint32_t nbx = (uint32_t)(fp.w + 7) / 8;
+    int ri = (int)(blk % nbx) * 8 + lx, rj = (int)(blk / nbx) * 4 + ly;
+    p.valid = ri < fp.w && rj < fp.h;
+    p.i = fp.x + ri; p.j = fp.y + rj;
+    p.out = rowmajor ? (uint32_t)rj * (uint32_t)fp.w + (uint32_t)ri        // image order
+                     : (uint32_t)ri * (uint32_t)fp.h + (uint32_t)rj;       // distributed/main.go:82
+    return p;
+}

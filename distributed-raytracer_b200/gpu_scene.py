@@ -1,0 +1,150 @@
+"""Python handle over the C ABI (include/rt_b200.h): scene create / frame set / render region.
+
+Mirrors the lifecycle of the reference worker (paths under /root/reference/):
+  register()  worker/distributed/main.go:101-129  -> GpuScene(...)          (rt_scene_create)
+  BulkTrace   worker/distributed/main.go:46-91    -> GpuScene.bulk_trace()  (rt_bulk_trace)
+  draw()      worker/sequential/main.go:15-32     -> GpuScene.render_region()
+Inputs are flat numpy arrays (the SoA flattening of state.Environment).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def make_scene_desc(scene, device=0, precision=_lib.FP32_FAST, flags=0):
+    """scene: dict(meshes=[dict(verts, normals, faces, materials)], obj_pos, obj_mesh).
+    Returns (SceneDesc, keepalive list)."""
+    keep = []
+    n = len(scene["meshes"])
+    descs = (_lib.MeshDesc * max(1, n))()
+    for k, m in enumerate(scene["meshes"]):
+        v = _c(m["verts"], np.float64).reshape(-1, 3)
+        nr = _c(m["normals"], np.float64).reshape(-1, 3)
+        f = _c(m["faces"], np.uint32).reshape(-1, 7)
+        mt = _c(m["materials"], np.float64).reshape(-1, 10)
+        keep += [v, nr, f, mt]
+        descs[k] = _lib.MeshDesc(v.ctypes.data, v.shape[0], nr.ctypes.data if nr.size else None, nr.shape[0],
+                                 f.ctypes.data if f.size else None, f.shape[0], mt.ctypes.data if mt.size else None,
+                                 mt.shape[0])
+    op = _c(scene["obj_pos"], np.float64).reshape(-1, 3)
+    om = _c(scene["obj_mesh"], np.uint32).reshape(-1)
+    keep += [op, om, descs]
+    d = _lib.SceneDesc(descs, n, op.ctypes.data if op.size else None, om.ctypes.data if om.size else None, op.shape[0],
+                       device, precision, flags)
+    return d, keep
+
+
+def make_camera(cam13, tan_half_fov=float("nan")):
+    cam13 = np.asarray(cam13, dtype=np.float64).reshape(13)
+    c = _lib.Camera()
+    for k in range(3):
+        c.pos[k], c.forward[k], c.left[k], c.up[k] = cam13[k], cam13[3 + k], cam13[6 + k], cam13[9 + k]
+    c.fov = cam13[12]
+    c.tan_half_fov = tan_half_fov
+    return c
+
+
+class GpuScene:
+    def __init__(self, scene, device=0, precision=_lib.FP32_FAST, flags=0):
+        self._L = _lib.load()
+        desc, keep = make_scene_desc(scene, device, precision, flags)
+        h = C.c_void_p()
+        rc = self._L.rt_scene_create(C.byref(desc), C.byref(h))
+        if rc != 0:
+            raise _lib.RtError(rc, (self._L.rt_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+        self.precision = precision
+        self.n_objects = desc.n_objects
+        self.n_meshes = desc.n_meshes
+        if "camera" in scene and "lights" in scene:
+            self.set_frame(scene["camera"], scene["lights"])
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.RtError(rc, (self._L.rt_last_error(self.h) or b"").decode())
+
+    def set_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan")):
+        cam = make_camera(cam13, tan_half_fov)
+        lights = _c(lights, np.float64).reshape(-1, 6)
+        op = None if obj_pos is None else _c(obj_pos, np.float64)
+        self._check(self._L.rt_frame_set(self.h, C.byref(cam), lights.ctypes.data if lights.size else None, lights.shape[0],
+                                         op.ctypes.data if op is not None else None))
+
+    def render_region(self, W, H, x=0, y=0, w=None, h=None, flags=0, out=None):
+        w = W - x if w is None else w
+        h = H - y if h is None else h
+        if out is None:
+            out = np.empty((w * h, 3), dtype=np.uint8)
+        self._check(self._L.rt_render_region(self.h, W, H, x, y, w, h, out.ctypes.data, flags))
+        return out
+
+    def bulk_trace(self, cam13, lights, W, H, x, y, w, h, obj_pos=None, flags=0, out=None, tan_half_fov=float("nan")):
+        cam = make_camera(cam13, tan_half_fov)
+        lights = _c(lights, np.float64).reshape(-1, 6)
+        op = None if obj_pos is None else _c(obj_pos, np.float64)
+        if out is None:
+            out = np.empty((w * h, 3), dtype=np.uint8)
+        self._check(self._L.rt_bulk_trace(self.h, C.byref(cam), lights.ctypes.data if lights.size else None, lights.shape[0],
+                                          op.ctypes.data if op is not None else None, W, H, x, y, w, h, out.ctypes.data, flags))
+        return out
+
+    def render_region_debug(self, W, H, x=0, y=0, w=None, h=None, flags=0):
+        w = W - x if w is None else w
+        h = H - y if h is None else h
+        n = w * h
+        rgb = np.empty((n, 3), dtype=np.uint8)
+        col = np.empty((n, 3), dtype=np.float64)
+        face = np.empty(n, dtype=np.int32)
+        obj = np.empty(n, dtype=np.int32)
+        lit = np.empty(n, dtype=np.uint32)
+        self._check(self._L.rt_render_region_debug(self.h, W, H, x, y, w, h, rgb.ctypes.data, col.ctypes.data, face.ctypes.data,
+                                                   obj.ctypes.data, lit.ctypes.data, flags))
+        return rgb, col, face, obj, lit
+
+    def render_region_device(self, W, H, x, y, w, h, d_out_ptr, stream_ptr=None, flags=0):
+        self._check(self._L.rt_render_region_device(self.h, W, H, x, y, w, h, d_out_ptr, stream_ptr, flags))
+
+    def render_tiles_device(self, W, H, tile_w, tile_h, rank, n_ranks, d_out_ptr, stream_ptr=None, flags=0):
+        self._check(self._L.rt_render_tiles_device(self.h, W, H, tile_w, tile_h, rank, n_ranks, d_out_ptr, stream_ptr, flags))
+
+    def untile_device(self, W, H, tile_w, tile_h, n_ranks, d_all_tiles_ptr, d_out_ptr, stream_ptr=None, flags=0):
+        self._check(self._L.rt_untile_device(self.h, W, H, tile_w, tile_h, n_ranks, d_all_tiles_ptr, d_out_ptr, stream_ptr, flags))
+
+    def stats(self):
+        st = _lib.Stats()
+        self._check(self._L.rt_get_stats(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def bvh_info(self, mesh=0):
+        bi = _lib.BvhInfo()
+        self._check(self._L.rt_get_bvh_info(self.h, mesh, C.byref(bi)))
+        return bi.as_dict()
+
+    def synchronize(self):
+        self._check(self._L.rt_synchronize(self.h))
+
+    def cancel(self):
+        self._L.rt_cancel(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.rt_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def tiles_per_rank(W, H, tile_w, tile_h, n_ranks):
+    n_tiles = ((W + tile_w - 1) // tile_w) * ((H + tile_h - 1) // tile_h)
+    return (n_tiles + n_ranks - 1) // n_ranks

@@ -1,0 +1,185 @@
+/*
+ * rt_b200.h -- C ABI of the B200 (sm_100a) GPU render backend.
+ *
+ * Drop-in boundary for the render hot path of MWindels/distributed-raytracer: the per-pixel
+ * double loop in worker/distributed/main.go:67-88 (Tracer.BulkTrace) and
+ * worker/sequential/main.go:21-28 (draw), i.e. every call of
+ * tracer.Trace (worker/shared/tracer/tracer.go:81-91), is replaced by ONE call of
+ * rt_bulk_trace / rt_render_region per screen region.  master/pool, comms.proto, registration and
+ * heartbeats are untouched.  The cgo binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types; every pointer argument is caller-owned and is not retained
+ *    after the call returns (cgo rule: C may not keep Go pointers) -- the library copies.
+ *  - every entry point returns 0 on success, a negative rt_status otherwise; no exception crosses
+ *    the ABI; rt_last_error() returns a message (per handle, or a thread-local one for handle-less
+ *    failures when called with NULL).
+ *  - handles are internally synchronised (per-handle mutex): BulkTrace may be entered concurrently
+ *    from several goroutines (final_report.pdf p.6 s2.3); calls may arrive on any OS thread.
+ *  - there is NO CPU fallback: without a CUDA device / the sm_100a kernels every call fails with
+ *    RT_ERR_CUDA.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+typedef enum {
+    RT_OK            = 0,
+    RT_ERR_INVALID   = -1,  /* bad argument (NULL, out-of-range index, empty region ...)          */
+    RT_ERR_CUDA      = -2,  /* CUDA runtime / no device / kernel image missing                    */
+    RT_ERR_OOM       = -3,  /* host or device allocation failed                                   */
+    RT_ERR_STATE     = -4,  /* rt_render_* before rt_frame_set, destroyed handle ...               */
+    RT_ERR_CANCELLED = -5   /* rt_cancel() hit while rendering (ctx.Err(), distributed/main.go:73) */
+} rt_status;
+
+/* precision modes (BASELINE.json north_star) */
+#define RT_FP64_EXACT 0u   /* mirrors the reference's float64 arithmetic order; bit-exact vs worker/sequential */
+#define RT_FP32_FAST  1u   /* fp32 BVH traversal + intersection; fp64 re-intersection of the winner + fp64 shading */
+
+/* scene-create flags */
+#define RT_SCENE_DEFAULT     0u
+
+/* render flags */
+#define RT_LAYOUT_COLMAJOR   0x0u  /* out index (i*h + j)   -- BulkTrace, distributed/main.go:82            */
+#define RT_LAYOUT_ROWMAJOR   0x1u  /* out index (j*w + i)   -- image order                                  */
+#define RT_QUANT_RGB255      0x0u  /* uint8(255*c)          -- colour.RGB.RGB(), colour.go:59-61            */
+#define RT_QUANT_RGBA16_SHR8 0x2u  /* uint32(0xFFFF*c) >> 8 -- colour.RGB.RGBA() + go-sdl2 Surface.Set      */
+#define RT_FLAG_COUNT        0x4u  /* accumulate traversal counters (slower; for roofline accounting)       */
+#define RT_FLAG_BRUTE_FORCE  0x8u  /* FP64_EXACT only: ignore the BVH, test every face (debug / parity)     */
+#define RT_FLAG_SIMPLE       0x10u /* FP32_FAST only: one-thread-per-ray kernels without persistent refill  */
+
+typedef struct rt_scene rt_scene;
+
+/* One immutable mesh (shared/state/mesh.go:100-106, flattened).  All arrays object-space. */
+typedef struct {
+    const double   *verts;       /* n_verts*3                                         mesh.go:101  */
+    uint32_t        n_verts;
+    const double   *normals;     /* n_normals*3, already normalised (mesh.go:202); n_normals==0
+                                    selects the flat-normal path (object.go:82,91-95)              */
+    uint32_t        n_normals;
+    const uint32_t *faces;       /* n_faces*7: v0 v1 v2 n0 n1 n2 mat, in ENUMERATION ORDER; the face
+                                    index reported/tie-broken on is the position in this array
+                                    (mesh.go:21-27)                           */
+    uint32_t        n_faces;
+    const double   *materials;   /* n_materials*10: Ka[3] Kd[3] Ks[3] Ns              mesh.go:94-97 */
+    uint32_t        n_materials;
+} rt_mesh_desc;
+
+typedef struct {
+    const rt_mesh_desc *meshes;
+    uint32_t            n_meshes;
+    const double       *obj_pos;    /* n_objects*3   state.Object.Pos, object.go:17-22               */
+    const uint32_t     *obj_mesh;   /* n_objects     index into meshes                               */
+    uint32_t            n_objects;
+    int32_t             device;     /* CUDA ordinal                                                  */
+    uint32_t            precision;  /* RT_FP64_EXACT | RT_FP32_FAST                                  */
+    uint32_t            flags;      /* RT_SCENE_*                                                    */
+} rt_scene_desc;
+
+/* state.Camera (camera.go:20-24) + tan(Fov/2) computed by the host with Go's own math.Tan
+ * (tracer.go:17) so the frame constant is bit-identical; pass NaN to let the library use its
+ * restatement of Go's math.Tan. */
+typedef struct {
+    double pos[3], forward[3], left[3], up[3];
+    double fov;
+    double tan_half_fov;
+} rt_camera;
+
+/* state.Light (light.go:10-13); col already float64 in [0,1] (colour.NewRGB, colour.go:28-30) */
+typedef struct {
+    double pos[3];
+    double col[3];
+} rt_light;
+
+typedef struct {
+    uint64_t primary_rays;     /* = w*h of the last render                                         */
+    uint64_t shadow_rays;      /* = hit pixels * lights (tracer.go:60-64)                          */
+    uint64_t hit_pixels;
+    uint64_t nodes_fetched;    /* BVH node records fetched      (only with RT_FLAG_COUNT)          */
+    uint64_t tris_fetched;     /* triangle records fetched      (only with RT_FLAG_COUNT)          */
+    uint64_t node_bytes;       /* sizeof one node record                                           */
+    uint64_t tri_bytes;        /* sizeof one triangle record in the active precision               */
+    float    ms_primary;       /* CUDA-event durations of the last render's kernels, on the        */
+    float    ms_shade;         /* library's stream (valid after a synchronous render call)         */
+    float    ms_write;
+    float    ms_total;
+} rt_stats;
+
+typedef struct {
+    uint64_t n_faces, n_nodes, n_leaves;
+    uint32_t max_depth, max_leaf;
+    float    ms_build;         /* CUDA-event time of the whole on-GPU build of this mesh            */
+    float    sah_cost;
+} rt_bvh_info;
+
+/* ---- lifecycle (register(): distributed/main.go:101-129 => create; re-register => destroy+create) */
+int  rt_scene_create(const rt_scene_desc *desc, rt_scene **out);
+void rt_scene_destroy(rt_scene *scene);
+const char *rt_last_error(const rt_scene *scene);
+int  rt_abi_version(void);
+int  rt_device_count(void);
+
+/* ---- per-frame mutable state (the gob `diff`: distributed/main.go:56-64, environment.go:65-69) -- */
+int rt_frame_set(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights,
+                 const double *obj_pos /* n_objects*3 or NULL = unchanged */);
+
+/* ---- render one screen region (distributed/main.go:67-88; sequential/main.go:21-28) ------------
+ * Pixel (x+i, y+j), i<w, j<h, of a screen_w x screen_h screen (tracer.go:81 takes the FULL screen
+ * size).  out_rgb: w*h*3 bytes, HOST memory (pageable or pinned), misses are (0,0,0).  Blocks until
+ * the bytes are in out_rgb. */
+int rt_render_region(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t x, uint32_t y,
+                     uint32_t w, uint32_t h, uint8_t *out_rgb, uint32_t flags);
+
+/* frame_set + render_region atomically under the handle lock: what one BulkTrace RPC does. */
+int rt_bulk_trace(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights,
+                  const double *obj_pos, uint32_t screen_w, uint32_t screen_h, uint32_t x, uint32_t y,
+                  uint32_t w, uint32_t h, uint8_t *out_rgb, uint32_t flags);
+
+/* Parity/debug variant: any of the outputs may be NULL.  out_colour: w*h*3 float64 (the value
+ * tracer.Trace returns), out_face: w*h int32 face index of the primary hit (-1 = miss), out_obj:
+ * w*h int32 object index, out_lit: w*h uint32 bit k = light k contributed (tracer.go:64). */
+int rt_render_region_debug(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t x, uint32_t y,
+                           uint32_t w, uint32_t h, uint8_t *out_rgb, double *out_colour, int32_t *out_face,
+                           int32_t *out_obj, uint32_t *out_lit, uint32_t flags);
+
+/* Device-resident variant: d_out_rgb is DEVICE memory on the scene's device (w*h*3 bytes); the work
+ * is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the library's own stream) and the
+ * call returns without synchronising when stream != NULL. */
+int rt_render_region_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t x, uint32_t y,
+                            uint32_t w, uint32_t h, void *d_out_rgb, void *stream, uint32_t flags);
+
+/* Multi-GPU screen-tile sharding (master/main.go:54-91 partition(), re-designed as interleaved
+ * tiles): the full screen is cut into tile_w x tile_h tiles numbered row-major; this call renders
+ * tiles t with t % n_ranks == rank and packs them, in increasing t, into d_out_tiles (DEVICE,
+ * n_local_tiles * tile_w*tile_h*3 bytes, each tile row-major, edge tiles padded with zeros). */
+int rt_render_tiles_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w,
+                           uint32_t tile_h, uint32_t rank, uint32_t n_ranks, void *d_out_tiles,
+                           void *stream, uint32_t flags);
+/* Inverse of the packing above, run on the gathering rank: d_all_tiles holds the n_ranks packed
+ * buffers back to back (each padded to tiles_per_rank_max tiles); writes the screen_w*screen_h*3
+ * framebuffer d_out_rgb in `flags` layout. */
+int rt_untile_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h,
+                     uint32_t n_ranks, const void *d_all_tiles, void *d_out_rgb, void *stream, uint32_t flags);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+int rt_get_stats(rt_scene *scene, rt_stats *out);
+int rt_get_bvh_info(rt_scene *scene, uint32_t mesh, rt_bvh_info *out);
+int rt_synchronize(rt_scene *scene);
+/* ask an in-flight render on this handle to stop (checked between kernels) */
+int rt_cancel(rt_scene *scene);
+
+/* pinned host buffers so out_rgb can be DMA'd without a staging copy (optional) */
+void *rt_host_alloc(size_t bytes);
+void  rt_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

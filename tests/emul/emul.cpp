@@ -1,0 +1,273 @@
+// emul.cpp -- TEST-ONLY CPU replay of the device code (built by tests/, never shipped or linked into
+// librt_b200.so; the product has no CPU path).  It compiles the very same RT_HD functions the sm_100a
+// kernels are made of (csrc/rt_bvh.cuh builder bodies, csrc/rt_traverse.cuh traversal + shading,
+// csrc/rt_exact.cuh reference-order fp64 math) with g++ and runs one loop iteration per CUDA thread.
+// Purpose: catch logic errors in the kernels on the GPU-less build box, and compare the kernels'
+// arithmetic against the oracle before a GPU is available.  The persistent warp-cooperative
+// primary kernel (warp intrinsics) is not replayed here; it is checked on the GPU against the
+// simple kernel and the oracle.
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared (see tests/emul_build.py)
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "../../distributed-raytracer_b200/csrc/rt_types.h"
+#include "../../distributed-raytracer_b200/csrc/rt_bvh.cuh"
+#include "../../distributed-raytracer_b200/csrc/rt_traverse.cuh"
+
+struct EmulMesh {
+    std::vector<RtNode> nodes;
+    std::vector<rt_f4> tri32;
+    std::vector<double> tri64, fverts, fnormals, materials;
+    std::vector<uint32_t> fmat;
+    MeshView view;
+    uint32_t max_depth = 0, n_leaves = 0;
+};
+
+struct EmulScene {
+    std::vector<EmulMesh> meshes;
+    std::vector<MeshView> views;
+    std::vector<ObjRec> objs;
+    uint32_t precision;
+};
+
+static void build_mesh(EmulMesh &m, int max_leaf) {
+    const uint32_t n = (uint32_t)(m.fverts.size() / 9);
+    MeshView &v = m.view;
+    memset(&v, 0, sizeof v);
+    v.n_faces = n;
+    if (n == 0) return;
+    // k_mesh_bounds
+    float lo[3] = { HUGE_VALF, HUGE_VALF, HUGE_VALF }, hi[3] = { -HUGE_VALF, -HUGE_VALF, -HUGE_VALF };
+    for (uint32_t f = 0; f < n; f++)
+        for (int q = 0; q < 3; q++)
+            for (int k = 0; k < 3; k++) {
+                double c = m.fverts[9 * (size_t)f + 3 * q + k];
+                lo[k] = fminf(lo[k], f32_down(c));
+                hi[k] = fmaxf(hi[k], f32_up(c));
+            }
+    BuildParams bp = make_build_params(lo, hi, v.lo, v.hi);
+    std::vector<BoxF> leafbox(n);
+    std::vector<unsigned long long> keys(n);
+    std::vector<uint32_t> vals(n);
+    for (uint32_t f = 0; f < n; f++) leaf_morton_thread(f, m.fverts.data(), bp, leafbox.data(), keys.data(), vals.data());
+    // radix sort (stable) of (key, face)
+    std::vector<uint32_t> perm(n);
+    std::iota(perm.begin(), perm.end(), 0u);
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<unsigned long long> skeys(n);
+    std::vector<uint32_t> svals(n);
+    for (uint32_t i = 0; i < n; i++) { skeys[i] = keys[perm[i]]; svals[i] = vals[perm[i]]; }
+    m.tri32.resize(3 * (size_t)n);
+    m.tri64.resize(10 * (size_t)n);
+    for (uint32_t i = 0; i < n; i++) gather_tri_thread(i, m.fverts.data(), svals.data(), m.tri32.data(), m.tri64.data());
+    if (n == 1) {
+        v.root_ref = rt_leaf_ref(0, 1);
+        m.n_leaves = 1;
+    } else {
+        const int ni = (int)n - 1;
+        std::vector<KarrasNode> kn(ni);
+        std::vector<int> pint(ni), pleaf(n);
+        for (int i = 0; i < ni; i++) karras_thread(i, skeys.data(), (int)n, kn.data(), pint.data(), pleaf.data());
+        std::vector<BoxF> ibox(ni);
+        std::vector<float> icost(ni);
+        std::vector<unsigned char> coll(ni);
+        std::vector<unsigned int> flags(ni, 0u);
+        for (int i = 0; i < (int)n; i++)
+            refit_sah_thread(i, svals.data(), leafbox.data(), kn.data(), pint.data(), pleaf.data(), ibox.data(), icost.data(),
+                             coll.data(), flags.data(), max_leaf);
+        if (coll[0]) {
+            v.root_ref = rt_leaf_ref(0, n);
+            m.n_leaves = 1;
+        } else {
+            m.nodes.resize(ni);
+            std::vector<int> front[2] = { std::vector<int>(ni), std::vector<int>(ni) };
+            std::vector<int> cnt(ni + 1), off(ni + 1);
+            front[0][0] = 0;
+            int fsize = 1, base = 0, cur = 0, depth = 0;
+            while (fsize > 0) {
+                for (int p = 0; p < fsize; p++) emit_count_thread(p, front[cur].data(), kn.data(), coll.data(), cnt.data());
+                int acc = 0;
+                for (int p = 0; p < fsize; p++) { off[p] = acc; acc += cnt[p]; }
+                for (int p = 0; p < fsize; p++)
+                    m.n_leaves += emit_write_thread(p, front[cur].data(), fsize, base, kn.data(), coll.data(), off.data(),
+                                                    svals.data(), leafbox.data(), ibox.data(), m.nodes.data(),
+                                                    front[cur ^ 1].data());
+                base += fsize;
+                fsize = acc;
+                cur ^= 1;
+                depth++;
+            }
+            m.nodes.resize(base);
+            v.n_nodes = (uint32_t)base;
+            v.root_ref = 0;
+            m.max_depth = (uint32_t)depth;
+        }
+    }
+    v.nodes = m.nodes.data(); v.tri32 = m.tri32.data(); v.tri64 = m.tri64.data();
+}
+
+extern "C" {
+
+void *emul_scene_create(const rt_scene_desc *desc, int max_leaf) {
+    EmulScene *s = new EmulScene();
+    s->precision = desc->precision;
+    s->meshes.resize(desc->n_meshes);
+    for (uint32_t k = 0; k < desc->n_meshes; k++) {
+        const rt_mesh_desc &d = desc->meshes[k];
+        EmulMesh &m = s->meshes[k];
+        const size_t nf = d.n_faces;
+        m.fverts.resize(9 * nf);
+        m.fmat.resize(nf);
+        if (d.n_normals) m.fnormals.resize(9 * nf);
+        for (size_t f = 0; f < nf; f++) {
+            const uint32_t *fc = d.faces + 7 * f;
+            for (int v = 0; v < 3; v++)
+                for (int c = 0; c < 3; c++) {
+                    m.fverts[9 * f + 3 * v + c] = d.verts[3 * (size_t)fc[v] + c];
+                    if (d.n_normals) m.fnormals[9 * f + 3 * v + c] = d.normals[3 * (size_t)fc[3 + v] + c];
+                }
+            m.fmat[f] = fc[6];
+        }
+        m.materials.assign(d.materials, d.materials + 10 * (size_t)d.n_materials);
+        build_mesh(m, max_leaf);
+        m.view.fverts = m.fverts.data();
+        m.view.fnormals = d.n_normals ? m.fnormals.data() : nullptr;
+        m.view.fmat = m.fmat.data();
+        m.view.materials = m.materials.data();
+    }
+    for (auto &m : s->meshes) s->views.push_back(m.view);
+    s->objs.resize(desc->n_objects);
+    for (uint32_t k = 0; k < desc->n_objects; k++) {
+        for (int c = 0; c < 3; c++) s->objs[k].pos[c] = desc->obj_pos[3 * (size_t)k + c];
+        s->objs[k].mesh = desc->obj_mesh[k];
+        s->objs[k].pad = 0;
+    }
+    return s;
+}
+
+void emul_scene_destroy(void *h) { delete (EmulScene *)h; }
+
+// BVH structural facts for tests: n_nodes, max_depth, n_leaves; validates that every face is in exactly
+// one leaf and that every child box contains its subtree.  Returns 0 if valid, else an error code.
+int emul_bvh_check(void *h, uint32_t mesh, uint32_t *out_nodes, uint32_t *out_depth, uint32_t *out_leaves) {
+    EmulScene *s = (EmulScene *)h;
+    EmulMesh &m = s->meshes[mesh];
+    *out_nodes = m.view.n_nodes; *out_depth = m.max_depth; *out_leaves = m.n_leaves;
+    const uint32_t n = m.view.n_faces;
+    if (n == 0) return 0;
+    std::vector<int> seen(n, 0);
+    struct Item { int ref; BoxF box; };
+    std::vector<Item> stack;
+    BoxF root; for (int k = 0; k < 3; k++) { root.lo[k] = m.view.lo[k]; root.hi[k] = m.view.hi[k]; }
+    stack.push_back({ m.view.root_ref, root });
+    while (!stack.empty()) {
+        Item it = stack.back(); stack.pop_back();
+        if (it.ref >= 0) {
+            if ((uint32_t)it.ref >= m.view.n_nodes) return 1;
+            const RtNode &nd = m.nodes[it.ref];
+            BoxF b0 = { { nd.a.x, nd.a.z, nd.c.x }, { nd.a.y, nd.a.w, nd.c.y } };
+            BoxF b1 = { { nd.b.x, nd.b.z, nd.c.z }, { nd.b.y, nd.b.w, nd.c.w } };
+            for (int k = 0; k < 3; k++) {
+                if (b0.lo[k] < it.box.lo[k] || b0.hi[k] > it.box.hi[k]) return 2;
+                if (b1.lo[k] < it.box.lo[k] || b1.hi[k] > it.box.hi[k]) return 2;
+            }
+            stack.push_back({ nd.d.x, b0 });
+            stack.push_back({ nd.d.y, b1 });
+        } else {
+            uint32_t first = rt_leaf_first(it.ref), count = rt_leaf_count(it.ref);
+            if (first + count > n) return 3;
+            for (uint32_t k = first; k < first + count; k++) {
+                int f = (int)m.tri64[10 * (size_t)k + 9];
+                if (f < 0 || (uint32_t)f >= n) return 4;
+                seen[f]++;
+                for (int q = 0; q < 3; q++)
+                    for (int c = 0; c < 3; c++) {
+                        double x = m.fverts[9 * (size_t)f + 3 * q + c];
+                        if (x <= (double)it.box.lo[c] || x >= (double)it.box.hi[c]) return 5;   // strictly inside (padded)
+                    }
+            }
+        }
+    }
+    for (uint32_t f = 0; f < n; f++) if (seen[f] != 1) return 6;
+    return 0;
+}
+
+// One frame through the same pipeline the kernels implement: K2 -> K4 -> K5.
+// flags: RT_FLAG_BRUTE_FORCE, RT_LAYOUT_ROWMAJOR, RT_QUANT_RGBA16_SHR8.  counters: [nodes, tris] (may be NULL).
+int emul_render(void *h, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, uint32_t W, uint32_t H, uint32_t x,
+                uint32_t y, uint32_t w, uint32_t hh, uint32_t flags, uint8_t *out_rgb, double *out_colour, int32_t *out_face,
+                int32_t *out_obj, uint32_t *out_lit, unsigned long long *counters) {
+    EmulScene *s = (EmulScene *)h;
+    FrameParams fp;
+    memset(&fp, 0, sizeof fp);
+    for (int k = 0; k < 3; k++) { fp.cam_pos[k] = cam->pos[k]; fp.fwd[k] = cam->forward[k]; fp.left[k] = cam->left[k]; fp.up[k] = cam->up[k]; }
+    fp.tan_half = cam->tan_half_fov;
+    fp.W = (int)W; fp.H = (int)H; fp.x = (int)x; fp.y = (int)y; fp.w = (int)w; fp.h = (int)hh;
+    fp.n_lights = (int)n_lights; fp.n_obj = (int)s->objs.size();
+    SceneView sc;
+    sc.meshes = s->views.data(); sc.objs = s->objs.data(); sc.lights = reinterpret_cast<const LightRec *>(lights);
+    const bool brute = (flags & RT_FLAG_BRUTE_FORCE) != 0, rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0,
+               sdl = (flags & RT_QUANT_RGBA16_SHR8) != 0;
+    const size_t npix = (size_t)w * hh;
+    if (out_rgb) memset(out_rgb, 0, 3 * npix);
+    if (out_colour) memset(out_colour, 0, sizeof(double) * 3 * npix);
+    if (out_face) for (size_t k = 0; k < npix; k++) out_face[k] = -1;
+    if (out_obj) for (size_t k = 0; k < npix; k++) out_obj[k] = -1;
+    if (out_lit) memset(out_lit, 0, sizeof(uint32_t) * npix);
+    Counters c; c.nodes = 0; c.tris = 0;
+    const uint32_t nrays = ray_count(fp);
+    std::vector<HitRec> hits;
+    // K2
+    for (uint32_t ray = 0; ray < nrays; ray++) {
+        PixMap pm = map_ray(ray, fp, false);
+        if (!pm.valid) continue;
+        HitRec hr; hr.pix = ray; hr.t = 0.f;
+        if (s->precision == RT_FP64_EXACT) {
+            TraceExact tr;
+            dv d = primary_dir_exact(pm.i, pm.j, fp);
+            if (!trace_exact(sc, fp, dv_ld(fp.cam_pos), d, brute, tr, &c)) continue;
+            hr.obj = tr.obj; hr.face = tr.face;
+        } else {
+            // mirrors primary_dir32 of render.cu
+            int hw = fp.W / 2, hh2 = fp.H / 2;
+            float phw = (float)fp.tan_half, phh = phw * (float)fp.H / (float)fp.W;
+            float si = phw * ((float)(hw - pm.i) - 0.5f) / (float)hw, sj = phh * ((float)(hh2 - pm.j) - 0.5f) / (float)hh2;
+            float dx = (float)fp.fwd[0] + (float)fp.left[0] * si + (float)fp.up[0] * sj;
+            float dy = (float)fp.fwd[1] + (float)fp.left[1] * si + (float)fp.up[1] * sj;
+            float dz = (float)fp.fwd[2] + (float)fp.left[2] * si + (float)fp.up[2] * sj;
+            float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            TraceFast tr;
+            if (!trace_fast_nearest(sc, fp, dv_ld(fp.cam_pos), dv_make((double)(dx * inv), (double)(dy * inv), (double)(dz * inv)),
+                                    true, tr, &c))
+                continue;
+            hr.obj = tr.obj; hr.face = tr.face; hr.t = tr.t;
+        }
+        hits.push_back(hr);
+    }
+    // K4 + K5
+    for (const HitRec &hr : hits) {
+        PixMap pm = map_ray(hr.pix, fp, rowmajor);
+        double col[3];
+        uint32_t lit = s->precision == RT_FP64_EXACT
+                           ? shade_hit<true>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, &c)
+                           : shade_hit<false>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, false, col, &c);
+        size_t o = pm.out;
+        if (out_rgb) for (int k = 0; k < 3; k++) out_rgb[3 * o + k] = quantise_exact(col[k], sdl);
+        if (out_colour) for (int k = 0; k < 3; k++) out_colour[3 * o + k] = col[k];
+        if (out_face) out_face[o] = hr.face;
+        if (out_obj) out_obj[o] = hr.obj;
+        if (out_lit) out_lit[o] = lit;
+    }
+    if (counters) { counters[0] = c.nodes; counters[1] = c.tris; counters[2] = hits.size(); }
+    return 0;
+}
+
+unsigned long long emul_morton63(double x, double y, double z) { return morton63(x, y, z); }
+
+}  // extern "C"
