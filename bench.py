@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the render hot path (BASELINE.json):
+Mrays/s (primary + shadow rays) on the 4K render of Suzanne subdivided to 991 232 triangles, 2 lights, FP32_FAST.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one frame = per-frame state upload (camera, lights) + K2 primary + K4 shadow/shade + K5 framebuffer
+(+ at N>1: gather of the interleaved tile buffers to rank 0 and the de-interleave kernel).
+`value`  : whole-job Mrays/s with the scene and BVH resident in HBM and the framebuffer left on the device.
+`e2e`    : the same frames through the reference-facing call (Tracer.BulkTrace -> rt_bulk_trace) with HOST buffers:
+           frame state H2D and the w*h*3-byte result D2H (pinned) inside the timed region.
+`roofline`, `cpu_baseline`: see DESIGN.md "Measurement".
+Rays per frame = W*H primary + (hit pixels) * (lights) shadow (tracer.go:60-64), identical for GPU and CPU arms.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C3: Suzanne subdivided x5 (991232 tris) @3840x2160, 2 lights, example camera, FP32_FAST"
+W, H = 3840, 2160
+SUBDIV = 5
+N_LIGHTS = 2
+METRIC = "Mrays/s (primary+shadow)"
+SCENE_JSON = os.path.join(ROOT, "tests", "golden", "example", "scene.json")
+
+
+def build_workload():
+    """Scene arrays of config 3, produced through the product's own loader (C++ host mirror) + workloads.subdivide."""
+    from distributed_raytracer_b200 import host, workloads
+    env = host.Environment(SCENE_JSON)
+    sc = env.scene_arrays()
+    sc["meshes"] = [workloads.subdivide(sc["meshes"][0], SUBDIV)]
+    sc["lights"] = sc["lights"][:N_LIGHTS]
+    env.close()
+    return sc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu_index = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_cpu_rate(sc, n_threads, budget_s, mode_name="rtree"):
+    """Times the CPU oracle (reference-shaped R-tree walk, /root/reference/worker/sequential semantics) on a bounded,
+    strided pixel sample of the same workload.  Returns (Mrays/s, rays, seconds, stride)."""
+    from oracle import oracle as orc
+    S = orc.Scene(sc)
+    S.set_frame(sc["camera"], sc["lights"], tan_half_fov=sc.get("tan_half_fov", float("nan")))
+    mode = orc.RTREE if mode_name == "rtree" else orc.CULLED
+    if mode == orc.RTREE:
+        S.build_rtrees()                                  # scene load (mesh.go:208), not part of the frame time
+    t0 = time.perf_counter()
+    _, _, _, st = S.render_region(W, H, mode=mode, n_threads=n_threads, step=512, phase=5, want_colour=False, want_face=False)
+    probe = time.perf_counter() - t0
+    rate = (st["primary_rays"] + st["shadow_rays"]) / max(probe, 1e-6)
+    full_rays = W * H * 1.2
+    stride = max(1, int(round(full_rays / max(rate * budget_s, 1.0))))
+    t0 = time.perf_counter()
+    _, _, _, st = S.render_region(W, H, mode=mode, n_threads=n_threads, step=stride, phase=0, want_colour=False, want_face=False)
+    dt = time.perf_counter() - t0
+    rays = st["primary_rays"] + st["shadow_rays"]
+    S.close()
+    return rays / dt / 1e6, rays, dt, stride
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  The Go binary cannot be built in this
+    image (no Go toolchain), so this is the oracle port, reference-shaped (R-tree (3,2,5) candidate walk with
+    box.go's predicate, no tmax, full nearest-hit shadow queries), run on all host threads."""
+    if rank != 0:
+        return
+    sc = build_workload()
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    S = orc.Scene(sc)
+    S.set_frame(sc["camera"], sc["lights"], tan_half_fov=sc["tan_half_fov"])
+    S.build_rtrees()
+    # size the per-step sample so that the whole run ends within ~2 minutes
+    t0 = time.perf_counter()
+    _, _, _, st = S.render_region(W, H, mode=orc.RTREE, n_threads=0, step=512, phase=5, want_colour=False, want_face=False)
+    rate = (st["primary_rays"] + st["shadow_rays"]) / max(time.perf_counter() - t0, 1e-6)
+    per_step_s = max(0.5, min(6.0, 100.0 / max(1, args.steps + args.warmup)))
+    stride = max(1, int(round(W * H * 1.2 / max(rate * per_step_s, 1.0))))
+    times, rays = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        _, _, _, st = S.render_region(W, H, mode=orc.RTREE, n_threads=0, step=stride, phase=it % stride, want_colour=False,
+                                      want_face=False)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            rays += st["primary_rays"] + st["shadow_rays"]
+    total = sum(times)
+    value = rays / total / 1e6
+    sample = "every %d-th pixel of the 4K frame per step (column-major region index %% %d), R-tree walk" % (stride, stride)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "C restatement of worker/sequential's Go path (oracle port), not the Go binary"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--simple", action="store_true", help="use the one-thread-per-ray primary kernel (RT_FLAG_SIMPLE)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import distributed_raytracer_b200 as rt
+    from distributed_raytracer_b200 import host, parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the render backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+
+    render_flags = rt.FLAG_SIMPLE if args.simple else 0
+    sc = build_workload() if rank == 0 else None
+    if world > 1:
+        # scene broadcast once over NCCL/NVLink; every rank builds the same LBVH locally
+        frame = [(sc["camera"], sc["lights"], sc["tan_half_fov"])] if rank == 0 else [None]
+        dist.broadcast_object_list(frame, src=0)
+        cam13, lights, tan_half = frame[0]
+        sc_r = parallel.broadcast_scene(sc, src=0, device=dev)
+    else:
+        cam13, lights, tan_half = sc["camera"], sc["lights"], sc["tan_half_fov"]
+        sc_r = sc
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stream = torch.cuda.Stream(dev)            # one explicit stream orders flush, render kernels and NCCL
+    torch.cuda.set_stream(stream)
+
+    if world == 1:
+        g = rt.GpuScene(sc_r, device=local_rank, precision=rt.FP32_FAST)
+        fb = torch.empty(W * H * 3, dtype=torch.uint8, device=dev)
+
+        def step():
+            g.set_frame(cam13, lights, tan_half_fov=tan_half)
+            g.render_region_device(W, H, 0, 0, W, H, fb.data_ptr(), stream.cuda_stream, render_flags | rt.LAYOUT_COLMAJOR)
+        launches_per_step = 3
+        bvh = g.bvh_info()
+    else:
+        r = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=(32, 16), device_index=local_rank)
+        g = r.backend.scene
+
+        def step():
+            r.render_frame(cam13, lights, tan_half_fov=tan_half, flags=render_flags)
+        launches_per_step = 3 + (1 if rank == 0 else 0)
+        bvh = g.bvh_info()
+
+    # ---- counting pass (outside the timed region): algorithmic traversal work of one frame ----
+    if world == 1:
+        g.set_frame(cam13, lights, tan_half_fov=tan_half)
+        g.render_region_device(W, H, 0, 0, W, H, fb.data_ptr(), None, render_flags | rt.FLAG_COUNT)
+    else:
+        g.set_frame(cam13, lights, tan_half_fov=tan_half)
+        g.render_tiles_device(W, H, 32, 16, rank, world, r.local.data_ptr(), None, render_flags | rt.FLAG_COUNT)
+    cnt = g.stats()
+    hits_local, prim_local = cnt["hit_pixels"], cnt["primary_rays"]
+    rays_local = prim_local + cnt["shadow_rays"]
+    if world > 1:
+        t = torch.tensor([float(rays_local), float(hits_local)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        rays_frame, hits_frame = int(t[0].item()), int(t[1].item())
+        rays_frame = W * H + hits_frame * len(lights)     # tile padding beyond the screen is not a ray
+    else:
+        rays_frame, hits_frame = W * H + hits_local * len(lights), hits_local
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: exactly K steps, barrier + synchronize on both sides, device timing, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = {"primary": [], "shade": [], "write": []}
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                     # L2 flush between timed iterations (not timed)
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+        st = g.stats()                                    # synchronises; per-kernel CUDA-event durations of this step
+        for name in kern_ms:
+            kern_ms[name].append(st["ms_" + name])
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = dev_ms / args.steps
+    value = rays_frame / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: the reference-facing call with host buffers (H2D frame state + D2H pixels inside the timed region) ----
+    e2e = None
+    h2d = 8 * (14 + 6 * len(lights) + 3)                  # rt_camera + lights + object position
+    if world == 1:
+        L = rt._lib.load()
+        nbytes = W * H * 3
+        pinned = L.rt_host_alloc(nbytes)
+        out = np.ctypeslib.as_array((__import__("ctypes").c_uint8 * nbytes).from_address(pinned))
+        tr_scene = rt.GpuScene(sc_r, device=local_rank, precision=rt.FP32_FAST)
+        for _ in range(args.warmup):
+            tr_scene.bulk_trace(cam13, lights, W, H, 0, 0, W, H, out=out, tan_half_fov=tan_half)
+        t_e2e = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            tr_scene.bulk_trace(cam13, lights, W, H, 0, 0, W, H, out=out, tan_half_fov=tan_half)   # blocks until bytes are in `out`
+            t_e2e.append(time.perf_counter() - t0)
+        checksum = int(out[::4097].astype(np.uint64).sum())
+        e2e_ms = 1e3 * sum(t_e2e) / len(t_e2e)
+        e2e = {"value": rays_frame / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": e2e_ms, "call": "rt_bulk_trace (what Tracer.BulkTrace issues per WorkOrder), pinned host out buffer",
+               "checksum": checksum}
+        tr_scene.close()
+        L.rt_host_free(pinned)
+    else:
+        # N>1: frame state to every rank + tiles + gather + untile + D2H of the framebuffer on rank 0
+        nbytes = W * H * 3
+        host_fb = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        t_e2e = []
+        for it in range(args.warmup + args.steps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            t0 = time.perf_counter()
+            fbt = r.render_frame(cam13, lights, tan_half_fov=tan_half, flags=render_flags)
+            if rank == 0:
+                host_fb.copy_(fbt, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            if it >= args.warmup:
+                t_e2e.append(time.perf_counter() - t0)
+        tt = torch.tensor([sum(t_e2e)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = 1e3 * float(tt.item()) / args.steps
+        e2e = {"value": rays_frame / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_ms,
+               "call": "TileShardedRenderer.render_frame + framebuffer D2H on rank 0 (pinned)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (algorithmic bytes / its CUDA-event duration) ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    avg = {k: sum(v) / max(1, len(v)) for k, v in kern_ms.items()}
+    nb, tb = cnt["node_bytes"], cnt["tri_bytes"]
+    alg = {
+        # K2: node + triangle records fetched by primary rays + one 16 B HitRec per hit
+        "primary": cnt["nodes_primary"] * nb + cnt["tris_primary"] * tb + hits_local * 16,
+        # K4: shadow-ray records + per hit: HitRec 16, face verts 72, face normals 72, material idx 4 + material 80, colour 24 + lit 4
+        "shade": cnt["nodes_shade"] * nb + cnt["tris_shade"] * tb + hits_local * (16 + 72 + 72 + 4 + 80 + 24 + 4),
+        # K5: per hit HitRec 16 + colour 24 + lit 4 read, 3 bytes written
+        "write": hits_local * (16 + 24 + 4 + 3),
+    }
+    dom = max(avg, key=lambda k: avg[k])
+    achieved = alg[dom] / (avg[dom] * 1e-3) / 1e9 if avg[dom] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": {"primary": "k_primary_fast_" + ("simple" if args.simple else "persistent"), "shade": "k_shade", "write": "k_write"}[dom],
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": avg[dom],
+                "kernels_ms": avg, "algorithmic_bytes": alg,
+                "per_ray": {"nodes_primary": cnt["nodes_primary"] / max(1, prim_local), "tris_primary": cnt["tris_primary"] / max(1, prim_local),
+                            "nodes_shadow": cnt["nodes_shade"] / max(1, cnt["shadow_rays"]), "tris_shadow": cnt["tris_shade"] / max(1, cnt["shadow_rays"])}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, rays, dt, stride = oracle_cpu_rate(sc, n_threads=1, budget_s=15.0)
+        cpu_baseline = {"value": v, "unit": "Mrays/s", "cores": 1, "kind": "port",
+                        "sample": "every %d-th pixel of the same 4K frame (%d rays, %.1f s), single thread like worker/sequential, "
+                                  "reference-shaped R-tree walk (C restatement, not the Go binary)" % (stride, rays, dt)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_frame": rays_frame, "hit_pixels": hits_frame, "frames_per_s": 1e3 / ms_per_step,
+                   "l2": "256 MiB device memset between timed steps (L2 flush)", "precision": "FP32_FAST traversal, fp64 shading",
+                   "parallelism": "screen tiles 32x16 round-robin over %d rank(s)" % world, "bvh": bvh,
+                   "primary_kernel": "simple" if args.simple else "persistent"},
+        "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "wall_s_timed_region": wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

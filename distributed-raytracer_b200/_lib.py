@@ -46,7 +46,8 @@ class Light(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("hit_pixels", C.c_uint64),
-                ("nodes_fetched", C.c_uint64), ("tris_fetched", C.c_uint64), ("node_bytes", C.c_uint64),
+                ("nodes_fetched", C.c_uint64), ("tris_fetched", C.c_uint64), ("nodes_primary", C.c_uint64),
+                ("tris_primary", C.c_uint64), ("nodes_shade", C.c_uint64), ("tris_shade", C.c_uint64), ("node_bytes", C.c_uint64),
                 ("tri_bytes", C.c_uint64), ("ms_primary", C.c_float), ("ms_shade", C.c_float), ("ms_write", C.c_float),
                 ("ms_total", C.c_float)]
 

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, SceneView sc, boo
             hit_lit[h] = lit;
         }
     }
-    if (COUNT) flush_counters(gstats, c);
+    if (COUNT) flush_counters(gstats ? gstats + 1 : nullptr, c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -325,9 +325,9 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
                 olz = (float)(fp.cam_pos[2] - job.h_obj0_pos[2]);
     int per_sm = 0;
     cudaError_t e;
-#define LAUNCH_PERSISTENT(COUNTF, TOPN)                                                                                  \
+#define LAUNCH_PERSISTENT(COUNTF, TOPN, REFILL)                                                                          \
     do {                                                                                                                 \
-        auto kern = k_primary_fast_persistent<COUNTF, TOPN, 20>;                                                         \
+        auto kern = k_primary_fast_persistent<COUNTF, TOPN, REFILL>;                                                     \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);                                        \
         if (e != cudaSuccess) return e;                                                                                  \
         if (per_sm < 1) per_sm = 1;                                                                                      \
@@ -336,8 +336,17 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
         if (g > need) g = need;                                                                                          \
         kern<<<g, 128, 0, st>>>(fp, m, olx, oly, olz, job.d_hits, job.d_counters, job.d_stats);                          \
     } while (0)
-    if (job.top_in_smem) { if (count) LAUNCH_PERSISTENT(true, 256); else LAUNCH_PERSISTENT(false, 256); }
-    else { if (count) LAUNCH_PERSISTENT(true, 0); else LAUNCH_PERSISTENT(false, 0); }
+#define LAUNCH_REFILL(COUNTF, TOPN)                                                                                      \
+    do {                                                                                                                 \
+        if (job.refill_below <= 1) LAUNCH_PERSISTENT(COUNTF, TOPN, 1);                                                   \
+        else if (job.refill_below <= 8) LAUNCH_PERSISTENT(COUNTF, TOPN, 8);                                              \
+        else if (job.refill_below <= 16) LAUNCH_PERSISTENT(COUNTF, TOPN, 16);                                            \
+        else if (job.refill_below <= 24) LAUNCH_PERSISTENT(COUNTF, TOPN, 24);                                            \
+        else LAUNCH_PERSISTENT(COUNTF, TOPN, 32);                                                                        \
+    } while (0)
+    if (job.top_in_smem) { if (count) LAUNCH_REFILL(true, 256); else LAUNCH_REFILL(false, 256); }
+    else { if (count) LAUNCH_REFILL(true, 0); else LAUNCH_REFILL(false, 0); }
+#undef LAUNCH_REFILL
 #undef LAUNCH_PERSISTENT
     return cudaGetLastError();
 }

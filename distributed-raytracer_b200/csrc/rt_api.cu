@@ -22,6 +22,7 @@ struct rt_scene {
     int sm_count = 148;
     int max_leaf = 4;
     bool top_in_smem = true;
+    int refill_below = 24;
 
     std::vector<MeshDevice> meshes;
     std::vector<MeshView> h_views;
@@ -183,12 +184,15 @@ void collect_stats(rt_scene *s) {
     if (!s->stats_pending) return;
     unsigned int counters[4] = { 0, 0, 0, 0 };
     cudaMemcpy(counters, s->d_counters, sizeof counters, cudaMemcpyDeviceToHost);
-    Counters c; c.nodes = 0; c.tris = 0;
-    cudaMemcpy(&c, s->d_stats, sizeof c, cudaMemcpyDeviceToHost);
+    Counters c[2];
+    memset(c, 0, sizeof c);
+    cudaMemcpy(c, s->d_stats, sizeof c, cudaMemcpyDeviceToHost);
     s->stats.hit_pixels = counters[1];
     s->stats.shadow_rays = (uint64_t)counters[1] * (uint64_t)s->frame.n_lights;
-    s->stats.nodes_fetched = c.nodes;
-    s->stats.tris_fetched = c.tris;
+    s->stats.nodes_primary = c[0].nodes; s->stats.tris_primary = c[0].tris;
+    s->stats.nodes_shade = c[1].nodes; s->stats.tris_shade = c[1].tris;
+    s->stats.nodes_fetched = c[0].nodes + c[1].nodes;
+    s->stats.tris_fetched = c[0].tris + c[1].tris;
     s->stats.node_bytes = RT_NODE_BYTES;
     s->stats.tri_bytes = s->precision == RT_FP64_EXACT ? RT_TRI64_BYTES : RT_TRI32_BYTES;
     cudaEventElapsedTime(&s->stats.ms_primary, s->ev[0], s->ev[1]);
@@ -232,9 +236,10 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
         for (int k = 0; k < 3; k++) job.h_obj0_pos[k] = s->h_objs[0].pos[k];
     }
     job.top_in_smem = s->top_in_smem;
+    job.refill_below = s->refill_below;
 
     CU(s, cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned int), st));
-    CU(s, cudaMemsetAsync(s->d_stats, 0, sizeof(Counters), st));
+    CU(s, cudaMemsetAsync(s->d_stats, 0, 2 * sizeof(Counters), st));
     // background: sequential/main.go:17 surface.FillRect(nil, 0); distributed/main.go:70 default 0,0,0
     CU(s, cudaMemsetAsync(d_rgb, 0, out_bytes, st));
     if (job.d_out_colour) CU(s, cudaMemsetAsync(job.d_out_colour, 0, sizeof(double) * 3 * npix_out, st));
@@ -334,6 +339,7 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->precision = desc->precision;
     s->max_leaf = env_int("RT_B200_MAX_LEAF", 4);
     s->top_in_smem = env_int("RT_B200_TOP_SMEM", 1) != 0;
+    s->refill_below = env_int("RT_B200_REFILL", 24);
     memset(&s->stats, 0, sizeof s->stats);
     memset(&s->frame, 0, sizeof s->frame);
     int rc = RT_OK;
@@ -350,7 +356,7 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     CUB_(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto &e : s->ev) CUB_(cudaEventCreate(&e));
     CUB_(cudaMalloc((void **)&s->d_counters, 4 * sizeof(unsigned int)));
-    CUB_(cudaMalloc((void **)&s->d_stats, sizeof(Counters)));
+    CUB_(cudaMalloc((void **)&s->d_stats, 2 * sizeof(Counters)));
 
     s->meshes.resize(desc->n_meshes);
     s->h_views.resize(desc->n_meshes);

@@ -41,7 +41,7 @@ struct RenderJob {
     double   *d_hit_colour;   // 3 per hit
     uint32_t *d_hit_lit;      // per hit
     unsigned int *d_counters; // [0]=next ray (primary), [1]=hit count, [2]=next hit (shade), [3]=next hit (write)
-    Counters *d_stats;        // nodes/tris (RT_FLAG_COUNT) or nullptr
+    Counters *d_stats;        // [0] = K2 primary, [1] = K4 shadow rays (filled with RT_FLAG_COUNT)
     // outputs (device)
     uint8_t  *d_out_rgb;
     double   *d_out_colour;   // optional dense debug outputs
@@ -53,6 +53,7 @@ struct RenderJob {
     MeshView  h_mesh0;        // host copy of object 0's mesh view
     double    h_obj0_pos[3];
     bool      top_in_smem;    // keep the first levels of the BVH in shared memory (single-mesh scenes)
+    int       refill_below;   // persistent kernel: refill a warp when fewer lanes than this are live
 };
 
 // render.cu : enqueue K2 (primary) / K4 (shadow+shade) / K5 (framebuffer) on `st`

@@ -102,8 +102,12 @@ typedef struct {
     uint64_t primary_rays;     /* = w*h of the last render                                         */
     uint64_t shadow_rays;      /* = hit pixels * lights (tracer.go:60-64)                          */
     uint64_t hit_pixels;
-    uint64_t nodes_fetched;    /* BVH node records fetched      (only with RT_FLAG_COUNT)          */
-    uint64_t tris_fetched;     /* triangle records fetched      (only with RT_FLAG_COUNT)          */
+    uint64_t nodes_fetched;    /* BVH node records fetched, all kernels (only with RT_FLAG_COUNT)  */
+    uint64_t tris_fetched;     /* triangle records fetched, all kernels (only with RT_FLAG_COUNT)  */
+    uint64_t nodes_primary;    /* ... by the primary kernel (K2)                                   */
+    uint64_t tris_primary;
+    uint64_t nodes_shade;      /* ... by the shadow rays of the shade kernel (K4)                  */
+    uint64_t tris_shade;
     uint64_t node_bytes;       /* sizeof one node record                                           */
     uint64_t tri_bytes;        /* sizeof one triangle record in the active precision               */
     float    ms_primary;       /* CUDA-event durations of the last render's kernels, on the        */

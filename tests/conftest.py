@@ -1,0 +1,62 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+EXAMPLE_SCENE = os.path.join(GOLDEN, "example", "scene.json")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Builds every native artefact (CUDA library, host mirror, oracle) once per session."""
+    import __graft_entry__ as ge
+    ge.build()
+    return True
+
+
+@pytest.fixture(scope="session")
+def example_scene():
+    from oracle import scene_loader as sl
+    return sl.environment_from_file(EXAMPLE_SCENE)
+
+
+@pytest.fixture(scope="session")
+def example_oracle(example_scene):
+    from oracle import oracle as orc
+    return orc.Scene(example_scene)
+
+
+def random_soup_scene(n_tris, seed, with_normals=False, n_obj=1, n_lights=2, extent=1.0, half=0.15):
+    """Small random scene: float32-origin vertices, integer Ns, several objects sharing one mesh."""
+    rng = np.random.default_rng(seed)
+    cen = rng.uniform(-extent, extent, size=(n_tris, 1, 3))
+    verts = (cen + rng.uniform(-half, half, size=(n_tris, 3, 3))).reshape(-1, 3).astype(np.float32).astype(np.float64)
+    faces = np.zeros((n_tris, 7), dtype=np.uint32)
+    faces[:, 0:3] = np.arange(3 * n_tris).reshape(-1, 3)
+    faces[:, 6] = rng.integers(0, 2, size=n_tris)
+    normals = np.zeros((0, 3))
+    if with_normals:
+        nr = rng.normal(size=(3 * n_tris, 3)).astype(np.float32).astype(np.float64)
+        nr /= np.sqrt((nr * nr).sum(axis=1))[:, None]
+        normals = nr
+        faces[:, 3:6] = np.arange(3 * n_tris).reshape(-1, 3)
+    mats = np.array([[0.1, 0.1, 0.1, 0.8, 0.7, 0.6, 0.5, 0.5, 0.5, 10.0],
+                     [0.05, 0.1, 0.2, 0.3, 0.9, 0.4, 0.2, 0.3, 0.9, 3.0]]).astype(np.float32).astype(np.float64)
+    obj_pos = np.array([[0.0, 0.0, 0.0], [0.7, -0.4, -1.5], [-0.9, 0.5, 0.8]])[:n_obj]
+    lights = np.array([[0.0, 0.0, 10.0, 0.0, 1.0, 0.0], [3.0, 10.0, 10.0, 1.0, 0.0, 0.0], [-4.0, -10.0, 6.0, 0.0, 0.0, 1.0],
+                       [6.0, 1.0, 8.0, 1.0, 1.0, 1.0]])[:n_lights]
+    from oracle import scene_loader as sl
+    cam = sl.new_camera([0.2, 0.1, 5.0], [-0.05, -0.02, -1.0], 1.0)
+    return {"meshes": [{"verts": verts, "normals": normals, "faces": faces, "materials": mats}],
+            "obj_pos": obj_pos, "obj_mesh": np.zeros(n_obj, dtype=np.uint32), "lights": lights, "camera": cam}

@@ -200,21 +200,47 @@ int emul_bvh_check(void *h, uint32_t mesh, uint32_t *out_nodes, uint32_t *out_de
 
 // One frame through the same pipeline the kernels implement: K2 -> K4 -> K5.
 // flags: RT_FLAG_BRUTE_FORCE, RT_LAYOUT_ROWMAJOR, RT_QUANT_RGBA16_SHR8.  counters: [nodes, tris] (may be NULL).
-int emul_render(void *h, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, uint32_t W, uint32_t H, uint32_t x,
-                uint32_t y, uint32_t w, uint32_t hh, uint32_t flags, uint8_t *out_rgb, double *out_colour, int32_t *out_face,
-                int32_t *out_obj, uint32_t *out_lit, unsigned long long *counters) {
-    EmulScene *s = (EmulScene *)h;
+static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uint32_t flags, size_t npix, uint8_t *out_rgb,
+                       double *out_colour, int32_t *out_face, int32_t *out_obj, uint32_t *out_lit, unsigned long long *counters);
+
+static FrameParams frame_of(EmulScene *s, const rt_camera *cam, uint32_t n_lights, uint32_t W, uint32_t H) {
     FrameParams fp;
     memset(&fp, 0, sizeof fp);
     for (int k = 0; k < 3; k++) { fp.cam_pos[k] = cam->pos[k]; fp.fwd[k] = cam->forward[k]; fp.left[k] = cam->left[k]; fp.up[k] = cam->up[k]; }
     fp.tan_half = cam->tan_half_fov;
-    fp.W = (int)W; fp.H = (int)H; fp.x = (int)x; fp.y = (int)y; fp.w = (int)w; fp.h = (int)hh;
+    fp.W = (int)W; fp.H = (int)H; fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
     fp.n_lights = (int)n_lights; fp.n_obj = (int)s->objs.size();
+    return fp;
+}
+
+int emul_render(void *h, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, uint32_t W, uint32_t H, uint32_t x,
+                uint32_t y, uint32_t w, uint32_t hh, uint32_t flags, uint8_t *out_rgb, double *out_colour, int32_t *out_face,
+                int32_t *out_obj, uint32_t *out_lit, unsigned long long *counters) {
+    EmulScene *s = (EmulScene *)h;
+    FrameParams fp = frame_of(s, cam, n_lights, W, H);
+    fp.x = (int)x; fp.y = (int)y; fp.w = (int)w; fp.h = (int)hh;
+    return render_core(s, fp, lights, flags, (size_t)w * hh, out_rgb, out_colour, out_face, out_obj, out_lit, counters);
+}
+
+// multi-GPU tile mode of map_ray (rt_render_tiles_device): packed tiles of rank `rank`
+int emul_render_tiles(void *h, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, uint32_t W, uint32_t H,
+                      uint32_t tw, uint32_t th, uint32_t rank, uint32_t n_ranks, uint32_t flags, uint8_t *out_tiles) {
+    EmulScene *s = (EmulScene *)h;
+    FrameParams fp = frame_of(s, cam, n_lights, W, H);
+    fp.tile_w = (int)tw; fp.tile_h = (int)th; fp.tiles_x = (int)((W + tw - 1) / tw);
+    uint32_t n_tiles = (uint32_t)fp.tiles_x * ((H + th - 1) / th);
+    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
+    fp.n_local_tiles = (int)(n_tiles > rank ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
+    return render_core(s, fp, lights, flags & ~RT_LAYOUT_ROWMAJOR, (size_t)fp.n_local_tiles * tw * th, out_tiles, nullptr, nullptr,
+                       nullptr, nullptr, nullptr);
+}
+
+static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uint32_t flags, size_t npix, uint8_t *out_rgb,
+                       double *out_colour, int32_t *out_face, int32_t *out_obj, uint32_t *out_lit, unsigned long long *counters) {
     SceneView sc;
     sc.meshes = s->views.data(); sc.objs = s->objs.data(); sc.lights = reinterpret_cast<const LightRec *>(lights);
     const bool brute = (flags & RT_FLAG_BRUTE_FORCE) != 0, rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0,
                sdl = (flags & RT_QUANT_RGBA16_SHR8) != 0;
-    const size_t npix = (size_t)w * hh;
     if (out_rgb) memset(out_rgb, 0, 3 * npix);
     if (out_colour) memset(out_colour, 0, sizeof(double) * 3 * npix);
     if (out_face) for (size_t k = 0; k < npix; k++) out_face[k] = -1;

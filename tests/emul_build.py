@@ -31,6 +31,8 @@ def lib():
         L.emul_bvh_check.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 3
         L.emul_render.restype = C.c_int
         L.emul_render.argtypes = [C.c_void_p, C.POINTER(_lib.Camera), C.c_void_p] + [C.c_uint32] * 8 + [C.c_void_p] * 6
+        L.emul_render_tiles.restype = C.c_int
+        L.emul_render_tiles.argtypes = [C.c_void_p, C.POINTER(_lib.Camera), C.c_void_p] + [C.c_uint32] * 8 + [C.c_void_p]
         L.emul_morton63.restype = C.c_uint64
         L.emul_morton63.argtypes = [C.c_double] * 3
         _LIB = L
@@ -64,6 +66,14 @@ class EmulScene:
         lib().emul_render(self.h, C.byref(cam), lights.ctypes.data, lights.shape[0], W, H, x, y, w, h, flags,
                           rgb.ctypes.data, col.ctypes.data, face.ctypes.data, obj.ctypes.data, lit.ctypes.data, cnt.ctypes.data)
         return rgb, col, face, obj, lit, cnt
+
+    def render_tiles(self, cam13, lights, W, H, tw, th, rank, n_ranks, out, flags=0):
+        from oracle import oracle as orc
+        cam = rt.make_camera(cam13, orc.go_tan(float(cam13[12]) / 2.0))
+        lights = np.ascontiguousarray(lights, dtype=np.float64).reshape(-1, 6)
+        lib().emul_render_tiles(self.h, C.byref(cam), lights.ctypes.data, lights.shape[0], W, H, tw, th, rank, n_ranks, flags,
+                                out.ctypes.data)
+        return out
 
     def close(self):
         if self.h:

@@ -1,0 +1,161 @@
+"""CPU: replays the device code (the RT_HD functions the sm_100a kernels are made of: LBVH builder bodies,
+fp64-exact and fp32-fast traversal, fused shadow+shade, quantisers, ray<->pixel maps) through tests/emul and
+compares it with the oracle.  This is what can be proven about the kernels without a GPU; the -m gpu tests
+repeat the same comparisons through the C ABI on the real device."""
+import numpy as np
+import pytest
+
+import emul_build as eb
+from conftest import random_soup_scene
+from oracle import oracle as orc
+
+import distributed_raytracer_b200 as rt
+from distributed_raytracer_b200 import workloads
+
+
+def oracle_render(sc, W, H, **kw):
+    S = orc.Scene(sc)
+    return S.render_region(W, H, mode=orc.CULLED, **kw)
+
+
+def check_exact(sc, W, H, max_leaf=4, flags=0):
+    rgb_o, col_o, face_o, st = oracle_render(sc, W, H)
+    E = eb.EmulScene(sc, rt.FP64_EXACT, max_leaf)
+    rc = E.bvh_check()
+    assert rc[0] == 0, "BVH structure invalid: code %d" % rc[0]
+    rgb, col, face, obj, lit, cnt = E.render(sc["camera"], sc["lights"], W, H, flags=flags)
+    assert np.array_equal(face, face_o)
+    assert np.array_equal(col.view(np.uint64), col_o.view(np.uint64))      # bit-exact float64 colours
+    assert np.array_equal(rgb, rgb_o)
+    assert int(cnt[2]) == st["hit_pixels"]
+    E.close()
+    return st
+
+
+def check_fast(sc, W, H, max_leaf=4):
+    rgb_o, col_o, face_o, st = oracle_render(sc, W, H)
+    E = eb.EmulScene(sc, rt.FP32_FAST, max_leaf)
+    assert E.bvh_check()[0] == 0
+    rgb, col, face, obj, lit, cnt = E.render(sc["camera"], sc["lights"], W, H)
+    E.close()
+    within = (np.abs(rgb.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= 1).mean()
+    same_face = (face == face_o).mean()
+    return within, same_face
+
+
+@pytest.mark.parametrize("max_leaf", [1, 4, 8])
+def test_exact_replay_bit_identical_on_example(example_scene, max_leaf):
+    st = check_exact(example_scene, 320, 240, max_leaf)
+    assert st["hit_pixels"] == 5820
+
+
+def test_exact_replay_brute_force_flag(example_scene):
+    check_exact(example_scene, 96, 72, flags=rt.FLAG_BRUTE_FORCE)
+
+
+@pytest.mark.parametrize("kw", [dict(n_tris=300, seed=11), dict(n_tris=500, seed=12, with_normals=True),
+                                dict(n_tris=150, seed=13, n_obj=3, n_lights=4), dict(n_tris=1, seed=14, half=1.2, extent=0.2), dict(n_tris=2, seed=15, half=1.2, extent=0.2),
+                                dict(n_tris=3, seed=16, half=1.2, extent=0.2), dict(n_tris=40, seed=17, half=1.5)])
+def test_exact_replay_bit_identical_on_random_scenes(kw):
+    sc = random_soup_scene(**kw)
+    st = check_exact(sc, 80, 60)
+    assert st["hit_pixels"] > 0
+
+
+def test_exact_replay_on_subdivided_suzanne(example_scene):
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 2)]
+    assert sc["meshes"][0]["faces"].shape[0] == 968 * 16
+    check_exact(sc, 160, 120)
+
+
+def test_exact_replay_with_duplicate_triangles():
+    # identical triangles => identical Morton keys (index tie-break in the Karras tree) and exact-distance
+    # ties that must resolve to the lowest face index
+    sc = random_soup_scene(n_tris=20, seed=21)
+    m = sc["meshes"][0]
+    m["verts"] = np.concatenate([m["verts"]] * 4, axis=0)
+    f = m["faces"].copy()
+    m["faces"] = np.concatenate([f, f + [60, 60, 60, 0, 0, 0, 0], f + [120, 120, 120, 0, 0, 0, 0], f + [180, 180, 180, 0, 0, 0, 0]]).astype(np.uint32)
+    rgb_o, col_o, face_o, st = oracle_render(sc, 64, 48)
+    assert st["nearest_ties"] > 0 and face_o.max() < 20
+    check_exact(sc, 64, 48)
+    check_exact(sc, 64, 48, max_leaf=1)
+
+
+def test_fast_replay_within_tolerance(example_scene):
+    within, same_face = check_fast(example_scene, 320, 240)
+    assert within >= 0.999 and same_face >= 0.999       # north_star: <= 1 LSB on >= 99.9 % of the pixels
+
+
+@pytest.mark.parametrize("kw", [dict(n_tris=400, seed=31, with_normals=True), dict(n_tris=150, seed=32, n_obj=3, n_lights=4)])
+def test_fast_replay_random_scenes(kw):
+    within, same_face = check_fast(random_soup_scene(**kw), 96, 72)
+    assert within >= 0.995 and same_face >= 0.995       # tiny random soups have many silhouette pixels
+
+
+def test_region_layout_quantiser(example_scene):
+    W, H, x, y, w, h = 96, 72, 30, 20, 41, 33
+    S = orc.Scene(example_scene)
+    E = eb.EmulScene(example_scene, rt.FP64_EXACT)
+    for flags, layout, quant in [(0, orc.L_COLMAJOR, orc.Q_RGB255), (rt.LAYOUT_ROWMAJOR, orc.L_ROWMAJOR, orc.Q_RGB255),
+                                 (rt.QUANT_RGBA16_SHR8, orc.L_COLMAJOR, orc.Q_RGBA16_SHR8)]:
+        rgb_o, col_o, face_o, _ = S.render_region(W, H, x, y, w, h, layout=layout, quant=quant)
+        rgb, col, face, obj, lit, cnt = E.render(example_scene["camera"], example_scene["lights"], W, H, x, y, w, h, flags=flags)
+        assert np.array_equal(rgb, rgb_o) and np.array_equal(face, face_o)
+    # odd screen size: integer half sizes (tracer.go:16), ragged 8x4 blocks
+    rgb_o, _, face_o, _ = S.render_region(101, 67)
+    rgb, _, face, _, _, _ = E.render(example_scene["camera"], example_scene["lights"], 101, 67)
+    assert np.array_equal(rgb, rgb_o) and np.array_equal(face, face_o)
+    E.close()
+
+
+def numpy_untile(all_tiles, W, H, tw, th, n_ranks):
+    """Mirror of k_untile (render.cu), row-major output."""
+    tiles_x = (W + tw - 1) // tw
+    per_rank = rt.tiles_per_rank(W, H, tw, th, n_ranks)
+    tiles = all_tiles.reshape(n_ranks, per_rank, th, tw, 3)
+    jj, ii = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    t = (jj // th) * tiles_x + ii // tw
+    return tiles[t % n_ranks, t // n_ranks, jj % th, ii % tw]
+
+
+@pytest.mark.parametrize("W,H,tw,th,n", [(96, 72, 32, 16, 3), (100, 70, 16, 8, 2), (64, 48, 8, 4, 8)])
+def test_tile_sharding_maps(example_scene, W, H, tw, th, n):
+    E = eb.EmulScene(example_scene, rt.FP64_EXACT)
+    ref, _, _, _, _, _ = E.render(example_scene["camera"], example_scene["lights"], W, H, flags=rt.LAYOUT_ROWMAJOR)
+    per = rt.tiles_per_rank(W, H, tw, th, n)
+    bufs = []
+    for r in range(n):
+        out = np.zeros(per * tw * th * 3, dtype=np.uint8)
+        E.render_tiles(example_scene["camera"], example_scene["lights"], W, H, tw, th, r, n, out)
+        bufs.append(out)
+    img = numpy_untile(np.concatenate(bufs), W, H, tw, th, n)
+    assert np.array_equal(img, ref.reshape(H, W, 3))
+    E.close()
+
+
+def test_bvh_builder_structure():
+    rng = np.random.default_rng(5)
+    for n in [1, 2, 3, 5, 17, 64, 257, 1500]:
+        sc = random_soup_scene(n_tris=n, seed=100 + n)
+        for max_leaf in (1, 4, 16):
+            E = eb.EmulScene(sc, rt.FP32_FAST, max_leaf)
+            rc, n_nodes, depth, n_leaves = E.bvh_check()
+            assert rc == 0, (n, max_leaf, rc)
+            assert n_nodes <= max(n - 1, 0) and depth <= 94
+            if max_leaf == 1 and n > 1:
+                assert n_nodes == n - 1 and n_leaves == n
+            E.close()
+    # Morton code: bit interleave of 21-bit cells, x most significant
+    L = eb.lib()
+    assert L.emul_morton63(0.0, 0.0, 0.0) == 0
+    assert L.emul_morton63(1.0, 1.0, 1.0) == (1 << 63) - 1
+    assert L.emul_morton63(0.5, 0.0, 0.0) == 1 << 62 and L.emul_morton63(0.0, 0.5, 0.0) == 1 << 61 and L.emul_morton63(0.0, 0.0, 0.5) == 1 << 60
+    a = rng.uniform(0, 1, (200, 3))
+    for p in a:
+        q = (np.minimum(p * 2 ** 21, 2 ** 21 - 1)).astype(np.int64)
+        want = 0
+        for b in range(21):
+            want |= ((int(q[0]) >> b) & 1) << (3 * b + 2) | ((int(q[1]) >> b) & 1) << (3 * b + 1) | ((int(q[2]) >> b) & 1) << (3 * b)
+        assert L.emul_morton63(*p) == want

@@ -1,0 +1,295 @@
+"""GPU (-m gpu): parity of the sm_100a kernels with the oracle, called through the C ABI (librt_b200.so).
+
+Bars (BASELINE.json north_star): FP64_EXACT -- nearest-hit face index per primary ray and the float64 colours
+bit-exact, bytes identical under both quantisers; FP32_FAST -- <= 1 LSB per 8-bit channel on >= 99.9 % of the
+pixels and the hit-face index equal on >= 99.9 %."""
+import numpy as np
+import pytest
+
+from conftest import EXAMPLE_SCENE, random_soup_scene
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+LSB_TOL = 1          # FP32_FAST: max |delta| per 8-bit channel ...
+LSB_FRAC = 0.999     # ... on at least this fraction of the pixels
+
+
+@pytest.fixture(scope="module")
+def rt(built):
+    import distributed_raytracer_b200 as rt
+    if rt._lib.load().rt_device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests cannot run (there is no CPU fallback)")
+    return rt
+
+
+def oracle_render(sc, W, H, x=0, y=0, w=None, h=None, **kw):
+    S = orc.Scene(sc)
+    return S.render_region(W, H, x, y, w, h, mode=orc.CULLED, **kw)
+
+
+def assert_exact(rt, sc, W, H, flags=0):
+    rgb_o, col_o, face_o, st = oracle_render(sc, W, H)
+    g = rt.GpuScene(sc, precision=rt.FP64_EXACT)
+    rgb, col, face, obj, lit = g.render_region_debug(W, H, flags=flags)
+    stats = g.stats()
+    g.close()
+    assert np.array_equal(face, face_o), "%d face mismatches" % (face != face_o).sum()
+    assert np.array_equal(col.view(np.uint64), col_o.view(np.uint64))
+    assert np.array_equal(rgb, rgb_o)
+    assert stats["hit_pixels"] == st["hit_pixels"] and stats["shadow_rays"] == st["shadow_rays"]
+    return st
+
+
+def fast_fractions(rt, sc, W, H, flags=0):
+    rgb_o, col_o, face_o, st = oracle_render(sc, W, H)
+    g = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    rgb, col, face, obj, lit = g.render_region_debug(W, H, flags=flags)
+    g.close()
+    within = (np.abs(rgb.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= LSB_TOL).mean()
+    return within, (face == face_o).mean(), rgb, face
+
+
+def test_c1_exact_bit_identical(rt, example_scene):
+    st = assert_exact(rt, example_scene, 320, 240)
+    assert st["hit_pixels"] == 5820
+
+
+def test_c1_exact_matches_golden_fixture(rt, example_scene):
+    import os
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "c1_320x240.npz"))
+    g = rt.GpuScene(example_scene, precision=rt.FP64_EXACT)
+    rgb, col, face, obj, lit = g.render_region_debug(320, 240)
+    sdl = g.render_region(320, 240, flags=rt.QUANT_RGBA16_SHR8)
+    g.close()
+    hit = gold["hit_index"]
+    assert np.array_equal(face, gold["face"].astype(np.int32))
+    assert np.array_equal(col[hit].view(np.uint64), gold["colour_bits"])
+    assert np.array_equal(rgb[hit], gold["rgb"]) and np.array_equal(sdl[hit], gold["sdl"])
+    assert not rgb[face < 0].any() and (obj[face >= 0] == 0).all() and (obj[face < 0] == -1).all()
+
+
+def test_c1_exact_brute_force_kernel(rt, example_scene):
+    assert_exact(rt, example_scene, 160, 120, flags=rt.FLAG_BRUTE_FORCE)
+
+
+def test_c2_exact_1080p_one_light(rt, example_scene):
+    sc = dict(example_scene)
+    sc["lights"] = example_scene["lights"][:1]            # C2: lights[0] only
+    assert_exact(rt, sc, 1920, 1080)
+
+
+@pytest.mark.parametrize("kw", [dict(n_tris=300, seed=11), dict(n_tris=500, seed=12, with_normals=True),
+                                dict(n_tris=150, seed=13, n_obj=3, n_lights=4), dict(n_tris=1, seed=14, half=1.2, extent=0.2),
+                                dict(n_tris=2, seed=15, half=1.2, extent=0.2), dict(n_tris=40, seed=17, half=1.5)])
+def test_exact_random_scenes(rt, kw):
+    st = assert_exact(rt, random_soup_scene(**kw), 160, 120)
+    assert st["hit_pixels"] > 0
+
+
+def test_exact_duplicate_triangles_tie_break(rt):
+    sc = random_soup_scene(n_tris=20, seed=21)
+    m = sc["meshes"][0]
+    m["verts"] = np.concatenate([m["verts"]] * 4, axis=0)
+    f = m["faces"].copy()
+    m["faces"] = np.concatenate([f + [60 * k, 60 * k, 60 * k, 0, 0, 0, 0] for k in range(4)]).astype(np.uint32)
+    _, _, face_o, st = oracle_render(sc, 64, 48)
+    assert st["nearest_ties"] > 0
+    assert_exact(rt, sc, 64, 48)
+
+
+def test_exact_subdivided_suzanne(rt, example_scene):
+    from distributed_raytracer_b200 import workloads
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 3)]      # 61 952 faces
+    sc["lights"] = example_scene["lights"][:2]
+    assert_exact(rt, sc, 480, 270)
+
+
+def test_exact_region_layout_quantiser(rt, example_scene):
+    W, H, x, y, w, h = 203, 151, 61, 40, 83, 67          # odd sizes: integer halves (tracer.go:16), ragged blocks
+    g = rt.GpuScene(example_scene, precision=rt.FP64_EXACT)
+    for flags, layout, quant in [(0, orc.L_COLMAJOR, orc.Q_RGB255), (rt.LAYOUT_ROWMAJOR, orc.L_ROWMAJOR, orc.Q_RGB255),
+                                 (rt.QUANT_RGBA16_SHR8, orc.L_COLMAJOR, orc.Q_RGBA16_SHR8),
+                                 (rt.LAYOUT_ROWMAJOR | rt.QUANT_RGBA16_SHR8, orc.L_ROWMAJOR, orc.Q_RGBA16_SHR8)]:
+        rgb_o, _, face_o, _ = oracle_render(example_scene, W, H, x, y, w, h, layout=layout, quant=quant)
+        rgb = g.render_region(W, H, x, y, w, h, flags=flags)
+        assert np.array_equal(rgb, rgb_o)
+    g.close()
+
+
+def test_fast_c1_within_tolerance_both_kernels(rt, example_scene):
+    w1, f1, rgb_p, face_p = fast_fractions(rt, example_scene, 320, 240)                      # persistent kernel
+    w2, f2, rgb_s, face_s = fast_fractions(rt, example_scene, 320, 240, flags=rt.FLAG_SIMPLE)
+    assert w1 >= LSB_FRAC and f1 >= LSB_FRAC and w2 >= LSB_FRAC and f2 >= LSB_FRAC
+    # both kernels run the same per-ray arithmetic => identical images
+    assert np.array_equal(face_p, face_s) and np.array_equal(rgb_p, rgb_s)
+
+
+def test_fast_1080p_two_lights(rt, example_scene):
+    sc = dict(example_scene)
+    sc["lights"] = example_scene["lights"][:2]
+    within, same, _, _ = fast_fractions(rt, sc, 1920, 1080)
+    assert within >= LSB_FRAC and same >= LSB_FRAC
+
+
+def test_fast_subdivided_suzanne(rt, example_scene):
+    from distributed_raytracer_b200 import workloads
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 3)]
+    sc["lights"] = example_scene["lights"][:2]
+    within, same, _, _ = fast_fractions(rt, sc, 960, 540)
+    assert within >= LSB_FRAC and same >= LSB_FRAC
+
+
+@pytest.mark.parametrize("kw", [dict(n_tris=400, seed=31, with_normals=True), dict(n_tris=150, seed=32, n_obj=3, n_lights=4),
+                                dict(n_tris=1, seed=14, half=1.2, extent=0.2)])
+def test_fast_random_scenes(rt, kw):
+    within, same, _, _ = fast_fractions(rt, random_soup_scene(**kw), 160, 120)
+    assert within >= 0.995 and same >= 0.995          # tiny soups: many silhouette pixels per frame
+
+
+def test_fast_tiles_equal_region_render(rt, example_scene):
+    """Multi-GPU tile path on one GPU: every rank's packed tiles, gathered and de-interleaved, reproduce the
+    plain region render byte for byte."""
+    import torch
+    W, H, tw, th, n = 333, 187, 32, 16, 3
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    ref = g.render_region(W, H, flags=rt.LAYOUT_ROWMAJOR)
+    per = rt.tiles_per_rank(W, H, tw, th, n)
+    allt = torch.zeros(n * per * tw * th * 3, dtype=torch.uint8, device="cuda")
+    for r in range(n):
+        part = allt[r * per * tw * th * 3:(r + 1) * per * tw * th * 3]
+        g.render_tiles_device(W, H, tw, th, r, n, part.data_ptr(), None)
+    out = torch.zeros(W * H * 3, dtype=torch.uint8, device="cuda")
+    g.untile_device(W, H, tw, th, n, allt.data_ptr(), out.data_ptr(), None, flags=rt.LAYOUT_ROWMAJOR)
+    torch.cuda.synchronize()
+    g.close()
+    assert np.array_equal(out.cpu().numpy().reshape(-1, 3), ref)
+
+
+def test_fast_device_output_and_streams(rt, example_scene):
+    import torch
+    W, H = 320, 240
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    ref = g.render_region(W, H)
+    out = torch.zeros(W * H * 3, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        g.render_region_device(W, H, 0, 0, W, H, out.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(out.cpu().numpy().reshape(-1, 3), ref)
+    out.zero_()
+    g.render_region_device(W, H, 0, 0, W, H, out.data_ptr(), None)          # library stream, synchronous
+    assert np.array_equal(out.cpu().numpy().reshape(-1, 3), ref)
+    g.close()
+
+
+def test_full_size_c3_properties(rt, example_scene):
+    """BASELINE config 3 at full size (991 232 faces, 3840x2160, 2 lights, FP32_FAST): the oracle is too slow for the
+    whole frame, so size-independent properties + an oracle check of a 1/64 pixel sample."""
+    from distributed_raytracer_b200 import workloads
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 5)]
+    assert sc["meshes"][0]["faces"].shape[0] == 991232
+    sc["lights"] = example_scene["lights"][:2]
+    W, H = 3840, 2160
+    g = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    info = g.bvh_info()
+    assert info["n_faces"] == 991232 and 0 < info["n_nodes"] < 991232 and info["max_depth"] < 94
+    rgb, col, face, obj, lit = g.render_region_debug(W, H)
+    stats = g.stats()
+    # determinism + the two primary kernels agree (persistent refill order must not change any pixel)
+    rgb2 = g.render_region(W, H)
+    rgb3, _, face3, _, _ = g.render_region_debug(W, H, flags=rt.FLAG_SIMPLE)
+    assert np.array_equal(rgb, rgb2) and np.array_equal(rgb, rgb3) and np.array_equal(face, face3)
+    hit = face >= 0
+    assert stats["hit_pixels"] == int(hit.sum()) and stats["primary_rays"] == W * H
+    assert 0.08 < hit.mean() < 0.12                                       # ~10.1 % of the primary rays hit
+    assert not rgb[~hit].any() and (face[hit] < 991232).all()
+    # subdividing does not move the surface: a face index maps back to its coarse parent (f >> 10), so the
+    # coarse render of the original 968-face mesh must agree on the parent index almost everywhere
+    g.close()
+    g0 = rt.GpuScene(dict(example_scene, lights=sc["lights"]), precision=rt.FP32_FAST)
+    _, _, face0, _, _ = g0.render_region_debug(W, H)
+    g0.close()
+    both = hit & (face0 >= 0)
+    assert ((face >= 0) == (face0 >= 0)).mean() > 0.9995
+    assert ((face[both] >> 10) == face0[both]).mean() > 0.999
+    # oracle on a bounded sample: every 64th region-linear pixel
+    S = orc.Scene(sc)
+    rgb_o, _, face_o, st = S.render_region(W, H, step=64, phase=7, want_colour=False)
+    idx = np.arange(W * H) % 64 == 7
+    within = (np.abs(rgb[idx].astype(np.int32) - rgb_o[idx].astype(np.int32)).max(axis=1) <= LSB_TOL).mean()
+    same = (face[idx] == face_o[idx]).mean()
+    assert within >= LSB_FRAC and same >= LSB_FRAC, (within, same)
+
+
+def test_counting_build_reports_traversal_work(rt, example_scene):
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    a = g.render_region(320, 240)
+    s0 = g.stats()
+    b = g.render_region(320, 240, flags=rt.FLAG_COUNT)
+    s1 = g.stats()
+    g.close()
+    assert np.array_equal(a, b)
+    assert s0["nodes_fetched"] == 0 and s1["nodes_fetched"] > 0 and s1["tris_fetched"] > 0
+    assert s1["node_bytes"] == 64 and s1["tri_bytes"] == 48 and s1["primary_rays"] == 320 * 240 and s1["ms_total"] > 0
+
+
+def test_errors_and_lifecycle(rt, example_scene):
+    sc = {k: v for k, v in example_scene.items() if k not in ("camera", "lights")}
+    g = rt.GpuScene(sc)
+    with pytest.raises(rt.RtError) as ei:
+        g.render_region(64, 48)                                 # render before rt_frame_set
+    assert ei.value.code == rt._lib.RT_ERR_STATE
+    g.set_frame(example_scene["camera"], example_scene["lights"])
+    with pytest.raises(rt.RtError) as ei:
+        g.render_region(64, 48, 32, 0, 64, 48)                  # region exceeds the screen
+    assert ei.value.code == rt._lib.RT_ERR_INVALID
+    ref = g.render_region(64, 48)
+    g.set_frame(example_scene["camera"], example_scene["lights"][:0])      # no lights: ambient only
+    amb = g.render_region(64, 48)
+    assert set(np.unique(amb)) <= {0, int(255 * float(np.float32(0.1)))}
+    g.close()
+    # re-registration = destroy + create, repeatedly (distributed/main.go:146-185): must be leak-free and repeatable
+    import torch
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(5):
+        g = rt.GpuScene(example_scene)
+        assert np.array_equal(g.render_region(64, 48), ref)
+        g.close()
+    assert abs(torch.cuda.mem_get_info()[0] - free0) < 64 << 20
+    # object positions are per-frame state (the gob diff): moving the object moves the image
+    g = rt.GpuScene(example_scene)
+    moved = g.bulk_trace(example_scene["camera"], example_scene["lights"], 64, 48, 0, 0, 64, 48, obj_pos=[[1.5, 1.0, -1.0]])
+    g.close()
+    assert not np.array_equal(moved, ref)
+    S = orc.Scene(example_scene)
+    S.set_frame(example_scene["camera"], example_scene["lights"], obj_pos=[[1.5, 1.0, -1.0]])
+    rgb_o, _, _, _ = S.render_region(64, 48)
+    assert (np.abs(moved.astype(int) - rgb_o.astype(int)).max(axis=1) <= 1).mean() >= 0.99
+
+
+def test_host_tracer_bulk_trace_and_draw(rt, example_scene):
+    """The reference-facing interface: Tracer.BulkTrace (distributed/main.go:46-91) over partition() rectangles
+    (master/main.go:54-91) reassembles into the same screen as draw() (sequential/main.go:15-32)."""
+    from distributed_raytracer_b200 import host
+    W, H = 320, 240
+    env = host.Environment(EXAMPLE_SCENE)
+    tr = host.Tracer(env, W, H, precision=rt.FP64_EXACT)
+    rgb_o, _, _, _ = oracle_render(example_scene, W, H, layout=orc.L_ROWMAJOR)
+    sdl_o, _, _, _ = oracle_render(example_scene, W, H, layout=orc.L_ROWMAJOR, quant=orc.Q_RGBA16_SHR8)
+    screen = np.zeros((W, H, 3), dtype=np.uint8)
+    rects = host.partition(W, H, 8)
+    assert len(rects) == 8
+    for (x, y, w, h) in rects:
+        res = tr.BulkTrace(x, y, w, h)                           # results[i*h + j]
+        screen[x:x + w, y:y + h] = res.reshape(w, h, 3)
+    assert np.array_equal(screen.transpose(1, 0, 2), rgb_o.reshape(H, W, 3))
+    assert np.array_equal(tr.draw(), sdl_o.reshape(H, W, 3))     # SDL quantiser, Appendix B-6
+    assert np.array_equal(tr.draw(rt.QUANT_RGB255), rgb_o.reshape(H, W, 3))
+    assert tr.BulkTrace(0, 0, 0, 0).shape == (0, 3)
+    tr.close()
+    env.close()
