@@ -44,44 +44,59 @@ def build_workload():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region.  Polls NVML (the source nvidia-smi reads) every few ms from a
+    thread, because a timed region of a few hundred ms is too short for `nvidia-smi -lms`; falls back to nvidia-smi."""
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu_index = [], None, gpu_index
+        self.gpu_index, self.rows, self.stop_flag, self.thread, self.max_mhz = gpu_index, [], False, None, None
+
+    def _poll_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                  int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.004)
+        nv.nvmlShutdown()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml  # noqa: F401
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.thread = None
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return self._nvidia_smi_once()
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
         for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            bits |= r[1]
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                 0x80: "hw_power_brake_slowdown"}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in names.items() if bits & b), "samples": len(sm),
+                "power_w_max": max(r[2] for r in self.rows), "source": "nvml poll, 4 ms period, inside the timed region"}
+
+    def _nvidia_smi_once(self):
+        try:
+            out = subprocess.check_output(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                                           "--format=csv,noheader,nounits", "-i", str(self.gpu_index)], text=True)
+            c = [x.strip() for x in out.strip().split(",")]
+            return {"sm_mhz": float(c[0]), "sm_max_mhz": float(c[1]), "reasons": [c[2]], "samples": 1, "source": "nvidia-smi (single sample)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
 
 
 def oracle_cpu_rate(sc, n_threads, budget_s, mode_name="rtree"):
@@ -150,11 +165,11 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--simple", action="store_true", help="use the one-thread-per-ray primary kernel (RT_FLAG_SIMPLE)")
+    ap.add_argument("--persistent", action="store_true", help="use the persistent warp-cooperative primary kernel (RT_FLAG_PERSISTENT)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -184,7 +199,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
 
-    render_flags = rt.FLAG_SIMPLE if args.simple else 0
+    render_flags = rt.FLAG_PERSISTENT if args.persistent else 0
     sc = build_workload() if rank == 0 else None
     if world > 1:
         # scene broadcast once over NCCL/NVLink; every rank builds the same LBVH locally
@@ -236,6 +251,11 @@ def main():
     else:
         rays_frame, hits_frame = W * H + hits_local * len(lights), hits_local
 
+    # ---- clock ramp (untimed, not a step): the GPU idles at ~120 MHz; give DVFS ~0.4 s of work to reach its load clocks ----
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < 0.4:
+        flush.zero_()
+        torch.cuda.synchronize(dev)
     # ---- warm-up ----
     for _ in range(args.warmup):
         step()
@@ -353,7 +373,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": {"primary": "k_primary_fast_" + ("simple" if args.simple else "persistent"), "shade": "k_shade", "write": "k_write"}[dom],
+                "kernel": {"primary": "k_primary_fast_" + ("persistent" if args.persistent else "simple"), "shade": "k_shade", "write": "k_write"}[dom],
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": avg[dom],
                 "kernels_ms": avg, "algorithmic_bytes": alg,
                 "per_ray": {"nodes_primary": cnt["nodes_primary"] / max(1, prim_local), "tris_primary": cnt["tris_primary"] / max(1, prim_local),
@@ -373,7 +393,7 @@ def main():
         "config": {"workload": WORKLOAD, "rays_per_frame": rays_frame, "hit_pixels": hits_frame, "frames_per_s": 1e3 / ms_per_step,
                    "l2": "256 MiB device memset between timed steps (L2 flush)", "precision": "FP32_FAST traversal, fp64 shading",
                    "parallelism": "screen tiles 32x16 round-robin over %d rank(s)" % world, "bvh": bvh,
-                   "primary_kernel": "simple" if args.simple else "persistent"},
+                   "primary_kernel": "persistent" if args.persistent else "simple"},
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "clocks": clocks, "wall_s_timed_region": wall,
     }

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "librt_b200.so")
 FP64_EXACT, FP32_FAST = 0, 1
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0x0, 0x1
 QUANT_RGB255, QUANT_RGBA16_SHR8 = 0x0, 0x2
-FLAG_COUNT, FLAG_BRUTE_FORCE, FLAG_SIMPLE = 0x4, 0x8, 0x10
+FLAG_COUNT, FLAG_BRUTE_FORCE, FLAG_SIMPLE, FLAG_PERSISTENT = 0x4, 0x8, 0x10, 0x20
 
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_STATE, RT_ERR_CANCELLED = 0, -1, -2, -3, -4, -5
 

@@ -147,7 +147,10 @@ k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, floa
         append_hit(finished && face >= 0, ray, 0, face, tbest, hits, &counters[1]);
         if (finished) have = false;
 
-        // ---- refill idle lanes: ballot + one atomicAdd per warp + shuffle ----
+        // ---- refill idle lanes: ballot to find them, ONE atomicAdd per warp claims popc(idle) consecutive rays, the
+        // base is shuffled to every lane and each idle lane takes base + its popc-rank among the idle lanes.
+        // (Claiming larger chunks per warp was measured 2x SLOWER -- profiles/r01_explore_b_*: warps then spread over
+        // 8x more image rows and the BVH working set of the chip no longer fits L1/L2.) ----
         unsigned idle = __ballot_sync(FULL, !have);
         if (idle && !exhausted) {
             unsigned n = __popc(idle);
@@ -230,8 +233,8 @@ k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, floa
 // ---------------------------------------------------------------------------------------------
 // K4: fused shadow rays + Phong shading, one thread per primary hit; warps claim 32 hits at a time
 // ---------------------------------------------------------------------------------------------
-template <bool EXACT, bool COUNT>
-__global__ void __launch_bounds__(128) k_shade(FrameParams fp, SceneView sc, bool brute, const HitRec *__restrict__ hits,
+template <bool EXACT, bool COUNT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView sc, bool brute, const HitRec *__restrict__ hits,
                                                 unsigned int *counters, double *__restrict__ hit_colour,
                                                 uint32_t *__restrict__ hit_lit, Counters *gstats) {
     const unsigned lane = threadIdx.x & 31;
@@ -242,12 +245,14 @@ __global__ void __launch_bounds__(128) k_shade(FrameParams fp, SceneView sc, boo
         if (lane == 0) base = atomicAdd(&counters[2], 32u);
         base = __shfl_sync(FULL, base, 0);
         if (base >= nhits) break;
-        unsigned h = base + lane;
-        if (h < nhits) {
-            HitRec hr = hits[h];
-            PixMap pm = map_ray(hr.pix, fp, false);
-            double col[3];
-            uint32_t lit = shade_hit<EXACT>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, COUNT ? &c : nullptr);
+        // every lane runs shade_hit (its light loop reconverges with __syncwarp); lanes past the end redo the last hit
+        const bool valid = base + lane < nhits;
+        unsigned h = valid ? base + lane : nhits - 1;
+        HitRec hr = hits[h];
+        PixMap pm = map_ray(hr.pix, fp, false);
+        double col[3];
+        uint32_t lit = shade_hit<EXACT>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, (COUNT && valid) ? &c : nullptr);
+        if (valid) {
             hit_colour[3 * (size_t)h] = col[0]; hit_colour[3 * (size_t)h + 1] = col[1]; hit_colour[3 * (size_t)h + 2] = col[2];
             hit_lit[h] = lit;
         }
@@ -313,7 +318,8 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
         else k_primary_exact<false><<<nblk, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_stats);
         return cudaGetLastError();
     }
-    const bool simple = (job.flags & RT_FLAG_SIMPLE) != 0 || fp.n_obj != 1 || !job.single_mesh;
+    const bool want_persistent = (job.flags & RT_FLAG_PERSISTENT) != 0 || (job.primary_persistent && !(job.flags & RT_FLAG_SIMPLE));
+    const bool simple = !want_persistent || fp.n_obj != 1 || !job.single_mesh;
     if (simple) {
         if (count) k_primary_fast_simple<true><<<nblk, 128, 0, st>>>(fp, sc, job.d_hits, job.d_counters, job.d_stats);
         else k_primary_fast_simple<false><<<nblk, 128, 0, st>>>(fp, sc, job.d_hits, job.d_counters, job.d_stats);
@@ -358,13 +364,18 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
     const unsigned g = (unsigned)job.sm_count * 8u;
+#define LAUNCH_SHADE(EX, CN, MB) k_shade<EX, CN, MB><<<g, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats)
     if (job.precision == RT_FP64_EXACT) {
-        if (count) k_shade<true, true><<<g, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
-        else k_shade<true, false><<<g, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
+        if (count) LAUNCH_SHADE(true, true, 1); else LAUNCH_SHADE(true, false, 1);
+    } else if (count) {
+        LAUNCH_SHADE(false, true, 1);
     } else {
-        if (count) k_shade<false, true><<<g, 128, 0, st>>>(fp, sc, false, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
-        else k_shade<false, false><<<g, 128, 0, st>>>(fp, sc, false, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
+        if (job.shade_minb >= 8) LAUNCH_SHADE(false, false, 8);
+        else if (job.shade_minb >= 6) LAUNCH_SHADE(false, false, 6);
+        else if (job.shade_minb >= 5) LAUNCH_SHADE(false, false, 5);
+        else LAUNCH_SHADE(false, false, 1);
     }
+#undef LAUNCH_SHADE
     return cudaGetLastError();
 }
 

@@ -23,6 +23,8 @@ struct rt_scene {
     int max_leaf = 4;
     bool top_in_smem = true;
     int refill_below = 24;
+    int shade_minb = 8;
+    bool primary_persistent = false;
 
     std::vector<MeshDevice> meshes;
     std::vector<MeshView> h_views;
@@ -237,6 +239,8 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
     }
     job.top_in_smem = s->top_in_smem;
     job.refill_below = s->refill_below;
+    job.shade_minb = s->shade_minb;
+    job.primary_persistent = s->primary_persistent;
 
     CU(s, cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned int), st));
     CU(s, cudaMemsetAsync(s->d_stats, 0, 2 * sizeof(Counters), st));
@@ -338,8 +342,10 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->device = desc->device;
     s->precision = desc->precision;
     s->max_leaf = env_int("RT_B200_MAX_LEAF", 4);
-    s->top_in_smem = env_int("RT_B200_TOP_SMEM", 1) != 0;
-    s->refill_below = env_int("RT_B200_REFILL", 24);
+    s->shade_minb = env_int("RT_B200_SHADE_MINB", 8);
+    s->primary_persistent = env_int("RT_B200_PERSISTENT", 0) != 0;
+    s->top_in_smem = env_int("RT_B200_TOP_SMEM", 0) != 0;
+    s->refill_below = env_int("RT_B200_REFILL", 1);
     memset(&s->stats, 0, sizeof s->stats);
     memset(&s->frame, 0, sizeof s->frame);
     int rc = RT_OK;

@@ -41,20 +41,20 @@ RT_HD dv dv_norm(dv a) {                                                        
     return dv_make(DDIV(a.x, mag), DDIV(a.y, mag), DDIV(a.z, mag));
 }
 
-// Go math.Max / math.Min: NaN-propagating, Max(+0,-0)=+0, Min(+0,-0)=-0 (Go stdlib math/dim.go)
+// Go math.Max / math.Min (Go stdlib math/dim.go): Max(x,+Inf)=+Inf even against NaN, otherwise NaN-propagating,
+// Max(+0,-0)=+0, Min(+0,-0)=-0.  Written so that the common case (ordered, not both zero) is one compare + select;
+// the rare cases sit behind two cheap tests (tests/test_emul.py checks every special case against the oracle).
 RT_HD double go_max(double x, double y) {
-    if (isinf(x) && x > 0) return x;
-    if (isinf(y) && y > 0) return y;
-    if (x != x || y != y) return x + y;   // NaN
-    if (x == 0 && x == y) return signbit(x) ? y : x;
-    return x > y ? x : y;
+    double r = x > y ? x : y;
+    if (!(x == x && y == y)) r = (x > 1.7976931348623157e308 || y > 1.7976931348623157e308) ? HUGE_VAL : x + y;
+    else if (x == 0 && y == 0) r = signbit(x) ? y : x;
+    return r;
 }
 RT_HD double go_min(double x, double y) {
-    if (isinf(x) && x < 0) return x;
-    if (isinf(y) && y < 0) return y;
-    if (x != x || y != y) return x + y;   // NaN
-    if (x == 0 && x == y) return signbit(x) ? x : y;
-    return x < y ? x : y;
+    double r = x < y ? x : y;
+    if (!(x == x && y == y)) r = (x < -1.7976931348623157e308 || y < -1.7976931348623157e308) ? -HUGE_VAL : x + y;
+    else if (x == 0 && y == 0) r = signbit(x) ? x : y;
+    return r;
 }
 
 RT_HD bool go_is_odd_int(double x) {

@@ -53,6 +53,8 @@ struct RenderJob {
     MeshView  h_mesh0;        // host copy of object 0's mesh view
     double    h_obj0_pos[3];
     bool      top_in_smem;    // keep the first levels of the BVH in shared memory (single-mesh scenes)
+    bool      primary_persistent;  // default primary kernel of FP32_FAST (RT_B200_PERSISTENT=1), overridable per call
+    int       shade_minb;     // K4 occupancy experiment: min resident CTAs per SM (register cap)
     int       refill_below;   // persistent kernel: refill a warp when fewer lanes than this are live
 };
 

@@ -23,11 +23,22 @@ struct SceneView {
     const LightRec *lights;
 };
 
+#define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); } while (0)
+
+// Warp-level helpers of the per-ray loops.  On the device the traversal is a while-while loop: every lane walks
+// internal nodes, POSTPONES the first leaf it meets and keeps descending until all lanes of the converged group hold
+// a leaf (vote), then all lanes intersect their leaves together -- otherwise triangle tests run at ~10 % SIMD
+// efficiency (profiles/r01_*).  On the host (tests/emul) one "lane" runs alone, so the vote is the lane's own flag.
 #if defined(__CUDA_ARCH__)
-#define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); } while (0)
+#define RT_ALL_LANES(pred) (!__any_sync(__activemask(), !(pred)))
+#define RT_SYNCWARP() __syncwarp()
+#define RT_RCP(x) __fdividef(1.0f, (x))
 #else
-#define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); } while (0)
+#define RT_ALL_LANES(pred) (pred)
+#define RT_SYNCWARP() do { } while (0)
+#define RT_RCP(x) (1.0f / (x))
 #endif
+#define RT_DONE 0x7fffffff
 
 RT_HD rt_f4 ld_f4(const rt_f4 *p) {
 #if defined(__CUDA_ARCH__)
@@ -101,9 +112,10 @@ RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bo
     if (!slab64(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], o, idir, cull_bound(best), tin)) return;
     int stack[RT_STACK_SIZE];
     int sp = 0;
-    int ref = m.root_ref;
-    for (;;) {
-        if (ref >= 0) {
+    int ref = m.root_ref, leaf = 0;
+    if (ref < 0) { leaf = ref; ref = RT_DONE; }
+    while (ref != RT_DONE || leaf < 0) {
+        while (ref >= 0 && ref != RT_DONE) {
             const RtNode *n = m.nodes + ref;
             rt_f4 a = ld_f4(&n->a), b = ld_f4(&n->b), c = ld_f4(&n->c);
             rt_i4 ch = ld_i4(&n->d);
@@ -117,11 +129,14 @@ RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bo
                 if (t1 < t0) { nearc = ch.y; farc = ch.x; }
                 stack[sp++] = farc;
                 ref = nearc;
-                continue;
-            } else if (h0) { ref = ch.x; continue; }
-            else if (h1) { ref = ch.y; continue; }
-        } else {
-            uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
+            } else if (h0) ref = ch.x;
+            else if (h1) ref = ch.y;
+            else ref = sp ? stack[--sp] : RT_DONE;
+            if (ref < 0 && leaf == 0) { leaf = ref; ref = sp ? stack[--sp] : RT_DONE; }   // postpone the first leaf
+            if (RT_ALL_LANES(leaf != 0)) break;
+        }
+        while (leaf < 0) {
+            uint32_t first = rt_leaf_first(leaf), count = rt_leaf_count(leaf);
             RT_COUNT(cnt, tris, count);
             for (uint32_t k = first; k < first + count; k++) {
                 const double *p = m.tri64 + 10 * (size_t)k;
@@ -129,9 +144,9 @@ RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bo
                 consider_exact(dv_make(q0.x, q0.y, q1.x), dv_make(q1.y, q2.x, q2.y), dv_make(q3.x, q3.y, q4.x),
                                (int)q4.y, o, d, best);
             }
+            leaf = 0;
+            if (ref < 0) { leaf = ref; ref = sp ? stack[--sp] : RT_DONE; }
         }
-        if (sp == 0) break;
-        ref = stack[--sp];
     }
 }
 
@@ -168,7 +183,7 @@ struct RayF { float ox, oy, oz, dx, dy, dz, ix, iy, iz, ax, ay, az; };   // i = 
 RT_HD float safe_rcp(float d) {
     const float eps = 8.2718061e-25f;   // 2^-80
     float ad = fabsf(d) > eps ? d : copysignf(eps, d);
-    return 1.0f / ad;
+    return RT_RCP(ad);
 }
 RT_HD RayF make_rayf(float ox, float oy, float oz, float dx, float dy, float dz) {
     RayF r;
@@ -190,22 +205,25 @@ RT_HD bool slab32(float lox, float hix, float loy, float hiy, float loz, float h
     return tmin <= tmax;
 }
 
-// fp32 Moller-Trumbore, same acceptance rules as triangle.go:37-77 (two-sided, inclusive, t >= 0)
+// fp32 Moller-Trumbore, same acceptance rules as triangle.go:37-77 (two-sided, inclusive, t >= 0).  The range tests
+// are done on the un-normalised numerators against |det| so that the reciprocal is only paid by accepted hits.
 RT_HD bool tri_test32(rt_f4 v0, rt_f4 v1, rt_f4 v2, const RayF &r, float &t, float &u, float &v) {
     float e1x = v1.x - v0.x, e1y = v1.y - v0.y, e1z = v1.z - v0.z;
     float e2x = v2.x - v0.x, e2y = v2.y - v0.y, e2z = v2.z - v0.z;
     float px = fmaf(r.dy, e2z, -(r.dz * e2y)), py = fmaf(r.dz, e2x, -(r.dx * e2z)), pz = fmaf(r.dx, e2y, -(r.dy * e2x));
     float det = fmaf(e1x, px, fmaf(e1y, py, e1z * pz));
-    if (det == 0.0f) return false;
-    float inv = 1.0f / det;
+    float ad = fabsf(det);
     float tx = r.ox - v0.x, ty = r.oy - v0.y, tz = r.oz - v0.z;
-    u = fmaf(tx, px, fmaf(ty, py, tz * pz)) * inv;
-    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    float un = copysignf(1.0f, det) * fmaf(tx, px, fmaf(ty, py, tz * pz));
+    if (!(un >= 0.0f && un <= ad) || det == 0.0f) return false;
     float qx = fmaf(ty, e1z, -(tz * e1y)), qy = fmaf(tz, e1x, -(tx * e1z)), qz = fmaf(tx, e1y, -(ty * e1x));
-    v = fmaf(r.dx, qx, fmaf(r.dy, qy, r.dz * qz)) * inv;
-    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
-    t = fmaf(e2x, qx, fmaf(e2y, qy, e2z * qz)) * inv;
-    return t >= 0.0f;
+    float vn = copysignf(1.0f, det) * fmaf(r.dx, qx, fmaf(r.dy, qy, r.dz * qz));
+    if (!(vn >= 0.0f && un + vn <= ad)) return false;
+    float tn = copysignf(1.0f, det) * fmaf(e2x, qx, fmaf(e2y, qy, e2z * qz));
+    if (!(tn >= 0.0f)) return false;
+    float inv = RT_RCP(ad);
+    t = tn * inv; u = un * inv; v = vn * inv;
+    return true;
 }
 
 // Simple per-ray traversal of one mesh (object space).  ANY: stop at the first hit with t <= tbest.
@@ -218,9 +236,10 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
     bool found = false;
     int stack[RT_STACK_SIZE];
     int sp = 0;
-    int ref = m.root_ref;
-    for (;;) {
-        if (ref >= 0) {
+    int ref = m.root_ref, leaf = 0;
+    if (ref < 0) { leaf = ref; ref = RT_DONE; }
+    while (ref != RT_DONE || leaf < 0) {
+        while (ref >= 0 && ref != RT_DONE) {
             const RtNode *n = m.nodes + ref;
             rt_f4 a = ld_f4(&n->a), b = ld_f4(&n->b), c = ld_f4(&n->c);
             rt_i4 ch = ld_i4(&n->d);
@@ -233,11 +252,14 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
                 if (t1 < t0) { nearc = ch.y; farc = ch.x; }
                 stack[sp++] = farc;
                 ref = nearc;
-                continue;
-            } else if (h0) { ref = ch.x; continue; }
-            else if (h1) { ref = ch.y; continue; }
-        } else {
-            uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
+            } else if (h0) ref = ch.x;
+            else if (h1) ref = ch.y;
+            else ref = sp ? stack[--sp] : RT_DONE;
+            if (ref < 0 && leaf == 0) { leaf = ref; ref = sp ? stack[--sp] : RT_DONE; }   // postpone the first leaf
+            if (RT_ALL_LANES(leaf != 0)) break;
+        }
+        while (leaf < 0) {
+            uint32_t first = rt_leaf_first(leaf), count = rt_leaf_count(leaf);
             RT_COUNT(cnt, tris, count);
             for (uint32_t k = first; k < first + count; k++) {
                 const rt_f4 *p = m.tri32 + 3 * (size_t)k;
@@ -249,15 +271,14 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
 #else
                     int f; { float w = v0.w; memcpy(&f, &w, 4); }
 #endif
-                    if (ANY) { if (t <= tbest) { face = f; tbest = t; return true; } }
-                    else if (t < tbest || (t == tbest && found && f < face) || (t == tbest && !found)) {
-                        tbest = t; face = f; found = true;
-                    }
+                    if (ANY) { if (t <= tbest) { face = f; tbest = t; found = true; } }
+                    else if (t < tbest || (t == tbest && (!found || f < face))) { tbest = t; face = f; found = true; }
                 }
             }
+            leaf = 0;
+            if (ANY && found) { ref = RT_DONE; break; }           // any-hit: single exit so the warp reconverges
+            if (ref < 0) { leaf = ref; ref = sp ? stack[--sp] : RT_DONE; }
         }
-        if (sp == 0) break;
-        ref = stack[--sp];
     }
     return found;
 }
@@ -315,6 +336,7 @@ RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int 
     double c[3] = { mat[0], mat[1], mat[2] };                                    // tracer.go:56
     uint32_t lit_mask = 0;
     for (int l = 0; l < fp.n_lights; l++) {
+        RT_SYNCWARP();                       // every lane of the warp runs this loop (k_shade): reconverge per light
         const LightRec &L = sc.lights[l];
         dv Lv = dv_sub(dv_ld(L.pos), P);
         dv Ld = dv_norm(Lv);                                                     // tracer.go:61
@@ -338,6 +360,7 @@ RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int 
             bool shaded = trace_fast_nearest(sc, fp, so, Ld, false, s, cnt);
             lit = !shaded || lightLen < (double)s.t + RT_SHADOW_BIAS;
         }
+        RT_SYNCWARP();
         if (lit) {
             lit_mask |= 1u << (l & 31);
             phong_light_exact(c, mat, N, Ld, cam, P, L.col);                     // tracer.go:65-72

@@ -53,7 +53,8 @@ typedef enum {
 #define RT_QUANT_RGBA16_SHR8 0x2u  /* uint32(0xFFFF*c) >> 8 -- colour.RGB.RGBA() + go-sdl2 Surface.Set      */
 #define RT_FLAG_COUNT        0x4u  /* accumulate traversal counters (slower; for roofline accounting)       */
 #define RT_FLAG_BRUTE_FORCE  0x8u  /* FP64_EXACT only: ignore the BVH, test every face (debug / parity)     */
-#define RT_FLAG_SIMPLE       0x10u /* FP32_FAST only: one-thread-per-ray kernels without persistent refill  */
+#define RT_FLAG_SIMPLE       0x10u /* FP32_FAST only: one-thread-per-ray primary kernel (the default: fastest measured) */
+#define RT_FLAG_PERSISTENT   0x20u /* FP32_FAST only: persistent warp-cooperative primary kernel (ballot/shuffle refill) */
 
 typedef struct rt_scene rt_scene;
 

@@ -48,6 +48,9 @@ def lib():
         L.orc_go_tan.argtypes = [C.c_double]
         L.orc_go_pow.restype = C.c_double
         L.orc_go_pow.argtypes = [C.c_double, C.c_double]
+        for fn in (L.orc_go_max, L.orc_go_min):
+            fn.restype = C.c_double
+            fn.argtypes = [C.c_double, C.c_double]
         L.orc_scene_create.restype = C.c_void_p
         L.orc_scene_create.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_scene_destroy.argtypes = [C.c_void_p]

@@ -56,6 +56,9 @@ static inline double go_min(double x, double y) {
     return x < y ? x : y;
 }
 
+double orc_go_max(double x, double y) { return go_max(x, y); }
+double orc_go_min(double x, double y) { return go_min(x, y); }
+
 /* ============================ Go stdlib math ================================ */
 /* math/tan.go (pure Go Cephes routine; no amd64 assembly).  Only the x < 2^29 branch
  * (no Payne-Hanek reduction) is restated; larger |x| falls back to libm. */

@@ -24,6 +24,8 @@ extern "C" {
 /* ---- Go math library restatements (Go stdlib, math/tan.go, math/pow.go) -- */
 double orc_go_tan(double x);
 double orc_go_pow(double x, double y);
+double orc_go_max(double x, double y);   /* math.Max, Go stdlib math/dim.go */
+double orc_go_min(double x, double y);   /* math.Min */
 
 /* ---- shared/geom ---------------------------------------------------------- */
 /* triangle.go:37-77.  tri = P1,P2,P3 (9 doubles).  Returns 1 on hit and

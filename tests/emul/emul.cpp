@@ -295,5 +295,8 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
 }
 
 unsigned long long emul_morton63(double x, double y, double z) { return morton63(x, y, z); }
+double emul_go_max(double x, double y) { return go_max(x, y); }
+double emul_go_min(double x, double y) { return go_min(x, y); }
+double emul_go_pow(double x, double y) { return go_pow(x, y); }
 
 }  // extern "C"

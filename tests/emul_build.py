@@ -33,6 +33,9 @@ def lib():
         L.emul_render.argtypes = [C.c_void_p, C.POINTER(_lib.Camera), C.c_void_p] + [C.c_uint32] * 8 + [C.c_void_p] * 6
         L.emul_render_tiles.restype = C.c_int
         L.emul_render_tiles.argtypes = [C.c_void_p, C.POINTER(_lib.Camera), C.c_void_p] + [C.c_uint32] * 8 + [C.c_void_p]
+        for fn in (L.emul_go_max, L.emul_go_min, L.emul_go_pow):
+            fn.restype = C.c_double
+            fn.argtypes = [C.c_double, C.c_double]
         L.emul_morton63.restype = C.c_uint64
         L.emul_morton63.argtypes = [C.c_double] * 3
         _LIB = L

@@ -120,7 +120,7 @@ def test_exact_region_layout_quantiser(rt, example_scene):
 
 
 def test_fast_c1_within_tolerance_both_kernels(rt, example_scene):
-    w1, f1, rgb_p, face_p = fast_fractions(rt, example_scene, 320, 240)                      # persistent kernel
+    w1, f1, rgb_p, face_p = fast_fractions(rt, example_scene, 320, 240, flags=rt.FLAG_PERSISTENT)
     w2, f2, rgb_s, face_s = fast_fractions(rt, example_scene, 320, 240, flags=rt.FLAG_SIMPLE)
     assert w1 >= LSB_FRAC and f1 >= LSB_FRAC and w2 >= LSB_FRAC and f2 >= LSB_FRAC
     # both kernels run the same per-ray arithmetic => identical images
@@ -202,7 +202,7 @@ def test_full_size_c3_properties(rt, example_scene):
     stats = g.stats()
     # determinism + the two primary kernels agree (persistent refill order must not change any pixel)
     rgb2 = g.render_region(W, H)
-    rgb3, _, face3, _, _ = g.render_region_debug(W, H, flags=rt.FLAG_SIMPLE)
+    rgb3, _, face3, _, _ = g.render_region_debug(W, H, flags=rt.FLAG_PERSISTENT)
     assert np.array_equal(rgb, rgb2) and np.array_equal(rgb, rgb3) and np.array_equal(face, face3)
     hit = face >= 0
     assert stats["hit_pixels"] == int(hit.sum()) and stats["primary_rays"] == W * H

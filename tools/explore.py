@@ -48,13 +48,19 @@ def run_variant(sc, name, env, flags=0, reps=5, precision=rt.FP32_FAST, W=bench.
 if __name__ == "__main__":
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     sc = bench.build_workload()
-    base = {"RT_B200_MAX_LEAF": 4, "RT_B200_TOP_SMEM": 1, "RT_B200_REFILL": 24}
+    base = {"RT_B200_MAX_LEAF": 4, "RT_B200_TOP_SMEM": 0, "RT_B200_REFILL": 1, "RT_B200_SHADE_MINB": 1}
+    which = sys.argv[2:] if len(sys.argv) > 2 else ["kernels", "shade", "leaf"]
     run_variant(sc, "default", dict(base))
-    run_variant(sc, "simple", dict(base), flags=rt.FLAG_SIMPLE)
-    run_variant(sc, "no_top_smem", dict(base, RT_B200_TOP_SMEM=0))
-    for r in (1, 8, 16, 32):
-        run_variant(sc, "refill%d" % r, dict(base, RT_B200_REFILL=r))
-    for ml in (1, 2, 8, 16):
-        run_variant(sc, "maxleaf%d" % ml, dict(base, RT_B200_MAX_LEAF=ml))
-    if not quick:
+    if "kernels" in which:
+        run_variant(sc, "simple", dict(base), flags=rt.FLAG_SIMPLE)
+        run_variant(sc, "top_smem", dict(base, RT_B200_TOP_SMEM=1))
+        for r in (8, 16, 24, 32):
+            run_variant(sc, "refill%d" % r, dict(base, RT_B200_REFILL=r))
+    if "shade" in which:
+        for mb in (5, 6, 8):
+            run_variant(sc, "shade_minb%d" % mb, dict(base, RT_B200_SHADE_MINB=mb), flags=rt.FLAG_SIMPLE)
+    if "leaf" in which:
+        for ml in (1, 2, 8):
+            run_variant(sc, "maxleaf%d" % ml, dict(base, RT_B200_MAX_LEAF=ml), flags=rt.FLAG_SIMPLE)
+    if not quick and "exact" in which:
         run_variant(sc, "exact_c3", dict(base), precision=rt.FP64_EXACT, reps=2)
