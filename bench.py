@@ -59,7 +59,7 @@ class ClockSampler:
             try:
                 self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
                                   int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)),
-                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0, time.perf_counter()))
             except Exception:
                 pass
             time.sleep(0.004)
@@ -73,10 +73,14 @@ class ClockSampler:
         except Exception:
             self.thread = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=2)
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[3] <= t1]
+            # an NVML query can take longer than a short timed region: fall back to the samples nearest to it
+            self.rows = inside if len(inside) >= 2 else sorted(self.rows, key=lambda r: abs(r[3] - 0.5 * (t0 + t1)))[:3]
         if not self.rows:
             return self._nvidia_smi_once()
         sm = sorted(r[0] for r in self.rows)
@@ -87,7 +91,7 @@ class ClockSampler:
                  0x80: "hw_power_brake_slowdown"}
         return {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(n for b, n in names.items() if bits & b), "samples": len(sm),
-                "power_w_max": max(r[2] for r in self.rows), "source": "nvml poll, 4 ms period, inside the timed region"}
+                "power_w_max": max(r[2] for r in self.rows), "source": "nvml poll (4 ms period) over the timed region"}
 
     def _nvidia_smi_once(self):
         try:
@@ -251,6 +255,9 @@ def main():
     else:
         rays_frame, hits_frame = W * H + hits_local * len(lights), hits_local
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # ---- clock ramp (untimed, not a step): the GPU idles at ~120 MHz; give DVFS ~0.4 s of work to reach its load clocks ----
     t_ramp = time.perf_counter()
     while time.perf_counter() - t_ramp < 0.4:
@@ -262,9 +269,6 @@ def main():
     torch.cuda.synchronize(dev)
 
     # ---- timed region: exactly K steps, barrier + synchronize on both sides, device timing, max over ranks ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -288,7 +292,7 @@ def main():
         t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall0 + wall) if rank == 0 else None
     ms_per_step = dev_ms / args.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
 
@@ -378,6 +382,21 @@ def main():
                 "kernels_ms": avg, "algorithmic_bytes": alg,
                 "per_ray": {"nodes_primary": cnt["nodes_primary"] / max(1, prim_local), "tris_primary": cnt["tris_primary"] / max(1, prim_local),
                             "nodes_shadow": cnt["nodes_shade"] / max(1, cnt["shadow_rays"]), "tris_shadow": cnt["tris_shade"] / max(1, cnt["shadow_rays"])}}
+
+    # flop side of the traversal roofline: F_alg / measured FMA peak, for the record (the path is bytes-bound)
+    import ctypes
+    fp32_peak, fp64_peak = ctypes.c_double(0), ctypes.c_double(0)
+    L = rt._lib.load()
+    L.rt_measure_fma_peak(local_rank, 0, ctypes.byref(fp32_peak))
+    L.rt_measure_fma_peak(local_rank, 1, ctypes.byref(fp64_peak))
+    F_BOX, F_TRI, F_SHADE_HIT, F_SHADE_LIGHT = 48, 60, 250, 150       # flops per node visit / triangle test / hit / (hit, light)
+    flops32 = (cnt["nodes_primary"] + cnt["nodes_shade"]) * F_BOX + (cnt["tris_primary"] + cnt["tris_shade"]) * F_TRI
+    flops64 = hits_local * (F_SHADE_HIT + F_SHADE_LIGHT * len(lights))
+    roofline["fma_peak_tflops_measured"] = {"fp32": fp32_peak.value, "fp64": fp64_peak.value}
+    roofline["flop_side"] = {"fp32_flops": flops32, "fp64_flops": flops64,
+                             "t_flops_ms": 1e3 * (flops32 / max(fp32_peak.value, 1e-9) + flops64 / max(fp64_peak.value, 1e-9)) / 1e12,
+                             "t_bytes_ms": 1e3 * sum(alg.values()) / (peak * 1e9),
+                             "t_measured_ms": sum(avg.values())}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

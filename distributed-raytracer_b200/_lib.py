@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")   # override: kernel-variant experiments
 
 FP64_EXACT, FP32_FAST = 0, 1
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0x0, 0x1
@@ -18,7 +18,7 @@ RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_STATE, RT_ERR_CANCELLED =
 ABI_SYMBOLS = (
     "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set",
     "rt_render_region", "rt_bulk_trace", "rt_render_region_debug", "rt_render_region_device", "rt_render_tiles_device",
-    "rt_untile_device", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free",
+    "rt_untile_device", "rt_measure_fma_peak", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free",
 )
 
 
@@ -104,6 +104,8 @@ def load():
     L.rt_render_tiles_device.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, vp, u32]
     L.rt_untile_device.restype = C.c_int
     L.rt_untile_device.argtypes = [vp, u32, u32, u32, u32, u32, vp, vp, vp, u32]
+    L.rt_measure_fma_peak.restype = C.c_int
+    L.rt_measure_fma_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.rt_get_stats.restype = C.c_int
     L.rt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.rt_get_bvh_info.restype = C.c_int

@@ -300,7 +300,43 @@ __global__ void k_untile(const uint8_t *__restrict__ tiles, uint8_t *__restrict_
     out[dst] = tiles[src]; out[dst + 1] = tiles[src + 1]; out[dst + 2] = tiles[src + 2];
 }
 
+// FMA-pipe peak: 8 independent dependent-chains per thread, all operands in registers
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T *out, int iters, T a, T b) {
+    T x0 = a + (T)threadIdx.x, x1 = x0 + (T)1, x2 = x0 + (T)2, x3 = x0 + (T)3, x4 = x0 + (T)4, x5 = x0 + (T)5, x6 = x0 + (T)6, x7 = x0 + (T)7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == (T)123456789) out[0] = s;   // never true: keeps the chain alive
+}
+
 }  // namespace
+
+cudaError_t rt_fma_peak(bool fp64, int sm_count, double *tflops) {
+    const int iters = 1 << 14, threads = 256, blocks = sm_count * 8;
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 64);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(a);
+        if (fp64) k_fma_peak<double><<<blocks, threads>>>((double *)d, iters, 0.999999, 1e-9);
+        else k_fma_peak<float><<<blocks, threads>>>((float *)d, iters, 0.999999f, 1e-9f);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    e = cudaGetLastError();
+    *tflops = 2.0 * 8.0 * (double)iters * threads * blocks / (best * 1e-3) / 1e12;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    return e;
+}
 
 // ---------------------------------------------------------------------------------------------
 // launchers

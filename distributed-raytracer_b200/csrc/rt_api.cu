@@ -529,6 +529,17 @@ int rt_cancel(rt_scene *s) {
     return RT_OK;
 }
 
+int rt_measure_fma_peak(int device, int fp64, double *out_tflops) {
+    if (!out_tflops) return fail(nullptr, RT_ERR_INVALID, "NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return fail(nullptr, RT_ERR_CUDA, "no such CUDA device"); }
+    CU(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    CU(nullptr, rt_fma_peak(fp64 != 0, prop.multiProcessorCount, out_tflops));
+    return RT_OK;
+}
+
 void *rt_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }

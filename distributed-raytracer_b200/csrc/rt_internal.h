@@ -64,3 +64,6 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st);
 cudaError_t rt_launch_write(const RenderJob &job, cudaStream_t st);
 cudaError_t rt_launch_untile(const uint8_t *d_tiles, uint8_t *d_out, int W, int H, int tile_w, int tile_h, int n_ranks,
                              int tiles_per_rank_max, bool rowmajor, cudaStream_t st);
+
+// render.cu : FMA-pipe micro-benchmark
+cudaError_t rt_fma_peak(bool fp64, int sm_count, double *tflops);

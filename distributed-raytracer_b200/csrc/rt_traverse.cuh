@@ -25,20 +25,16 @@ struct SceneView {
 
 #define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); } while (0)
 
-// Warp-level helpers of the per-ray loops.  On the device the traversal is a while-while loop: every lane walks
-// internal nodes, POSTPONES the first leaf it meets and keeps descending until all lanes of the converged group hold
-// a leaf (vote), then all lanes intersect their leaves together -- otherwise triangle tests run at ~10 % SIMD
-// efficiency (profiles/r01_*).  On the host (tests/emul) one "lane" runs alone, so the vote is the lane's own flag.
+// Measured on B200 (profiles/r01_ab_traversal_shape_mt_sync_minmax.txt), config 3:
+//  * loop shape: the plain "if internal node ... else leaf" loop below beats a while-while loop with postponed
+//    leaves (no gain) and a while-while loop with a warp vote (30 % slower) -- kept simple.
+//  * the light loop of shade_hit needs an explicit __syncwarp() per light: without it the lanes of a warp never
+//    reconverge after the first shadow ray and the rest of the kernel runs at ~4 active lanes.
 #if defined(__CUDA_ARCH__)
-#define RT_ALL_LANES(pred) (!__any_sync(__activemask(), !(pred)))
 #define RT_SYNCWARP() __syncwarp()
-#define RT_RCP(x) __fdividef(1.0f, (x))
 #else
-#define RT_ALL_LANES(pred) (pred)
 #define RT_SYNCWARP() do { } while (0)
-#define RT_RCP(x) (1.0f / (x))
 #endif
-#define RT_DONE 0x7fffffff
 
 RT_HD rt_f4 ld_f4(const rt_f4 *p) {
 #if defined(__CUDA_ARCH__)
@@ -112,10 +108,9 @@ RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bo
     if (!slab64(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], o, idir, cull_bound(best), tin)) return;
     int stack[RT_STACK_SIZE];
     int sp = 0;
-    int ref = m.root_ref, leaf = 0;
-    if (ref < 0) { leaf = ref; ref = RT_DONE; }
-    while (ref != RT_DONE || leaf < 0) {
-        while (ref >= 0 && ref != RT_DONE) {
+    int ref = m.root_ref;
+    for (;;) {
+        if (ref >= 0) {
             const RtNode *n = m.nodes + ref;
             rt_f4 a = ld_f4(&n->a), b = ld_f4(&n->b), c = ld_f4(&n->c);
             rt_i4 ch = ld_i4(&n->d);
@@ -129,14 +124,11 @@ RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bo
                 if (t1 < t0) { nearc = ch.y; farc = ch.x; }
                 stack[sp++] = farc;
                 ref = nearc;
-            } else if (h0) ref = ch.x;
-            else if (h1) ref = ch.y;
-            else ref = sp ? stack[--sp] : RT_DONE;
-            if (ref < 0 && leaf == 0) { leaf = ref; ref = sp ? stack[--sp] : RT_DONE; }   // postpone the first leaf
-            if (RT_ALL_LANES(leaf != 0)) break;
-        }
-        while (leaf < 0) {
-            uint32_t first = rt_leaf_first(leaf), count = rt_leaf_count(leaf);
+                continue;
+            } else if (h0) { ref = ch.x; continue; }
+            else if (h1) { ref = ch.y; continue; }
+        } else {
+            uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
             RT_COUNT(cnt, tris, count);
             for (uint32_t k = first; k < first + count; k++) {
                 const double *p = m.tri64 + 10 * (size_t)k;
@@ -144,9 +136,9 @@ RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bo
                 consider_exact(dv_make(q0.x, q0.y, q1.x), dv_make(q1.y, q2.x, q2.y), dv_make(q3.x, q3.y, q4.x),
                                (int)q4.y, o, d, best);
             }
-            leaf = 0;
-            if (ref < 0) { leaf = ref; ref = sp ? stack[--sp] : RT_DONE; }
         }
+        if (sp == 0) break;
+        ref = stack[--sp];
     }
 }
 
@@ -183,7 +175,7 @@ struct RayF { float ox, oy, oz, dx, dy, dz, ix, iy, iz, ax, ay, az; };   // i = 
 RT_HD float safe_rcp(float d) {
     const float eps = 8.2718061e-25f;   // 2^-80
     float ad = fabsf(d) > eps ? d : copysignf(eps, d);
-    return RT_RCP(ad);
+    return 1.0f / ad;
 }
 RT_HD RayF make_rayf(float ox, float oy, float oz, float dx, float dy, float dz) {
     RayF r;
@@ -221,7 +213,7 @@ RT_HD bool tri_test32(rt_f4 v0, rt_f4 v1, rt_f4 v2, const RayF &r, float &t, flo
     if (!(vn >= 0.0f && un + vn <= ad)) return false;
     float tn = copysignf(1.0f, det) * fmaf(e2x, qx, fmaf(e2y, qy, e2z * qz));
     if (!(tn >= 0.0f)) return false;
-    float inv = RT_RCP(ad);
+    float inv = 1.0f / ad;
     t = tn * inv; u = un * inv; v = vn * inv;
     return true;
 }
@@ -236,10 +228,9 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
     bool found = false;
     int stack[RT_STACK_SIZE];
     int sp = 0;
-    int ref = m.root_ref, leaf = 0;
-    if (ref < 0) { leaf = ref; ref = RT_DONE; }
-    while (ref != RT_DONE || leaf < 0) {
-        while (ref >= 0 && ref != RT_DONE) {
+    int ref = m.root_ref;
+    for (;;) {
+        if (ref >= 0) {
             const RtNode *n = m.nodes + ref;
             rt_f4 a = ld_f4(&n->a), b = ld_f4(&n->b), c = ld_f4(&n->c);
             rt_i4 ch = ld_i4(&n->d);
@@ -252,14 +243,11 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
                 if (t1 < t0) { nearc = ch.y; farc = ch.x; }
                 stack[sp++] = farc;
                 ref = nearc;
-            } else if (h0) ref = ch.x;
-            else if (h1) ref = ch.y;
-            else ref = sp ? stack[--sp] : RT_DONE;
-            if (ref < 0 && leaf == 0) { leaf = ref; ref = sp ? stack[--sp] : RT_DONE; }   // postpone the first leaf
-            if (RT_ALL_LANES(leaf != 0)) break;
-        }
-        while (leaf < 0) {
-            uint32_t first = rt_leaf_first(leaf), count = rt_leaf_count(leaf);
+                continue;
+            } else if (h0) { ref = ch.x; continue; }
+            else if (h1) { ref = ch.y; continue; }
+        } else {
+            uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
             RT_COUNT(cnt, tris, count);
             for (uint32_t k = first; k < first + count; k++) {
                 const rt_f4 *p = m.tri32 + 3 * (size_t)k;
@@ -271,14 +259,13 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
 #else
                     int f; { float w = v0.w; memcpy(&f, &w, 4); }
 #endif
-                    if (ANY) { if (t <= tbest) { face = f; tbest = t; found = true; } }
+                    if (ANY) { if (t <= tbest) { face = f; tbest = t; return true; } }
                     else if (t < tbest || (t == tbest && (!found || f < face))) { tbest = t; face = f; found = true; }
                 }
             }
-            leaf = 0;
-            if (ANY && found) { ref = RT_DONE; break; }           // any-hit: single exit so the warp reconverges
-            if (ref < 0) { leaf = ref; ref = sp ? stack[--sp] : RT_DONE; }
         }
+        if (sp == 0) break;
+        ref = stack[--sp];
     }
     return found;
 }

@@ -180,6 +180,11 @@ int rt_synchronize(rt_scene *scene);
 /* ask an in-flight render on this handle to stop (checked between kernels) */
 int rt_cancel(rt_scene *scene);
 
+/* Register-resident FMA micro-benchmark (roofline denominator of the flop side): runs `iters`
+ * dependent-chain FMAs per thread on a full grid and returns the measured TFLOP/s (2 flops per FMA).
+ * fp64 != 0 selects double precision. */
+int rt_measure_fma_peak(int device, int fp64, double *out_tflops);
+
 /* pinned host buffers so out_rgb can be DMA'd without a staging copy (optional) */
 void *rt_host_alloc(size_t bytes);
 void  rt_host_free(void *p);
