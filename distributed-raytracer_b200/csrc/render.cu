@@ -23,6 +23,13 @@ __device__ __forceinline__ void flush_counters(Counters *g, const Counters &c) {
     }
 }
 
+// lights / object positions come by value (a __grid_constant__ parameter may have its address taken) when they fit
+__device__ __forceinline__ SceneView bind_frame(SceneView sc, const InlineFrame &fr) {
+    if (fr.use_lights) sc.lights = fr.lights;
+    if (fr.use_objs) sc.objs = fr.objs;
+    return sc;
+}
+
 // append this lane's hit (if any) to the compact hit list; all 32 lanes must call
 __device__ __forceinline__ void append_hit(bool hit, uint32_t ray, int obj, int face, float t, HitRec *hits,
                                            unsigned int *hit_count) {
@@ -42,8 +49,9 @@ __device__ __forceinline__ void append_hit(bool hit, uint32_t ray, int obj, int 
 // K2, FP64_EXACT: one thread per ray, 8x4 pixel block per warp
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_primary_exact(FrameParams fp, SceneView sc, bool brute, HitRec *hits,
-                                                        unsigned int *counters, Counters *gstats) {
+__global__ void __launch_bounds__(128) k_primary_exact(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr, bool brute,
+                                                        HitRec *hits, unsigned int *counters, Counters *gstats) {
+    const SceneView sc = bind_frame(sc_in, fr);
     uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nrays = ray_count(fp);
     Counters c; c.nodes = 0; c.tris = 0;
@@ -78,8 +86,9 @@ __device__ __forceinline__ void primary_dir32(int i, int j, const FrameParams &f
 // K2, FP32_FAST, simple variant: one thread per ray (any number of objects)
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_primary_fast_simple(FrameParams fp, SceneView sc, HitRec *hits,
-                                                              unsigned int *counters, Counters *gstats) {
+__global__ void __launch_bounds__(128) k_primary_fast_simple(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
+                                                              HitRec *hits, unsigned int *counters, Counters *gstats) {
+    const SceneView sc = bind_frame(sc_in, fr);
     uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nrays = ray_count(fp);
     Counters c; c.nodes = 0; c.tris = 0;
@@ -234,9 +243,11 @@ k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, floa
 // K4: fused shadow rays + Phong shading, one thread per primary hit; warps claim 32 hits at a time
 // ---------------------------------------------------------------------------------------------
 template <bool EXACT, bool COUNT, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView sc, bool brute, const HitRec *__restrict__ hits,
-                                                unsigned int *counters, double *__restrict__ hit_colour,
-                                                uint32_t *__restrict__ hit_lit, Counters *gstats) {
+__global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr, bool brute,
+                                                      const HitRec *__restrict__ hits, unsigned int *counters,
+                                                      double *__restrict__ hit_colour, uint32_t *__restrict__ hit_lit,
+                                                      Counters *gstats) {
+    const SceneView sc = bind_frame(sc_in, fr);
     const unsigned lane = threadIdx.x & 31;
     const unsigned int nhits = counters[1];
     Counters c; c.nodes = 0; c.tris = 0;
@@ -350,15 +361,15 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
     const unsigned nblk = (nrays + 127) / 128;
     if (job.precision == RT_FP64_EXACT) {
         const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
-        if (count) k_primary_exact<true><<<nblk, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_stats);
-        else k_primary_exact<false><<<nblk, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_stats);
+        if (count) k_primary_exact<true><<<nblk, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_stats);
+        else k_primary_exact<false><<<nblk, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_stats);
         return cudaGetLastError();
     }
     const bool want_persistent = (job.flags & RT_FLAG_PERSISTENT) != 0 || (job.primary_persistent && !(job.flags & RT_FLAG_SIMPLE));
     const bool simple = !want_persistent || fp.n_obj != 1 || !job.single_mesh;
     if (simple) {
-        if (count) k_primary_fast_simple<true><<<nblk, 128, 0, st>>>(fp, sc, job.d_hits, job.d_counters, job.d_stats);
-        else k_primary_fast_simple<false><<<nblk, 128, 0, st>>>(fp, sc, job.d_hits, job.d_counters, job.d_stats);
+        if (count) k_primary_fast_simple<true><<<nblk, 128, 0, st>>>(fp, sc, job.fr, job.d_hits, job.d_counters, job.d_stats);
+        else k_primary_fast_simple<false><<<nblk, 128, 0, st>>>(fp, sc, job.fr, job.d_hits, job.d_counters, job.d_stats);
         return cudaGetLastError();
     }
     // persistent: one object; its mesh view and the object-space ray origin are passed by value
@@ -400,7 +411,7 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
     const unsigned g = (unsigned)job.sm_count * 8u;
-#define LAUNCH_SHADE(EX, CN, MB) k_shade<EX, CN, MB><<<g, 128, 0, st>>>(fp, sc, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats)
+#define LAUNCH_SHADE(EX, CN, MB) k_shade<EX, CN, MB><<<g, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats)
     if (job.precision == RT_FP64_EXACT) {
         if (count) LAUNCH_SHADE(true, true, 1); else LAUNCH_SHADE(true, false, 1);
     } else if (count) {

@@ -34,6 +34,7 @@ struct rt_scene {
     LightRec *d_lights = nullptr;
     uint32_t n_lights = 0, cap_lights = 0;
     FrameParams frame;
+    InlineFrame inline_frame;
     bool have_frame = false;
 
     // scratch
@@ -153,25 +154,32 @@ int frame_set_locked(rt_scene *s, const rt_camera *cam, const rt_light *lights, 
     fp.tan_half = std::isnan(cam->tan_half_fov) ? rt_go_tan(cam->fov / 2.0) : cam->tan_half_fov;   // tracer.go:17
     fp.n_lights = (int)n_lights;
     fp.n_obj = (int)s->h_objs.size();
-    // the device copies below must not overtake a render still in flight (library or caller stream)
-    CU(s, cudaStreamSynchronize(s->stream));
-    if (s->stats_pending && s->last_stream) CU(s, cudaStreamSynchronize(s->last_stream));
-    if (n_lights > s->cap_lights) {
-        cudaFree(s->d_lights); s->d_lights = nullptr; s->cap_lights = 0;
-        CU(s, cudaMalloc((void **)&s->d_lights, sizeof(LightRec) * n_lights));
-        s->cap_lights = n_lights;
-    }
-    if (n_lights) {
-        static_assert(sizeof(LightRec) == sizeof(rt_light), "light layout");
-        CU(s, cudaMemcpyAsync(s->d_lights, lights, sizeof(LightRec) * n_lights, cudaMemcpyHostToDevice, s->stream));
-    }
     s->n_lights = n_lights;
-    if (obj_pos && !s->h_objs.empty()) {
+    if (obj_pos)
         for (size_t k = 0; k < s->h_objs.size(); k++)
             for (int c = 0; c < 3; c++) s->h_objs[k].pos[c] = obj_pos[3 * k + c];
-        CU(s, cudaMemcpyAsync(s->d_objs, s->h_objs.data(), sizeof(ObjRec) * s->h_objs.size(), cudaMemcpyHostToDevice, s->stream));
+    InlineFrame &fr = s->inline_frame;
+    fr.use_lights = n_lights <= RT_INLINE_LIGHTS;
+    fr.use_objs = s->h_objs.size() <= RT_INLINE_OBJS;
+    static_assert(sizeof(LightRec) == sizeof(rt_light), "light layout");
+    if (fr.use_lights && n_lights) memcpy(fr.lights, lights, sizeof(LightRec) * n_lights);
+    if (fr.use_objs && !s->h_objs.empty()) memcpy(fr.objs, s->h_objs.data(), sizeof(ObjRec) * s->h_objs.size());
+    if (!fr.use_lights || (!fr.use_objs && obj_pos)) {
+        // large light / object sets live in device memory: the copies must not overtake a render still in flight
+        CU(s, cudaStreamSynchronize(s->stream));
+        if (s->last_stream) CU(s, cudaStreamSynchronize(s->last_stream));
+        if (!fr.use_lights) {
+            if (n_lights > s->cap_lights) {
+                cudaFree(s->d_lights); s->d_lights = nullptr; s->cap_lights = 0;
+                CU(s, cudaMalloc((void **)&s->d_lights, sizeof(LightRec) * n_lights));
+                s->cap_lights = n_lights;
+            }
+            CU(s, cudaMemcpyAsync(s->d_lights, lights, sizeof(LightRec) * n_lights, cudaMemcpyHostToDevice, s->stream));
+        }
+        if (!fr.use_objs && obj_pos)
+            CU(s, cudaMemcpyAsync(s->d_objs, s->h_objs.data(), sizeof(ObjRec) * s->h_objs.size(), cudaMemcpyHostToDevice, s->stream));
+        CU(s, cudaStreamSynchronize(s->stream));   // `lights` is caller memory: do not retain it
     }
-    CU(s, cudaStreamSynchronize(s->stream));   // `lights` is caller memory: do not retain it
     s->have_frame = true;
     return RT_OK;
 }
@@ -208,8 +216,7 @@ void collect_stats(rt_scene *s) {
 int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npix_out, const RenderOut &out) {
     if (!s->have_frame) return fail(s, RT_ERR_STATE, "render before rt_frame_set");
     CU(s, cudaSetDevice(s->device));
-    if (s->stats_pending) { cudaStreamSynchronize(s->last_stream); collect_stats(s); }
-    s->cancel.store(0);
+    s->cancel.store(0);   // stats of earlier frames are collected lazily (rt_get_stats): no per-frame host sync
     const size_t nrays = ray_count(fp);
     const size_t out_bytes = npix_out * 3;
     const bool dbg = out.h_colour || out.h_face || out.h_obj || out.h_lit;
@@ -223,6 +230,7 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
     memset(&job, 0, sizeof job);
     job.fp = fp;
     job.d_meshes = s->d_meshes; job.d_objs = s->d_objs; job.d_lights = s->d_lights;
+    job.fr = s->inline_frame;
     job.precision = s->precision; job.flags = flags;
     job.d_hits = s->d_hits; job.d_hit_colour = s->d_hit_colour; job.d_hit_lit = s->d_hit_lit;
     job.d_counters = s->d_counters; job.d_stats = s->d_stats;
@@ -348,6 +356,7 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->refill_below = env_int("RT_B200_REFILL", 1);
     memset(&s->stats, 0, sizeof s->stats);
     memset(&s->frame, 0, sizeof s->frame);
+    memset(&s->inline_frame, 0, sizeof s->inline_frame);
     int rc = RT_OK;
     auto bail = [&](int code) { lk.unlock(); std::string e = s->err; destroy_locked(s); delete s; g_err = e; return code; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(s, e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA); } } while (0)

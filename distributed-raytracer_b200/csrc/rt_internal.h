@@ -34,6 +34,7 @@ struct RenderJob {
     const MeshView *d_meshes;
     const ObjRec   *d_objs;
     const LightRec *d_lights;
+    InlineFrame fr;           // lights / object positions by value when they fit
     uint32_t precision;
     uint32_t flags;
     // scratch (device)

@@ -65,6 +65,12 @@ struct FrameParams {
     int tile_w, tile_h, tiles_x, rank, n_ranks, n_local_tiles;
 };
 
+// Per-frame mutable state small enough to travel BY VALUE as a __grid_constant__ kernel parameter: no device
+// upload, no host synchronisation per frame (the gob `diff` of a WorkOrder is < 1 KB: distributed/main.go:56-64).
+#define RT_INLINE_LIGHTS 8
+#define RT_INLINE_OBJS 4
+struct InlineFrame { LightRec lights[RT_INLINE_LIGHTS]; ObjRec objs[RT_INLINE_OBJS]; int use_lights, use_objs; };
+
 // primary-hit record appended by the primary kernel, consumed by the shade kernel (16 B)
 struct HitRec { uint32_t pix; int32_t obj; int32_t face; float t; };
 

@@ -65,12 +65,22 @@ def broadcast_scene(scene, src=0, group=None, device="cpu"):
 class GpuTileBackend:
     """Default backend: librt_b200.so on this rank's GPU (fails loudly without CUDA)."""
 
-    def __init__(self, scene, device_index, precision):
+    pipelined = True      # render and gather/untile run on two streams; consecutive frames overlap
+
+    def __init__(self, scene, device_index, precision, replicas=1):
         self.device = torch.device("cuda", device_index)
-        self.scene = GpuScene(scene, device=device_index, precision=precision)
+        # `replicas` > 1 is a benchmarking aid: frames cycle over several resident copies of the scene so that a frame's
+        # inputs (BVH, triangles, per-face shading data) were last touched `replicas` frames earlier and are no longer in
+        # L2 -- the pipelined multi-GPU loop cannot flush L2 between frames without serialising the pipeline.
+        self.scenes = [GpuScene(scene, device=device_index, precision=precision) for _ in range(max(1, replicas))]
+        self.scene = self.scenes[0]
+        self.turn = 0
+        self.comm_stream = torch.cuda.Stream(self.device)
 
     def set_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan")):
-        self.scene.set_frame(cam13, lights, obj_pos, tan_half_fov)
+        self.scene = self.scenes[self.turn % len(self.scenes)]
+        self.turn += 1
+        self.scene.set_frame(cam13, lights, obj_pos, tan_half_fov)     # host-only: the state travels as kernel parameters
 
     def alloc(self, nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -85,10 +95,15 @@ class GpuTileBackend:
 
 
 class TileShardedRenderer:
-    """Renders full frames with the screen tiles dealt round-robin over the ranks of `group`."""
+    """Renders full frames with the screen tiles dealt round-robin over the ranks of `group`.
+
+    With a pipelined backend the tile buffers are double-buffered: frame k is rendered on the caller's stream while the
+    gather + de-interleave of frame k-1 run on a second stream, so the per-frame cost on every rank is its render time,
+    not render + collective.  `render_frame` returns the framebuffer of the frame it enqueued; it is complete once
+    `wait()` (or a synchronize) has returned."""
 
     def __init__(self, scene, W, H, precision=_lib.FP32_FAST, tile=(32, 16), group=None, device_index=0, backend_factory=None,
-                 layout_flags=_lib.LAYOUT_ROWMAJOR):
+                 layout_flags=_lib.LAYOUT_ROWMAJOR, replicas=1):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_ranks = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -97,23 +112,56 @@ class TileShardedRenderer:
         if self.tw % 8 or self.th % 4:
             raise ValueError("tile size must be a multiple of 8x4")
         self.layout_flags = layout_flags
-        factory = backend_factory or GpuTileBackend
-        self.backend = factory(scene, device_index, precision)
+        self.backend = backend_factory(scene, device_index, precision) if backend_factory else \
+            GpuTileBackend(scene, device_index, precision, replicas)
+        self.pipelined = bool(getattr(self.backend, "pipelined", False)) and self.n_ranks > 1
         self.per_rank = tiles_per_rank(self.W, self.H, self.tw, self.th, self.n_ranks)
         self.tile_bytes = self.tw * self.th * 3
-        self.local = self.backend.alloc(self.per_rank * self.tile_bytes)
-        if hasattr(self.local, "zero_"):
-            self.local.zero_()
-        self.gathered = self.backend.alloc(self.n_ranks * self.per_rank * self.tile_bytes) if self.n_ranks > 1 else self.local
-        self.frame = self.backend.alloc(self.W * self.H * 3) if self.rank == 0 else None
+        nbuf = 2 if self.pipelined else 1
+        self.local = [self.backend.alloc(self.per_rank * self.tile_bytes) for _ in range(nbuf)]
+        for t in self.local:
+            t.zero_()
+        self.gathered = [self.backend.alloc(self.n_ranks * self.per_rank * self.tile_bytes) if self.n_ranks > 1 else self.local[k]
+                         for k in range(nbuf)]
+        self.frame = [self.backend.alloc(self.W * self.H * 3) if self.rank == 0 else None for _ in range(nbuf)]
+        self.seq = 0
+        self.rendered = [None] * nbuf     # event: tiles of the frame in slot k are rendered
+        self.gathered_ev = [None] * nbuf  # event: gather (+ untile) that read slot k is done
 
     def render_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan"), flags=0):
-        """Enqueues one frame; returns the framebuffer tensor on rank 0 (None elsewhere).  Asynchronous on
-        CUDA: the caller synchronises (torch.cuda.synchronize / events) before reading."""
+        """Enqueues one frame; returns the framebuffer tensor on rank 0 (None elsewhere).  Asynchronous on CUDA."""
+        k = self.seq % len(self.local)
+        self.seq += 1
         self.backend.set_frame(cam13, lights, obj_pos, tan_half_fov)
-        self.backend.render_tiles(self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local, flags)
-        if self.n_ranks > 1:
-            dist.all_gather_into_tensor(self.gathered, self.local, group=self.group)
-        if self.rank == 0:
-            self.backend.untile(self.W, self.H, self.tw, self.th, self.n_ranks, self.gathered, self.frame, self.layout_flags)
-        return self.frame
+        if not self.pipelined:
+            self.backend.render_tiles(self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
+            if self.n_ranks > 1:
+                dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group)
+            if self.rank == 0:
+                self.backend.untile(self.W, self.H, self.tw, self.th, self.n_ranks, self.gathered[k], self.frame[k], self.layout_flags)
+            return self.frame[k]
+        render_stream = torch.cuda.current_stream(self.backend.device)
+        if self.gathered_ev[k] is not None:
+            render_stream.wait_event(self.gathered_ev[k])          # slot k's previous gather must have read its tiles
+        self.backend.render_tiles(self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
+        ev = torch.cuda.Event()
+        ev.record(render_stream)
+        self.rendered[k] = ev
+        comm = self.backend.comm_stream
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group)
+            if self.rank == 0:
+                self.backend.untile(self.W, self.H, self.tw, self.th, self.n_ranks, self.gathered[k], self.frame[k], self.layout_flags)
+            done = torch.cuda.Event()
+            done.record(comm)
+        self.gathered_ev[k] = done
+        return self.frame[k]
+
+    def wait(self):
+        """Makes the caller's stream wait for every gather / de-interleave enqueued so far."""
+        if self.pipelined:
+            st = torch.cuda.current_stream(self.backend.device)
+            for e in self.gathered_ev:
+                if e is not None:
+                    st.wait_event(e)
