@@ -29,7 +29,8 @@ W, H = 3840, 2160
 SUBDIV = 5
 N_LIGHTS = 2
 METRIC = "Mrays/s (primary+shadow)"
-REPLICAS = 4      # N>1: resident scene copies the frames cycle over (inputs larger than L2; see parallel.GpuTileBackend)
+REPLICAS = 4      # resident scene copies / streams the frames cycle over (see parallel.GpuTileBackend)
+TILE = (32, 16)
 SCENE_JSON = os.path.join(ROOT, "tests", "golden", "example", "scene.json")
 
 
@@ -168,15 +169,20 @@ def run_reference(args, rank):
 
 
 def main():
+    global REPLICAS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", type=int, default=0, help="scene replicas / frames in flight (default %d)" % REPLICAS)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e loop (experiments only)")
     ap.add_argument("--persistent", action="store_true", help="use the persistent warp-cooperative primary kernel (RT_FLAG_PERSISTENT)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.replicas > 0:
+        REPLICAS = args.replicas
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -217,45 +223,50 @@ def main():
         sc_r = sc
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    stream = torch.cuda.Stream(dev)            # one explicit stream orders flush, render kernels and NCCL
+    stream = torch.cuda.Stream(dev)            # the "main" stream: flushes, timing events, serial passes
     torch.cuda.set_stream(stream)
 
-    if world == 1:
-        g = rt.GpuScene(sc_r, device=local_rank, precision=rt.FP32_FAST)
-        fb = torch.empty(W * H * 3, dtype=torch.uint8, device=dev)
+    # The render pipeline: REPLICAS resident scene copies, one stream each; frame k goes to replica k % REPLICAS, so
+    # several frames are in flight and a frame's inputs were last touched REPLICAS frames earlier (> L2).
+    r = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=TILE, device_index=local_rank, replicas=REPLICAS,
+                                     layout_flags=rt.LAYOUT_COLMAJOR)
+    g = r.backend.scenes[0]
+    bvh = g.bvh_info()
+    launches_per_step = 3 + (1 if (world > 1 and rank == 0) else 0)
 
-        def step():
-            g.set_frame(cam13, lights, tan_half_fov=tan_half)
-            g.render_region_device(W, H, 0, 0, W, H, fb.data_ptr(), stream.cuda_stream, render_flags | rt.LAYOUT_COLMAJOR)
-        launches_per_step = 3
-        bvh = g.bvh_info()
-    else:
-        r = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=(32, 16), device_index=local_rank, replicas=REPLICAS)
-        g = r.backend.scene
+    def step():
+        r.render_frame(cam13, lights, tan_half_fov=tan_half, flags=render_flags)
 
-        def step():
-            r.render_frame(cam13, lights, tan_half_fov=tan_half, flags=render_flags)
-        launches_per_step = 3 + (1 if rank == 0 else 0)
-        g.set_frame(cam13, lights, tan_half_fov=tan_half)
-        bvh = g.bvh_info()
+    # ---- counting pass (outside the timed region, serial): algorithmic traversal work of one frame on this rank ----
+    g.set_frame(cam13, lights, tan_half_fov=tan_half)
+    scratch = r.local[0] if world > 1 else r.frame[0]
 
-    # ---- counting pass (outside the timed region): algorithmic traversal work of one frame ----
-    if world == 1:
-        g.set_frame(cam13, lights, tan_half_fov=tan_half)
-        g.render_region_device(W, H, 0, 0, W, H, fb.data_ptr(), None, render_flags | rt.FLAG_COUNT)
-    else:
-        g.set_frame(cam13, lights, tan_half_fov=tan_half)
-        g.render_tiles_device(W, H, 32, 16, rank, world, r.local[0].data_ptr(), None, render_flags | rt.FLAG_COUNT)
+    def serial_frame(flags):
+        if world == 1:
+            g.render_region_device(W, H, 0, 0, W, H, scratch.data_ptr(), None, flags)
+        else:
+            g.render_tiles_device(W, H, TILE[0], TILE[1], rank, world, scratch.data_ptr(), None, flags)
+    serial_frame(render_flags | rt.FLAG_COUNT)
     cnt = g.stats()
     hits_local, prim_local = cnt["hit_pixels"], cnt["primary_rays"]
-    rays_local = prim_local + cnt["shadow_rays"]
     if world > 1:
-        t = torch.tensor([float(rays_local), float(hits_local)], device=dev, dtype=torch.float64)
+        t = torch.tensor([float(hits_local)], device=dev, dtype=torch.float64)
         dist.all_reduce(t)
-        rays_frame, hits_frame = int(t[0].item()), int(t[1].item())
-        rays_frame = W * H + hits_frame * len(lights)     # tile padding beyond the screen is not a ray
+        hits_frame = int(t[0].item())
     else:
-        rays_frame, hits_frame = W * H + hits_local * len(lights), hits_local
+        hits_frame = hits_local
+    rays_frame = W * H + hits_frame * len(lights)         # tile padding beyond the screen is not a ray
+
+    # ---- per-kernel durations (serial frames, L2 flushed before each, CUDA events on the launching stream) ----
+    kern_ms = {"primary": [], "shade": [], "write": []}
+    for _ in range(3 + min(args.steps, 20)):
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        serial_frame(render_flags)
+        st = g.stats()
+        for name in kern_ms:
+            kern_ms[name].append(st["ms_" + name])
+    kern_ms = {k: v[3:] for k, v in kern_ms.items()}
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -268,41 +279,26 @@ def main():
     # ---- warm-up ----
     for _ in range(args.warmup):
         step()
+    r.wait()
     torch.cuda.synchronize(dev)
 
     # ---- timed region: exactly K steps, barrier + synchronize on both sides, device timing, max over ranks ----
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kern_ms = {"primary": [], "shade": [], "write": []}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
+    ev0.record(stream)
+    r.start_after(ev0)
     for k in range(args.steps):
-        if world == 1:
-            flush.zero_()                                 # L2 flush between timed iterations (outside the per-step event pair)
-        ev[k][0].record(stream)
         step()
-        ev[k][1].record(stream)
-        if world == 1:
-            st = g.stats()                                # synchronises; per-kernel CUDA-event durations of this step
-            for name in kern_ms:
-                kern_ms[name].append(st["ms_" + name])
-    if world > 1:
-        r.wait()                                          # pipelined frames: the last gather/untile must be inside the timed region
-        ev_end = torch.cuda.Event(enable_timing=True)
-        ev_end.record(stream)
+    r.wait()                                              # the main stream waits for every frame (incl. gather / untile)
+    ev1.record(stream)
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
-    if world == 1:
-        dev_ms = sum(a.elapsed_time(b) for a, b in ev)    # L2 flushes between steps are outside the per-step event pairs
-    else:
-        # frames overlap across steps (render k+1 || gather k): time the whole K-step region on the device
-        dev_ms = ev[0][0].elapsed_time(ev_end)
-        st = g.stats()
-        for name in kern_ms:
-            kern_ms[name].append(st["ms_" + name])
+    dev_ms = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -314,7 +310,9 @@ def main():
     # ---- e2e: the reference-facing call with host buffers (H2D frame state + D2H pixels inside the timed region) ----
     e2e = None
     h2d = 8 * (14 + 6 * len(lights) + 3)                  # rt_camera + lights + object position
-    if world == 1:
+    if args.no_e2e:
+        e2e = {"value": None, "unit": "Mrays/s", "ms_per_step": None}
+    elif world == 1:
         L = rt._lib.load()
         nbytes = W * H * 3
         pinned = L.rt_host_alloc(nbytes)
@@ -323,7 +321,7 @@ def main():
         for _ in range(args.warmup):
             tr_scene.bulk_trace(cam13, lights, W, H, 0, 0, W, H, out=out, tan_half_fov=tan_half)
         t_e2e = []
-        for _ in range(args.steps):
+        for _ in range(min(args.steps, 50)):
             flush.zero_()
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
@@ -341,7 +339,8 @@ def main():
         nbytes = W * H * 3
         host_fb = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
         t_e2e = []
-        for it in range(args.warmup + args.steps):
+        e2e_steps = min(args.steps, 50)
+        for it in range(args.warmup + e2e_steps):
             flush.zero_()
             torch.cuda.synchronize(dev)
             dist.barrier()
@@ -356,7 +355,7 @@ def main():
                 t_e2e.append(time.perf_counter() - t0)
         tt = torch.tensor([sum(t_e2e)], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = 1e3 * float(tt.item()) / args.steps
+        e2e_ms = 1e3 * float(tt.item()) / e2e_steps
         e2e = {"value": rays_frame / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_ms,
                "call": "TileShardedRenderer.render_frame + framebuffer D2H on rank 0 (pinned)"}
@@ -426,9 +425,10 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_frame": rays_frame, "hit_pixels": hits_frame, "frames_per_s": 1e3 / ms_per_step,
-                   "l2": ("256 MiB device memset between timed steps (L2 flush, outside the per-step event pairs)" if world == 1 else
-                          "frames cycle over %d resident replicas of the scene per GPU (inputs last touched %d frames earlier, > L2); "
-                          "no flush inside the pipelined region" % (REPLICAS, REPLICAS)), "precision": "FP32_FAST traversal, fp64 shading",
+                   "l2": "frames cycle over %d resident replicas of the scene per GPU, one stream each (inputs last touched %d frames "
+                         "earlier: %d x ~290 MB > 126 MB L2); no flush inside the pipelined region; the per-kernel times of `roofline` "
+                         "come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS, REPLICAS),
+                   "frames_in_flight": REPLICAS, "precision": "FP32_FAST traversal, fp64 shading",
                    "parallelism": "screen tiles 32x16 round-robin over %d rank(s)" % world, "bvh": bvh,
                    "primary_kernel": "persistent" if args.persistent else "simple"},
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -7,7 +7,7 @@
 //   cub radix sort  (key, face) pairs                                  [library plumbing]
 //   k_karras        binary radix tree over the sorted keys (Karras 2012), parent links
 //   k_refit_sah     bottom-up boxes + SAH cost, collapse subtrees of <= max_leaf faces into leaves
-//   k_emit_count / scan / k_emit_write   BFS re-emission into 64 B traversal nodes (top of tree = prefix)
+//   k_emit_count / scan / k_emit_write   BFS re-emission into RT_W-wide traversal nodes (greedy surface-area collapse)
 //   k_gather_tris   triangle records in leaf order: 48 B fp32 and/or 80 B fp64
 #include "rt_internal.h"
 #include <cub/cub.cuh>
@@ -68,9 +68,9 @@ __global__ void k_refit_sah(int n, const uint32_t *__restrict__ vals, const BoxF
 }
 
 __global__ void k_emit_count(const int *__restrict__ frontier, int fsize, const KarrasNode *__restrict__ kn,
-                             const unsigned char *__restrict__ collapsed, int *__restrict__ cnt) {
+                             const unsigned char *__restrict__ collapsed, const BoxF *__restrict__ ibox, int *__restrict__ cnt) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < fsize) emit_count_thread(p, frontier, kn, collapsed, cnt);
+    if (p < fsize) emit_count_thread(p, frontier, kn, collapsed, ibox, cnt);
 }
 
 __global__ void k_emit_write(const int *__restrict__ frontier, int fsize, int level_base, const KarrasNode *__restrict__ kn,
@@ -223,7 +223,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStr
             int fsize = 1, base = 0, cur = 0, depth = 0;
             while (fsize > 0) {
                 unsigned int fb = (fsize + TB - 1) / TB;
-                k_emit_count<<<fb, TB, 0, st>>>(d_front[cur], fsize, d_kn, d_coll, d_cnt);
+                k_emit_count<<<fb, TB, 0, st>>>(d_front[cur], fsize, d_kn, d_coll, d_ibox, d_cnt);
                 CK(cudaGetLastError());
                 size_t tb = tmp_bytes;
                 CK(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_off, fsize, st));
@@ -238,9 +238,18 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStr
                 fsize = last_off + last_cnt;
                 cur ^= 1;
                 depth++;
-                if (depth > RT_STACK_SIZE - 2) { err = "BVH deeper than the traversal stack"; return false; }
+                if ((RT_W - 1) * depth + 2 > RT_STACK_SIZE) { err = "BVH deeper than the traversal stack"; return false; }
             }
             m.n_nodes = (uint32_t)base;
+            if ((size_t)base < (size_t)ni) {
+                // the wide tree has far fewer nodes than the binary one it was collapsed from: shrink the allocation
+                RtNode *tight = nullptr;
+                CK(cudaMalloc(&tight, sizeof(RtNode) * (size_t)base));
+                CK(cudaMemcpyAsync(tight, m.nodes, sizeof(RtNode) * (size_t)base, cudaMemcpyDeviceToDevice, st));
+                CK(cudaStreamSynchronize(st));
+                cudaFree(m.nodes);
+                m.nodes = tight;
+            }
             m.root_ref = 0;
             m.info.max_depth = (uint32_t)depth;
             unsigned int nl = 0;

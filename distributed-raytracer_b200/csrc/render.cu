@@ -1,5 +1,5 @@
 // render.cu -- the render kernels (sm_100a):
-//   K2  k_primary_*        primary-ray generation + nearest-hit BVH traversal, appends compact HitRecs
+//   K2  k_primary_*        primary-ray generation + nearest-hit wide-BVH traversal, appends compact HitRecs
 //   K3  Moller-Trumbore    device functions tri_test32 / tri_intersection_exact inlined in K2 and K4
 //   K4  k_shade            fused shadow rays + Phong shading per primary hit (fp64, reference order)
 //   K5  k_write            8-bit framebuffer writer (+ optional dense debug outputs)
@@ -108,58 +108,34 @@ __global__ void __launch_bounds__(128) k_primary_fast_simple(FrameParams fp, Sce
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2, FP32_FAST, persistent warp-cooperative variant (single object / single mesh).
+// K2, FP32_FAST, persistent warp-cooperative variant (single object / single mesh; RT_FLAG_PERSISTENT).
 //
 //  * persistent threads: grid = SMs x resident CTAs; every warp pulls rays from one global counter
-//  * refill: idle lanes are found with a ballot, ONE atomicAdd per warp claims popc(idle) rays, the base
-//    is shuffled to all lanes and each idle lane takes base + its rank among the idle lanes
-//  * traversal: per-lane while-while loop (internal nodes, then the postponed leaf); a lane that found
-//    a leaf keeps descending speculatively until every lane of the warp has one (__any_sync)
-//  * a warp whose live-lane count drops below REFILL_BELOW leaves the loop and refills
-//  * the first TOPN nodes (BFS order => the top levels of the tree) are served from shared memory
-//  * node = 4 x LDG.128, triangle = 3 x LDG.128 through the read-only path
+//  * refill: idle lanes are found with a ballot, ONE atomicAdd per warp claims popc(idle) consecutive rays, the
+//    base is shuffled to all lanes and each idle lane takes base + its popc-rank among the idle lanes
+//  * rays that miss the mesh's root box (90 % of a frame) leave their lane idle and the warp immediately claims
+//    more, so the traversal below always starts with (nearly) full warps
+// Round-1 measurements on B200 (profiles/r01_explore_*): a finer-grained version of this kernel (lanes refilled
+// while the others are still traversing, postponed-leaf loop with a warp vote, top 256 BFS nodes of the tree in
+// shared memory) was 8-15 % SLOWER than the plain one-thread-per-ray kernel above, the shared-memory tree top alone
+// cost 0.04 ms, and claiming 256-ray chunks per warp doubled the time (the chip-wide BVH working set stops fitting
+// L1/L2).  The hardware block scheduler + L1 already do what the software scheme was meant to; this kernel is kept
+// as the selectable north-star design, sharing the per-ray traversal with the default kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int SENTINEL = 0x7fffffff;
-
-template <bool COUNT, int TOPN, int REFILL_BELOW>
+template <bool COUNT>
 __global__ void __launch_bounds__(128, 4)
 k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, float olz, HitRec *hits, unsigned int *counters,
                           Counters *gstats) {
-    __shared__ RtNode s_top[TOPN > 0 ? TOPN : 1];
-    const int ntop = TOPN < (int)m.n_nodes ? TOPN : (int)m.n_nodes;
-    if (TOPN > 0) {
-        // cooperative 16-byte copy of the top of the tree
-        const float4 *src = reinterpret_cast<const float4 *>(m.nodes);
-        float4 *dst = reinterpret_cast<float4 *>(s_top);
-        for (int k = threadIdx.x; k < ntop * 4; k += blockDim.x) dst[k] = __ldg(src + k);
-        __syncthreads();
-    }
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t nrays = ray_count(fp);
     Counters c; c.nodes = 0; c.tris = 0;
-
-    int stack[RT_STACK_SIZE];
-    int sp = 0;
-    int ref = SENTINEL;       // SENTINEL => lane has no ray in flight
-    int leaf = 0;             // postponed leaf (negative ref) or 0
-    bool have = false;        // lane holds a ray whose result is not stored yet
+    bool have = false;        // lane holds a ray that passed the root box
     uint32_t ray = 0;
     RayF r = make_rayf(0, 0, 0, 0, 0, 1);
-    float tbest = 0.f;
-    int face = -1;
     bool exhausted = false;
-
     for (;;) {
-        // ---- store finished rays (warp-converged point) ----
-        bool finished = have && ref == SENTINEL && leaf == 0;
-        append_hit(finished && face >= 0, ray, 0, face, tbest, hits, &counters[1]);
-        if (finished) have = false;
-
-        // ---- refill idle lanes: ballot to find them, ONE atomicAdd per warp claims popc(idle) consecutive rays, the
-        // base is shuffled to every lane and each idle lane takes base + its popc-rank among the idle lanes.
-        // (Claiming larger chunks per warp was measured 2x SLOWER -- profiles/r01_explore_b_*: warps then spread over
-        // 8x more image rows and the BVH working set of the chip no longer fits L1/L2.) ----
+        // ---- refill idle lanes ----
         unsigned idle = __ballot_sync(FULL, !have);
         if (idle && !exhausted) {
             unsigned n = __popc(idle);
@@ -175,66 +151,22 @@ k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, floa
                         float dx, dy, dz;
                         primary_dir32(pm.i, pm.j, fp, dx, dy, dz);
                         r = make_rayf(olx, oly, olz, dx, dy, dz);
-                        tbest = 3.0e38f; face = -1;
                         float tin;
                         // root box; a miss needs no store at all (the framebuffer is pre-cleared)
-                        if (slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, tbest, tin)) {
-                            have = true; ray = my; sp = 0; leaf = 0; ref = m.root_ref;
-                            if (ref < 0) { leaf = ref; ref = SENTINEL; }   // the whole mesh is one leaf
-                        }
+                        if (slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, 3.0e38f, tin)) { have = true; ray = my; }
                     }
                 }
             }
         }
         unsigned live = __ballot_sync(FULL, have);
         if (live == 0) { if (exhausted) break; else continue; }
-        // most rays of a frame miss the root box: keep claiming rays until enough lanes are live
-        if (!exhausted && __popc(live) < REFILL_BELOW) continue;
-
-        // ---- traversal ----
-        while (ref != SENTINEL || leaf < 0) {
-            // internal nodes
-            while (ref >= 0 && ref != SENTINEL) {
-                rt_f4 a, b, cc; rt_i4 ch;
-                if (TOPN > 0 && ref < ntop) { a = s_top[ref].a; b = s_top[ref].b; cc = s_top[ref].c; ch = s_top[ref].d; }
-                else { const RtNode *n = m.nodes + ref; a = ld_f4(&n->a); b = ld_f4(&n->b); cc = ld_f4(&n->c); ch = ld_i4(&n->d); }
-                if (COUNT) c.nodes++;
-                float t0, t1;
-                bool h0 = slab32(a.x, a.y, a.z, a.w, cc.x, cc.y, r, tbest, t0);
-                bool h1 = slab32(b.x, b.y, b.z, b.w, cc.z, cc.w, r, tbest, t1);
-                if (h0 && h1) {
-                    int nearc = ch.x, farc = ch.y;
-                    if (t1 < t0) { nearc = ch.y; farc = ch.x; }
-                    stack[sp++] = farc;
-                    ref = nearc;
-                } else if (h0) ref = ch.x;
-                else if (h1) ref = ch.y;
-                else ref = sp ? stack[--sp] : SENTINEL;
-                // postpone the first leaf found and keep descending (speculative traversal)
-                if (ref < 0 && leaf == 0) { leaf = ref; ref = sp ? stack[--sp] : SENTINEL; }
-                // every lane of the converged group holds a leaf -> go intersect
-                if (!__any_sync(__activemask(), leaf == 0)) break;
-            }
-            // leaves
-            while (leaf < 0) {
-                uint32_t first = rt_leaf_first(leaf), count = rt_leaf_count(leaf);
-                if (COUNT) c.tris += count;
-                for (uint32_t k = first; k < first + count; k++) {
-                    const rt_f4 *p = m.tri32 + 3 * (size_t)k;
-                    rt_f4 v0 = ld_f4(p), v1 = ld_f4(p + 1), v2 = ld_f4(p + 2);
-                    float t, u, v;
-                    if (tri_test32(v0, v1, v2, r, t, u, v)) {
-                        int f = __float_as_int(v0.w);
-                        if (t < tbest || (t == tbest && (face < 0 || f < face))) { tbest = t; face = f; }
-                    }
-                }
-                // the node reached after the postponed leaf may itself be a leaf
-                leaf = 0;
-                if (ref < 0) { leaf = ref; ref = sp ? stack[--sp] : SENTINEL; }
-            }
-            // too few live lanes in this warp -> go back and refill
-            if (!exhausted && __popc(__activemask()) < REFILL_BELOW) break;
-        }
+        if (!exhausted && __popc(live) < 24) continue;    // keep claiming until the warp is (nearly) full
+        // ---- traverse: same per-ray loop as the default kernel ----
+        float tbest = 3.0e38f;
+        int face = -1;
+        bool hit = have && mesh_trace_fast<false>(m, r, tbest, face, COUNT ? &c : nullptr);
+        append_hit(hit, ray, 0, face, tbest, hits, &counters[1]);
+        have = false;
     }
     if (COUNT) flush_counters(gstats, c);
 }
@@ -297,18 +229,56 @@ __global__ void k_write(FrameParams fp, const HitRec *__restrict__ hits, const u
     }
 }
 
-// multi-GPU: gathered interleaved-tile buffers -> framebuffer (one thread per pixel)
-__global__ void k_untile(const uint8_t *__restrict__ tiles, uint8_t *__restrict__ out, int W, int H, int tw, int th,
-                         int n_ranks, int tiles_per_rank_max, bool rowmajor) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= W || j >= H) return;
-    int tiles_x = (W + tw - 1) / tw;
-    int t = (j / th) * tiles_x + (i / tw);
-    int rank = t % n_ranks, lt = t / n_ranks;
-    size_t src = ((size_t)(rank * tiles_per_rank_max + lt) * (size_t)(tw * th) + (size_t)((j % th) * tw + (i % tw))) * 3;
-    size_t dst = (rowmajor ? (size_t)j * W + i : (size_t)i * H + j) * 3;
-    out[dst] = tiles[src]; out[dst + 1] = tiles[src + 1]; out[dst + 2] = tiles[src + 2];
+// multi-GPU: gathered interleaved-tile buffers -> framebuffer.  One CTA per tile: the packed tile (tw*th*3 bytes,
+// contiguous) is staged in shared memory with 16-byte loads, then written out as 32-bit words that are contiguous in
+// the destination layout (a pixel column of th*3 bytes for the column-major BulkTrace layout, a pixel row of tw*3
+// bytes for the row-major one).  Tiles cut by the screen edge take the byte-wise path.
+__global__ void __launch_bounds__(128) k_untile(const uint8_t *__restrict__ tiles, uint8_t *__restrict__ out, int W, int H, int tw,
+                                                 int th, int n_ranks, int tiles_per_rank_max, bool rowmajor) {
+    extern __shared__ __align__(16) uint8_t s_tile[];
+    const int tiles_x = (W + tw - 1) / tw;
+    const int t = blockIdx.x;
+    const int tx0 = (t % tiles_x) * tw, ty0 = (t / tiles_x) * th;
+    const int rank = t % n_ranks, lt = t / n_ranks;
+    const size_t tile_bytes = (size_t)tw * th * 3;
+    const uint8_t *src = tiles + ((size_t)rank * tiles_per_rank_max + lt) * tile_bytes;
+    const uint4 *src4 = reinterpret_cast<const uint4 *>(src);           // tile_bytes is a multiple of 96
+    uint4 *dst4 = reinterpret_cast<uint4 *>(s_tile);
+    for (int k = threadIdx.x; k < (int)(tile_bytes / 16); k += blockDim.x) dst4[k] = __ldg(src4 + k);
+    __syncthreads();
+    const bool interior = tx0 + tw <= W && ty0 + th <= H && (H % 4 == 0) && (W % 4 == 0);
+    if (interior) {
+        if (rowmajor) {
+            const int words_per_row = tw * 3 / 4;                        // tw is a multiple of 8
+            for (int k = threadIdx.x; k < th * words_per_row; k += blockDim.x) {
+                int row = k / words_per_row, wd = k % words_per_row;
+                uint32_t v = *reinterpret_cast<const uint32_t *>(s_tile + (size_t)row * tw * 3 + 4 * wd);
+                *reinterpret_cast<uint32_t *>(out + ((size_t)(ty0 + row) * W + tx0) * 3 + 4 * wd) = v;
+            }
+        } else {
+            const int words_per_col = th * 3 / 4;                        // th is a multiple of 4
+            for (int k = threadIdx.x; k < tw * words_per_col; k += blockDim.x) {
+                int col = k / words_per_col, wd = k % words_per_col;
+                uint32_t v = 0;
+#pragma unroll
+                for (int bb = 0; bb < 4; bb++) {
+                    int byte = 4 * wd + bb;                              // byte within the column: pixel byte/3, channel byte%3
+                    int row = byte / 3, ch = byte % 3;
+                    v |= (uint32_t)s_tile[((size_t)row * tw + col) * 3 + ch] << (8 * bb);
+                }
+                *reinterpret_cast<uint32_t *>(out + ((size_t)(tx0 + col) * H + ty0) * 3 + 4 * wd) = v;
+            }
+        }
+    } else {
+        for (int k = threadIdx.x; k < tw * th; k += blockDim.x) {
+            int col = k % tw, row = k / tw;
+            int i = tx0 + col, j = ty0 + row;
+            if (i >= W || j >= H) continue;
+            size_t dst = (rowmajor ? (size_t)j * W + i : (size_t)i * H + j) * 3;
+            const uint8_t *p = s_tile + (size_t)k * 3;
+            out[dst] = p[0]; out[dst + 1] = p[1]; out[dst + 2] = p[2];
+        }
+    }
 }
 
 // FMA-pipe peak: 8 independent dependent-chains per thread, all operands in registers
@@ -378,9 +348,9 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
                 olz = (float)(fp.cam_pos[2] - job.h_obj0_pos[2]);
     int per_sm = 0;
     cudaError_t e;
-#define LAUNCH_PERSISTENT(COUNTF, TOPN, REFILL)                                                                          \
+#define LAUNCH_PERSISTENT(COUNTF)                                                                                        \
     do {                                                                                                                 \
-        auto kern = k_primary_fast_persistent<COUNTF, TOPN, REFILL>;                                                     \
+        auto kern = k_primary_fast_persistent<COUNTF>;                                                                   \
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);                                        \
         if (e != cudaSuccess) return e;                                                                                  \
         if (per_sm < 1) per_sm = 1;                                                                                      \
@@ -389,17 +359,7 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
         if (g > need) g = need;                                                                                          \
         kern<<<g, 128, 0, st>>>(fp, m, olx, oly, olz, job.d_hits, job.d_counters, job.d_stats);                          \
     } while (0)
-#define LAUNCH_REFILL(COUNTF, TOPN)                                                                                      \
-    do {                                                                                                                 \
-        if (job.refill_below <= 1) LAUNCH_PERSISTENT(COUNTF, TOPN, 1);                                                   \
-        else if (job.refill_below <= 8) LAUNCH_PERSISTENT(COUNTF, TOPN, 8);                                              \
-        else if (job.refill_below <= 16) LAUNCH_PERSISTENT(COUNTF, TOPN, 16);                                            \
-        else if (job.refill_below <= 24) LAUNCH_PERSISTENT(COUNTF, TOPN, 24);                                            \
-        else LAUNCH_PERSISTENT(COUNTF, TOPN, 32);                                                                        \
-    } while (0)
-    if (job.top_in_smem) { if (count) LAUNCH_REFILL(true, 256); else LAUNCH_REFILL(false, 256); }
-    else { if (count) LAUNCH_REFILL(true, 0); else LAUNCH_REFILL(false, 0); }
-#undef LAUNCH_REFILL
+    if (count) LAUNCH_PERSISTENT(true); else LAUNCH_PERSISTENT(false);
 #undef LAUNCH_PERSISTENT
     return cudaGetLastError();
 }
@@ -437,7 +397,9 @@ cudaError_t rt_launch_write(const RenderJob &job, cudaStream_t st) {
 
 cudaError_t rt_launch_untile(const uint8_t *d_tiles, uint8_t *d_out, int W, int H, int tile_w, int tile_h, int n_ranks,
                              int tiles_per_rank_max, bool rowmajor, cudaStream_t st) {
-    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    k_untile<<<g, b, 0, st>>>(d_tiles, d_out, W, H, tile_w, tile_h, n_ranks, tiles_per_rank_max, rowmajor);
+    const int tiles_x = (W + tile_w - 1) / tile_w, tiles_y = (H + tile_h - 1) / tile_h;
+    const size_t smem = (size_t)tile_w * tile_h * 3;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    k_untile<<<(unsigned)(tiles_x * tiles_y), 128, smem, st>>>(d_tiles, d_out, W, H, tile_w, tile_h, n_ranks, tiles_per_rank_max, rowmajor);
     return cudaGetLastError();
 }

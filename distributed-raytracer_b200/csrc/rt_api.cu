@@ -494,6 +494,7 @@ int rt_untile_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint3
                      void *d_out_rgb, void *stream, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_all_tiles || !d_out_rgb || !tile_w || !tile_h || !n_ranks || !W || !H) return fail(s, RT_ERR_INVALID, "rt_untile_device: bad argument");
+    if (tile_w % 8 || tile_h % 4 || (size_t)tile_w * tile_h * 3 > 48 * 1024) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4 and at most 16384 pixels");
     std::lock_guard<std::mutex> lk(s->mu);
     CU(s, cudaSetDevice(s->device));
     const uint32_t tiles_x = (W + tile_w - 1) / tile_w, tiles_y = (H + tile_h - 1) / tile_h;

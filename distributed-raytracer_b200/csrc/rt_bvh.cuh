@@ -213,46 +213,75 @@ RT_HD int child_class(int c, const unsigned char *collapsed) {
     return collapsed[c] ? 1 : 2;
 }
 
-RT_HD void emit_count_thread(int p, const int *frontier, const KarrasNode *kn, const unsigned char *collapsed, int *cnt) {
-    KarrasNode k = kn[frontier[p]];
-    cnt[p] = (child_class(k.left, collapsed) == 2) + (child_class(k.right, collapsed) == 2);
+// Children of the wide node rooted at Karras node `node`: start from its two children and keep replacing the
+// expandable child (internal, not collapsed) of largest surface area by its own two children until RT_W slots are
+// used.  out[] holds builder child codes (>= 0 internal Karras index, < 0 ~leaf).  Deterministic.
+RT_HD int expand_children(int node, const KarrasNode *kn, const unsigned char *collapsed, const BoxF *ibox, int out[RT_W]) {
+    out[0] = kn[node].left; out[1] = kn[node].right;
+    int n = 2;
+    while (n < RT_W) {
+        int best = -1;
+        float best_a = -1.0f;
+        for (int i = 0; i < n; i++)
+            if (child_class(out[i], collapsed) == 2) {
+                float a = box_half_area(ibox[out[i]]);
+                if (a > best_a) { best_a = a; best = i; }
+            }
+        if (best < 0) break;
+        int c = out[best];
+        out[best] = kn[c].left;
+        out[n++] = kn[c].right;
+    }
+    return n;
+}
+
+RT_HD void emit_count_thread(int p, const int *frontier, const KarrasNode *kn, const unsigned char *collapsed, const BoxF *ibox,
+                             int *cnt) {
+    int ch[RT_W];
+    int n = expand_children(frontier[p], kn, collapsed, ibox, ch);
+    int c = 0;
+    for (int i = 0; i < n; i++) c += child_class(ch[i], collapsed) == 2;
+    cnt[p] = c;
 }
 
 // writes traversal node (level_base + p); internal children go to the next BFS level. Returns #leaf children.
 RT_HD unsigned int emit_write_thread(int p, const int *frontier, int fsize, int level_base, const KarrasNode *kn,
                                      const unsigned char *collapsed, const int *off, const uint32_t *vals, const BoxF *leafbox,
                                      const BoxF *ibox, RtNode *nodes, int *next_frontier) {
-    KarrasNode k = kn[frontier[p]];
+    int ch[RT_W];
+    int n = expand_children(frontier[p], kn, collapsed, ibox, ch);
     int o = off[p];
     int next_base = level_base + fsize;
-    BoxF bx[2];
-    int ref[2];
-    int ch[2] = { k.left, k.right };
     unsigned int nleaf = 0;
-    for (int s = 0; s < 2; s++) {
-        int c = ch[s];
-        int cls = child_class(c, collapsed);
-        if (cls == 0) {
-            bx[s] = leafbox[vals[~c]];
-            ref[s] = rt_leaf_ref((uint32_t)~c, 1u);
-            nleaf++;
-        } else if (cls == 1) {
-            bx[s] = ibox[c];
-            KarrasNode ck = kn[c];
-            ref[s] = rt_leaf_ref((uint32_t)ck.lo, (uint32_t)(ck.hi - ck.lo + 1));
-            nleaf++;
-        } else {
-            bx[s] = ibox[c];
-            ref[s] = next_base + o;
-            next_frontier[o] = c;
-            o++;
-        }
-    }
     RtNode nd;
-    nd.a.x = bx[0].lo[0]; nd.a.y = bx[0].hi[0]; nd.a.z = bx[0].lo[1]; nd.a.w = bx[0].hi[1];
-    nd.b.x = bx[1].lo[0]; nd.b.y = bx[1].hi[0]; nd.b.z = bx[1].lo[1]; nd.b.w = bx[1].hi[1];
-    nd.c.x = bx[0].lo[2]; nd.c.y = bx[0].hi[2]; nd.c.z = bx[1].lo[2]; nd.c.w = bx[1].hi[2];
-    nd.d.x = ref[0]; nd.d.y = ref[1]; nd.d.z = 0; nd.d.w = 0;
+    for (int s = 0; s < RT_W; s++) {
+        BoxF bx;
+        int ref;
+        if (s >= n) {
+            for (int k = 0; k < 3; k++) { bx.lo[k] = 0.f; bx.hi[k] = 0.f; }
+            ref = RT_EMPTY;
+        } else {
+            int c = ch[s];
+            int cls = child_class(c, collapsed);
+            if (cls == 0) {
+                bx = leafbox[vals[~c]];
+                ref = rt_leaf_ref((uint32_t)~c, 1u);
+                nleaf++;
+            } else if (cls == 1) {
+                bx = ibox[c];
+                KarrasNode ck = kn[c];
+                ref = rt_leaf_ref((uint32_t)ck.lo, (uint32_t)(ck.hi - ck.lo + 1));
+                nleaf++;
+            } else {
+                bx = ibox[c];
+                ref = next_base + o;
+                next_frontier[o] = c;
+                o++;
+            }
+        }
+        nd.lox[s] = bx.lo[0]; nd.hix[s] = bx.hi[0]; nd.loy[s] = bx.lo[1]; nd.hiy[s] = bx.hi[1];
+        nd.loz[s] = bx.lo[2]; nd.hiz[s] = bx.hi[2]; nd.ref[s] = ref; nd.pad[s] = 0;
+    }
     nodes[level_base + p] = nd;
     return nleaf;
 }

@@ -61,6 +61,24 @@ RT_HD rt_d2 ld_d2(const double *p) {
 #endif
 }
 
+// one node visit = 7 * RT_W/4 vector loads (the pad array is never fetched)
+struct NodeRegs { float lox[RT_W], hix[RT_W], loy[RT_W], hiy[RT_W], loz[RT_W], hiz[RT_W]; int ref[RT_W]; };
+RT_HD void ld_node(const RtNode *n, NodeRegs &r) {
+    const rt_f4 *q = reinterpret_cast<const rt_f4 *>(n);
+    float *dst = r.lox;                       // the six box arrays are contiguous in both structs
+#pragma unroll
+    for (int k = 0; k < 6 * RT_W / 4; k++) {
+        rt_f4 v = ld_f4(q + k);
+        dst[4 * k] = v.x; dst[4 * k + 1] = v.y; dst[4 * k + 2] = v.z; dst[4 * k + 3] = v.w;
+    }
+    const rt_i4 *qi = reinterpret_cast<const rt_i4 *>(n->ref);
+#pragma unroll
+    for (int k = 0; k < RT_W / 4; k++) {
+        rt_i4 v = ld_i4(qi + k);
+        r.ref[4 * k] = v.x; r.ref[4 * k + 1] = v.y; r.ref[4 * k + 2] = v.z; r.ref[4 * k + 3] = v.w;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // FP64_EXACT
 // ------------------------------------------------------------------------------------------------
@@ -107,26 +125,29 @@ RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bo
     double tin;
     if (!slab64(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], o, idir, cull_bound(best), tin)) return;
     int stack[RT_STACK_SIZE];
+    double stack_t[RT_STACK_SIZE];
     int sp = 0;
     int ref = m.root_ref;
     for (;;) {
         if (ref >= 0) {
-            const RtNode *n = m.nodes + ref;
-            rt_f4 a = ld_f4(&n->a), b = ld_f4(&n->b), c = ld_f4(&n->c);
-            rt_i4 ch = ld_i4(&n->d);
+            NodeRegs n;
+            ld_node(m.nodes + ref, n);
             RT_COUNT(cnt, nodes, 1);
-            double cull = cull_bound(best);
-            double t0, t1;
-            bool h0 = slab64(a.x, a.y, a.z, a.w, c.x, c.y, o, idir, cull, t0);
-            bool h1 = slab64(b.x, b.y, b.z, b.w, c.z, c.w, o, idir, cull, t1);
-            if (h0 && h1) {
-                int nearc = ch.x, farc = ch.y;
-                if (t1 < t0) { nearc = ch.y; farc = ch.x; }
-                stack[sp++] = farc;
-                ref = nearc;
-                continue;
-            } else if (h0) { ref = ch.x; continue; }
-            else if (h1) { ref = ch.y; continue; }
+            const double cull = cull_bound(best);
+            int next = RT_EMPTY;
+            double tnext = 0.0;
+#pragma unroll
+            for (int k = 0; k < RT_W; k++) {
+                double t;
+                bool h = slab64(n.lox[k], n.hix[k], n.loy[k], n.hiy[k], n.loz[k], n.hiz[k], o, idir, cull, t) && n.ref[k] != RT_EMPTY;
+                if (h) {
+                    // continue with the nearest child, push the others (with their entry distance)
+                    if (next == RT_EMPTY) { next = n.ref[k]; tnext = t; }
+                    else if (t < tnext) { stack[sp] = next; stack_t[sp] = tnext; sp++; next = n.ref[k]; tnext = t; }
+                    else { stack[sp] = n.ref[k]; stack_t[sp] = t; sp++; }
+                }
+            }
+            if (next != RT_EMPTY) { ref = next; continue; }
         } else {
             uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
             RT_COUNT(cnt, tris, count);
@@ -137,8 +158,12 @@ RT_HD void mesh_nearest_exact(const MeshView &m, dv o, dv d, BestExact &best, bo
                                (int)q4.y, o, d, best);
             }
         }
-        if (sp == 0) break;
-        ref = stack[--sp];
+        // pop; entries that a closer hit has made irrelevant since they were pushed are skipped (conservative bound)
+        do {
+            if (sp == 0) return;
+            --sp;
+            ref = stack[sp];
+        } while (stack_t[sp] > cull_bound(best));
     }
 }
 
@@ -227,25 +252,27 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
     if (!slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, tbest, tin)) return false;
     bool found = false;
     int stack[RT_STACK_SIZE];
+    float stack_t[ANY ? 1 : RT_STACK_SIZE];
     int sp = 0;
     int ref = m.root_ref;
     for (;;) {
         if (ref >= 0) {
-            const RtNode *n = m.nodes + ref;
-            rt_f4 a = ld_f4(&n->a), b = ld_f4(&n->b), c = ld_f4(&n->c);
-            rt_i4 ch = ld_i4(&n->d);
+            NodeRegs n;
+            ld_node(m.nodes + ref, n);
             RT_COUNT(cnt, nodes, 1);
-            float t0, t1;
-            bool h0 = slab32(a.x, a.y, a.z, a.w, c.x, c.y, r, tbest, t0);
-            bool h1 = slab32(b.x, b.y, b.z, b.w, c.z, c.w, r, tbest, t1);
-            if (h0 && h1) {
-                int nearc = ch.x, farc = ch.y;
-                if (t1 < t0) { nearc = ch.y; farc = ch.x; }
-                stack[sp++] = farc;
-                ref = nearc;
-                continue;
-            } else if (h0) { ref = ch.x; continue; }
-            else if (h1) { ref = ch.y; continue; }
+            int next = RT_EMPTY;
+            float tnext = 0.0f;
+#pragma unroll
+            for (int k = 0; k < RT_W; k++) {
+                float t;
+                bool h = slab32(n.lox[k], n.hix[k], n.loy[k], n.hiy[k], n.loz[k], n.hiz[k], r, tbest, t) && n.ref[k] != RT_EMPTY;
+                if (h) {
+                    if (next == RT_EMPTY) { next = n.ref[k]; tnext = t; }
+                    else if (!ANY && t < tnext) { stack[sp] = next; stack_t[sp] = tnext; sp++; next = n.ref[k]; tnext = t; }
+                    else { stack[sp] = n.ref[k]; if (!ANY) stack_t[sp] = t; sp++; }
+                }
+            }
+            if (next != RT_EMPTY) { ref = next; continue; }
         } else {
             uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
             RT_COUNT(cnt, tris, count);
@@ -264,10 +291,13 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
                 }
             }
         }
-        if (sp == 0) break;
-        ref = stack[--sp];
+        // pop (nearest-hit mode skips entries that start beyond the current best hit)
+        do {
+            if (sp == 0) return found;
+            --sp;
+            ref = stack[sp];
+        } while (!ANY && stack_t[sp] > tbest);
     }
-    return found;
 }
 
 struct TraceFast { int face, obj; float t; };

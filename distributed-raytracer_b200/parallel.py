@@ -63,44 +63,53 @@ def broadcast_scene(scene, src=0, group=None, device="cpu"):
 
 
 class GpuTileBackend:
-    """Default backend: librt_b200.so on this rank's GPU (fails loudly without CUDA)."""
+    """Default backend: librt_b200.so on this rank's GPU (fails loudly without CUDA).
 
-    pipelined = True      # render and gather/untile run on two streams; consecutive frames overlap
+    `replicas` resident copies of the scene, each with its own scratch buffers and its own CUDA stream: consecutive frames
+    go to consecutive replicas, so (a) up to `replicas` frames are in flight and the latency-bound tail of one frame's
+    kernels (a few pathological rays with ~150 dependent traversal steps) overlaps the head of the next frame instead of
+    idling the GPU, and (b) a frame's inputs were last touched `replicas` frames earlier and are no longer in L2, which is
+    how the pipelined loop satisfies "inputs larger than L2" without a serialising flush."""
+
+    pipelined = True
 
     def __init__(self, scene, device_index, precision, replicas=1):
         self.device = torch.device("cuda", device_index)
-        # `replicas` > 1 is a benchmarking aid: frames cycle over several resident copies of the scene so that a frame's
-        # inputs (BVH, triangles, per-face shading data) were last touched `replicas` frames earlier and are no longer in
-        # L2 -- the pipelined multi-GPU loop cannot flush L2 between frames without serialising the pipeline.
         self.scenes = [GpuScene(scene, device=device_index, precision=precision) for _ in range(max(1, replicas))]
-        self.scene = self.scenes[0]
-        self.turn = 0
+        self.streams = [torch.cuda.Stream(self.device) for _ in self.scenes]
         self.comm_stream = torch.cuda.Stream(self.device)
 
-    def set_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan")):
-        self.scene = self.scenes[self.turn % len(self.scenes)]
-        self.turn += 1
-        self.scene.set_frame(cam13, lights, obj_pos, tan_half_fov)     # host-only: the state travels as kernel parameters
+    @property
+    def scene(self):
+        return self.scenes[0]
+
+    def n_slots(self):
+        return len(self.scenes)
+
+    def set_frame(self, slot, cam13, lights, obj_pos=None, tan_half_fov=float("nan")):
+        self.scenes[slot].set_frame(cam13, lights, obj_pos, tan_half_fov)   # host-only: the state travels as kernel parameters
 
     def alloc(self, nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
-    def render_tiles(self, W, H, tw, th, rank, n_ranks, out, flags=0):
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        self.scene.render_tiles_device(W, H, tw, th, rank, n_ranks, out.data_ptr(), st, flags)
+    def render_region(self, slot, W, H, out, flags=0):
+        self.scenes[slot].render_region_device(W, H, 0, 0, W, H, out.data_ptr(), self.streams[slot].cuda_stream, flags)
+
+    def render_tiles(self, slot, W, H, tw, th, rank, n_ranks, out, flags=0):
+        self.scenes[slot].render_tiles_device(W, H, tw, th, rank, n_ranks, out.data_ptr(), self.streams[slot].cuda_stream, flags)
 
     def untile(self, W, H, tw, th, n_ranks, all_tiles, out, flags=0):
         st = torch.cuda.current_stream(self.device).cuda_stream
-        self.scene.untile_device(W, H, tw, th, n_ranks, all_tiles.data_ptr(), out.data_ptr(), st, flags)
+        self.scenes[0].untile_device(W, H, tw, th, n_ranks, all_tiles.data_ptr(), out.data_ptr(), st, flags)
 
 
 class TileShardedRenderer:
-    """Renders full frames with the screen tiles dealt round-robin over the ranks of `group`.
+    """Renders full frames; with N > 1 ranks the screen tiles are dealt round-robin over the ranks of `group`.
 
-    With a pipelined backend the tile buffers are double-buffered: frame k is rendered on the caller's stream while the
-    gather + de-interleave of frame k-1 run on a second stream, so the per-frame cost on every rank is its render time,
-    not render + collective.  `render_frame` returns the framebuffer of the frame it enqueued; it is complete once
-    `wait()` (or a synchronize) has returned."""
+    Frames are pipelined over the backend's slots (scene replicas + streams): frame k renders on slot k % S while the
+    gather + de-interleave of earlier frames run on the communication stream.  `render_frame` returns the framebuffer of
+    the frame it enqueued (rank 0; None elsewhere); it is complete once `wait()` followed by a synchronize has returned.
+    With one rank there is nothing to gather: the frame is rendered straight into the framebuffer (region mode)."""
 
     def __init__(self, scene, W, H, precision=_lib.FP32_FAST, tile=(32, 16), group=None, device_index=0, backend_factory=None,
                  layout_flags=_lib.LAYOUT_ROWMAJOR, replicas=1):
@@ -114,54 +123,77 @@ class TileShardedRenderer:
         self.layout_flags = layout_flags
         self.backend = backend_factory(scene, device_index, precision) if backend_factory else \
             GpuTileBackend(scene, device_index, precision, replicas)
-        self.pipelined = bool(getattr(self.backend, "pipelined", False)) and self.n_ranks > 1
+        self.pipelined = bool(getattr(self.backend, "pipelined", False))
+        S = self.backend.n_slots() if self.pipelined else 1
+        self.S = S
         self.per_rank = tiles_per_rank(self.W, self.H, self.tw, self.th, self.n_ranks)
         self.tile_bytes = self.tw * self.th * 3
-        nbuf = 2 if self.pipelined else 1
-        self.local = [self.backend.alloc(self.per_rank * self.tile_bytes) for _ in range(nbuf)]
+        multi = self.n_ranks > 1
+        self.local = [self.backend.alloc(self.per_rank * self.tile_bytes) for _ in range(S)] if multi else []
         for t in self.local:
             t.zero_()
-        self.gathered = [self.backend.alloc(self.n_ranks * self.per_rank * self.tile_bytes) if self.n_ranks > 1 else self.local[k]
-                         for k in range(nbuf)]
-        self.frame = [self.backend.alloc(self.W * self.H * 3) if self.rank == 0 else None for _ in range(nbuf)]
+        self.gathered = [self.backend.alloc(self.n_ranks * self.per_rank * self.tile_bytes) for _ in range(S)] if multi else []
+        self.frame = [self.backend.alloc(self.W * self.H * 3) if self.rank == 0 else None for _ in range(S)]
         self.seq = 0
-        self.rendered = [None] * nbuf     # event: tiles of the frame in slot k are rendered
-        self.gathered_ev = [None] * nbuf  # event: gather (+ untile) that read slot k is done
+        self.done_ev = [None] * S        # event: everything that read or wrote slot k's buffers is finished
 
     def render_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan"), flags=0):
-        """Enqueues one frame; returns the framebuffer tensor on rank 0 (None elsewhere).  Asynchronous on CUDA."""
-        k = self.seq % len(self.local)
+        """Enqueues one frame; asynchronous on CUDA."""
+        k = self.seq % self.S
         self.seq += 1
-        self.backend.set_frame(cam13, lights, obj_pos, tan_half_fov)
         if not self.pipelined:
-            self.backend.render_tiles(self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
-            if self.n_ranks > 1:
-                dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group)
+            # injected (test) backend: plain sequential path on the current stream
+            self.backend.set_frame(cam13, lights, obj_pos, tan_half_fov)
+            if self.n_ranks == 1:
+                self.backend.render_tiles(self.W, self.H, self.tw, self.th, 0, 1, self._single_local(), flags)
+                self.backend.untile(self.W, self.H, self.tw, self.th, 1, self._single_local(), self.frame[0], self.layout_flags)
+                return self.frame[0]
+            self.backend.render_tiles(self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[0], flags)
+            dist.all_gather_into_tensor(self.gathered[0], self.local[0], group=self.group)
             if self.rank == 0:
-                self.backend.untile(self.W, self.H, self.tw, self.th, self.n_ranks, self.gathered[k], self.frame[k], self.layout_flags)
+                self.backend.untile(self.W, self.H, self.tw, self.th, self.n_ranks, self.gathered[0], self.frame[0], self.layout_flags)
+            return self.frame[0]
+        be = self.backend
+        st = be.streams[k]
+        be.set_frame(k, cam13, lights, obj_pos, tan_half_fov)
+        if self.done_ev[k] is not None:
+            st.wait_event(self.done_ev[k])                 # slot k's previous frame (incl. its gather) must be finished
+        if self.n_ranks == 1:
+            be.render_region(k, self.W, self.H, self.frame[k], flags | self.layout_flags)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.done_ev[k] = ev
             return self.frame[k]
-        render_stream = torch.cuda.current_stream(self.backend.device)
-        if self.gathered_ev[k] is not None:
-            render_stream.wait_event(self.gathered_ev[k])          # slot k's previous gather must have read its tiles
-        self.backend.render_tiles(self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
+        be.render_tiles(k, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
         ev = torch.cuda.Event()
-        ev.record(render_stream)
-        self.rendered[k] = ev
-        comm = self.backend.comm_stream
+        ev.record(st)
+        comm = be.comm_stream
         comm.wait_event(ev)
         with torch.cuda.stream(comm):
             dist.all_gather_into_tensor(self.gathered[k], self.local[k], group=self.group)
             if self.rank == 0:
-                self.backend.untile(self.W, self.H, self.tw, self.th, self.n_ranks, self.gathered[k], self.frame[k], self.layout_flags)
+                be.untile(self.W, self.H, self.tw, self.th, self.n_ranks, self.gathered[k], self.frame[k], self.layout_flags)
             done = torch.cuda.Event()
             done.record(comm)
-        self.gathered_ev[k] = done
+        self.done_ev[k] = done
         return self.frame[k]
 
-    def wait(self):
-        """Makes the caller's stream wait for every gather / de-interleave enqueued so far."""
+    def _single_local(self):
+        if not self.local:
+            self.local = [self.backend.alloc(self.per_rank * self.tile_bytes)]
+        return self.local[0]
+
+    def start_after(self, event):
+        """Makes every slot stream (and the communication stream) wait for `event` (start of a timed region)."""
         if self.pipelined:
-            st = torch.cuda.current_stream(self.backend.device)
-            for e in self.gathered_ev:
+            for st in self.backend.streams:
+                st.wait_event(event)
+            self.backend.comm_stream.wait_event(event)
+
+    def wait(self):
+        """Makes the caller's current stream wait for every frame enqueued so far."""
+        if self.pipelined:
+            cur = torch.cuda.current_stream(self.backend.device)
+            for e in self.done_ev:
                 if e is not None:
-                    st.wait_event(e)
+                    cur.wait_event(e)

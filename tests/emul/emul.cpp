@@ -91,7 +91,7 @@ static void build_mesh(EmulMesh &m, int max_leaf) {
             front[0][0] = 0;
             int fsize = 1, base = 0, cur = 0, depth = 0;
             while (fsize > 0) {
-                for (int p = 0; p < fsize; p++) emit_count_thread(p, front[cur].data(), kn.data(), coll.data(), cnt.data());
+                for (int p = 0; p < fsize; p++) emit_count_thread(p, front[cur].data(), kn.data(), coll.data(), ibox.data(), cnt.data());
                 int acc = 0;
                 for (int p = 0; p < fsize; p++) { off[p] = acc; acc += cnt[p]; }
                 for (int p = 0; p < fsize; p++)
@@ -171,14 +171,16 @@ int emul_bvh_check(void *h, uint32_t mesh, uint32_t *out_nodes, uint32_t *out_de
         if (it.ref >= 0) {
             if ((uint32_t)it.ref >= m.view.n_nodes) return 1;
             const RtNode &nd = m.nodes[it.ref];
-            BoxF b0 = { { nd.a.x, nd.a.z, nd.c.x }, { nd.a.y, nd.a.w, nd.c.y } };
-            BoxF b1 = { { nd.b.x, nd.b.z, nd.c.z }, { nd.b.y, nd.b.w, nd.c.w } };
-            for (int k = 0; k < 3; k++) {
-                if (b0.lo[k] < it.box.lo[k] || b0.hi[k] > it.box.hi[k]) return 2;
-                if (b1.lo[k] < it.box.lo[k] || b1.hi[k] > it.box.hi[k]) return 2;
+            int used = 0;
+            for (int c = 0; c < RT_W; c++) {
+                if (nd.ref[c] == RT_EMPTY) continue;
+                used++;
+                BoxF b = { { nd.lox[c], nd.loy[c], nd.loz[c] }, { nd.hix[c], nd.hiy[c], nd.hiz[c] } };
+                for (int k = 0; k < 3; k++)
+                    if (b.lo[k] < it.box.lo[k] || b.hi[k] > it.box.hi[k]) return 2;
+                stack.push_back({ nd.ref[c], b });
             }
-            stack.push_back({ nd.d.x, b0 });
-            stack.push_back({ nd.d.y, b1 });
+            if (used < 2) return 7;
         } else {
             uint32_t first = rt_leaf_first(it.ref), count = rt_leaf_count(it.ref);
             if (first + count > n) return 3;
@@ -200,6 +202,7 @@ int emul_bvh_check(void *h, uint32_t mesh, uint32_t *out_nodes, uint32_t *out_de
 
 // One frame through the same pipeline the kernels implement: K2 -> K4 -> K5.
 // flags: RT_FLAG_BRUTE_FORCE, RT_LAYOUT_ROWMAJOR, RT_QUANT_RGBA16_SHR8.  counters: [nodes, tris] (may be NULL).
+static uint32_t *g_cost_primary = nullptr, *g_cost_shade = nullptr;   // optional per-pixel node+triangle fetch counts
 static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uint32_t flags, size_t npix, uint8_t *out_rgb,
                        double *out_colour, int32_t *out_face, int32_t *out_obj, uint32_t *out_lit, unsigned long long *counters);
 
@@ -254,6 +257,8 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
         PixMap pm = map_ray(ray, fp, false);
         if (!pm.valid) continue;
         HitRec hr; hr.pix = ray; hr.t = 0.f;
+        Counters before = c;
+        struct CostNote { Counters &c; Counters b; uint32_t *dst; size_t o; ~CostNote() { if (dst) dst[o] = (uint32_t)((c.nodes - b.nodes) + (c.tris - b.tris)); } } note{ c, before, g_cost_primary, pm.out };
         if (s->precision == RT_FP64_EXACT) {
             TraceExact tr;
             dv d = primary_dir_exact(pm.i, pm.j, fp);
@@ -280,10 +285,12 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
     for (const HitRec &hr : hits) {
         PixMap pm = map_ray(hr.pix, fp, rowmajor);
         double col[3];
+        Counters before = c;
         uint32_t lit = s->precision == RT_FP64_EXACT
                            ? shade_hit<true>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, &c)
                            : shade_hit<false>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, false, col, &c);
         size_t o = pm.out;
+        if (g_cost_shade) g_cost_shade[o] = (uint32_t)((c.nodes - before.nodes) + (c.tris - before.tris));
         if (out_rgb) for (int k = 0; k < 3; k++) out_rgb[3 * o + k] = quantise_exact(col[k], sdl);
         if (out_colour) for (int k = 0; k < 3; k++) out_colour[3 * o + k] = col[k];
         if (out_face) out_face[o] = hr.face;
@@ -294,6 +301,7 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
     return 0;
 }
 
+void emul_set_cost_buffers(uint32_t *primary, uint32_t *shade) { g_cost_primary = primary; g_cost_shade = shade; }
 unsigned long long emul_morton63(double x, double y, double z) { return morton63(x, y, z); }
 double emul_go_max(double x, double y) { return go_max(x, y); }
 double emul_go_min(double x, double y) { return go_min(x, y); }

@@ -145,7 +145,8 @@ def test_bvh_builder_structure():
             assert rc == 0, (n, max_leaf, rc)
             assert n_nodes <= max(n - 1, 0) and depth <= 94
             if max_leaf == 1 and n > 1:
-                assert n_nodes == n - 1 and n_leaves == n
+                # a 4-wide node has 2..4 children: (n-1)/3 <= nodes <= n-1; every face is its own leaf
+                assert (n - 1 + 2) // 3 <= n_nodes <= n - 1 and n_leaves == n
             E.close()
     # Morton code: bit interleave of 21-bit cells, x most significant
     L = eb.lib()

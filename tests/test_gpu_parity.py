@@ -150,20 +150,22 @@ def test_fast_random_scenes(rt, kw):
     assert within >= 0.995 and same >= 0.995          # tiny soups: many silhouette pixels per frame
 
 
-def test_fast_tiles_equal_region_render(rt, example_scene):
-    """Multi-GPU tile path on one GPU: every rank's packed tiles, gathered and de-interleaved, reproduce the
-    plain region render byte for byte."""
+@pytest.mark.parametrize("W,H,tw,th,n,layout", [(333, 187, 32, 16, 3, "row"), (352, 192, 32, 16, 3, "row"), (352, 192, 32, 16, 8, "col"),
+                                               (340, 200, 64, 32, 2, "col"), (333, 187, 8, 4, 5, "col")])
+def test_fast_tiles_equal_region_render(rt, example_scene, W, H, tw, th, n, layout):
+    """Multi-GPU tile path on one GPU: every rank's packed tiles, gathered and de-interleaved (fast word path for interior
+    tiles, byte path for tiles cut by the screen edge), reproduce the plain region render byte for byte."""
     import torch
-    W, H, tw, th, n = 333, 187, 32, 16, 3
+    flags = rt.LAYOUT_ROWMAJOR if layout == "row" else rt.LAYOUT_COLMAJOR
     g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
-    ref = g.render_region(W, H, flags=rt.LAYOUT_ROWMAJOR)
+    ref = g.render_region(W, H, flags=flags)
     per = rt.tiles_per_rank(W, H, tw, th, n)
     allt = torch.zeros(n * per * tw * th * 3, dtype=torch.uint8, device="cuda")
     for r in range(n):
         part = allt[r * per * tw * th * 3:(r + 1) * per * tw * th * 3]
         g.render_tiles_device(W, H, tw, th, r, n, part.data_ptr(), None)
-    out = torch.zeros(W * H * 3, dtype=torch.uint8, device="cuda")
-    g.untile_device(W, H, tw, th, n, allt.data_ptr(), out.data_ptr(), None, flags=rt.LAYOUT_ROWMAJOR)
+    out = torch.full((W * H * 3,), 77, dtype=torch.uint8, device="cuda")
+    g.untile_device(W, H, tw, th, n, allt.data_ptr(), out.data_ptr(), None, flags=flags)
     torch.cuda.synchronize()
     g.close()
     assert np.array_equal(out.cpu().numpy().reshape(-1, 3), ref)
@@ -235,7 +237,7 @@ def test_counting_build_reports_traversal_work(rt, example_scene):
     g.close()
     assert np.array_equal(a, b)
     assert s0["nodes_fetched"] == 0 and s1["nodes_fetched"] > 0 and s1["tris_fetched"] > 0
-    assert s1["node_bytes"] == 64 and s1["tri_bytes"] == 48 and s1["primary_rays"] == 320 * 240 and s1["ms_total"] > 0
+    assert s1["node_bytes"] == 112 and s1["tri_bytes"] == 48 and s1["primary_rays"] == 320 * 240 and s1["ms_total"] > 0
 
 
 def test_errors_and_lifecycle(rt, example_scene):

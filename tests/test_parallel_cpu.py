@@ -34,6 +34,11 @@ class EmulTileBackend:
     def set_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan")):
         self.cam, self.lights = np.asarray(cam13), np.asarray(lights)
 
+    pipelined = False
+
+    def n_slots(self):
+        return 1
+
     def alloc(self, nbytes):
         return torch.zeros(nbytes, dtype=torch.uint8)
 
