@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", type=int, default=0, help="scene replicas / frames in flight (default %d)" % REPLICAS)
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e loop (experiments only)")
+    ap.add_argument("--mode", default="peer", choices=["peer", "gather"], help="N>1: peer-memory framebuffer writer or NCCL gather")
     ap.add_argument("--persistent", action="store_true", help="use the persistent warp-cooperative primary kernel (RT_FLAG_PERSISTENT)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -229,17 +230,17 @@ def main():
     # The render pipeline: REPLICAS resident scene copies, one stream each; frame k goes to replica k % REPLICAS, so
     # several frames are in flight and a frame's inputs were last touched REPLICAS frames earlier (> L2).
     r = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=TILE, device_index=local_rank, replicas=REPLICAS,
-                                     layout_flags=rt.LAYOUT_COLMAJOR)
+                                     layout_flags=rt.LAYOUT_COLMAJOR, mode=args.mode)
     g = r.backend.scenes[0]
     bvh = g.bvh_info()
-    launches_per_step = 3 + (1 if (world > 1 and rank == 0) else 0)
+    launches_per_step = 3 if world == 1 else (4 if args.mode == "peer" else 3 + (1 if rank == 0 else 0))   # K2 K4 K5 (+ clear-tiles | untile)
 
     def step():
         r.render_frame(cam13, lights, tan_half_fov=tan_half, flags=render_flags)
 
     # ---- counting pass (outside the timed region, serial): algorithmic traversal work of one frame on this rank ----
     g.set_frame(cam13, lights, tan_half_fov=tan_half)
-    scratch = r.local[0] if world > 1 else r.frame[0]
+    scratch = r.frame[0] if world == 1 else torch.empty(rt.tiles_per_rank(W, H, TILE[0], TILE[1], world) * TILE[0] * TILE[1] * 3, dtype=torch.uint8, device=dev)
 
     def serial_frame(flags):
         if world == 1:
@@ -292,6 +293,7 @@ def main():
     r.start_after(ev0)
     for k in range(args.steps):
         step()
+    t_enqueue = time.perf_counter() - wall0               # host time to enqueue the K frames (diagnostic: host- vs device-bound)
     r.wait()                                              # the main stream waits for every frame (incl. gather / untile)
     ev1.record(stream)
     torch.cuda.synchronize(dev)
@@ -299,6 +301,7 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - wall0
     dev_ms = ev0.elapsed_time(ev1)
+    print("[bench] rank %d: %.3f ms per step on this rank" % (rank, dev_ms / args.steps), file=sys.stderr, flush=True)
     if world > 1:
         t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -428,8 +431,10 @@ def main():
                    "l2": "frames cycle over %d resident replicas of the scene per GPU, one stream each (inputs last touched %d frames "
                          "earlier: %d x ~290 MB > 126 MB L2); no flush inside the pipelined region; the per-kernel times of `roofline` "
                          "come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS, REPLICAS),
-                   "frames_in_flight": REPLICAS, "precision": "FP32_FAST traversal, fp64 shading",
-                   "parallelism": "screen tiles 32x16 round-robin over %d rank(s)" % world, "bvh": bvh,
+                   "frames_in_flight": REPLICAS, "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps, "precision": "FP32_FAST traversal, fp64 shading",
+                   "parallelism": ("screen tiles 32x16 round-robin over %d rank(s)" % world) + ("" if world == 1 else
+                                   ("; K5 stores hit pixels into rank 0's framebuffer over NVLink peer memory (CUDA IPC), 4-byte all_reduce as barrier"
+                                    if args.mode == "peer" else "; NCCL all_gather of packed tiles + de-interleave on rank 0")), "bvh": bvh,
                    "primary_kernel": "persistent" if args.persistent else "simple"},
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "clocks": clocks, "wall_s_timed_region": wall,

@@ -281,6 +281,94 @@ __global__ void __launch_bounds__(128) k_untile(const uint8_t *__restrict__ tile
     }
 }
 
+// multi-GPU, peer-memory push: copies THIS rank's packed tiles (local) into the full framebuffer `out` in its final
+// layout; `out` normally lives on rank 0's GPU (CUDA IPC mapping), so the stores travel over NVLink.  One CTA per local
+// tile: staged in shared memory with 16-byte loads, written as 16-byte vectors that exactly cover the tile's column
+// (column-major BulkTrace layout) or row (row-major) segments -- wide, aligned, coalesced transactions are what the link
+// wants (scattered 1-byte stores from the framebuffer writer cost 17 % of the frame at N = 2, profiles/r01_peer_*).
+template <typename VEC>
+__device__ __forceinline__ void push_segments(const uint8_t *s_tile, uint8_t *out, int n_seg, int seg_bytes, size_t seg_stride_out,
+                                              size_t out_base, int tw, bool rowmajor) {
+    const int vpb = (int)sizeof(VEC);
+    const int vecs_per_seg = seg_bytes / vpb;
+    for (int k = threadIdx.x; k < n_seg * vecs_per_seg; k += blockDim.x) {
+        const int seg = k / vecs_per_seg, v = k % vecs_per_seg;
+        VEC val;
+        uint8_t *vb = reinterpret_cast<uint8_t *>(&val);
+        if (rowmajor) {
+            val = *reinterpret_cast<const VEC *>(s_tile + (size_t)seg * seg_bytes + (size_t)v * vpb);      // a tile row is contiguous
+        } else {
+#pragma unroll
+            for (int b = 0; b < vpb; b++) {
+                const int byte = v * vpb + b;                       // byte within the column segment
+                vb[b] = s_tile[((size_t)(byte / 3) * tw + seg) * 3 + byte % 3];
+            }
+        }
+        *reinterpret_cast<VEC *>(out + out_base + (size_t)seg * seg_stride_out + (size_t)v * vpb) = val;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_push_tiles(FrameParams fp, bool rowmajor, const uint8_t *__restrict__ tiles,
+                                                     uint8_t *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t s_tile[];
+    const int lt = blockIdx.x;
+    const uint32_t t = (uint32_t)lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
+    const int tw = fp.tile_w, th = fp.tile_h, W = fp.W, H = fp.H;
+    const int tx0 = (int)(t % (uint32_t)fp.tiles_x) * tw, ty0 = (int)(t / (uint32_t)fp.tiles_x) * th;
+    if (tx0 >= W || ty0 >= H) return;
+    const size_t tile_bytes = (size_t)tw * th * 3;
+    const uint4 *src4 = reinterpret_cast<const uint4 *>(tiles + (size_t)lt * tile_bytes);
+    uint4 *dst4 = reinterpret_cast<uint4 *>(s_tile);
+    for (int k = threadIdx.x; k < (int)(tile_bytes / 16); k += blockDim.x) dst4[k] = __ldg(src4 + k);
+    __syncthreads();
+    const bool interior = tx0 + tw <= W && ty0 + th <= H;
+    const int n_seg = rowmajor ? th : tw, seg_bytes = (rowmajor ? tw : th) * 3;
+    const size_t stride = (size_t)(rowmajor ? W : H) * 3;
+    const size_t base = (rowmajor ? (size_t)ty0 * W + tx0 : (size_t)tx0 * H + ty0) * 3;
+    if (interior && seg_bytes % 16 == 0 && stride % 16 == 0 && base % 16 == 0)
+        push_segments<uint4>(s_tile, out, n_seg, seg_bytes, stride, base, tw, rowmajor);
+    else if (interior && stride % 4 == 0 && base % 4 == 0)
+        push_segments<uint32_t>(s_tile, out, n_seg, seg_bytes, stride, base, tw, rowmajor);
+    else
+        for (int k = threadIdx.x; k < tw * th; k += blockDim.x) {
+            int i = tx0 + k % tw, j = ty0 + k / tw;
+            if (i >= W || j >= H) continue;
+            size_t dst = (rowmajor ? (size_t)j * W + i : (size_t)i * H + j) * 3;
+            const uint8_t *p = s_tile + (size_t)k * 3;
+            out[dst] = p[0]; out[dst + 1] = p[1]; out[dst + 2] = p[2];
+        }
+}
+
+// multi-GPU, peer-memory writer: clears the pixels of THIS rank's tiles in the full framebuffer `out` (which may live on
+// another GPU, mapped through CUDA IPC / NVLink).  One CTA per local tile; interior tiles are cleared with 32-bit words
+// that exactly cover the tile's column (or row) segments, so no byte owned by another rank is ever touched.
+__global__ void __launch_bounds__(128) k_clear_tiles(FrameParams fp, bool rowmajor, uint8_t *__restrict__ out) {
+    const int lt = blockIdx.x;
+    const uint32_t t = (uint32_t)lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
+    const int tw = fp.tile_w, th = fp.tile_h, W = fp.W, H = fp.H;
+    const int tx0 = (int)(t % (uint32_t)fp.tiles_x) * tw, ty0 = (int)(t / (uint32_t)fp.tiles_x) * th;
+    if (tx0 >= W || ty0 >= H) return;
+    const bool interior = tx0 + tw <= W && ty0 + th <= H && (H % 4 == 0) && (W % 4 == 0);
+    if (interior) {
+        if (rowmajor) {
+            const int wpr = tw * 3 / 4;
+            for (int k = threadIdx.x; k < th * wpr; k += blockDim.x)
+                *reinterpret_cast<uint32_t *>(out + ((size_t)(ty0 + k / wpr) * W + tx0) * 3 + 4 * (k % wpr)) = 0u;
+        } else {
+            const int wpc = th * 3 / 4;
+            for (int k = threadIdx.x; k < tw * wpc; k += blockDim.x)
+                *reinterpret_cast<uint32_t *>(out + ((size_t)(tx0 + k / wpc) * H + ty0) * 3 + 4 * (k % wpc)) = 0u;
+        }
+    } else {
+        for (int k = threadIdx.x; k < tw * th; k += blockDim.x) {
+            int i = tx0 + k % tw, j = ty0 + k / tw;
+            if (i >= W || j >= H) continue;
+            size_t dst = (rowmajor ? (size_t)j * W + i : (size_t)i * H + j) * 3;
+            out[dst] = 0; out[dst + 1] = 0; out[dst + 2] = 0;
+        }
+    }
+}
+
 // FMA-pipe peak: 8 independent dependent-chains per thread, all operands in registers
 template <typename T>
 __global__ void __launch_bounds__(256) k_fma_peak(T *out, int iters, T a, T b) {
@@ -401,5 +489,19 @@ cudaError_t rt_launch_untile(const uint8_t *d_tiles, uint8_t *d_out, int W, int 
     const size_t smem = (size_t)tile_w * tile_h * 3;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
     k_untile<<<(unsigned)(tiles_x * tiles_y), 128, smem, st>>>(d_tiles, d_out, W, H, tile_w, tile_h, n_ranks, tiles_per_rank_max, rowmajor);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_clear_tiles(const FrameParams &fp, bool rowmajor, uint8_t *d_out, cudaStream_t st) {
+    if (fp.n_local_tiles <= 0) return cudaSuccess;
+    k_clear_tiles<<<(unsigned)fp.n_local_tiles, 128, 0, st>>>(fp, rowmajor, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_push_tiles(const FrameParams &fp, bool rowmajor, const uint8_t *d_tiles, uint8_t *d_out, cudaStream_t st) {
+    if (fp.n_local_tiles <= 0) return cudaSuccess;
+    const size_t smem = (size_t)fp.tile_w * fp.tile_h * 3;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    k_push_tiles<<<(unsigned)fp.n_local_tiles, 128, smem, st>>>(fp, rowmajor, d_tiles, d_out);
     return cudaGetLastError();
 }

@@ -253,7 +253,8 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
     CU(s, cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned int), st));
     CU(s, cudaMemsetAsync(s->d_stats, 0, 2 * sizeof(Counters), st));
     // background: sequential/main.go:17 surface.FillRect(nil, 0); distributed/main.go:70 default 0,0,0
-    CU(s, cudaMemsetAsync(d_rgb, 0, out_bytes, st));
+    if (fp.tile_final) CU(s, rt_launch_clear_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, d_rgb, st));   // only this rank's pixels (peer framebuffer)
+    else CU(s, cudaMemsetAsync(d_rgb, 0, out_bytes, st));
     if (job.d_out_colour) CU(s, cudaMemsetAsync(job.d_out_colour, 0, sizeof(double) * 3 * npix_out, st));
     if (job.d_out_face) CU(s, cudaMemsetAsync(job.d_out_face, 0xff, sizeof(int32_t) * npix_out, st));
     if (job.d_out_obj) CU(s, cudaMemsetAsync(job.d_out_obj, 0xff, sizeof(int32_t) * npix_out, st));
@@ -310,7 +311,7 @@ int region_params(rt_scene *s, FrameParams &fp, uint32_t W, uint32_t H, uint32_t
     if ((uint64_t)x + w > W || (uint64_t)y + h > H) return fail(s, RT_ERR_INVALID, "region exceeds the screen");
     fp = s->frame;
     fp.W = (int)W; fp.H = (int)H; fp.x = (int)x; fp.y = (int)y; fp.w = (int)w; fp.h = (int)h;
-    fp.tile_w = fp.tile_h = fp.tiles_x = fp.rank = fp.n_ranks = fp.n_local_tiles = 0;
+    fp.tile_w = fp.tile_h = fp.tiles_x = fp.rank = fp.n_ranks = fp.n_local_tiles = fp.tile_final = 0;
     return RT_OK;
 }
 
@@ -484,10 +485,92 @@ int rt_render_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w,
     const uint32_t n_tiles = (uint32_t)fp.tiles_x * tiles_y;
     fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
     fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
+    fp.tile_final = 0;
     RenderOut o; o.d_rgb = (uint8_t *)d_out_tiles; o.ext_stream = (cudaStream_t)stream; o.async = stream != nullptr;
     int rc = render_locked(s, fp, flags & ~RT_LAYOUT_ROWMAJOR, (size_t)fp.n_local_tiles * tile_w * tile_h, o);
     if (rc == RT_OK && !o.async) { CU(s, cudaStreamSynchronize(s->stream)); collect_stats(s); }
     return rc;
+}
+
+int rt_render_tiles_peer(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
+                         void *d_framebuffer, void *stream, uint32_t flags) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!d_framebuffer) return fail(s, RT_ERR_INVALID, "d_framebuffer is NULL");
+    if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "bad screen size");
+    if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4");
+    if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
+    std::lock_guard<std::mutex> lk(s->mu);
+    FrameParams fp = s->frame;
+    fp.W = (int)W; fp.H = (int)H; fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
+    fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
+    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
+    const uint32_t tiles_y = (H + tile_h - 1) / tile_h;
+    const uint32_t n_tiles = (uint32_t)fp.tiles_x * tiles_y;
+    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
+    fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
+    fp.tile_final = 1;
+    RenderOut o; o.d_rgb = (uint8_t *)d_framebuffer; o.ext_stream = (cudaStream_t)stream; o.async = stream != nullptr;
+    int rc = render_locked(s, fp, flags, (size_t)W * H, o);
+    if (rc == RT_OK && !o.async) { CU(s, cudaStreamSynchronize(s->stream)); collect_stats(s); }
+    return rc;
+}
+
+int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
+                         const void *d_tiles, void *d_framebuffer, void *stream, uint32_t flags) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!d_tiles || !d_framebuffer || !W || !H) return fail(s, RT_ERR_INVALID, "rt_push_tiles_device: bad argument");
+    if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4 || (size_t)tile_w * tile_h * 3 > 48 * 1024)
+        return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4 and at most 16384 pixels");
+    if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(s, cudaSetDevice(s->device));
+    FrameParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.W = (int)W; fp.H = (int)H; fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
+    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
+    const uint32_t n_tiles = (uint32_t)fp.tiles_x * ((H + tile_h - 1) / tile_h);
+    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
+    fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, st));
+    if (!stream) CU(s, cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+// ---- device buffers shareable between the per-GPU processes of one box (CUDA IPC over NVLink / NVSwitch) ----
+int rt_device_alloc(int device, size_t bytes, void **out) {
+    if (!out || bytes == 0) return fail(nullptr, RT_ERR_INVALID, "rt_device_alloc: bad argument");
+    CU(nullptr, cudaSetDevice(device));
+    CU(nullptr, cudaMalloc(out, bytes));
+    return RT_OK;
+}
+int rt_device_free(int device, void *p) {
+    if (!p) return RT_OK;
+    CU(nullptr, cudaSetDevice(device));
+    CU(nullptr, cudaFree(p));
+    return RT_OK;
+}
+int rt_ipc_export(void *d_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!d_ptr || !handle) return fail(nullptr, RT_ERR_INVALID, "rt_ipc_export: NULL argument");
+    cudaIpcMemHandle_t h;
+    CU(nullptr, cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return RT_OK;
+}
+int rt_ipc_open(int device, const unsigned char handle[64], void **out) {
+    if (!handle || !out) return fail(nullptr, RT_ERR_INVALID, "rt_ipc_open: NULL argument");
+    CU(nullptr, cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(nullptr, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+int rt_ipc_close(int device, void *p) {
+    if (!p) return RT_OK;
+    CU(nullptr, cudaSetDevice(device));
+    CU(nullptr, cudaIpcCloseMemHandle(p));
+    return RT_OK;
 }
 
 int rt_untile_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t n_ranks, const void *d_all_tiles,

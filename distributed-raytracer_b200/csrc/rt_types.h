@@ -70,6 +70,7 @@ struct FrameParams {
     int n_lights, n_obj;
     // tile mode (multi-GPU): if tile_w > 0 the region-linear pixel index maps through interleaved tiles
     int tile_w, tile_h, tiles_x, rank, n_ranks, n_local_tiles;
+    int tile_final;      // tile mode: output index = position in the FULL framebuffer (peer-memory writer), not in the packed tiles
 };
 
 // Per-frame mutable state small enough to travel BY VALUE as a __grid_constant__ kernel parameter: no device
@@ -110,6 +111,8 @@ RT_HD PixMap map_ray(uint32_t r, const FrameParams &fp, bool rowmajor) {
         p.j = (int)(t / (uint32_t)fp.tiles_x) * fp.tile_h + ty;
         p.out = lt * (uint32_t)(fp.tile_w * fp.tile_h) + (uint32_t)(ty * fp.tile_w + tx);
         p.valid = p.i < fp.W && p.j < fp.H;
+        if (fp.tile_final && p.valid)
+            p.out = rowmajor ? (uint32_t)p.j * (uint32_t)fp.W + (uint32_t)p.i : (uint32_t)p.i * (uint32_t)fp.H + (uint32_t)p.j;
         return p;
     }
     uint32_t nbx = (uint32_t)(fp.w + 7) / 8;

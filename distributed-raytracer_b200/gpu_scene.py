@@ -114,6 +114,12 @@ class GpuScene:
     def render_tiles_device(self, W, H, tile_w, tile_h, rank, n_ranks, d_out_ptr, stream_ptr=None, flags=0):
         self._check(self._L.rt_render_tiles_device(self.h, W, H, tile_w, tile_h, rank, n_ranks, d_out_ptr, stream_ptr, flags))
 
+    def render_tiles_peer(self, W, H, tile_w, tile_h, rank, n_ranks, d_framebuffer_ptr, stream_ptr=None, flags=0):
+        self._check(self._L.rt_render_tiles_peer(self.h, W, H, tile_w, tile_h, rank, n_ranks, d_framebuffer_ptr, stream_ptr, flags))
+
+    def push_tiles_device(self, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr=None, flags=0):
+        self._check(self._L.rt_push_tiles_device(self.h, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags))
+
     def untile_device(self, W, H, tile_w, tile_h, n_ranks, d_all_tiles_ptr, d_out_ptr, stream_ptr=None, flags=0):
         self._check(self._L.rt_untile_device(self.h, W, H, tile_w, tile_h, n_ranks, d_all_tiles_ptr, d_out_ptr, stream_ptr, flags))
 
@@ -148,3 +154,36 @@ class GpuScene:
 def tiles_per_rank(W, H, tile_w, tile_h, n_ranks):
     n_tiles = ((W + tile_w - 1) // tile_w) * ((H + tile_h - 1) // tile_h)
     return (n_tiles + n_ranks - 1) // n_ranks
+
+
+class DeviceBuffer:
+    """A library-allocated device buffer that can be shared with the other per-GPU processes of the box (CUDA IPC).
+    Exposes __cuda_array_interface__ so torch.as_tensor(buf, device=...) gives a zero-copy uint8 view."""
+
+    def __init__(self, device, nbytes=None, ipc_handle=None):
+        self._L = _lib.load()
+        self.device, self.nbytes, self.owner = device, nbytes, ipc_handle is None
+        p = C.c_void_p()
+        if ipc_handle is None:
+            rc = self._L.rt_device_alloc(device, nbytes, C.byref(p))
+        else:
+            rc = self._L.rt_ipc_open(device, ipc_handle, C.byref(p))
+        if rc != 0:
+            raise _lib.RtError(rc, (self._L.rt_last_error(None) or b"").decode())
+        self.ptr = p.value
+
+    def export(self):
+        h = C.create_string_buffer(64)
+        rc = self._L.rt_ipc_export(self.ptr, h)
+        if rc != 0:
+            raise _lib.RtError(rc, (self._L.rt_last_error(None) or b"").decode())
+        return h.raw
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            (self._L.rt_device_free if self.owner else self._L.rt_ipc_close)(self.device, self.ptr)
+            self.ptr = None

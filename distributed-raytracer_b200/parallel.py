@@ -20,8 +20,10 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .gpu_scene import GpuScene, tiles_per_rank
+from .gpu_scene import DeviceBuffer, GpuScene, tiles_per_rank
 
+import os as _os
+_NO_BARRIER = bool(int(_os.environ.get("RT_B200_NO_BARRIER", "0")))   # timing experiments only: frames are then unsynchronised
 _MESH_KEYS = (("verts", np.float64, 3), ("normals", np.float64, 3), ("faces", np.uint32, 7), ("materials", np.float64, 10))
 
 
@@ -98,6 +100,12 @@ class GpuTileBackend:
     def render_tiles(self, slot, W, H, tw, th, rank, n_ranks, out, flags=0):
         self.scenes[slot].render_tiles_device(W, H, tw, th, rank, n_ranks, out.data_ptr(), self.streams[slot].cuda_stream, flags)
 
+    def render_tiles_peer(self, slot, W, H, tw, th, rank, n_ranks, frame_ptr, flags=0):
+        self.scenes[slot].render_tiles_peer(W, H, tw, th, rank, n_ranks, frame_ptr, self.streams[slot].cuda_stream, flags)
+
+    def push_tiles(self, slot, W, H, tw, th, rank, n_ranks, tiles, frame_ptr, flags=0):
+        self.scenes[slot].push_tiles_device(W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr, self.streams[slot].cuda_stream, flags)
+
     def untile(self, W, H, tw, th, n_ranks, all_tiles, out, flags=0):
         st = torch.cuda.current_stream(self.device).cuda_stream
         self.scenes[0].untile_device(W, H, tw, th, n_ranks, all_tiles.data_ptr(), out.data_ptr(), st, flags)
@@ -112,7 +120,7 @@ class TileShardedRenderer:
     With one rank there is nothing to gather: the frame is rendered straight into the framebuffer (region mode)."""
 
     def __init__(self, scene, W, H, precision=_lib.FP32_FAST, tile=(32, 16), group=None, device_index=0, backend_factory=None,
-                 layout_flags=_lib.LAYOUT_ROWMAJOR, replicas=1):
+                 layout_flags=_lib.LAYOUT_ROWMAJOR, replicas=1, mode="peer"):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_ranks = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -129,13 +137,39 @@ class TileShardedRenderer:
         self.per_rank = tiles_per_rank(self.W, self.H, self.tw, self.th, self.n_ranks)
         self.tile_bytes = self.tw * self.th * 3
         multi = self.n_ranks > 1
+        # mode "peer": every rank pushes its rendered tiles straight into rank 0's framebuffer over NVLink (CUDA IPC
+        # mapping, wide coalesced stores) -- no gather, no de-interleave, only a tiny barrier collective per frame.
+        # mode "gather": packed tile buffers + all_gather + de-interleave on rank 0 (the NCCL-only baseline).
+        self.mode = mode if (multi and self.pipelined) else "gather"
+        self.peer_bufs = []
+        if self.mode == "peer":
+            self._init_peer(device_index)
         self.local = [self.backend.alloc(self.per_rank * self.tile_bytes) for _ in range(S)] if multi else []
         for t in self.local:
             t.zero_()
-        self.gathered = [self.backend.alloc(self.n_ranks * self.per_rank * self.tile_bytes) for _ in range(S)] if multi else []
-        self.frame = [self.backend.alloc(self.W * self.H * 3) if self.rank == 0 else None for _ in range(S)]
+        self.gathered = [self.backend.alloc(self.n_ranks * self.per_rank * self.tile_bytes) for _ in range(S)] \
+            if (multi and self.mode != "peer") else []
+        if self.mode != "peer":
+            self.frame = [self.backend.alloc(self.W * self.H * 3) if self.rank == 0 else None for _ in range(S)]
         self.seq = 0
         self.done_ev = [None] * S        # event: everything that read or wrote slot k's buffers is finished
+
+    def _init_peer(self, device_index):
+        nbytes = self.W * self.H * 3
+        handles = [None]
+        if self.rank == 0:
+            self.peer_bufs = [DeviceBuffer(device_index, nbytes) for _ in range(self.S)]
+            handles = [[b.export() for b in self.peer_bufs]]
+        dist.broadcast_object_list(handles, src=0, group=self.group)
+        if self.rank != 0:
+            self.peer_bufs = [DeviceBuffer(device_index, nbytes, ipc_handle=h) for h in handles[0]]
+        self.frame = [torch.as_tensor(b, device=self.backend.device) if self.rank == 0 else None for b in self.peer_bufs]
+        if self.rank == 0:
+            for f in self.frame:
+                f.zero_()
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.backend.device)
+        torch.cuda.synchronize(self.backend.device)
+        dist.barrier(group=self.group)
 
     def render_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan"), flags=0):
         """Enqueues one frame; asynchronous on CUDA."""
@@ -163,6 +197,23 @@ class TileShardedRenderer:
             ev = torch.cuda.Event()
             ev.record(st)
             self.done_ev[k] = ev
+            return self.frame[k]
+        if self.mode == "peer":
+            # every rank renders its tiles locally, then pushes them into rank 0's framebuffer k over NVLink (16-byte
+            # coalesced stores); the all_reduce is only the "everybody has written" barrier
+            be.render_tiles(k, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
+            be.push_tiles(k, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], self.peer_bufs[k].ptr,
+                          self.layout_flags)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            comm = be.comm_stream
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                if not _NO_BARRIER:
+                    dist.all_reduce(self.flag, group=self.group)
+                done = torch.cuda.Event()
+                done.record(comm)
+            self.done_ev[k] = done
             return self.frame[k]
         be.render_tiles(k, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
         ev = torch.cuda.Event()

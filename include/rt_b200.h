@@ -167,6 +167,25 @@ int rt_render_region_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_
 int rt_render_tiles_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w,
                            uint32_t tile_h, uint32_t rank, uint32_t n_ranks, void *d_out_tiles,
                            void *stream, uint32_t flags);
+/* Peer-memory variant (the multi-GPU path of choice): renders the same tiles, but the framebuffer writer stores each hit
+ * pixel -- and the clear of this rank's tiles -- straight into the FULL screen_w*screen_h*3 framebuffer d_framebuffer in
+ * `flags` layout.  d_framebuffer may live on another GPU of the box (rt_ipc_open of rank 0's buffer): the stores travel
+ * over NVLink as the kernel runs, so there is no gather and no de-interleave; the ranks only need a barrier afterwards.
+ * Pixels of other ranks' tiles are never touched. */
+int rt_render_tiles_peer(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h,
+                         uint32_t rank, uint32_t n_ranks, void *d_framebuffer, void *stream, uint32_t flags);
+/* Peer-memory push (preferred across GPUs): copies this rank's packed tiles (output of rt_render_tiles_device, local) into
+ * the FULL framebuffer d_framebuffer in `flags` layout with 16-byte coalesced stores.  d_framebuffer normally is rank 0's
+ * buffer opened with rt_ipc_open, so the stores travel over NVLink; no gather, no de-interleave on rank 0. */
+int rt_push_tiles_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h,
+                         uint32_t rank, uint32_t n_ranks, const void *d_tiles, void *d_framebuffer, void *stream,
+                         uint32_t flags);
+/* Device buffers shareable between the one-process-per-GPU ranks of a box (CUDA IPC; 64-byte opaque handles) */
+int rt_device_alloc(int device, size_t bytes, void **out);
+int rt_device_free(int device, void *p);
+int rt_ipc_export(void *d_ptr, unsigned char handle[64]);
+int rt_ipc_open(int device, const unsigned char handle[64], void **out);
+int rt_ipc_close(int device, void *p);
 /* Inverse of the packing above, run on the gathering rank: d_all_tiles holds the n_ranks packed
  * buffers back to back (each padded to tiles_per_rank_max tiles); writes the screen_w*screen_h*3
  * framebuffer d_out_rgb in `flags` layout. */

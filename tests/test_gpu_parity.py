@@ -171,6 +171,62 @@ def test_fast_tiles_equal_region_render(rt, example_scene, W, H, tw, th, n, layo
     assert np.array_equal(out.cpu().numpy().reshape(-1, 3), ref)
 
 
+@pytest.mark.parametrize("W,H,tw,th,n,layout", [(352, 192, 32, 16, 3, "col"), (352, 192, 32, 16, 8, "row"), (333, 187, 32, 16, 4, "col")])
+def test_fast_peer_writer_equals_region_render(rt, example_scene, W, H, tw, th, n, layout):
+    """rt_render_tiles_peer (the framebuffer writer storing straight into the full framebuffer, as it does over NVLink into rank
+    0's memory): all ranks emulated on one GPU, writing into ONE shared buffer through the library's shareable allocation,
+    must reproduce the region render; bytes of other ranks' tiles must never be touched."""
+    import torch
+    flags = rt.LAYOUT_ROWMAJOR if layout == "row" else rt.LAYOUT_COLMAJOR
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    ref = g.render_region(W, H, flags=flags)
+    buf = rt.DeviceBuffer(0, W * H * 3)
+    assert len(buf.export()) == 64
+    fb = torch.as_tensor(buf, device="cuda")
+    fb.fill_(77)
+    g.render_tiles_peer(W, H, tw, th, 1, n, buf.ptr, None, flags)           # one rank only: the rest must keep the fill value
+    one = fb.cpu().numpy().reshape(-1, 3).copy()
+    i, j = (np.arange(W * H) % W, np.arange(W * H) // W) if layout == "row" else (np.arange(W * H) // H, np.arange(W * H) % H)
+    owner = ((j // th) * ((W + tw - 1) // tw) + i // tw) % n
+    assert (one[owner != 1] == 77).all() and np.array_equal(one[owner == 1], ref[owner == 1])
+    for r in range(n):
+        g.render_tiles_peer(W, H, tw, th, r, n, buf.ptr, None, flags)
+    torch.cuda.synchronize()
+    assert np.array_equal(fb.cpu().numpy().reshape(-1, 3), ref)
+    g.close()
+    del fb
+    buf.close()
+
+
+@pytest.mark.parametrize("W,H,tw,th,n,layout", [(352, 192, 32, 16, 3, "col"), (352, 192, 32, 16, 8, "row"), (333, 187, 32, 16, 4, "col"),
+                                               (3840, 2160, 32, 16, 8, "col"), (640, 360, 8, 4, 2, "row")])
+def test_fast_push_tiles_equals_region_render(rt, example_scene, W, H, tw, th, n, layout):
+    """rt_render_tiles_device + rt_push_tiles_device (what every rank does towards rank 0's framebuffer over NVLink): all ranks
+    emulated on one GPU pushing into ONE shareable buffer reproduce the region render; a single rank leaves every other
+    rank's bytes untouched (16-byte vector path for 4K, word and byte paths for the odd sizes)."""
+    import torch
+    flags = rt.LAYOUT_ROWMAJOR if layout == "row" else rt.LAYOUT_COLMAJOR
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    ref = g.render_region(W, H, flags=flags)
+    buf = rt.DeviceBuffer(0, W * H * 3)
+    fb = torch.as_tensor(buf, device="cuda")
+    fb.fill_(77)
+    per = rt.tiles_per_rank(W, H, tw, th, n)
+    tiles = torch.zeros(per * tw * th * 3, dtype=torch.uint8, device="cuda")
+    i, j = (np.arange(W * H) % W, np.arange(W * H) // W) if layout == "row" else (np.arange(W * H) // H, np.arange(W * H) % H)
+    owner = ((j // th) * ((W + tw - 1) // tw) + i // tw) % n
+    for r in [1] + [q for q in range(n) if q != 1]:
+        g.render_tiles_device(W, H, tw, th, r, n, tiles.data_ptr(), None)
+        g.push_tiles_device(W, H, tw, th, r, n, tiles.data_ptr(), buf.ptr, None, flags)
+        if r == 1:
+            one = fb.cpu().numpy().reshape(-1, 3)
+            assert (one[owner != 1] == 77).all() and np.array_equal(one[owner == 1], ref[owner == 1])
+    assert np.array_equal(fb.cpu().numpy().reshape(-1, 3), ref)
+    g.close()
+    del fb
+    buf.close()
+
+
 def test_fast_device_output_and_streams(rt, example_scene):
     import torch
     W, H = 320, 240
