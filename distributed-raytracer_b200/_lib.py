@@ -18,7 +18,7 @@ RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_STATE, RT_ERR_CANCELLED =
 ABI_SYMBOLS = (
     "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set",
     "rt_render_region", "rt_bulk_trace", "rt_render_region_debug", "rt_render_region_device", "rt_render_tiles_device",
-    "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
+    "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
     "rt_ipc_close", "rt_measure_fma_peak", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free",
 )
 
@@ -107,6 +107,8 @@ def load():
     L.rt_render_tiles_peer.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, vp, u32]
     L.rt_push_tiles_device.restype = C.c_int
     L.rt_push_tiles_device.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, u32]
+    L.rt_render_push_tiles.restype = C.c_int
+    L.rt_render_push_tiles.argtypes = [vp, C.POINTER(Camera), vp, u32, vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, u32]
     L.rt_device_alloc.restype = C.c_int
     L.rt_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
     L.rt_device_free.restype = C.c_int

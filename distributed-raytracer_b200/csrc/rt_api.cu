@@ -537,6 +537,34 @@ int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
     return RT_OK;
 }
 
+// rt_frame_set + rt_render_tiles_device + rt_push_tiles_device in one call (one lock, one ctypes/cgo crossing per frame)
+int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
+                         uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks, void *d_tiles, void *d_framebuffer,
+                         void *stream, uint32_t flags) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!d_tiles || !d_framebuffer || !stream) return fail(s, RT_ERR_INVALID, "rt_render_push_tiles: NULL buffer or stream");
+    if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "bad screen size");
+    if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4 || (size_t)tile_w * tile_h * 3 > 48 * 1024)
+        return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4 and at most 16384 pixels");
+    if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
+    std::lock_guard<std::mutex> lk(s->mu);
+    int rc = frame_set_locked(s, cam, lights, n_lights, obj_pos);
+    if (rc != RT_OK) return rc;
+    FrameParams fp = s->frame;
+    fp.W = (int)W; fp.H = (int)H; fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
+    fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
+    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
+    const uint32_t n_tiles = (uint32_t)fp.tiles_x * ((H + tile_h - 1) / tile_h);
+    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
+    fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
+    fp.tile_final = 0;
+    RenderOut o; o.d_rgb = (uint8_t *)d_tiles; o.ext_stream = (cudaStream_t)stream; o.async = true;
+    rc = render_locked(s, fp, flags & ~RT_LAYOUT_ROWMAJOR, (size_t)fp.n_local_tiles * tile_w * tile_h, o);
+    if (rc != RT_OK) return rc;
+    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, (cudaStream_t)stream));
+    return RT_OK;
+}
+
 // ---- device buffers shareable between the per-GPU processes of one box (CUDA IPC over NVLink / NVSwitch) ----
 int rt_device_alloc(int device, size_t bytes, void **out) {
     if (!out || bytes == 0) return fail(nullptr, RT_ERR_INVALID, "rt_device_alloc: bad argument");

@@ -50,6 +50,19 @@ def make_camera(cam13, tan_half_fov=float("nan")):
     return c
 
 
+class FrameState:
+    """Per-frame mutable state (camera, lights, object positions) marshalled ONCE into the C structs of the ABI, so that the
+    per-frame call is a single pointer hand-off (matters when a frame is ~0.1 ms)."""
+
+    def __init__(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan")):
+        self.cam = make_camera(cam13, tan_half_fov)
+        self._lights = _c(lights, np.float64).reshape(-1, 6)
+        self.n_lights = self._lights.shape[0]
+        self.lights_ptr = self._lights.ctypes.data if self._lights.size else None
+        self._obj = None if obj_pos is None else _c(obj_pos, np.float64)
+        self.obj_ptr = self._obj.ctypes.data if self._obj is not None else None
+
+
 class GpuScene:
     def __init__(self, scene, device=0, precision=_lib.FP32_FAST, flags=0):
         self._L = _lib.load()
@@ -119,6 +132,14 @@ class GpuScene:
 
     def push_tiles_device(self, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr=None, flags=0):
         self._check(self._L.rt_push_tiles_device(self.h, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags))
+
+    def render_push_tiles(self, frame, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags=0):
+        """frame = FrameState (prebuilt ctypes camera + lights): one C call per frame."""
+        self._check(self._L.rt_render_push_tiles(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr, W, H, tile_w,
+                                                 tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags))
+
+    def set_frame_state(self, frame):
+        self._check(self._L.rt_frame_set(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr))
 
     def untile_device(self, W, H, tile_w, tile_h, n_ranks, d_all_tiles_ptr, d_out_ptr, stream_ptr=None, flags=0):
         self._check(self._L.rt_untile_device(self.h, W, H, tile_w, tile_h, n_ranks, d_all_tiles_ptr, d_out_ptr, stream_ptr, flags))

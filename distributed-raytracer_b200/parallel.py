@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .gpu_scene import DeviceBuffer, GpuScene, tiles_per_rank
+from .gpu_scene import DeviceBuffer, FrameState, GpuScene, tiles_per_rank
 
 import os as _os
 _NO_BARRIER = bool(int(_os.environ.get("RT_B200_NO_BARRIER", "0")))   # timing experiments only: frames are then unsynchronised
@@ -103,6 +103,9 @@ class GpuTileBackend:
     def render_tiles_peer(self, slot, W, H, tw, th, rank, n_ranks, frame_ptr, flags=0):
         self.scenes[slot].render_tiles_peer(W, H, tw, th, rank, n_ranks, frame_ptr, self.streams[slot].cuda_stream, flags)
 
+    def render_push_tiles(self, slot, frame, W, H, tw, th, rank, n_ranks, tiles, frame_ptr, flags=0):
+        self.scenes[slot].render_push_tiles(frame, W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr, self.streams[slot].cuda_stream, flags)
+
     def push_tiles(self, slot, W, H, tw, th, rank, n_ranks, tiles, frame_ptr, flags=0):
         self.scenes[slot].push_tiles_device(W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr, self.streams[slot].cuda_stream, flags)
 
@@ -153,6 +156,7 @@ class TileShardedRenderer:
             self.frame = [self.backend.alloc(self.W * self.H * 3) if self.rank == 0 else None for _ in range(S)]
         self.seq = 0
         self.done_ev = [None] * S        # event: everything that read or wrote slot k's buffers is finished
+        self._events = [(torch.cuda.Event(), torch.cuda.Event()) for _ in range(S)] if self.pipelined else []
 
     def _init_peer(self, device_index):
         nbytes = self.W * self.H * 3
@@ -171,10 +175,14 @@ class TileShardedRenderer:
         torch.cuda.synchronize(self.backend.device)
         dist.barrier(group=self.group)
 
-    def render_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan"), flags=0):
-        """Enqueues one frame; asynchronous on CUDA."""
+    def render_frame(self, cam13, lights=None, obj_pos=None, tan_half_fov=float("nan"), flags=0):
+        """Enqueues one frame; asynchronous on CUDA.  `cam13` may be a prebuilt FrameState (then `lights` etc. are ignored)."""
         k = self.seq % self.S
         self.seq += 1
+        if self.pipelined and isinstance(cam13, FrameState):
+            return self._render_frame_fast(k, cam13, flags)
+        if isinstance(cam13, FrameState):
+            raise TypeError("FrameState needs the pipelined GPU backend")
         if not self.pipelined:
             # injected (test) backend: plain sequential path on the current stream
             self.backend.set_frame(cam13, lights, obj_pos, tan_half_fov)
@@ -225,6 +233,33 @@ class TileShardedRenderer:
             if self.rank == 0:
                 be.untile(self.W, self.H, self.tw, self.th, self.n_ranks, self.gathered[k], self.frame[k], self.layout_flags)
             done = torch.cuda.Event()
+            done.record(comm)
+        self.done_ev[k] = done
+        return self.frame[k]
+
+    def _render_frame_fast(self, k, frame, flags):
+        be = self.backend
+        st = be.streams[k]
+        if self.done_ev[k] is not None:
+            st.wait_event(self.done_ev[k])
+        if self.n_ranks == 1:
+            be.scenes[k].set_frame_state(frame)
+            be.render_region(k, self.W, self.H, self.frame[k], flags | self.layout_flags)
+            ev = self._events[k][0]
+            ev.record(st)
+            self.done_ev[k] = ev
+            return self.frame[k]
+        if self.mode != "peer":
+            raise RuntimeError("FrameState fast path is implemented for the peer mode")
+        be.render_push_tiles(k, frame, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], self.peer_bufs[k].ptr,
+                             flags | self.layout_flags)
+        ev, done = self._events[k]
+        ev.record(st)
+        comm = be.comm_stream
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            if not _NO_BARRIER:
+                dist.all_reduce(self.flag, group=self.group)
             done.record(comm)
         self.done_ev[k] = done
         return self.frame[k]

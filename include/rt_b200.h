@@ -180,6 +180,11 @@ int rt_render_tiles_peer(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, 
 int rt_push_tiles_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h,
                          uint32_t rank, uint32_t n_ranks, const void *d_tiles, void *d_framebuffer, void *stream,
                          uint32_t flags);
+/* rt_frame_set + rt_render_tiles_device + rt_push_tiles_device in ONE call (the per-frame call of a rank in the multi-GPU
+ * pipeline: at 8 GPUs a frame is ~0.12 ms, so host crossings matter).  Asynchronous: `stream` must not be NULL. */
+int rt_render_push_tiles(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos,
+                         uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
+                         void *d_tiles, void *d_framebuffer, void *stream, uint32_t flags);
 /* Device buffers shareable between the one-process-per-GPU ranks of a box (CUDA IPC; 64-byte opaque handles) */
 int rt_device_alloc(int device, size_t bytes, void **out);
 int rt_device_free(int device, void *p);
