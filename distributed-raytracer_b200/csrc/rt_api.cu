@@ -301,7 +301,8 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
     if (out.h_obj) CU(s, cudaMemcpyAsync(out.h_obj, job.d_out_obj, sizeof(int32_t) * npix_out, cudaMemcpyDeviceToHost, st));
     if (out.h_lit) CU(s, cudaMemcpyAsync(out.h_lit, job.d_out_lit, sizeof(uint32_t) * npix_out, cudaMemcpyDeviceToHost, st));
     CU(s, cudaStreamSynchronize(st));
-    collect_stats(s);
+    // counters and event times are read lazily by rt_get_stats: two blocking device->host copies per call would be on
+    // the critical path of concurrent BulkTrace callers
     return RT_OK;
 }
 

@@ -175,12 +175,14 @@ class TileShardedRenderer:
         torch.cuda.synchronize(self.backend.device)
         dist.barrier(group=self.group)
 
-    def render_frame(self, cam13, lights=None, obj_pos=None, tan_half_fov=float("nan"), flags=0):
-        """Enqueues one frame; asynchronous on CUDA.  `cam13` may be a prebuilt FrameState (then `lights` etc. are ignored)."""
+    def render_frame(self, cam13, lights=None, obj_pos=None, tan_half_fov=float("nan"), flags=0, to_host=False):
+        """Enqueues one frame; asynchronous on CUDA.  `cam13` may be a prebuilt FrameState (then `lights` etc. are ignored).
+        to_host (FrameState path): rank 0 also copies the finished framebuffer into its pinned host buffer
+        `host_frame[slot]` (returned instead of the device tensor); valid after wait() + synchronize."""
         k = self.seq % self.S
         self.seq += 1
         if self.pipelined and isinstance(cam13, FrameState):
-            return self._render_frame_fast(k, cam13, flags)
+            return self._render_frame_fast(k, cam13, flags, to_host)
         if isinstance(cam13, FrameState):
             raise TypeError("FrameState needs the pipelined GPU backend")
         if not self.pipelined:
@@ -237,18 +239,32 @@ class TileShardedRenderer:
         self.done_ev[k] = done
         return self.frame[k]
 
-    def _render_frame_fast(self, k, frame, flags):
+    def _host_frames(self):
+        if not hasattr(self, "host_frame"):
+            self.host_frame = [torch.empty(self.W * self.H * 3, dtype=torch.uint8, pin_memory=True) if self.rank == 0 else None
+                               for _ in range(self.S)]
+        return self.host_frame
+
+    def _render_frame_fast(self, k, frame, flags, to_host=False):
         be = self.backend
         st = be.streams[k]
-        if self.done_ev[k] is not None:
-            st.wait_event(self.done_ev[k])
+        # Slot reuse.  Device-only frames: wait for the barrier of the frame that used this slot S frames ago.  With the
+        # device->host copy on rank 0, the copy of frame f sits between the barriers of f and f+1 on rank 0's communication
+        # stream, so "barrier of frame f+1 has completed" (a collective: it needs rank 0) tells EVERY rank that rank 0 has
+        # finished reading slot k -- hence the wait on the next slot's event.
+        gate = self.done_ev[(k + 1) % self.S] if (to_host and self.S > 1) else self.done_ev[k]
+        if gate is not None:
+            st.wait_event(gate)
         if self.n_ranks == 1:
             be.scenes[k].set_frame_state(frame)
             be.render_region(k, self.W, self.H, self.frame[k], flags | self.layout_flags)
             ev = self._events[k][0]
+            if to_host:
+                with torch.cuda.stream(st):
+                    self._host_frames()[k].copy_(self.frame[k], non_blocking=True)
             ev.record(st)
             self.done_ev[k] = ev
-            return self.frame[k]
+            return self._host_frames()[k] if to_host else self.frame[k]
         if self.mode != "peer":
             raise RuntimeError("FrameState fast path is implemented for the peer mode")
         be.render_push_tiles(k, frame, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], self.peer_bufs[k].ptr,
@@ -260,8 +276,12 @@ class TileShardedRenderer:
         with torch.cuda.stream(comm):
             if not _NO_BARRIER:
                 dist.all_reduce(self.flag, group=self.group)
+            if to_host and self.rank == 0:
+                self._host_frames()[k].copy_(self.frame[k], non_blocking=True)
             done.record(comm)
         self.done_ev[k] = done
+        if to_host:
+            return self._host_frames()[k]
         return self.frame[k]
 
     def _single_local(self):
