@@ -190,18 +190,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     import __graft_entry__ as ge
-    if rank == 0:
-        ge.build()
     if args.impl == "reference":
+        if rank == 0:
+            ge.build()
         run_reference(args, rank)
         return
 
     import numpy as np
     import torch
     import torch.distributed as dist
-    import distributed_raytracer_b200 as rt
-    from distributed_raytracer_b200 import host, parallel
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the render backend has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -209,7 +206,13 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    # rank 0 (re)builds the native libraries if needed; the other ranks must not load them while they are being written
+    if rank == 0:
+        ge.build()
+    if world > 1:
         dist.barrier()
+    import distributed_raytracer_b200 as rt
+    from distributed_raytracer_b200 import host, parallel
 
     render_flags = rt.FLAG_PERSISTENT if args.persistent else 0
     sc = build_workload() if rank == 0 else None

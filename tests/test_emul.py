@@ -83,6 +83,30 @@ def test_exact_replay_with_duplicate_triangles():
     check_exact(sc, 64, 48, max_leaf=1)
 
 
+def soup_config_scene(n_tris, example_scene, n_lights=8, angle_deg=0.0):
+    """Config-4-shaped scene at test size: random soup (no normals, default material), ring of white lights, orbit camera."""
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.triangle_soup(n_tris, half=0.05)]
+    sc["lights"] = workloads.ring_lights(n_lights)
+    sc["camera"] = workloads.orbit_camera([1.0, 1.0, -1.0], 6.0, np.deg2rad(angle_deg), 0.5, 1.04719755)
+    return sc
+
+
+def test_exact_replay_soup_flat_normals_eight_lights(example_scene):
+    sc = soup_config_scene(5000, example_scene, angle_deg=33.0)
+    st = check_exact(sc, 120, 68)
+    assert st["hit_pixels"] > 500 and st["shadow_rays"] == 8 * st["hit_pixels"]
+
+
+def test_orbit_camera_matches_reference_basis(example_scene):
+    # workloads.orbit_camera builds the basis exactly like state.NewCamera (camera.go:35-44)
+    from oracle import scene_loader as sl
+    cam = workloads.orbit_camera([1.0, 1.0, -1.0], 6.0, np.deg2rad(57.0), 0.3, 1.0)
+    ref = sl.new_camera(cam[0:3], np.array([1.0, 1.0, -1.0]) - cam[0:3], 1.0)
+    assert np.array_equal(cam.view(np.uint64), ref.view(np.uint64))
+    assert np.array_equal(workloads.orbit_camera([1.0, 1.0, -1.0], 6.0, 0.0, 0.0, 1.04719755)[0:3], example_scene["camera"][0:3])
+
+
 def test_fast_replay_within_tolerance(example_scene):
     within, same_face = check_fast(example_scene, 320, 240)
     assert within >= 0.999 and same_face >= 0.999       # north_star: <= 1 LSB on >= 99.9 % of the pixels

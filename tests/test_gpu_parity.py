@@ -88,6 +88,20 @@ def test_exact_random_scenes(rt, kw):
     assert st["hit_pixels"] > 0
 
 
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_soup_flat_normals_eight_lights_orbit_camera(rt, example_scene, precision):
+    """Config-4-shaped scene at test size (random soup without vertex normals => Triangle.Normal path, default material, 8 white
+    lights on a ring) seen from a rotated orbit camera (config 5)."""
+    from test_emul import soup_config_scene
+    sc = soup_config_scene(20000, example_scene, angle_deg=33.0)
+    if precision == "exact":
+        st = assert_exact(rt, sc, 320, 180)
+        assert st["hit_pixels"] > 2000 and st["shadow_rays"] == 8 * st["hit_pixels"]
+    else:
+        within, same, _, _ = fast_fractions(rt, sc, 320, 180)
+        assert within >= 0.995 and same >= 0.995      # a soup of tiny triangles is all silhouette
+
+
 def test_exact_duplicate_triangles_tie_break(rt):
     sc = random_soup_scene(n_tris=20, seed=21)
     m = sc["meshes"][0]
