@@ -344,6 +344,62 @@ def test_errors_and_lifecycle(rt, example_scene):
     assert (np.abs(moved.astype(int) - rgb_o.astype(int)).max(axis=1) <= 1).mean() >= 0.99
 
 
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_many_lights_and_objects_use_the_device_frame_path(rt, precision):
+    """More than 8 lights / 4 objects do not fit the by-value frame parameters: the library then keeps them in device memory
+    (synchronised uploads).  Same parity bar."""
+    sc = random_soup_scene(n_tris=120, seed=41, n_obj=3, n_lights=4, with_normals=True)
+    rng = np.random.default_rng(3)
+    sc["lights"] = np.concatenate([sc["lights"], np.column_stack([rng.uniform(-8, 8, (7, 2)), np.full(7, 9.0), rng.uniform(0, 1, (7, 3)).round(2)])])
+    sc["obj_pos"] = np.concatenate([sc["obj_pos"], [[1.6, 1.1, -0.5], [-1.7, -1.2, 0.3], [0.1, 1.9, -2.0]]])
+    sc["obj_mesh"] = np.zeros(6, dtype=np.uint32)
+    assert sc["lights"].shape[0] == 11 and sc["obj_pos"].shape[0] == 6
+    if precision == "exact":
+        st = assert_exact(rt, sc, 160, 120)
+        assert st["shadow_rays"] == 11 * st["hit_pixels"]
+    else:
+        within, same, _, _ = fast_fractions(rt, sc, 160, 120)
+        assert within >= 0.99 and same >= 0.99
+    # moving the objects per frame through the device path
+    g = rt.GpuScene(sc, precision=rt.FP64_EXACT)
+    moved = sc["obj_pos"] + [0.2, -0.1, 0.05]
+    rgb = g.bulk_trace(sc["camera"], sc["lights"], 96, 72, 0, 0, 96, 72, obj_pos=moved)
+    g.close()
+    S = orc.Scene(sc)
+    S.set_frame(sc["camera"], sc["lights"], obj_pos=moved)
+    rgb_o, _, _, _ = S.render_region(96, 72)
+    assert np.array_equal(rgb, rgb_o)
+
+
+def test_concurrent_bulk_trace_on_one_handle(rt, example_scene):
+    """gRPC serves every BulkTrace on its own goroutine (final_report.pdf p.6): concurrent calls on ONE handle, with different
+    frame states and regions, must each get their own consistent result (rt_bulk_trace = frame_set + render under one lock)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from distributed_raytracer_b200 import workloads
+    W, H = 192, 108
+    cams = [workloads.orbit_camera([1.0, 1.0, -1.0], 6.0, np.deg2rad(20.0 * k), 0.2 * k, 1.04719755) for k in range(4)]
+    rects = [(0, 0, 96, 108), (96, 0, 96, 108), (0, 0, 192, 54), (48, 27, 100, 60)]
+    S = orc.Scene(example_scene)
+    want = []
+    for cam, (x, y, w, h) in zip(cams, rects):
+        S.set_frame(cam, example_scene["lights"])
+        want.append(S.render_region(W, H, x, y, w, h)[0])
+    g = rt.GpuScene(example_scene, precision=rt.FP64_EXACT)
+
+    def call(k):
+        out = []
+        for _ in range(25):
+            x, y, w, h = rects[k]
+            out.append(g.bulk_trace(cams[k], example_scene["lights"], W, H, x, y, w, h).copy())
+        return out
+    with ThreadPoolExecutor(4) as pool:
+        got = list(pool.map(call, range(4)))
+    g.close()
+    for k in range(4):
+        for res in got[k]:
+            assert np.array_equal(res, want[k])
+
+
 def test_host_tracer_bulk_trace_and_draw(rt, example_scene):
     """The reference-facing interface: Tracer.BulkTrace (distributed/main.go:46-91) over partition() rectangles
     (master/main.go:54-91) reassembles into the same screen as draw() (sequential/main.go:15-32)."""
