@@ -204,6 +204,72 @@ __global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView s
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4, split form (RT_B200_SPLIT_SHADE=1): the same arithmetic as k_shade in three kernels, so that the fp64 parts run with
+// fully converged warps and the shadow rays get a lean, high-occupancy traversal kernel with one thread per (hit, light):
+//   k_hit_geometry : per hit   -- fp64 re-intersection of the winner, normal                      -> hit_geom (P, N)
+//   k_shadow       : per (hit, light), light-major so that a warp holds 32 neighbouring hits of ONE light -> lit bits
+//   k_phong        : per hit   -- Phong accumulation over the lights in order, using the lit bits  -> hit colour
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_hit_geometry(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
+                                                       const HitRec *__restrict__ hits, const unsigned int *counters,
+                                                       double *__restrict__ hit_geom, uint32_t *__restrict__ hit_lit) {
+    const SceneView sc = bind_frame(sc_in, fr);
+    const unsigned int nhits = counters[1];
+    for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < nhits; h += gridDim.x * blockDim.x) {
+        HitRec hr = hits[h];
+        PixMap pm = map_ray(hr.pix, fp, false);
+        HitGeom g = hit_geometry(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t);
+        double *q = hit_geom + 6 * (size_t)h;
+        q[0] = g.P.x; q[1] = g.P.y; q[2] = g.P.z; q[3] = g.N.x; q[4] = g.N.y; q[5] = g.N.z;
+        hit_lit[h] = 0u;
+    }
+}
+
+template <bool EXACT, bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr, bool brute,
+                                                 const HitRec *__restrict__ hits, unsigned int *counters,
+                                                 const double *__restrict__ hit_geom, uint32_t *hit_lit, Counters *gstats) {
+    const SceneView sc = bind_frame(sc_in, fr);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned int nhits = counters[1];
+    const unsigned long long npairs = (unsigned long long)nhits * (unsigned long long)fp.n_lights;
+    Counters c; c.nodes = 0; c.tris = 0;
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&counters[2], 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= npairs) break;
+        unsigned long long q = (unsigned long long)base + lane;
+        if (q < npairs) {
+            const int l = (int)(q / nhits);
+            const unsigned h = (unsigned)(q % nhits);
+            const double *g = hit_geom + 6 * (size_t)h;
+            dv Ld;
+            if (light_visible<EXACT>(sc, fp, dv_make(g[0], g[1], g[2]), hits[h].obj, l, brute, Ld, COUNT ? &c : nullptr))
+                atomicOr(&hit_lit[h], 1u << l);
+        }
+    }
+    if (COUNT) flush_counters(gstats ? gstats + 1 : nullptr, c);
+}
+
+__global__ void __launch_bounds__(128) k_phong(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
+                                                const HitRec *__restrict__ hits, const unsigned int *counters,
+                                                const double *__restrict__ hit_geom, const uint32_t *__restrict__ hit_lit,
+                                                double *__restrict__ hit_colour) {
+    const SceneView sc = bind_frame(sc_in, fr);
+    const unsigned int nhits = counters[1];
+    for (unsigned h = blockIdx.x * blockDim.x + threadIdx.x; h < nhits; h += gridDim.x * blockDim.x) {
+        HitRec hr = hits[h];
+        const double *q = hit_geom + 6 * (size_t)h;
+        HitGeom g;
+        g.P = dv_make(q[0], q[1], q[2]); g.N = dv_make(q[3], q[4], q[5]);
+        double col[3];
+        phong_from_mask(sc, fp, g, hit_material(sc, hr.obj, hr.face), hit_lit[h], col);
+        hit_colour[3 * (size_t)h] = col[0]; hit_colour[3 * (size_t)h + 1] = col[1]; hit_colour[3 * (size_t)h + 2] = col[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5: 8-bit framebuffer writer.  Misses were pre-cleared (sequential/main.go:17 FillRect(nil,0);
 // distributed/main.go:70 default 0,0,0).  Quantisers: colour.go:59-61 and colour.go:54-56 (+ SDL >>8).
 // ---------------------------------------------------------------------------------------------
@@ -459,6 +525,19 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
     const unsigned g = (unsigned)job.sm_count * 8u;
+    if (job.split_shade && fp.n_lights <= 32 && job.d_hit_geom) {
+        k_hit_geometry<<<g, 128, 0, st>>>(fp, sc, job.fr, job.d_hits, job.d_counters, job.d_hit_geom, job.d_hit_lit);
+        const unsigned gs = (unsigned)job.sm_count * 12u;
+        if (job.precision == RT_FP64_EXACT) {
+            if (count) k_shadow<true, true><<<gs, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_hit_geom, job.d_hit_lit, job.d_stats);
+            else k_shadow<true, false><<<gs, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_hit_geom, job.d_hit_lit, job.d_stats);
+        } else {
+            if (count) k_shadow<false, true><<<gs, 128, 0, st>>>(fp, sc, job.fr, false, job.d_hits, job.d_counters, job.d_hit_geom, job.d_hit_lit, job.d_stats);
+            else k_shadow<false, false><<<gs, 128, 0, st>>>(fp, sc, job.fr, false, job.d_hits, job.d_counters, job.d_hit_geom, job.d_hit_lit, job.d_stats);
+        }
+        k_phong<<<g, 128, 0, st>>>(fp, sc, job.fr, job.d_hits, job.d_counters, job.d_hit_geom, job.d_hit_lit, job.d_hit_colour);
+        return cudaGetLastError();
+    }
 #define LAUNCH_SHADE(EX, CN, MB) k_shade<EX, CN, MB><<<g, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats)
     if (job.precision == RT_FP64_EXACT) {
         if (count) LAUNCH_SHADE(true, true, 1); else LAUNCH_SHADE(true, false, 1);

@@ -39,6 +39,7 @@ struct rt_scene {
 
     // scratch
     HitRec *d_hits = nullptr; double *d_hit_colour = nullptr; uint32_t *d_hit_lit = nullptr; size_t cap_rays = 0;
+    double *d_hit_geom = nullptr; bool split_shade = false;
     unsigned int *d_counters = nullptr; Counters *d_stats = nullptr;
     uint8_t *d_rgb = nullptr; size_t cap_rgb = 0;
     double *d_dbg_colour = nullptr; int32_t *d_dbg_face = nullptr, *d_dbg_obj = nullptr; uint32_t *d_dbg_lit = nullptr;
@@ -80,7 +81,7 @@ void destroy_locked(rt_scene *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (auto &m : s->meshes) free_mesh(m);
     cudaFree(s->d_meshes); cudaFree(s->d_objs); cudaFree(s->d_lights);
-    cudaFree(s->d_hits); cudaFree(s->d_hit_colour); cudaFree(s->d_hit_lit); cudaFree(s->d_counters); cudaFree(s->d_stats);
+    cudaFree(s->d_hits); cudaFree(s->d_hit_colour); cudaFree(s->d_hit_lit); cudaFree(s->d_hit_geom); cudaFree(s->d_counters); cudaFree(s->d_stats);
     cudaFree(s->d_rgb); cudaFree(s->d_dbg_colour); cudaFree(s->d_dbg_face); cudaFree(s->d_dbg_obj); cudaFree(s->d_dbg_lit);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
@@ -121,11 +122,12 @@ int flatten_mesh(const rt_mesh_desc &d, std::vector<double> &fverts, std::vector
 
 int ensure_scratch(rt_scene *s, size_t nrays, size_t out_bytes, bool need_rgb, bool dbg, size_t npix_out) {
     if (nrays > s->cap_rays) {
-        cudaFree(s->d_hits); cudaFree(s->d_hit_colour); cudaFree(s->d_hit_lit);
-        s->d_hits = nullptr; s->d_hit_colour = nullptr; s->d_hit_lit = nullptr; s->cap_rays = 0;
+        cudaFree(s->d_hits); cudaFree(s->d_hit_colour); cudaFree(s->d_hit_lit); cudaFree(s->d_hit_geom);
+        s->d_hits = nullptr; s->d_hit_colour = nullptr; s->d_hit_lit = nullptr; s->d_hit_geom = nullptr; s->cap_rays = 0;
         CU(s, cudaMalloc((void **)&s->d_hits, sizeof(HitRec) * nrays));
         CU(s, cudaMalloc((void **)&s->d_hit_colour, sizeof(double) * 3 * nrays));
         CU(s, cudaMalloc((void **)&s->d_hit_lit, sizeof(uint32_t) * nrays));
+        if (s->split_shade) CU(s, cudaMalloc((void **)&s->d_hit_geom, sizeof(double) * 6 * nrays));
         s->cap_rays = nrays;
     }
     if (need_rgb && out_bytes > s->cap_rgb) {
@@ -233,6 +235,7 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
     job.fr = s->inline_frame;
     job.precision = s->precision; job.flags = flags;
     job.d_hits = s->d_hits; job.d_hit_colour = s->d_hit_colour; job.d_hit_lit = s->d_hit_lit;
+    job.d_hit_geom = s->d_hit_geom; job.split_shade = s->split_shade;
     job.d_counters = s->d_counters; job.d_stats = s->d_stats;
     job.d_out_rgb = d_rgb;
     job.d_out_colour = out.h_colour ? s->d_dbg_colour : nullptr;
@@ -354,6 +357,7 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->max_leaf = env_int("RT_B200_MAX_LEAF", 4);
     s->shade_minb = env_int("RT_B200_SHADE_MINB", 8);
     s->primary_persistent = env_int("RT_B200_PERSISTENT", 0) != 0;
+    s->split_shade = env_int("RT_B200_SPLIT_SHADE", 0) != 0;
     s->top_in_smem = env_int("RT_B200_TOP_SMEM", 0) != 0;
     s->refill_below = env_int("RT_B200_REFILL", 1);
     memset(&s->stats, 0, sizeof s->stats);

@@ -41,6 +41,8 @@ struct RenderJob {
     HitRec   *d_hits;         // capacity = ray_count
     double   *d_hit_colour;   // 3 per hit
     uint32_t *d_hit_lit;      // per hit
+    double   *d_hit_geom;     // split K4: 6 per hit (P, N) or nullptr
+    bool      split_shade;
     unsigned int *d_counters; // [0]=next ray (primary), [1]=hit count, [2]=next hit (shade), [3]=next hit (write)
     Counters *d_stats;        // [0] = K2 primary, [1] = K4 shadow rays (filled with RT_FLAG_COUNT)
     // outputs (device)

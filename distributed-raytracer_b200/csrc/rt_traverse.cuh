@@ -330,9 +330,9 @@ RT_HD bool trace_fast_nearest(const SceneView &sc, const FrameParams &fp, dv o, 
 // ------------------------------------------------------------------------------------------------
 // shading of one primary hit (both modes): tracer.go:53-77.  Returns the lit mask.
 // ------------------------------------------------------------------------------------------------
-template <bool EXACT>
-RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int j, int obj, int face, float t32,
-                         bool brute, double col[3], Counters *cnt) {
+// geometry of one primary hit in the reference's arithmetic: world hit point (object.go:109) and normal (object.go:90-95)
+struct HitGeom { dv P, N; };
+RT_HD HitGeom hit_geometry(const SceneView &sc, const FrameParams &fp, int i, int j, int obj, int face, float t32) {
     dv cam = dv_ld(fp.cam_pos);
     dv d = primary_dir_exact(i, j, fp);                                         // tracer.go:86
     const ObjRec &ob = sc.objs[obj];
@@ -347,40 +347,77 @@ RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int 
             h.t = (double)t32; h.ip = dv_add(ol, dv_scale(d, h.t)); h.r1 = 1.0; h.r2 = 0.0; h.r3 = 0.0;
         }
     }
-    dv P = dv_add(h.ip, pos);                                                    // object.go:109
-    dv N = hit_normal_exact(m, face, h.r1, h.r2, h.r3);                          // object.go:90-95
-    const double *mat = m.materials + 10 * (size_t)m.fmat[face];
+    HitGeom g;
+    g.P = dv_add(h.ip, pos);                                                     // object.go:109
+    g.N = hit_normal_exact(m, face, h.r1, h.r2, h.r3);                           // object.go:90-95
+    return g;
+}
+
+// tracer.go:61-64 : is light l visible from hit point P of object `obj`?  Ld = unit vector towards the light.
+template <bool EXACT>
+RT_HD bool light_visible(const SceneView &sc, const FrameParams &fp, dv P, int obj, int l, bool brute, dv &Ld, Counters *cnt) {
+    const LightRec &L = sc.lights[l];
+    dv Lv = dv_sub(dv_ld(L.pos), P);
+    Ld = dv_norm(Lv);                                                            // tracer.go:61
+    dv so = dv_add(P, dv_scale(Ld, RT_SHADOW_BIAS));                             // tracer.go:64
+    double lightLen = dv_len(Lv);
+    if (EXACT) {
+        TraceExact s;
+        bool shaded = trace_exact(sc, fp, so, Ld, brute, s, cnt);
+        return !shaded || lightLen < dv_len(dv_sub(s.ip, P));                    // tracer.go:64
+    } else if (fp.n_obj == 1) {
+        // one object: "nearest hit, then compare with the light distance" == any hit with
+        // t + bias <= lightLen  
+        const ObjRec &ob = sc.objs[obj];
+        RayF r = make_rayf((float)(so.x - ob.pos[0]), (float)(so.y - ob.pos[1]), (float)(so.z - ob.pos[2]), (float)Ld.x,
+                           (float)Ld.y, (float)Ld.z);
+        float tmax = (float)(lightLen - RT_SHADOW_BIAS);
+        int f = -1;
+        return !mesh_trace_fast<true>(sc.meshes[ob.mesh], r, tmax, f, cnt);
+    } else {
+        TraceFast s;
+        bool shaded = trace_fast_nearest(sc, fp, so, Ld, false, s, cnt);
+        return !shaded || lightLen < (double)s.t + RT_SHADOW_BIAS;
+    }
+}
+
+RT_HD const double *hit_material(const SceneView &sc, int obj, int face) {
+    const MeshView &m = sc.meshes[sc.objs[obj].mesh];
+    return m.materials + 10 * (size_t)m.fmat[face];
+}
+
+// tracer.go:53-77 with the shadow queries already answered (lit_mask bit l = light l visible): lights in order
+RT_HD void phong_from_mask(const SceneView &sc, const FrameParams &fp, const HitGeom &g, const double *mat, uint32_t lit_mask,
+                           double col[3]) {
+    dv cam = dv_ld(fp.cam_pos);
+    double c[3] = { mat[0], mat[1], mat[2] };                                    // tracer.go:56
+    for (int l = 0; l < fp.n_lights; l++) {
+        if ((lit_mask >> l) & 1u) {
+            const LightRec &L = sc.lights[l];
+            dv Ld = dv_norm(dv_sub(dv_ld(L.pos), g.P));                          // tracer.go:61 (same bits as in light_visible)
+            phong_light_exact(c, mat, g.N, Ld, cam, g.P, L.col);                 // tracer.go:65-72
+        }
+    }
+    col[0] = c[0]; col[1] = c[1]; col[2] = c[2];
+}
+
+// fused form: geometry, one shadow query per light, Phong accumulation (both modes).  Returns the lit mask.
+template <bool EXACT>
+RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int j, int obj, int face, float t32,
+                         bool brute, double col[3], Counters *cnt) {
+    dv cam = dv_ld(fp.cam_pos);
+    HitGeom g = hit_geometry(sc, fp, i, j, obj, face, t32);
+    const double *mat = hit_material(sc, obj, face);
     double c[3] = { mat[0], mat[1], mat[2] };                                    // tracer.go:56
     uint32_t lit_mask = 0;
     for (int l = 0; l < fp.n_lights; l++) {
         RT_SYNCWARP();                       // every lane of the warp runs this loop (k_shade): reconverge per light
-        const LightRec &L = sc.lights[l];
-        dv Lv = dv_sub(dv_ld(L.pos), P);
-        dv Ld = dv_norm(Lv);                                                     // tracer.go:61
-        dv so = dv_add(P, dv_scale(Ld, RT_SHADOW_BIAS));                         // tracer.go:64
-        double lightLen = dv_len(Lv);
-        bool lit;
-        if (EXACT) {
-            TraceExact s;
-            bool shaded = trace_exact(sc, fp, so, Ld, brute, s, cnt);
-            lit = !shaded || lightLen < dv_len(dv_sub(s.ip, P));                 // tracer.go:64
-        } else if (fp.n_obj == 1) {
-            // one object: "nearest hit, then compare with the light distance" == any hit with
-            // t + bias <= lightLen  
-            RayF r = make_rayf((float)(so.x - pos.x), (float)(so.y - pos.y), (float)(so.z - pos.z), (float)Ld.x,
-                               (float)Ld.y, (float)Ld.z);
-            float tmax = (float)(lightLen - RT_SHADOW_BIAS);
-            int f = -1;
-            lit = !mesh_trace_fast<true>(m, r, tmax, f, cnt);
-        } else {
-            TraceFast s;
-            bool shaded = trace_fast_nearest(sc, fp, so, Ld, false, s, cnt);
-            lit = !shaded || lightLen < (double)s.t + RT_SHADOW_BIAS;
-        }
+        dv Ld;
+        bool lit = light_visible<EXACT>(sc, fp, g.P, obj, l, brute, Ld, cnt);
         RT_SYNCWARP();
         if (lit) {
             lit_mask |= 1u << (l & 31);
-            phong_light_exact(c, mat, N, Ld, cam, P, L.col);                     // tracer.go:65-72
+            phong_light_exact(c, mat, g.N, Ld, cam, g.P, sc.lights[l].col);      // tracer.go:65-72
         }
     }
     col[0] = c[0]; col[1] = c[1]; col[2] = c[2];
