@@ -12,11 +12,16 @@ LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0x0, 0x1
 QUANT_RGB255, QUANT_RGBA16_SHR8 = 0x0, 0x2
 FLAG_COUNT, FLAG_BRUTE_FORCE, FLAG_SIMPLE, FLAG_PERSISTENT = 0x4, 0x8, 0x10, 0x20
 
+
+def LANE(k):
+    """RT_LANE(k): lane selector of the device API, carried in bits 24..31 of `flags`."""
+    return int(k) << 24
+
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_STATE, RT_ERR_CANCELLED = 0, -1, -2, -3, -4, -5
 
 # every symbol include/rt_b200.h declares
 ABI_SYMBOLS = (
-    "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set",
+    "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set", "rt_frame_set_lane", "rt_lane_count",
     "rt_render_region", "rt_bulk_trace", "rt_render_region_debug", "rt_render_region_device", "rt_render_tiles_device",
     "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
     "rt_ipc_close", "rt_measure_fma_peak", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free",
@@ -93,6 +98,10 @@ def load():
     L.rt_device_count.restype = C.c_int
     L.rt_frame_set.restype = C.c_int
     L.rt_frame_set.argtypes = [vp, C.POINTER(Camera), vp, u32, vp]
+    L.rt_frame_set_lane.restype = C.c_int
+    L.rt_frame_set_lane.argtypes = [vp, u32, C.POINTER(Camera), vp, u32, vp]
+    L.rt_lane_count.restype = C.c_int
+    L.rt_lane_count.argtypes = [vp]
     L.rt_render_region.restype = C.c_int
     L.rt_render_region.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, u32]
     L.rt_bulk_trace.restype = C.c_int

@@ -4,51 +4,71 @@
 //   rt_scene_create   <- register():        worker/distributed/main.go:101-129 (immutable meshes arrive once)
 //   rt_frame_set      <- BulkTrace diff:    worker/distributed/main.go:56-64  (camera, lights, object positions)
 //   rt_render_region  <- BulkTrace loop:    worker/distributed/main.go:67-88  /  draw(): worker/sequential/main.go:21-28
+//   rt_bulk_trace     <- one BulkTrace RPC: both of the above for one WorkOrder, concurrently callable
 // No CPU fallback exists: every path below needs a CUDA device and the sm_100a kernels.
 #include "rt_internal.h"
 #include "go_math.h"
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include <new>
 
-struct rt_scene {
+// Per-call mutable resources.  The reference worker serves every BulkTrace RPC on its own goroutine against ONE immutable
+// scene (worker/distributed/main.go:27-32: "No lock here because we never mutate this data"); a Lane is what one such call
+// needs on the GPU: a stream, timing events, the hit-list scratch, staging buffers and its own copy of the frame state.
+// Lane 0 belongs to the stateful two-call API (rt_frame_set + rt_render_*) and is the default of the device API; lanes >= 1
+// form the pool that concurrent rt_bulk_trace calls draw from.  Scratch is allocated on a lane's first use.
+struct Lane {
     std::mutex mu;
-    std::string err;
-    int device = 0;
-    uint32_t precision = RT_FP32_FAST;
+    bool busy = false;                 // pool bookkeeping (guarded by rt_scene::mu)
     cudaStream_t stream = nullptr;
-    int sm_count = 148;
-    int max_leaf = 4;
-    bool top_in_smem = true;
-    int refill_below = 24;
-    int shade_minb = 8;
-    bool primary_persistent = false;
-
-    std::vector<MeshDevice> meshes;
-    std::vector<MeshView> h_views;
-    MeshView *d_meshes = nullptr;
-    std::vector<ObjRec> h_objs;
-    ObjRec *d_objs = nullptr;
-    LightRec *d_lights = nullptr;
-    uint32_t n_lights = 0, cap_lights = 0;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    // frame state of the call in flight (environment.go:65-69)
     FrameParams frame;
     InlineFrame inline_frame;
     bool have_frame = false;
-
+    std::vector<ObjRec> h_objs;
+    ObjRec *d_objs = nullptr;
+    LightRec *d_lights = nullptr;
+    uint32_t cap_lights = 0;
     // scratch
-    HitRec *d_hits = nullptr; double *d_hit_colour = nullptr; uint32_t *d_hit_lit = nullptr; size_t cap_rays = 0;
-    double *d_hit_geom = nullptr; bool split_shade = false;
+    HitRec *d_hits = nullptr; double *d_hit_colour = nullptr; uint32_t *d_hit_lit = nullptr; double *d_hit_geom = nullptr;
+    size_t cap_rays = 0;
     unsigned int *d_counters = nullptr; Counters *d_stats = nullptr;
     uint8_t *d_rgb = nullptr; size_t cap_rgb = 0;
     double *d_dbg_colour = nullptr; int32_t *d_dbg_face = nullptr, *d_dbg_obj = nullptr; uint32_t *d_dbg_lit = nullptr;
     size_t cap_dbg = 0;
     uint8_t *h_pinned = nullptr; size_t cap_pinned = 0;
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t last_stream = nullptr;
     bool stats_pending = false;
     rt_stats stats;
+};
+
+struct rt_scene {
+    std::mutex mu;                     // lane pool + error string
+    std::condition_variable cv;
+    std::string err;
+    int device = 0;
+    uint32_t precision = RT_FP32_FAST;
+    int sm_count = 148;
+    int max_leaf = 4;
+    bool top_in_smem = false;
+    int refill_below = 1;
+    int shade_minb = 8;
+    bool primary_persistent = false;
+    bool split_shade = false;
+
+    // immutable after rt_scene_create
+    std::vector<MeshDevice> meshes;
+    std::vector<MeshView> h_views;
+    MeshView *d_meshes = nullptr;
+    std::vector<ObjRec> h_objs;        // initial object positions (the lanes keep per-frame copies)
+
+    std::vector<std::unique_ptr<Lane>> lanes;
+    std::atomic<int> last_lane{ 0 };   // lane of the most recent call (rt_get_stats)
     std::atomic<int> cancel{ 0 };
 };
 
@@ -57,7 +77,7 @@ namespace {
 thread_local std::string g_err;
 
 int fail(rt_scene *s, int code, const std::string &msg) {
-    if (s) s->err = msg;
+    if (s) { std::lock_guard<std::mutex> lk(s->mu); s->err = msg; }
     g_err = msg;
     return code;
 }
@@ -76,16 +96,23 @@ void free_mesh(MeshDevice &m) {
     m = MeshDevice();
 }
 
-void destroy_locked(rt_scene *s) {
+void destroy_lane(Lane &L) {
+    if (L.stream) cudaStreamSynchronize(L.stream);
+    cudaFree(L.d_objs); cudaFree(L.d_lights);
+    cudaFree(L.d_hits); cudaFree(L.d_hit_colour); cudaFree(L.d_hit_lit); cudaFree(L.d_hit_geom); cudaFree(L.d_counters); cudaFree(L.d_stats);
+    cudaFree(L.d_rgb); cudaFree(L.d_dbg_colour); cudaFree(L.d_dbg_face); cudaFree(L.d_dbg_obj); cudaFree(L.d_dbg_lit);
+    if (L.h_pinned) cudaFreeHost(L.h_pinned);
+    for (auto &e : L.ev) if (e) cudaEventDestroy(e);
+    if (L.stream) cudaStreamDestroy(L.stream);
+}
+
+void destroy_all(rt_scene *s) {
     cudaSetDevice(s->device);
-    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (auto &lp : s->lanes) destroy_lane(*lp);
+    s->lanes.clear();
     for (auto &m : s->meshes) free_mesh(m);
-    cudaFree(s->d_meshes); cudaFree(s->d_objs); cudaFree(s->d_lights);
-    cudaFree(s->d_hits); cudaFree(s->d_hit_colour); cudaFree(s->d_hit_lit); cudaFree(s->d_hit_geom); cudaFree(s->d_counters); cudaFree(s->d_stats);
-    cudaFree(s->d_rgb); cudaFree(s->d_dbg_colour); cudaFree(s->d_dbg_face); cudaFree(s->d_dbg_obj); cudaFree(s->d_dbg_lit);
-    if (s->h_pinned) cudaFreeHost(s->h_pinned);
-    for (auto &e : s->ev) if (e) cudaEventDestroy(e);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaFree(s->d_meshes);
+    s->d_meshes = nullptr;
 }
 
 int env_int(const char *name, int dflt) {
@@ -120,69 +147,98 @@ int flatten_mesh(const rt_mesh_desc &d, std::vector<double> &fverts, std::vector
     return RT_OK;
 }
 
-int ensure_scratch(rt_scene *s, size_t nrays, size_t out_bytes, bool need_rgb, bool dbg, size_t npix_out) {
-    if (nrays > s->cap_rays) {
-        cudaFree(s->d_hits); cudaFree(s->d_hit_colour); cudaFree(s->d_hit_lit); cudaFree(s->d_hit_geom);
-        s->d_hits = nullptr; s->d_hit_colour = nullptr; s->d_hit_lit = nullptr; s->d_hit_geom = nullptr; s->cap_rays = 0;
-        CU(s, cudaMalloc((void **)&s->d_hits, sizeof(HitRec) * nrays));
-        CU(s, cudaMalloc((void **)&s->d_hit_colour, sizeof(double) * 3 * nrays));
-        CU(s, cudaMalloc((void **)&s->d_hit_lit, sizeof(uint32_t) * nrays));
-        if (s->split_shade) CU(s, cudaMalloc((void **)&s->d_hit_geom, sizeof(double) * 6 * nrays));
-        s->cap_rays = nrays;
+// ---- lane pool ---------------------------------------------------------------------------------
+// a free pool lane for a concurrent rt_bulk_trace (lanes >= 1; lane 0 if the scene has a single lane)
+Lane *acquire_lane(rt_scene *s, int *index) {
+    std::unique_lock<std::mutex> lk(s->mu);
+    const int n = (int)s->lanes.size();
+    for (;;) {
+        for (int k = (n > 1 ? 1 : 0); k < n; k++)
+            if (!s->lanes[k]->busy) { s->lanes[k]->busy = true; *index = k; return s->lanes[k].get(); }
+        s->cv.wait(lk);
     }
-    if (need_rgb && out_bytes > s->cap_rgb) {
-        cudaFree(s->d_rgb); s->d_rgb = nullptr; s->cap_rgb = 0;
-        CU(s, cudaMalloc((void **)&s->d_rgb, out_bytes));
-        s->cap_rgb = out_bytes;
+}
+void release_lane(rt_scene *s, Lane *L) {
+    { std::lock_guard<std::mutex> lk(s->mu); L->busy = false; }
+    s->cv.notify_one();
+}
+// lane of a device-API call: bits 24..31 of `flags` (RT_LANE(k)); nullptr + error if out of range
+Lane *device_lane(rt_scene *s, uint32_t flags, int *index) {
+    int k = (int)(flags >> 24);
+    if (k >= (int)s->lanes.size()) { fail(s, RT_ERR_INVALID, "lane index (flags bits 24..31) out of range"); return nullptr; }
+    *index = k;
+    return s->lanes[k].get();
+}
+
+int ensure_scratch(rt_scene *s, Lane &L, size_t nrays, size_t out_bytes, bool need_rgb, bool dbg, size_t npix_out) {
+    if (!L.d_counters) {
+        CU(s, cudaMalloc((void **)&L.d_counters, 4 * sizeof(unsigned int)));
+        CU(s, cudaMalloc((void **)&L.d_stats, 2 * sizeof(Counters)));
     }
-    if (dbg && npix_out > s->cap_dbg) {
-        cudaFree(s->d_dbg_colour); cudaFree(s->d_dbg_face); cudaFree(s->d_dbg_obj); cudaFree(s->d_dbg_lit);
-        s->d_dbg_colour = nullptr; s->d_dbg_face = nullptr; s->d_dbg_obj = nullptr; s->d_dbg_lit = nullptr; s->cap_dbg = 0;
-        CU(s, cudaMalloc((void **)&s->d_dbg_colour, sizeof(double) * 3 * npix_out));
-        CU(s, cudaMalloc((void **)&s->d_dbg_face, sizeof(int32_t) * npix_out));
-        CU(s, cudaMalloc((void **)&s->d_dbg_obj, sizeof(int32_t) * npix_out));
-        CU(s, cudaMalloc((void **)&s->d_dbg_lit, sizeof(uint32_t) * npix_out));
-        s->cap_dbg = npix_out;
+    if (nrays > L.cap_rays) {
+        cudaFree(L.d_hits); cudaFree(L.d_hit_colour); cudaFree(L.d_hit_lit); cudaFree(L.d_hit_geom);
+        L.d_hits = nullptr; L.d_hit_colour = nullptr; L.d_hit_lit = nullptr; L.d_hit_geom = nullptr; L.cap_rays = 0;
+        CU(s, cudaMalloc((void **)&L.d_hits, sizeof(HitRec) * nrays));
+        CU(s, cudaMalloc((void **)&L.d_hit_colour, sizeof(double) * 3 * nrays));
+        CU(s, cudaMalloc((void **)&L.d_hit_lit, sizeof(uint32_t) * nrays));
+        if (s->split_shade) CU(s, cudaMalloc((void **)&L.d_hit_geom, sizeof(double) * 6 * nrays));
+        L.cap_rays = nrays;
+    }
+    if (need_rgb && out_bytes > L.cap_rgb) {
+        cudaFree(L.d_rgb); L.d_rgb = nullptr; L.cap_rgb = 0;
+        CU(s, cudaMalloc((void **)&L.d_rgb, out_bytes));
+        L.cap_rgb = out_bytes;
+    }
+    if (dbg && npix_out > L.cap_dbg) {
+        cudaFree(L.d_dbg_colour); cudaFree(L.d_dbg_face); cudaFree(L.d_dbg_obj); cudaFree(L.d_dbg_lit);
+        L.d_dbg_colour = nullptr; L.d_dbg_face = nullptr; L.d_dbg_obj = nullptr; L.d_dbg_lit = nullptr; L.cap_dbg = 0;
+        CU(s, cudaMalloc((void **)&L.d_dbg_colour, sizeof(double) * 3 * npix_out));
+        CU(s, cudaMalloc((void **)&L.d_dbg_face, sizeof(int32_t) * npix_out));
+        CU(s, cudaMalloc((void **)&L.d_dbg_obj, sizeof(int32_t) * npix_out));
+        CU(s, cudaMalloc((void **)&L.d_dbg_lit, sizeof(uint32_t) * npix_out));
+        L.cap_dbg = npix_out;
     }
     return RT_OK;
 }
 
-int frame_set_locked(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos) {
+// frame state of one call into lane L (caller holds L.mu)
+int frame_set_lane(rt_scene *s, Lane &L, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos) {
     if (!cam) return fail(s, RT_ERR_INVALID, "rt_frame_set: camera is NULL");
     if (n_lights && !lights) return fail(s, RT_ERR_INVALID, "rt_frame_set: lights is NULL");
     CU(s, cudaSetDevice(s->device));
-    FrameParams &fp = s->frame;
+    FrameParams &fp = L.frame;
     for (int k = 0; k < 3; k++) { fp.cam_pos[k] = cam->pos[k]; fp.fwd[k] = cam->forward[k]; fp.left[k] = cam->left[k]; fp.up[k] = cam->up[k]; }
     fp.tan_half = std::isnan(cam->tan_half_fov) ? rt_go_tan(cam->fov / 2.0) : cam->tan_half_fov;   // tracer.go:17
     fp.n_lights = (int)n_lights;
-    fp.n_obj = (int)s->h_objs.size();
-    s->n_lights = n_lights;
+    fp.n_obj = (int)L.h_objs.size();
     if (obj_pos)
-        for (size_t k = 0; k < s->h_objs.size(); k++)
-            for (int c = 0; c < 3; c++) s->h_objs[k].pos[c] = obj_pos[3 * k + c];
-    InlineFrame &fr = s->inline_frame;
+        for (size_t k = 0; k < L.h_objs.size(); k++)
+            for (int c = 0; c < 3; c++) L.h_objs[k].pos[c] = obj_pos[3 * k + c];
+    InlineFrame &fr = L.inline_frame;
     fr.use_lights = n_lights <= RT_INLINE_LIGHTS;
-    fr.use_objs = s->h_objs.size() <= RT_INLINE_OBJS;
+    fr.use_objs = L.h_objs.size() <= RT_INLINE_OBJS;
     static_assert(sizeof(LightRec) == sizeof(rt_light), "light layout");
     if (fr.use_lights && n_lights) memcpy(fr.lights, lights, sizeof(LightRec) * n_lights);
-    if (fr.use_objs && !s->h_objs.empty()) memcpy(fr.objs, s->h_objs.data(), sizeof(ObjRec) * s->h_objs.size());
-    if (!fr.use_lights || (!fr.use_objs && obj_pos)) {
+    if (fr.use_objs && !L.h_objs.empty()) memcpy(fr.objs, L.h_objs.data(), sizeof(ObjRec) * L.h_objs.size());
+    if (!fr.use_lights || !fr.use_objs) {
         // large light / object sets live in device memory: the copies must not overtake a render still in flight
-        CU(s, cudaStreamSynchronize(s->stream));
-        if (s->last_stream) CU(s, cudaStreamSynchronize(s->last_stream));
+        CU(s, cudaStreamSynchronize(L.stream));
+        if (L.last_stream) CU(s, cudaStreamSynchronize(L.last_stream));
         if (!fr.use_lights) {
-            if (n_lights > s->cap_lights) {
-                cudaFree(s->d_lights); s->d_lights = nullptr; s->cap_lights = 0;
-                CU(s, cudaMalloc((void **)&s->d_lights, sizeof(LightRec) * n_lights));
-                s->cap_lights = n_lights;
+            if (n_lights > L.cap_lights) {
+                cudaFree(L.d_lights); L.d_lights = nullptr; L.cap_lights = 0;
+                CU(s, cudaMalloc((void **)&L.d_lights, sizeof(LightRec) * n_lights));
+                L.cap_lights = n_lights;
             }
-            CU(s, cudaMemcpyAsync(s->d_lights, lights, sizeof(LightRec) * n_lights, cudaMemcpyHostToDevice, s->stream));
+            CU(s, cudaMemcpyAsync(L.d_lights, lights, sizeof(LightRec) * n_lights, cudaMemcpyHostToDevice, L.stream));
         }
-        if (!fr.use_objs && obj_pos)
-            CU(s, cudaMemcpyAsync(s->d_objs, s->h_objs.data(), sizeof(ObjRec) * s->h_objs.size(), cudaMemcpyHostToDevice, s->stream));
-        CU(s, cudaStreamSynchronize(s->stream));   // `lights` is caller memory: do not retain it
+        if (!fr.use_objs) {
+            if (!L.d_objs) CU(s, cudaMalloc((void **)&L.d_objs, sizeof(ObjRec) * L.h_objs.size()));
+            CU(s, cudaMemcpyAsync(L.d_objs, L.h_objs.data(), sizeof(ObjRec) * L.h_objs.size(), cudaMemcpyHostToDevice, L.stream));
+        }
+        CU(s, cudaStreamSynchronize(L.stream));   // `lights` is caller memory: do not retain it
     }
-    s->have_frame = true;
+    L.have_frame = true;
     return RT_OK;
 }
 
@@ -192,69 +248,69 @@ struct RenderOut {
     cudaStream_t ext_stream = nullptr; bool async = false;
 };
 
-void collect_stats(rt_scene *s) {
-    if (!s->stats_pending) return;
+void collect_stats(rt_scene *s, Lane &L) {
+    if (!L.stats_pending) return;
     unsigned int counters[4] = { 0, 0, 0, 0 };
-    cudaMemcpy(counters, s->d_counters, sizeof counters, cudaMemcpyDeviceToHost);
+    cudaMemcpy(counters, L.d_counters, sizeof counters, cudaMemcpyDeviceToHost);
     Counters c[2];
     memset(c, 0, sizeof c);
-    cudaMemcpy(c, s->d_stats, sizeof c, cudaMemcpyDeviceToHost);
-    s->stats.hit_pixels = counters[1];
-    s->stats.shadow_rays = (uint64_t)counters[1] * (uint64_t)s->frame.n_lights;
-    s->stats.nodes_primary = c[0].nodes; s->stats.tris_primary = c[0].tris;
-    s->stats.nodes_shade = c[1].nodes; s->stats.tris_shade = c[1].tris;
-    s->stats.nodes_fetched = c[0].nodes + c[1].nodes;
-    s->stats.tris_fetched = c[0].tris + c[1].tris;
-    s->stats.node_bytes = RT_NODE_BYTES;
-    s->stats.tri_bytes = s->precision == RT_FP64_EXACT ? RT_TRI64_BYTES : RT_TRI32_BYTES;
-    cudaEventElapsedTime(&s->stats.ms_primary, s->ev[0], s->ev[1]);
-    cudaEventElapsedTime(&s->stats.ms_shade, s->ev[1], s->ev[2]);
-    cudaEventElapsedTime(&s->stats.ms_write, s->ev[2], s->ev[3]);
-    cudaEventElapsedTime(&s->stats.ms_total, s->ev[0], s->ev[3]);
-    s->stats_pending = false;
+    cudaMemcpy(c, L.d_stats, sizeof c, cudaMemcpyDeviceToHost);
+    L.stats.hit_pixels = counters[1];
+    L.stats.shadow_rays = (uint64_t)counters[1] * (uint64_t)L.frame.n_lights;
+    L.stats.nodes_primary = c[0].nodes; L.stats.tris_primary = c[0].tris;
+    L.stats.nodes_shade = c[1].nodes; L.stats.tris_shade = c[1].tris;
+    L.stats.nodes_fetched = c[0].nodes + c[1].nodes;
+    L.stats.tris_fetched = c[0].tris + c[1].tris;
+    L.stats.node_bytes = RT_NODE_BYTES;
+    L.stats.tri_bytes = s->precision == RT_FP64_EXACT ? RT_TRI64_BYTES : RT_TRI32_BYTES;
+    cudaEventElapsedTime(&L.stats.ms_primary, L.ev[0], L.ev[1]);
+    cudaEventElapsedTime(&L.stats.ms_shade, L.ev[1], L.ev[2]);
+    cudaEventElapsedTime(&L.stats.ms_write, L.ev[2], L.ev[3]);
+    cudaEventElapsedTime(&L.stats.ms_total, L.ev[0], L.ev[3]);
+    L.stats_pending = false;
 }
 
-// the whole render path: clear -> K2 -> K4 -> K5 -> (copy out)
-int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npix_out, const RenderOut &out) {
-    if (!s->have_frame) return fail(s, RT_ERR_STATE, "render before rt_frame_set");
+// the whole render path on one lane: clear -> K2 -> K4 -> K5 -> (copy out).  Caller holds L.mu.
+int render_lane(rt_scene *s, Lane &L, const FrameParams &fp, uint32_t flags, size_t npix_out, const RenderOut &out) {
+    if (!L.have_frame) return fail(s, RT_ERR_STATE, "render before rt_frame_set");
     CU(s, cudaSetDevice(s->device));
     s->cancel.store(0);   // stats of earlier frames are collected lazily (rt_get_stats): no per-frame host sync
     const size_t nrays = ray_count(fp);
     const size_t out_bytes = npix_out * 3;
     const bool dbg = out.h_colour || out.h_face || out.h_obj || out.h_lit;
     const bool internal_rgb = out.d_rgb == nullptr;
-    int rc = ensure_scratch(s, nrays, out_bytes, internal_rgb, dbg, npix_out);
+    int rc = ensure_scratch(s, L, nrays, out_bytes, internal_rgb, dbg, npix_out);
     if (rc != RT_OK) return rc;
-    cudaStream_t st = out.ext_stream ? out.ext_stream : s->stream;
-    uint8_t *d_rgb = internal_rgb ? s->d_rgb : out.d_rgb;
+    cudaStream_t st = out.ext_stream ? out.ext_stream : L.stream;
+    uint8_t *d_rgb = internal_rgb ? L.d_rgb : out.d_rgb;
 
     RenderJob job;
     memset(&job, 0, sizeof job);
     job.fp = fp;
-    job.d_meshes = s->d_meshes; job.d_objs = s->d_objs; job.d_lights = s->d_lights;
-    job.fr = s->inline_frame;
-    job.precision = s->precision; job.flags = flags;
-    job.d_hits = s->d_hits; job.d_hit_colour = s->d_hit_colour; job.d_hit_lit = s->d_hit_lit;
-    job.d_hit_geom = s->d_hit_geom; job.split_shade = s->split_shade;
-    job.d_counters = s->d_counters; job.d_stats = s->d_stats;
+    job.d_meshes = s->d_meshes; job.d_objs = L.d_objs; job.d_lights = L.d_lights;
+    job.fr = L.inline_frame;
+    job.precision = s->precision; job.flags = flags & 0x00ffffffu;
+    job.d_hits = L.d_hits; job.d_hit_colour = L.d_hit_colour; job.d_hit_lit = L.d_hit_lit;
+    job.d_hit_geom = L.d_hit_geom; job.split_shade = s->split_shade;
+    job.d_counters = L.d_counters; job.d_stats = L.d_stats;
     job.d_out_rgb = d_rgb;
-    job.d_out_colour = out.h_colour ? s->d_dbg_colour : nullptr;
-    job.d_out_face = out.h_face ? s->d_dbg_face : nullptr;
-    job.d_out_obj = out.h_obj ? s->d_dbg_obj : nullptr;
-    job.d_out_lit = out.h_lit ? s->d_dbg_lit : nullptr;
+    job.d_out_colour = out.h_colour ? L.d_dbg_colour : nullptr;
+    job.d_out_face = out.h_face ? L.d_dbg_face : nullptr;
+    job.d_out_obj = out.h_obj ? L.d_dbg_obj : nullptr;
+    job.d_out_lit = out.h_lit ? L.d_dbg_lit : nullptr;
     job.sm_count = s->sm_count;
-    job.single_mesh = s->h_objs.size() == 1;
+    job.single_mesh = L.h_objs.size() == 1;
     if (job.single_mesh) {
-        job.h_mesh0 = s->h_views[s->h_objs[0].mesh];
-        for (int k = 0; k < 3; k++) job.h_obj0_pos[k] = s->h_objs[0].pos[k];
+        job.h_mesh0 = s->h_views[L.h_objs[0].mesh];
+        for (int k = 0; k < 3; k++) job.h_obj0_pos[k] = L.h_objs[0].pos[k];
     }
     job.top_in_smem = s->top_in_smem;
     job.refill_below = s->refill_below;
     job.shade_minb = s->shade_minb;
     job.primary_persistent = s->primary_persistent;
 
-    CU(s, cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned int), st));
-    CU(s, cudaMemsetAsync(s->d_stats, 0, 2 * sizeof(Counters), st));
+    CU(s, cudaMemsetAsync(L.d_counters, 0, 4 * sizeof(unsigned int), st));
+    CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), st));
     // background: sequential/main.go:17 surface.FillRect(nil, 0); distributed/main.go:70 default 0,0,0
     if (fp.tile_final) CU(s, rt_launch_clear_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, d_rgb, st));   // only this rank's pixels (peer framebuffer)
     else CU(s, cudaMemsetAsync(d_rgb, 0, out_bytes, st));
@@ -263,19 +319,19 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
     if (job.d_out_obj) CU(s, cudaMemsetAsync(job.d_out_obj, 0xff, sizeof(int32_t) * npix_out, st));
     if (job.d_out_lit) CU(s, cudaMemsetAsync(job.d_out_lit, 0, sizeof(uint32_t) * npix_out, st));
 
-    CU(s, cudaEventRecord(s->ev[0], st));
+    CU(s, cudaEventRecord(L.ev[0], st));
     CU(s, rt_launch_primary(job, st));
-    CU(s, cudaEventRecord(s->ev[1], st));
+    CU(s, cudaEventRecord(L.ev[1], st));
     if (s->cancel.load()) { cudaStreamSynchronize(st); return fail(s, RT_ERR_CANCELLED, "cancelled"); }
     CU(s, rt_launch_shade(job, st));
-    CU(s, cudaEventRecord(s->ev[2], st));
+    CU(s, cudaEventRecord(L.ev[2], st));
     CU(s, rt_launch_write(job, st));
-    CU(s, cudaEventRecord(s->ev[3], st));
+    CU(s, cudaEventRecord(L.ev[3], st));
 
-    s->stats.primary_rays = (uint64_t)fp.w * (uint64_t)fp.h;
-    if (fp.tile_w > 0) s->stats.primary_rays = nrays;
-    s->stats_pending = true;
-    s->last_stream = st;
+    L.stats.primary_rays = (uint64_t)fp.w * (uint64_t)fp.h;
+    if (fp.tile_w > 0) L.stats.primary_rays = nrays;
+    L.stats_pending = true;
+    L.last_stream = st;
     if (out.async) return RT_OK;
 
     // copy results to the caller's host buffers
@@ -288,15 +344,15 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
             CU(s, cudaMemcpyAsync(out.h_rgb, d_rgb, out_bytes, cudaMemcpyDeviceToHost, st));
             CU(s, cudaStreamSynchronize(st));
         } else {
-            if (out_bytes > s->cap_pinned) {
-                if (s->h_pinned) cudaFreeHost(s->h_pinned);
-                s->h_pinned = nullptr; s->cap_pinned = 0;
-                CU(s, cudaMallocHost((void **)&s->h_pinned, out_bytes));
-                s->cap_pinned = out_bytes;
+            if (out_bytes > L.cap_pinned) {
+                if (L.h_pinned) cudaFreeHost(L.h_pinned);
+                L.h_pinned = nullptr; L.cap_pinned = 0;
+                CU(s, cudaMallocHost((void **)&L.h_pinned, out_bytes));
+                L.cap_pinned = out_bytes;
             }
-            CU(s, cudaMemcpyAsync(s->h_pinned, d_rgb, out_bytes, cudaMemcpyDeviceToHost, st));
+            CU(s, cudaMemcpyAsync(L.h_pinned, d_rgb, out_bytes, cudaMemcpyDeviceToHost, st));
             CU(s, cudaStreamSynchronize(st));
-            memcpy(out.h_rgb, s->h_pinned, out_bytes);
+            memcpy(out.h_rgb, L.h_pinned, out_bytes);
         }
     }
     if (out.h_colour) CU(s, cudaMemcpyAsync(out.h_colour, job.d_out_colour, sizeof(double) * 3 * npix_out, cudaMemcpyDeviceToHost, st));
@@ -309,14 +365,39 @@ int render_locked(rt_scene *s, const FrameParams &fp, uint32_t flags, size_t npi
     return RT_OK;
 }
 
-int region_params(rt_scene *s, FrameParams &fp, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h) {
+int region_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h) {
     if (W == 0 || H == 0 || w == 0 || h == 0) return fail(s, RT_ERR_INVALID, "empty screen or region");
     if (W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "screen larger than 65536 pixels on a side");
     if ((uint64_t)x + w > W || (uint64_t)y + h > H) return fail(s, RT_ERR_INVALID, "region exceeds the screen");
-    fp = s->frame;
+    fp = L.frame;
     fp.W = (int)W; fp.H = (int)H; fp.x = (int)x; fp.y = (int)y; fp.w = (int)w; fp.h = (int)h;
     fp.tile_w = fp.tile_h = fp.tiles_x = fp.rank = fp.n_ranks = fp.n_local_tiles = fp.tile_final = 0;
     return RT_OK;
+}
+
+int tile_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank,
+                uint32_t n_ranks, bool need_smem_fit) {
+    if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "bad screen size");
+    if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4");
+    if (need_smem_fit && (size_t)tile_w * tile_h * 3 > 48 * 1024) return fail(s, RT_ERR_INVALID, "tile larger than 16384 pixels");
+    if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
+    fp = L.frame;
+    fp.W = (int)W; fp.H = (int)H; fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
+    fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
+    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
+    const uint32_t n_tiles = (uint32_t)fp.tiles_x * ((H + tile_h - 1) / tile_h);
+    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
+    fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
+    fp.tile_final = 0;
+    return RT_OK;
+}
+
+// the device API on a lane other than 0 inherits lane 0's frame state until it is given its own (rt_frame_set_lane)
+void inherit_frame(rt_scene *s, Lane &L, int idx) {
+    if (idx == 0 || L.have_frame) return;
+    Lane &L0 = *s->lanes[0];
+    if (!L0.have_frame || !L0.inline_frame.use_lights || !L0.inline_frame.use_objs) return;
+    L.frame = L0.frame; L.inline_frame = L0.inline_frame; L.h_objs = L0.h_objs; L.have_frame = true;
 }
 
 }  // namespace
@@ -332,7 +413,11 @@ int rt_device_count(void) {
     return n;
 }
 
-const char *rt_last_error(const rt_scene *scene) { return scene ? scene->err.c_str() : g_err.c_str(); }
+const char *rt_last_error(const rt_scene *scene) {
+    // the calling thread's last message (concurrent callers do not see each other's errors)
+    if (!g_err.empty() || !scene) return g_err.c_str();
+    return scene->err.c_str();
+}
 
 int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     if (!desc || !out) return fail(nullptr, RT_ERR_INVALID, "rt_scene_create: NULL argument");
@@ -351,7 +436,6 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     if (desc->device < 0 || desc->device >= ndev) return fail(nullptr, RT_ERR_INVALID, "device ordinal out of range");
     rt_scene *s = new (std::nothrow) rt_scene();
     if (!s) return fail(nullptr, RT_ERR_OOM, "out of host memory");
-    std::unique_lock<std::mutex> lk(s->mu);
     s->device = desc->device;
     s->precision = desc->precision;
     s->max_leaf = env_int("RT_B200_MAX_LEAF", 4);
@@ -360,12 +444,11 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->split_shade = env_int("RT_B200_SPLIT_SHADE", 0) != 0;
     s->top_in_smem = env_int("RT_B200_TOP_SMEM", 0) != 0;
     s->refill_below = env_int("RT_B200_REFILL", 1);
-    memset(&s->stats, 0, sizeof s->stats);
-    memset(&s->frame, 0, sizeof s->frame);
-    memset(&s->inline_frame, 0, sizeof s->inline_frame);
-    int rc = RT_OK;
-    auto bail = [&](int code) { lk.unlock(); std::string e = s->err; destroy_locked(s); delete s; g_err = e; return code; };
-#define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(s, e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA); } } while (0)
+    int n_lanes = env_int("RT_B200_LANES", 9);      // lane 0 + a pool of 8 for concurrent BulkTrace calls / frames in flight
+    if (n_lanes < 1) n_lanes = 1;
+    if (n_lanes > 64) n_lanes = 64;
+    auto bail = [&](int code, const std::string &msg) { destroy_all(s); delete s; g_err = msg; return code; };
+#define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
     CUB_(cudaSetDevice(s->device));
     {
         cudaDeviceProp prop;
@@ -374,11 +457,22 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
         // the kernels are compiled for sm_100a only: on any other device the first launch fails with
         // cudaErrorNoKernelImageForDevice and the error is returned (no fallback)
     }
-    CUB_(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    for (auto &e : s->ev) CUB_(cudaEventCreate(&e));
-    CUB_(cudaMalloc((void **)&s->d_counters, 4 * sizeof(unsigned int)));
-    CUB_(cudaMalloc((void **)&s->d_stats, 2 * sizeof(Counters)));
-
+    s->h_objs.resize(desc->n_objects);
+    for (uint32_t k = 0; k < desc->n_objects; k++) {
+        for (int c = 0; c < 3; c++) s->h_objs[k].pos[c] = desc->obj_pos[3 * (size_t)k + c];
+        s->h_objs[k].mesh = desc->obj_mesh[k]; s->h_objs[k].pad = 0;
+    }
+    for (int k = 0; k < n_lanes; k++) {
+        s->lanes.emplace_back(new Lane());
+        Lane &L = *s->lanes.back();
+        memset(&L.stats, 0, sizeof L.stats);
+        memset(&L.frame, 0, sizeof L.frame);
+        memset(&L.inline_frame, 0, sizeof L.inline_frame);
+        L.h_objs = s->h_objs;
+        CUB_(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        for (auto &e : L.ev) CUB_(cudaEventCreate(&e));
+    }
+    cudaStream_t st0 = s->lanes[0]->stream;
     s->meshes.resize(desc->n_meshes);
     s->h_views.resize(desc->n_meshes);
     for (uint32_t k = 0; k < desc->n_meshes; k++) {
@@ -386,58 +480,60 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
         MeshDevice &m = s->meshes[k];
         std::vector<double> fverts, fnormals; std::vector<uint32_t> fmat;
         std::string e;
-        rc = flatten_mesh(d, fverts, fnormals, fmat, e);
-        if (rc != RT_OK) { fail(s, rc, e); return bail(rc); }
+        int rc = flatten_mesh(d, fverts, fnormals, fmat, e);
+        if (rc != RT_OK) return bail(rc, e);
         m.n_faces = d.n_faces; m.n_materials = d.n_materials;
-        CUB_(upload(&m.fverts, fverts.data(), fverts.size(), s->stream));
-        if (!fnormals.empty()) CUB_(upload(&m.fnormals, fnormals.data(), fnormals.size(), s->stream));
-        CUB_(upload(&m.fmat, fmat.data(), fmat.size(), s->stream));
-        CUB_(upload(&m.materials, d.materials, (size_t)10 * d.n_materials, s->stream));
-        CUB_(cudaStreamSynchronize(s->stream));
-        if (!rt_build_bvh(m, s->precision == RT_FP32_FAST, s->precision == RT_FP64_EXACT, s->max_leaf, s->stream, e)) {
-            fail(s, RT_ERR_CUDA, "BVH build: " + e);
-            return bail(RT_ERR_CUDA);
-        }
+        CUB_(upload(&m.fverts, fverts.data(), fverts.size(), st0));
+        if (!fnormals.empty()) CUB_(upload(&m.fnormals, fnormals.data(), fnormals.size(), st0));
+        CUB_(upload(&m.fmat, fmat.data(), fmat.size(), st0));
+        CUB_(upload(&m.materials, d.materials, (size_t)10 * d.n_materials, st0));
+        CUB_(cudaStreamSynchronize(st0));
+        if (!rt_build_bvh(m, s->precision == RT_FP32_FAST, s->precision == RT_FP64_EXACT, s->max_leaf, st0, e))
+            return bail(RT_ERR_CUDA, "BVH build: " + e);
         MeshView &v = s->h_views[k];
         v.nodes = m.nodes; v.tri32 = m.tri32; v.tri64 = m.tri64; v.fverts = m.fverts; v.fnormals = m.fnormals; v.fmat = m.fmat;
         v.materials = m.materials; v.n_faces = m.n_faces; v.n_nodes = m.n_nodes; v.root_ref = m.root_ref;
         for (int c = 0; c < 3; c++) { v.lo[c] = m.lo[c]; v.hi[c] = m.hi[c]; }
     }
-    CUB_(upload(&s->d_meshes, s->h_views.data(), s->h_views.size(), s->stream));
-    s->h_objs.resize(desc->n_objects);
-    for (uint32_t k = 0; k < desc->n_objects; k++) {
-        for (int c = 0; c < 3; c++) s->h_objs[k].pos[c] = desc->obj_pos[3 * (size_t)k + c];
-        s->h_objs[k].mesh = desc->obj_mesh[k]; s->h_objs[k].pad = 0;
-    }
-    CUB_(upload(&s->d_objs, s->h_objs.data(), s->h_objs.size(), s->stream));
-    CUB_(cudaStreamSynchronize(s->stream));
+    CUB_(upload(&s->d_meshes, s->h_views.data(), s->h_views.size(), st0));
+    CUB_(cudaStreamSynchronize(st0));
 #undef CUB_
-    lk.unlock();
     *out = s;
     return RT_OK;
 }
 
 void rt_scene_destroy(rt_scene *scene) {
     if (!scene) return;
-    { std::lock_guard<std::mutex> lk(scene->mu); destroy_locked(scene); }
+    for (auto &lp : scene->lanes) { std::lock_guard<std::mutex> lk(lp->mu); }    // wait for calls in flight on every lane
+    destroy_all(scene);
     delete scene;
 }
 
+int rt_lane_count(rt_scene *s) { return s ? (int)s->lanes.size() : 0; }
+
 int rt_frame_set(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos) {
+    return rt_frame_set_lane(s, 0, cam, lights, n_lights, obj_pos);
+}
+
+int rt_frame_set_lane(rt_scene *s, uint32_t lane, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
-    std::lock_guard<std::mutex> lk(s->mu);
-    return frame_set_locked(s, cam, lights, n_lights, obj_pos);
+    if (lane >= s->lanes.size()) return fail(s, RT_ERR_INVALID, "lane index out of range");
+    Lane &L = *s->lanes[lane];
+    std::lock_guard<std::mutex> lk(L.mu);
+    return frame_set_lane(s, L, cam, lights, n_lights, obj_pos);
 }
 
 int rt_render_region_debug(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb,
                            double *out_colour, int32_t *out_face, int32_t *out_obj, uint32_t *out_lit, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
-    std::lock_guard<std::mutex> lk(s->mu);
+    Lane &L = *s->lanes[0];
+    std::lock_guard<std::mutex> lk(L.mu);
     FrameParams fp;
-    int rc = region_params(s, fp, W, H, x, y, w, h);
+    int rc = region_params(s, L, fp, W, H, x, y, w, h);
     if (rc != RT_OK) return rc;
     RenderOut o; o.h_rgb = out_rgb; o.h_colour = out_colour; o.h_face = out_face; o.h_obj = out_obj; o.h_lit = out_lit;
-    return render_locked(s, fp, flags, (size_t)w * h, o);
+    s->last_lane.store(0);
+    return render_lane(s, L, fp, flags, (size_t)w * h, o);
 }
 
 int rt_render_region(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb,
@@ -450,27 +546,42 @@ int rt_bulk_trace(rt_scene *s, const rt_camera *cam, const rt_light *lights, uin
                   uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!out_rgb) return fail(s, RT_ERR_INVALID, "out_rgb is NULL");
-    std::lock_guard<std::mutex> lk(s->mu);
-    int rc = frame_set_locked(s, cam, lights, n_lights, obj_pos);
-    if (rc != RT_OK) return rc;
-    FrameParams fp;
-    rc = region_params(s, fp, W, H, x, y, w, h);
-    if (rc != RT_OK) return rc;
-    RenderOut o; o.h_rgb = out_rgb;
-    return render_locked(s, fp, flags, (size_t)w * h, o);
+    int idx = 0;
+    Lane *Lp = acquire_lane(s, &idx);          // a free pool lane: concurrent calls run concurrently on the GPU
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(Lp->mu);
+        // an order without object positions renders the registered ones (LinkTo, environment.go:73-98)
+        if (!obj_pos) Lp->h_objs = s->h_objs;
+        rc = frame_set_lane(s, *Lp, cam, lights, n_lights, obj_pos);
+        FrameParams fp;
+        if (rc == RT_OK) rc = region_params(s, *Lp, fp, W, H, x, y, w, h);
+        if (rc == RT_OK) {
+            RenderOut o; o.h_rgb = out_rgb;
+            s->last_lane.store(idx);
+            rc = render_lane(s, *Lp, fp, flags, (size_t)w * h, o);
+        }
+    }
+    release_lane(s, Lp);
+    return rc;
 }
 
 int rt_render_region_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, void *d_out_rgb,
                             void *stream, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_out_rgb) return fail(s, RT_ERR_INVALID, "d_out_rgb is NULL");
-    std::lock_guard<std::mutex> lk(s->mu);
+    int idx = 0;
+    Lane *Lp = device_lane(s, flags, &idx);
+    if (!Lp) return RT_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(Lp->mu);
+    inherit_frame(s, *Lp, idx);
     FrameParams fp;
-    int rc = region_params(s, fp, W, H, x, y, w, h);
+    int rc = region_params(s, *Lp, fp, W, H, x, y, w, h);
     if (rc != RT_OK) return rc;
     RenderOut o; o.d_rgb = (uint8_t *)d_out_rgb; o.ext_stream = (cudaStream_t)stream; o.async = stream != nullptr;
-    rc = render_locked(s, fp, flags, (size_t)w * h, o);
-    if (rc == RT_OK && !o.async) { CU(s, cudaStreamSynchronize(s->stream)); collect_stats(s); }
+    s->last_lane.store(idx);
+    rc = render_lane(s, *Lp, fp, flags, (size_t)w * h, o);
+    if (rc == RT_OK && !o.async) { CU(s, cudaStreamSynchronize(Lp->stream)); collect_stats(s, *Lp); }
     return rc;
 }
 
@@ -478,22 +589,18 @@ int rt_render_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w,
                            void *d_out_tiles, void *stream, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_out_tiles) return fail(s, RT_ERR_INVALID, "d_out_tiles is NULL");
-    if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "bad screen size");
-    if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4");
-    if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
-    std::lock_guard<std::mutex> lk(s->mu);
-    FrameParams fp = s->frame;
-    fp.W = (int)W; fp.H = (int)H; fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
-    fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
-    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
-    const uint32_t tiles_y = (H + tile_h - 1) / tile_h;
-    const uint32_t n_tiles = (uint32_t)fp.tiles_x * tiles_y;
-    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
-    fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
-    fp.tile_final = 0;
+    int idx = 0;
+    Lane *Lp = device_lane(s, flags, &idx);
+    if (!Lp) return RT_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(Lp->mu);
+    inherit_frame(s, *Lp, idx);
+    FrameParams fp;
+    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false);
+    if (rc != RT_OK) return rc;
     RenderOut o; o.d_rgb = (uint8_t *)d_out_tiles; o.ext_stream = (cudaStream_t)stream; o.async = stream != nullptr;
-    int rc = render_locked(s, fp, flags & ~RT_LAYOUT_ROWMAJOR, (size_t)fp.n_local_tiles * tile_w * tile_h, o);
-    if (rc == RT_OK && !o.async) { CU(s, cudaStreamSynchronize(s->stream)); collect_stats(s); }
+    s->last_lane.store(idx);
+    rc = render_lane(s, *Lp, fp, flags & ~RT_LAYOUT_ROWMAJOR, (size_t)fp.n_local_tiles * tile_w * tile_h, o);
+    if (rc == RT_OK && !o.async) { CU(s, cudaStreamSynchronize(Lp->stream)); collect_stats(s, *Lp); }
     return rc;
 }
 
@@ -501,42 +608,35 @@ int rt_render_tiles_peer(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
                          void *d_framebuffer, void *stream, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_framebuffer) return fail(s, RT_ERR_INVALID, "d_framebuffer is NULL");
-    if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "bad screen size");
-    if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4");
-    if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
-    std::lock_guard<std::mutex> lk(s->mu);
-    FrameParams fp = s->frame;
-    fp.W = (int)W; fp.H = (int)H; fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
-    fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
-    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
-    const uint32_t tiles_y = (H + tile_h - 1) / tile_h;
-    const uint32_t n_tiles = (uint32_t)fp.tiles_x * tiles_y;
-    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
-    fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
+    int idx = 0;
+    Lane *Lp = device_lane(s, flags, &idx);
+    if (!Lp) return RT_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(Lp->mu);
+    inherit_frame(s, *Lp, idx);
+    FrameParams fp;
+    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false);
+    if (rc != RT_OK) return rc;
     fp.tile_final = 1;
     RenderOut o; o.d_rgb = (uint8_t *)d_framebuffer; o.ext_stream = (cudaStream_t)stream; o.async = stream != nullptr;
-    int rc = render_locked(s, fp, flags, (size_t)W * H, o);
-    if (rc == RT_OK && !o.async) { CU(s, cudaStreamSynchronize(s->stream)); collect_stats(s); }
+    s->last_lane.store(idx);
+    rc = render_lane(s, *Lp, fp, flags, (size_t)W * H, o);
+    if (rc == RT_OK && !o.async) { CU(s, cudaStreamSynchronize(Lp->stream)); collect_stats(s, *Lp); }
     return rc;
 }
 
 int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
                          const void *d_tiles, void *d_framebuffer, void *stream, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
-    if (!d_tiles || !d_framebuffer || !W || !H) return fail(s, RT_ERR_INVALID, "rt_push_tiles_device: bad argument");
-    if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4 || (size_t)tile_w * tile_h * 3 > 48 * 1024)
-        return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4 and at most 16384 pixels");
-    if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
-    std::lock_guard<std::mutex> lk(s->mu);
+    if (!d_tiles || !d_framebuffer) return fail(s, RT_ERR_INVALID, "rt_push_tiles_device: bad argument");
+    int idx = 0;
+    Lane *Lp = device_lane(s, flags, &idx);
+    if (!Lp) return RT_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(Lp->mu);
     CU(s, cudaSetDevice(s->device));
     FrameParams fp;
-    memset(&fp, 0, sizeof fp);
-    fp.W = (int)W; fp.H = (int)H; fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
-    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
-    const uint32_t n_tiles = (uint32_t)fp.tiles_x * ((H + tile_h - 1) / tile_h);
-    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
-    fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, true);
+    if (rc != RT_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : Lp->stream;
     CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, st));
     if (!stream) CU(s, cudaStreamSynchronize(st));
     return RT_OK;
@@ -548,23 +648,18 @@ int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *ligh
                          void *stream, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_tiles || !d_framebuffer || !stream) return fail(s, RT_ERR_INVALID, "rt_render_push_tiles: NULL buffer or stream");
-    if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "bad screen size");
-    if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4 || (size_t)tile_w * tile_h * 3 > 48 * 1024)
-        return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4 and at most 16384 pixels");
-    if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
-    std::lock_guard<std::mutex> lk(s->mu);
-    int rc = frame_set_locked(s, cam, lights, n_lights, obj_pos);
+    int idx = 0;
+    Lane *Lp = device_lane(s, flags, &idx);
+    if (!Lp) return RT_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(Lp->mu);
+    int rc = frame_set_lane(s, *Lp, cam, lights, n_lights, obj_pos);
     if (rc != RT_OK) return rc;
-    FrameParams fp = s->frame;
-    fp.W = (int)W; fp.H = (int)H; fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
-    fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
-    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
-    const uint32_t n_tiles = (uint32_t)fp.tiles_x * ((H + tile_h - 1) / tile_h);
-    fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
-    fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
-    fp.tile_final = 0;
+    FrameParams fp;
+    rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, true);
+    if (rc != RT_OK) return rc;
     RenderOut o; o.d_rgb = (uint8_t *)d_tiles; o.ext_stream = (cudaStream_t)stream; o.async = true;
-    rc = render_locked(s, fp, flags & ~RT_LAYOUT_ROWMAJOR, (size_t)fp.n_local_tiles * tile_w * tile_h, o);
+    s->last_lane.store(idx);
+    rc = render_lane(s, *Lp, fp, flags & ~RT_LAYOUT_ROWMAJOR, (size_t)fp.n_local_tiles * tile_w * tile_h, o);
     if (rc != RT_OK) return rc;
     CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, (cudaStream_t)stream));
     return RT_OK;
@@ -611,12 +706,13 @@ int rt_untile_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint3
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_all_tiles || !d_out_rgb || !tile_w || !tile_h || !n_ranks || !W || !H) return fail(s, RT_ERR_INVALID, "rt_untile_device: bad argument");
     if (tile_w % 8 || tile_h % 4 || (size_t)tile_w * tile_h * 3 > 48 * 1024) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4 and at most 16384 pixels");
-    std::lock_guard<std::mutex> lk(s->mu);
+    Lane &L = *s->lanes[0];
+    std::lock_guard<std::mutex> lk(L.mu);
     CU(s, cudaSetDevice(s->device));
     const uint32_t tiles_x = (W + tile_w - 1) / tile_w, tiles_y = (H + tile_h - 1) / tile_h;
     const uint32_t n_tiles = tiles_x * tiles_y;
     const uint32_t per_rank_max = (n_tiles + n_ranks - 1) / n_ranks;
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = stream ? (cudaStream_t)stream : L.stream;
     CU(s, rt_launch_untile((const uint8_t *)d_all_tiles, (uint8_t *)d_out_rgb, (int)W, (int)H, (int)tile_w, (int)tile_h, (int)n_ranks,
                            (int)per_rank_max, (flags & RT_LAYOUT_ROWMAJOR) != 0, st));
     if (!stream) CU(s, cudaStreamSynchronize(st));
@@ -625,16 +721,16 @@ int rt_untile_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint3
 
 int rt_get_stats(rt_scene *s, rt_stats *out) {
     if (!s || !out) return fail(s, RT_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(s->mu);
+    Lane &L = *s->lanes[s->last_lane.load()];
+    std::lock_guard<std::mutex> lk(L.mu);
     CU(s, cudaSetDevice(s->device));
-    if (s->stats_pending) { CU(s, cudaStreamSynchronize(s->last_stream)); collect_stats(s); }
-    *out = s->stats;
+    if (L.stats_pending) { CU(s, cudaStreamSynchronize(L.last_stream)); collect_stats(s, L); }
+    *out = L.stats;
     return RT_OK;
 }
 
 int rt_get_bvh_info(rt_scene *s, uint32_t mesh, rt_bvh_info *out) {
     if (!s || !out) return fail(s, RT_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(s->mu);
     if (mesh >= s->meshes.size()) return fail(s, RT_ERR_INVALID, "mesh index out of range");
     *out = s->meshes[mesh].info;
     return RT_OK;
@@ -642,10 +738,12 @@ int rt_get_bvh_info(rt_scene *s, uint32_t mesh, rt_bvh_info *out) {
 
 int rt_synchronize(rt_scene *s) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
-    std::lock_guard<std::mutex> lk(s->mu);
     CU(s, cudaSetDevice(s->device));
-    CU(s, cudaStreamSynchronize(s->stream));
-    if (s->stats_pending) { CU(s, cudaStreamSynchronize(s->last_stream)); collect_stats(s); }
+    for (auto &lp : s->lanes) {
+        std::lock_guard<std::mutex> lk(lp->mu);
+        CU(s, cudaStreamSynchronize(lp->stream));
+        if (lp->stats_pending) { CU(s, cudaStreamSynchronize(lp->last_stream)); collect_stats(s, *lp); }
+    }
     return RT_OK;
 }
 

@@ -138,8 +138,11 @@ class GpuScene:
         self._check(self._L.rt_render_push_tiles(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr, W, H, tile_w,
                                                  tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags))
 
-    def set_frame_state(self, frame):
-        self._check(self._L.rt_frame_set(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr))
+    def set_frame_state(self, frame, lane=0):
+        self._check(self._L.rt_frame_set_lane(self.h, lane, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr))
+
+    def lane_count(self):
+        return self._L.rt_lane_count(self.h)
 
     def untile_device(self, W, H, tile_w, tile_h, n_ranks, d_all_tiles_ptr, d_out_ptr, stream_ptr=None, flags=0):
         self._check(self._L.rt_untile_device(self.h, W, H, tile_w, tile_h, n_ranks, d_all_tiles_ptr, d_out_ptr, stream_ptr, flags))

@@ -75,9 +75,25 @@ class GpuTileBackend:
 
     pipelined = True
 
-    def __init__(self, scene, device_index, precision, replicas=1):
+    def __init__(self, scene, device_index, precision, replicas=1, shared_scene=False):
         self.device = torch.device("cuda", device_index)
-        self.scenes = [GpuScene(scene, device=device_index, precision=precision) for _ in range(max(1, replicas))]
+        n = max(1, replicas)
+        # shared_scene: ONE resident scene, the frames in flight use its lanes 1..n (how a registered worker serves concurrent
+        # orders); otherwise n resident copies (benchmarking: a frame's inputs were last touched n frames earlier)
+        self.shared = bool(shared_scene)
+        if self.shared:
+            import os
+            os.environ.setdefault("RT_B200_LANES", str(n + 1))
+            one = GpuScene(scene, device=device_index, precision=precision)
+            if one.lane_count() < n + 1:
+                raise RuntimeError("scene has %d lanes, %d frames in flight requested (RT_B200_LANES)" % (one.lane_count(), n))
+            self.scenes = [one] * n
+            self.lane_flags = [_lib.LANE(k + 1) for k in range(n)]
+            self.lanes = [k + 1 for k in range(n)]
+        else:
+            self.scenes = [GpuScene(scene, device=device_index, precision=precision) for _ in range(n)]
+            self.lane_flags = [0] * n
+            self.lanes = [0] * n
         self.streams = [torch.cuda.Stream(self.device) for _ in self.scenes]
         self.comm_stream = torch.cuda.Stream(self.device)
 
@@ -89,25 +105,33 @@ class GpuTileBackend:
         return len(self.scenes)
 
     def set_frame(self, slot, cam13, lights, obj_pos=None, tan_half_fov=float("nan")):
-        self.scenes[slot].set_frame(cam13, lights, obj_pos, tan_half_fov)   # host-only: the state travels as kernel parameters
+        self.set_frame_state(slot, FrameState(cam13, lights, obj_pos, tan_half_fov))
+
+    def set_frame_state(self, slot, frame):
+        self.scenes[slot].set_frame_state(frame, self.lanes[slot])     # host-only: the state travels as kernel parameters
 
     def alloc(self, nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
     def render_region(self, slot, W, H, out, flags=0):
-        self.scenes[slot].render_region_device(W, H, 0, 0, W, H, out.data_ptr(), self.streams[slot].cuda_stream, flags)
+        self.scenes[slot].render_region_device(W, H, 0, 0, W, H, out.data_ptr(), self.streams[slot].cuda_stream,
+                                               flags | self.lane_flags[slot])
 
     def render_tiles(self, slot, W, H, tw, th, rank, n_ranks, out, flags=0):
-        self.scenes[slot].render_tiles_device(W, H, tw, th, rank, n_ranks, out.data_ptr(), self.streams[slot].cuda_stream, flags)
+        self.scenes[slot].render_tiles_device(W, H, tw, th, rank, n_ranks, out.data_ptr(), self.streams[slot].cuda_stream,
+                                              flags | self.lane_flags[slot])
 
     def render_tiles_peer(self, slot, W, H, tw, th, rank, n_ranks, frame_ptr, flags=0):
-        self.scenes[slot].render_tiles_peer(W, H, tw, th, rank, n_ranks, frame_ptr, self.streams[slot].cuda_stream, flags)
+        self.scenes[slot].render_tiles_peer(W, H, tw, th, rank, n_ranks, frame_ptr, self.streams[slot].cuda_stream,
+                                            flags | self.lane_flags[slot])
 
     def render_push_tiles(self, slot, frame, W, H, tw, th, rank, n_ranks, tiles, frame_ptr, flags=0):
-        self.scenes[slot].render_push_tiles(frame, W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr, self.streams[slot].cuda_stream, flags)
+        self.scenes[slot].render_push_tiles(frame, W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr,
+                                            self.streams[slot].cuda_stream, flags | self.lane_flags[slot])
 
     def push_tiles(self, slot, W, H, tw, th, rank, n_ranks, tiles, frame_ptr, flags=0):
-        self.scenes[slot].push_tiles_device(W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr, self.streams[slot].cuda_stream, flags)
+        self.scenes[slot].push_tiles_device(W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr, self.streams[slot].cuda_stream,
+                                            flags | self.lane_flags[slot])
 
     def untile(self, W, H, tw, th, n_ranks, all_tiles, out, flags=0):
         st = torch.cuda.current_stream(self.device).cuda_stream
@@ -123,7 +147,7 @@ class TileShardedRenderer:
     With one rank there is nothing to gather: the frame is rendered straight into the framebuffer (region mode)."""
 
     def __init__(self, scene, W, H, precision=_lib.FP32_FAST, tile=(32, 16), group=None, device_index=0, backend_factory=None,
-                 layout_flags=_lib.LAYOUT_ROWMAJOR, replicas=1, mode="peer"):
+                 layout_flags=_lib.LAYOUT_ROWMAJOR, replicas=1, mode="peer", shared_scene=False):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n_ranks = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -133,7 +157,7 @@ class TileShardedRenderer:
             raise ValueError("tile size must be a multiple of 8x4")
         self.layout_flags = layout_flags
         self.backend = backend_factory(scene, device_index, precision) if backend_factory else \
-            GpuTileBackend(scene, device_index, precision, replicas)
+            GpuTileBackend(scene, device_index, precision, replicas, shared_scene)
         self.pipelined = bool(getattr(self.backend, "pipelined", False))
         S = self.backend.n_slots() if self.pipelined else 1
         self.S = S
@@ -256,7 +280,7 @@ class TileShardedRenderer:
         if gate is not None:
             st.wait_event(gate)
         if self.n_ranks == 1:
-            be.scenes[k].set_frame_state(frame)
+            be.set_frame_state(k, frame)
             be.render_region(k, self.W, self.H, self.frame[k], flags | self.layout_flags)
             ev = self._events[k][0]
             if to_host:

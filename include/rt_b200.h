@@ -56,6 +56,14 @@ typedef enum {
 #define RT_FLAG_SIMPLE       0x10u /* FP32_FAST only: one-thread-per-ray primary kernel (the default: fastest measured) */
 #define RT_FLAG_PERSISTENT   0x20u /* FP32_FAST only: persistent warp-cooperative primary kernel (ballot/shuffle refill) */
 
+/* Lanes.  A scene handle owns one immutable copy of the geometry (+ BVH) and several LANES -- per-call resources: stream,
+ * hit-list scratch, staging buffers, frame state -- the way the reference worker serves every BulkTrace RPC on its own
+ * goroutine against one shared immutable scene (worker/distributed/main.go:27-32).  Lane 0 serves the stateful two-call API
+ * (rt_frame_set + rt_render_*); concurrent rt_bulk_trace calls each take a free lane from the pool (lanes >= 1) and run
+ * concurrently on the GPU; the device API selects its lane with RT_LANE(k) in `flags` (default 0), at most one frame in
+ * flight per lane and stream.  RT_B200_LANES (environment, default 9) sets the number of lanes. */
+#define RT_LANE(k)           ((uint32_t)(k) << 24)
+
 typedef struct rt_scene rt_scene;
 
 /* One immutable mesh (shared/state/mesh.go:100-106, flattened).  All arrays object-space. */
@@ -134,6 +142,10 @@ int  rt_device_count(void);
 /* ---- per-frame mutable state (the gob `diff`: distributed/main.go:56-64, environment.go:65-69) -- */
 int rt_frame_set(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights,
                  const double *obj_pos /* n_objects*3 or NULL = unchanged */);
+/* the same for an explicit lane of the device API */
+int rt_frame_set_lane(rt_scene *scene, uint32_t lane, const rt_camera *cam, const rt_light *lights, uint32_t n_lights,
+                      const double *obj_pos);
+int rt_lane_count(rt_scene *scene);
 
 /* ---- render one screen region (distributed/main.go:67-88; sequential/main.go:21-28) ------------
  * Pixel (x+i, y+j), i<w, j<h, of a screen_w x screen_h screen (tracer.go:81 takes the FULL screen
@@ -142,7 +154,8 @@ int rt_frame_set(rt_scene *scene, const rt_camera *cam, const rt_light *lights, 
 int rt_render_region(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t x, uint32_t y,
                      uint32_t w, uint32_t h, uint8_t *out_rgb, uint32_t flags);
 
-/* frame_set + render_region atomically under the handle lock: what one BulkTrace RPC does. */
+/* frame state + render of one WorkOrder = what one BulkTrace RPC does.  Thread-safe and CONCURRENT: every call takes its own
+ * lane, so several goroutines can have orders in flight on one registered scene (obj_pos NULL = the registered positions). */
 int rt_bulk_trace(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights,
                   const double *obj_pos, uint32_t screen_w, uint32_t screen_h, uint32_t x, uint32_t y,
                   uint32_t w, uint32_t h, uint8_t *out_rgb, uint32_t flags);
