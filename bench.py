@@ -179,7 +179,8 @@ def main():
     ap.add_argument("--replicas", type=int, default=0, help="scene replicas / frames in flight (default %d)" % REPLICAS)
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e loop (experiments only)")
     ap.add_argument("--shared-scene", action="store_true", help="frames in flight share ONE resident scene (lanes) instead of replicas")
-    ap.add_argument("--mode", default="peer", choices=["peer", "gather"], help="N>1: peer-memory framebuffer writer or NCCL gather")
+    ap.add_argument("--mode", default="peer", choices=["peer", "peer_nccl", "gather"],
+                    help="N>1: peer-memory tile push with device-side hand-off flags | same push with an NCCL barrier | NCCL gather")
     ap.add_argument("--persistent", action="store_true", help="use the persistent warp-cooperative primary kernel (RT_FLAG_PERSISTENT)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -237,7 +238,8 @@ def main():
                                      layout_flags=rt.LAYOUT_COLMAJOR, mode=args.mode, shared_scene=args.shared_scene)
     g = r.backend.scenes[0]
     bvh = g.bvh_info()
-    launches_per_step = 3 if world == 1 else (4 if args.mode == "peer" else 3 + (1 if rank == 0 else 0))   # K2 K4 K5 (+ clear-tiles | untile)
+    # K2 K4 K5 (+ push-tiles (+ frame-complete on rank 0) | untile on rank 0); rank 0's count is the one reported
+    launches_per_step = 3 if world == 1 else ((5 if rank == 0 else 4) if args.mode == "peer" else 4)
 
     frame_state = rt.FrameState(cam13, lights, tan_half_fov=tan_half)   # camera + lights marshalled once; handed over per frame
 
@@ -306,6 +308,7 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
+    r.check_sync()                                        # a timed-out device-side hand-off would invalidate the run
     dev_ms = ev0.elapsed_time(ev1)
     print("[bench] rank %d: %.3f ms per step on this rank" % (rank, dev_ms / args.steps), file=sys.stderr, flush=True)
     if world > 1:
@@ -481,8 +484,10 @@ def main():
                          "come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS, REPLICAS),
                    "frames_in_flight": REPLICAS, "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps, "precision": "FP32_FAST traversal, fp64 shading",
                    "parallelism": ("screen tiles 32x16 round-robin over %d rank(s)" % world) + ("" if world == 1 else
-                                   ("; K5 stores hit pixels into rank 0's framebuffer over NVLink peer memory (CUDA IPC), 4-byte all_reduce as barrier"
-                                    if args.mode == "peer" else "; NCCL all_gather of packed tiles + de-interleave on rank 0")), "bvh": bvh,
+                                   {"peer": "; every rank pushes its tiles into rank 0's framebuffer over NVLink peer memory (CUDA IPC, 16-byte stores) and "
+                                            "the push kernel hands the frame over through arrive/consumed flags in rank 0's memory (no collective)",
+                                    "peer_nccl": "; tiles pushed into rank 0's framebuffer over NVLink peer memory, 4-byte all_reduce as barrier",
+                                    "gather": "; NCCL all_gather of packed tiles + de-interleave on rank 0"}[args.mode]), "bvh": bvh,
                    "primary_kernel": "persistent" if args.persistent else "simple"},
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "clocks": clocks, "wall_s_timed_region": wall,

@@ -4,6 +4,11 @@ GPU entry points raises; nothing here ever routes to a CPU implementation."""
 import ctypes as C
 import os
 
+# Frames in flight live on separate CUDA streams; with the default 8 hardware queues several streams share a queue and a
+# queue stalls at its first entry that has to wait (e.g. the consumer behind a frame hand-off wait).  Must be set before the
+# CUDA context exists, hence at import time; an explicit setting of the user wins.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")   # override: kernel-variant experiments
 
@@ -20,10 +25,12 @@ def LANE(k):
 RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_STATE, RT_ERR_CANCELLED = 0, -1, -2, -3, -4, -5
 
 # every symbol include/rt_b200.h declares
+SYNC_SLOT_BYTES = 256            # include/rt_b200.h: RT_SYNC_SLOT_BYTES
+
 ABI_SYMBOLS = (
     "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set", "rt_frame_set_lane", "rt_lane_count",
     "rt_render_region", "rt_bulk_trace", "rt_render_region_debug", "rt_render_region_device", "rt_render_tiles_device",
-    "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
+    "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_frame_complete_device", "rt_frame_release_device", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
     "rt_ipc_close", "rt_measure_fma_peak", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free",
 )
 
@@ -117,7 +124,11 @@ def load():
     L.rt_push_tiles_device.restype = C.c_int
     L.rt_push_tiles_device.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, u32]
     L.rt_render_push_tiles.restype = C.c_int
-    L.rt_render_push_tiles.argtypes = [vp, C.POINTER(Camera), vp, u32, vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, u32]
+    L.rt_render_push_tiles.argtypes = [vp, C.POINTER(Camera), vp, u32, vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, u32, vp, u32]
+    L.rt_frame_complete_device.restype = C.c_int
+    L.rt_frame_complete_device.argtypes = [vp, vp, u32, u32, u32, vp]
+    L.rt_frame_release_device.restype = C.c_int
+    L.rt_frame_release_device.argtypes = [vp, vp, u32, vp]
     L.rt_device_alloc.restype = C.c_int
     L.rt_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
     L.rt_device_free.restype = C.c_int

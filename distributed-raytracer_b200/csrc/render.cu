@@ -303,8 +303,9 @@ __global__ void __launch_bounds__(128) k_untile(const uint8_t *__restrict__ tile
                                                  int th, int n_ranks, int tiles_per_rank_max, bool rowmajor) {
     extern __shared__ __align__(16) uint8_t s_tile[];
     const int tiles_x = (W + tw - 1) / tw;
-    const int t = blockIdx.x;
-    const int tx0 = (t % tiles_x) * tw, ty0 = (t / tiles_x) * th;
+    const int TX = blockIdx.x % tiles_x, TY = blockIdx.x / tiles_x;      // one CTA per tile POSITION
+    const int t = (int)tile_id((uint32_t)TX, (uint32_t)TY, (uint32_t)tiles_x);
+    const int tx0 = TX * tw, ty0 = TY * th;
     const int rank = t % n_ranks, lt = t / n_ranks;
     const size_t tile_bytes = (size_t)tw * th * 3;
     const uint8_t *src = tiles + ((size_t)rank * tiles_per_rank_max + lt) * tile_bytes;
@@ -374,13 +375,14 @@ __device__ __forceinline__ void push_segments(const uint8_t *s_tile, uint8_t *ou
     }
 }
 
-__global__ void __launch_bounds__(128) k_push_tiles(FrameParams fp, bool rowmajor, const uint8_t *__restrict__ tiles,
-                                                     uint8_t *__restrict__ out) {
-    extern __shared__ __align__(16) uint8_t s_tile[];
+__device__ __forceinline__ void push_one_tile(const FrameParams &fp, bool rowmajor, const uint8_t *__restrict__ tiles,
+                                              uint8_t *__restrict__ out, uint8_t *s_tile) {
     const int lt = blockIdx.x;
     const uint32_t t = (uint32_t)lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
     const int tw = fp.tile_w, th = fp.tile_h, W = fp.W, H = fp.H;
-    const int tx0 = (int)(t % (uint32_t)fp.tiles_x) * tw, ty0 = (int)(t / (uint32_t)fp.tiles_x) * th;
+    uint32_t TX, TY;
+    tile_pos(t, (uint32_t)fp.tiles_x, TX, TY);
+    const int tx0 = (int)TX * tw, ty0 = (int)TY * th;
     if (tx0 >= W || ty0 >= H) return;
     const size_t tile_bytes = (size_t)tw * th * 3;
     const uint4 *src4 = reinterpret_cast<const uint4 *>(tiles + (size_t)lt * tile_bytes);
@@ -405,6 +407,69 @@ __global__ void __launch_bounds__(128) k_push_tiles(FrameParams fp, bool rowmajo
         }
 }
 
+// ---- frame hand-off flags in peer memory -------------------------------------------------------------------------
+// One 256-byte record per framebuffer slot, living next to the framebuffers on the gathering rank (CUDA IPC, reached over
+// NVLink by the others):  uint32 arrive[32] (arrive[r] = number of the last frame rank r has completely pushed into the
+// slot), consumed (number of the last frame the gathering rank is done with: the slot may be overwritten), error.
+// Frame numbers count per slot from 1.  Release/acquire at system scope orders the tile stores before the flag.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// waits until *p has reached `want` (wrap-safe); gives up after timeout_ms (a dead peer must not hang this GPU:
+// the reference's own order time-out is 2 s, master/main.go:35)
+__device__ bool spin_until(const uint32_t *p, uint32_t want, uint32_t timeout_ms) {
+    if ((int32_t)(ld_acquire_sys(p) - want) >= 0) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    for (;;) {
+        if ((int32_t)(ld_acquire_sys(p) - want) >= 0) return true;
+        __nanosleep(256);
+        if (globaltimer_ns() - t0 > (unsigned long long)timeout_ms * 1000000ull) return false;
+    }
+}
+
+// rank 0 (the gathering rank): frame `seq` of the slot is complete once every rank's arrive flag has reached it;
+// with `release` the slot is handed back at once (device-only consumer), else rt_frame_release_device does it after the consumer.
+__global__ void k_frame_complete(uint32_t *slot, uint32_t seq, int n_ranks, int release, uint32_t timeout_ms) {
+    const int r = (int)threadIdx.x;
+    if (r < n_ranks && !spin_until(slot + RT_SYNC_ARRIVE + r, seq, timeout_ms))
+        *(volatile uint32_t *)(slot + RT_SYNC_ERROR) = 0x100u + (uint32_t)r;
+    __syncwarp();
+    if (release && r == 0) { __threadfence_system(); st_release_sys(slot + RT_SYNC_CONSUMED, seq); }
+}
+__global__ void k_frame_release(uint32_t *slot, uint32_t seq) { __threadfence_system(); st_release_sys(slot + RT_SYNC_CONSUMED, seq); }
+
+__global__ void __launch_bounds__(128) k_push_tiles(FrameParams fp, bool rowmajor, const uint8_t *__restrict__ tiles,
+                                                     uint8_t *__restrict__ out, PushSync sy) {
+    extern __shared__ __align__(16) uint8_t s_tile[];
+    if (sy.slot) {                                  // the slot's previous frame must have been consumed before it is overwritten
+        if (threadIdx.x == 0 && !spin_until(sy.slot + RT_SYNC_CONSUMED, sy.seq - 1u, sy.timeout_ms))
+            *(volatile uint32_t *)(sy.slot + RT_SYNC_ERROR) = 0x200u + (uint32_t)fp.rank;
+        __syncthreads();
+    }
+    push_one_tile(fp, rowmajor, tiles, out, s_tile);
+    if (sy.slot) {                                  // last CTA to finish publishes "rank has pushed frame seq"
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(sy.blocks_done, 1u);
+            if (prev == gridDim.x - 1) {
+                *sy.blocks_done = 0u;               // next launch on this lane is stream-ordered after this one
+                __threadfence_system();
+                st_release_sys(sy.slot + RT_SYNC_ARRIVE + fp.rank, sy.seq);
+            }
+        }
+    }
+}
 // multi-GPU, peer-memory writer: clears the pixels of THIS rank's tiles in the full framebuffer `out` (which may live on
 // another GPU, mapped through CUDA IPC / NVLink).  One CTA per local tile; interior tiles are cleared with 32-bit words
 // that exactly cover the tile's column (or row) segments, so no byte owned by another rank is ever touched.
@@ -412,7 +477,9 @@ __global__ void __launch_bounds__(128) k_clear_tiles(FrameParams fp, bool rowmaj
     const int lt = blockIdx.x;
     const uint32_t t = (uint32_t)lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
     const int tw = fp.tile_w, th = fp.tile_h, W = fp.W, H = fp.H;
-    const int tx0 = (int)(t % (uint32_t)fp.tiles_x) * tw, ty0 = (int)(t / (uint32_t)fp.tiles_x) * th;
+    uint32_t TX, TY;
+    tile_pos(t, (uint32_t)fp.tiles_x, TX, TY);
+    const int tx0 = (int)TX * tw, ty0 = (int)TY * th;
     if (tx0 >= W || ty0 >= H) return;
     const bool interior = tx0 + tw <= W && ty0 + th <= H && (H % 4 == 0) && (W % 4 == 0);
     if (interior) {
@@ -577,10 +644,21 @@ cudaError_t rt_launch_clear_tiles(const FrameParams &fp, bool rowmajor, uint8_t 
     return cudaGetLastError();
 }
 
-cudaError_t rt_launch_push_tiles(const FrameParams &fp, bool rowmajor, const uint8_t *d_tiles, uint8_t *d_out, cudaStream_t st) {
+cudaError_t rt_launch_push_tiles(const FrameParams &fp, bool rowmajor, const uint8_t *d_tiles, uint8_t *d_out, const PushSync &sy,
+                                 cudaStream_t st) {
     if (fp.n_local_tiles <= 0) return cudaSuccess;
     const size_t smem = (size_t)fp.tile_w * fp.tile_h * 3;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    k_push_tiles<<<(unsigned)fp.n_local_tiles, 128, smem, st>>>(fp, rowmajor, d_tiles, d_out);
+    k_push_tiles<<<(unsigned)fp.n_local_tiles, 128, smem, st>>>(fp, rowmajor, d_tiles, d_out, sy);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_frame_complete(uint32_t *d_slot, uint32_t seq, int n_ranks, bool release, uint32_t timeout_ms, cudaStream_t st) {
+    k_frame_complete<<<1, 32, 0, st>>>(d_slot, seq, n_ranks, release ? 1 : 0, timeout_ms);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_frame_release(uint32_t *d_slot, uint32_t seq, cudaStream_t st) {
+    k_frame_release<<<1, 1, 0, st>>>(d_slot, seq);
     return cudaGetLastError();
 }

@@ -60,6 +60,7 @@ struct rt_scene {
     int shade_minb = 8;
     bool primary_persistent = false;
     bool split_shade = false;
+    uint32_t sync_timeout_ms = 2000;   // device-side wait on a peer's hand-off flag gives up after this (master/main.go:35: 2 s per order)
 
     // immutable after rt_scene_create
     std::vector<MeshDevice> meshes;
@@ -172,7 +173,8 @@ Lane *device_lane(rt_scene *s, uint32_t flags, int *index) {
 
 int ensure_scratch(rt_scene *s, Lane &L, size_t nrays, size_t out_bytes, bool need_rgb, bool dbg, size_t npix_out) {
     if (!L.d_counters) {
-        CU(s, cudaMalloc((void **)&L.d_counters, 4 * sizeof(unsigned int)));
+        CU(s, cudaMalloc((void **)&L.d_counters, 8 * sizeof(unsigned int)));     // [0..3] per-frame counters, [4] CTAs-done counter of k_push_tiles
+        CU(s, cudaMemset(L.d_counters, 0, 8 * sizeof(unsigned int)));
         CU(s, cudaMalloc((void **)&L.d_stats, 2 * sizeof(Counters)));
     }
     if (nrays > L.cap_rays) {
@@ -444,6 +446,7 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->split_shade = env_int("RT_B200_SPLIT_SHADE", 0) != 0;
     s->top_in_smem = env_int("RT_B200_TOP_SMEM", 0) != 0;
     s->refill_below = env_int("RT_B200_REFILL", 1);
+    s->sync_timeout_ms = (uint32_t)std::max(1, env_int("RT_B200_SYNC_TIMEOUT_MS", 2000));
     int n_lanes = env_int("RT_B200_LANES", 9);      // lane 0 + a pool of 8 for concurrent BulkTrace calls / frames in flight
     if (n_lanes < 1) n_lanes = 1;
     if (n_lanes > 64) n_lanes = 64;
@@ -637,7 +640,7 @@ int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
     int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, true);
     if (rc != RT_OK) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : Lp->stream;
-    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, st));
+    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, PushSync{}, st));
     if (!stream) CU(s, cudaStreamSynchronize(st));
     return RT_OK;
 }
@@ -645,7 +648,7 @@ int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
 // rt_frame_set + rt_render_tiles_device + rt_push_tiles_device in one call (one lock, one ctypes/cgo crossing per frame)
 int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
                          uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks, void *d_tiles, void *d_framebuffer,
-                         void *stream, uint32_t flags) {
+                         void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_tiles || !d_framebuffer || !stream) return fail(s, RT_ERR_INVALID, "rt_render_push_tiles: NULL buffer or stream");
     int idx = 0;
@@ -661,7 +664,29 @@ int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *ligh
     s->last_lane.store(idx);
     rc = render_lane(s, *Lp, fp, flags & ~RT_LAYOUT_ROWMAJOR, (size_t)fp.n_local_tiles * tile_w * tile_h, o);
     if (rc != RT_OK) return rc;
-    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, (cudaStream_t)stream));
+    PushSync sy{};
+    if (d_sync_slot) {
+        if (n_ranks > 32) return fail(s, RT_ERR_INVALID, "rt_render_push_tiles: the hand-off record holds 32 ranks");
+        sy.slot = (uint32_t *)d_sync_slot; sy.blocks_done = Lp->d_counters + 4; sy.seq = seq; sy.timeout_ms = s->sync_timeout_ms;
+    }
+    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, sy, (cudaStream_t)stream));
+    return RT_OK;
+}
+
+// gathering rank: frame `seq` of the slot is complete when all ranks have pushed it (waits ON THE DEVICE, in stream order)
+int rt_frame_complete_device(rt_scene *s, void *d_sync_slot, uint32_t seq, uint32_t n_ranks, uint32_t release, void *stream) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!d_sync_slot || !stream || n_ranks == 0 || n_ranks > 32) return fail(s, RT_ERR_INVALID, "rt_frame_complete_device: bad argument");
+    CU(s, cudaSetDevice(s->device));
+    CU(s, rt_launch_frame_complete((uint32_t *)d_sync_slot, seq, (int)n_ranks, release != 0, s->sync_timeout_ms, (cudaStream_t)stream));
+    return RT_OK;
+}
+
+int rt_frame_release_device(rt_scene *s, void *d_sync_slot, uint32_t seq, void *stream) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!d_sync_slot || !stream) return fail(s, RT_ERR_INVALID, "rt_frame_release_device: bad argument");
+    CU(s, cudaSetDevice(s->device));
+    CU(s, rt_launch_frame_release((uint32_t *)d_sync_slot, seq, (cudaStream_t)stream));
     return RT_OK;
 }
 

@@ -84,12 +84,30 @@ struct HitRec { uint32_t pix; int32_t obj; int32_t face; float t; };
 
 struct Counters { unsigned long long nodes, tris; };
 
+// frame hand-off record in peer memory (one per framebuffer slot, RT_SYNC_SLOT_BYTES = 256 in include/rt_b200.h), uint32 words:
+#define RT_SYNC_ARRIVE 0        // [0..31]  arrive[rank]
+#define RT_SYNC_CONSUMED 32
+#define RT_SYNC_ERROR 33
+struct PushSync { uint32_t *slot; unsigned int *blocks_done; uint32_t seq, timeout_ms; };
+
 // ------------------------------------------------------------------------------------------------
 // ray index <-> pixel mapping.  Rays are numbered so that 32 consecutive indices form an 8x4 pixel
 // block (coherent warps).  Region mode: blocks row-major over the region.  Tile mode (multi-GPU):
-// tiles t = lt*n_ranks + rank, each tile_w x tile_h (multiples of 8 x 4), blocks row-major in a tile.
+// tiles t = lt*n_ranks + rank at screen position tile_pos(t), each tile_w x tile_h (multiples of 8 x 4), blocks row-major in a tile.
 // ------------------------------------------------------------------------------------------------
-struct PixMap { int i, j; uint32_t out; bool valid; };   // i,j = absolute screen pixel; out = index in the output buffer
+struct PixMap { int i, j; uint32_t out; bool valid; };
+
+// Tile id t (owner rank = t % n_ranks, slot in the owner's packed buffer = t / n_ranks)  <->  tile position (X, Y) on the
+// screen.  Tile row Y is rotated by 3*Y positions: when n_ranks divides tiles_x (3840/32 = 120 = 8*15) the plain row-major
+// numbering would give every rank whole tile COLUMNS (vertical stripes; 9.6 % more hit pixels on the busiest of 8 ranks for
+// the C3 view); rotated, the owners form diagonals and the imbalance is < 1 % for 2..8 ranks.
+RT_HD void tile_pos(uint32_t t, uint32_t tiles_x, uint32_t &X, uint32_t &Y) {
+    Y = t / tiles_x;
+    X = (t % tiles_x + 3u * Y) % tiles_x;
+}
+RT_HD uint32_t tile_id(uint32_t X, uint32_t Y, uint32_t tiles_x) {
+    return Y * tiles_x + (X + tiles_x - (3u * Y) % tiles_x) % tiles_x;
+}   // i,j = absolute screen pixel; out = index in the output buffer
 
 RT_HD uint32_t ray_count(const FrameParams &fp) {
     if (fp.tile_w > 0) return (uint32_t)fp.n_local_tiles * (uint32_t)(fp.tile_w * fp.tile_h);
@@ -107,8 +125,10 @@ RT_HD PixMap map_ray(uint32_t r, const FrameParams &fp, bool rowmajor) {
         uint32_t bx = b % (uint32_t)(fp.tile_w / 8), by = b / (uint32_t)(fp.tile_w / 8);
         int tx = (int)bx * 8 + lx, ty = (int)by * 4 + ly;
         uint32_t t = lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
-        p.i = (int)(t % (uint32_t)fp.tiles_x) * fp.tile_w + tx;
-        p.j = (int)(t / (uint32_t)fp.tiles_x) * fp.tile_h + ty;
+        uint32_t TX, TY;
+        tile_pos(t, (uint32_t)fp.tiles_x, TX, TY);
+        p.i = (int)TX * fp.tile_w + tx;
+        p.j = (int)TY * fp.tile_h + ty;
         p.out = lt * (uint32_t)(fp.tile_w * fp.tile_h) + (uint32_t)(ty * fp.tile_w + tx);
         p.valid = p.i < fp.W && p.j < fp.H;
         if (fp.tile_final && p.valid)

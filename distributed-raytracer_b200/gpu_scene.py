@@ -133,10 +133,18 @@ class GpuScene:
     def push_tiles_device(self, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr=None, flags=0):
         self._check(self._L.rt_push_tiles_device(self.h, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags))
 
-    def render_push_tiles(self, frame, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags=0):
-        """frame = FrameState (prebuilt ctypes camera + lights): one C call per frame."""
+    def render_push_tiles(self, frame, W, H, tile_w, tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags=0,
+                          sync_slot_ptr=None, seq=0):
+        """frame = FrameState (prebuilt ctypes camera + lights): one C call per frame.  sync_slot_ptr/seq: device-side frame
+        hand-off through the slot's record in the gathering rank's memory (include/rt_b200.h)."""
         self._check(self._L.rt_render_push_tiles(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr, W, H, tile_w,
-                                                 tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, stream_ptr, flags))
+                                                 tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, sync_slot_ptr, seq, stream_ptr, flags))
+
+    def frame_complete_device(self, sync_slot_ptr, seq, n_ranks, release, stream_ptr):
+        self._check(self._L.rt_frame_complete_device(self.h, sync_slot_ptr, seq, n_ranks, 1 if release else 0, stream_ptr))
+
+    def frame_release_device(self, sync_slot_ptr, seq, stream_ptr):
+        self._check(self._L.rt_frame_release_device(self.h, sync_slot_ptr, seq, stream_ptr))
 
     def set_frame_state(self, frame, lane=0):
         self._check(self._L.rt_frame_set_lane(self.h, lane, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr))

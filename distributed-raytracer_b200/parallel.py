@@ -125,9 +125,15 @@ class GpuTileBackend:
         self.scenes[slot].render_tiles_peer(W, H, tw, th, rank, n_ranks, frame_ptr, self.streams[slot].cuda_stream,
                                             flags | self.lane_flags[slot])
 
-    def render_push_tiles(self, slot, frame, W, H, tw, th, rank, n_ranks, tiles, frame_ptr, flags=0):
+    def render_push_tiles(self, slot, frame, W, H, tw, th, rank, n_ranks, tiles, frame_ptr, flags=0, sync_slot_ptr=None, seq=0):
         self.scenes[slot].render_push_tiles(frame, W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr,
-                                            self.streams[slot].cuda_stream, flags | self.lane_flags[slot])
+                                            self.streams[slot].cuda_stream, flags | self.lane_flags[slot], sync_slot_ptr, seq)
+
+    def frame_complete(self, slot, sync_slot_ptr, seq, n_ranks, release):
+        self.scenes[slot].frame_complete_device(sync_slot_ptr, seq, n_ranks, release, self.streams[slot].cuda_stream)
+
+    def frame_release(self, slot, sync_slot_ptr, seq):
+        self.scenes[slot].frame_release_device(sync_slot_ptr, seq, self.streams[slot].cuda_stream)
 
     def push_tiles(self, slot, W, H, tw, th, rank, n_ranks, tiles, frame_ptr, flags=0):
         self.scenes[slot].push_tiles_device(W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr, self.streams[slot].cuda_stream,
@@ -165,18 +171,25 @@ class TileShardedRenderer:
         self.tile_bytes = self.tw * self.th * 3
         multi = self.n_ranks > 1
         # mode "peer": every rank pushes its rendered tiles straight into rank 0's framebuffer over NVLink (CUDA IPC
-        # mapping, wide coalesced stores) -- no gather, no de-interleave, only a tiny barrier collective per frame.
+        # mapping, wide coalesced stores) and the same kernel hands the frame over through flags in rank 0's memory
+        # (arrive / consumed, release-acquire at system scope): no gather, no de-interleave, no collective, ONE library call
+        # per frame and rank, and a rank only ever waits for rank 0's consumption of the slot, never for its siblings.
+        # mode "peer_nccl": same data path, a 4-byte all_reduce per frame as the barrier (kept for comparison).
         # mode "gather": packed tile buffers + all_gather + de-interleave on rank 0 (the NCCL-only baseline).
+        if mode not in ("peer", "peer_nccl", "gather"):
+            raise ValueError("mode must be peer, peer_nccl or gather")
         self.mode = mode if (multi and self.pipelined) else "gather"
         self.peer_bufs = []
-        if self.mode == "peer":
+        self.ctrl = None
+        self.slot_seq = [0] * S
+        if self.mode in ("peer", "peer_nccl"):
             self._init_peer(device_index)
         self.local = [self.backend.alloc(self.per_rank * self.tile_bytes) for _ in range(S)] if multi else []
         for t in self.local:
             t.zero_()
         self.gathered = [self.backend.alloc(self.n_ranks * self.per_rank * self.tile_bytes) for _ in range(S)] \
-            if (multi and self.mode != "peer") else []
-        if self.mode != "peer":
+            if (multi and self.mode == "gather") else []
+        if self.mode == "gather":
             self.frame = [self.backend.alloc(self.W * self.H * 3) if self.rank == 0 else None for _ in range(S)]
         self.seq = 0
         self.done_ev = [None] * S        # event: everything that read or wrote slot k's buffers is finished
@@ -185,16 +198,21 @@ class TileShardedRenderer:
     def _init_peer(self, device_index):
         nbytes = self.W * self.H * 3
         handles = [None]
+        cbytes = self.S * _lib.SYNC_SLOT_BYTES
         if self.rank == 0:
             self.peer_bufs = [DeviceBuffer(device_index, nbytes) for _ in range(self.S)]
-            handles = [[b.export() for b in self.peer_bufs]]
+            self.ctrl = DeviceBuffer(device_index, cbytes)                 # frame hand-off records, one per slot
+            handles = [[b.export() for b in self.peer_bufs] + [self.ctrl.export()]]
         dist.broadcast_object_list(handles, src=0, group=self.group)
         if self.rank != 0:
-            self.peer_bufs = [DeviceBuffer(device_index, nbytes, ipc_handle=h) for h in handles[0]]
+            self.peer_bufs = [DeviceBuffer(device_index, nbytes, ipc_handle=h) for h in handles[0][:-1]]
+            self.ctrl = DeviceBuffer(device_index, cbytes, ipc_handle=handles[0][-1])
         self.frame = [torch.as_tensor(b, device=self.backend.device) if self.rank == 0 else None for b in self.peer_bufs]
+        self.ctrl_view = torch.as_tensor(self.ctrl, device=self.backend.device).view(torch.int32).view(self.S, -1)
         if self.rank == 0:
             for f in self.frame:
                 f.zero_()
+            self.ctrl_view.zero_()
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.backend.device)
         torch.cuda.synchronize(self.backend.device)
         dist.barrier(group=self.group)
@@ -205,6 +223,8 @@ class TileShardedRenderer:
         `host_frame[slot]` (returned instead of the device tensor); valid after wait() + synchronize."""
         k = self.seq % self.S
         self.seq += 1
+        if self.pipelined and not isinstance(cam13, FrameState) and (self.n_ranks == 1 or self.mode != "gather"):
+            cam13 = FrameState(cam13, lights, obj_pos, tan_half_fov)
         if self.pipelined and isinstance(cam13, FrameState):
             return self._render_frame_fast(k, cam13, flags, to_host)
         if isinstance(cam13, FrameState):
@@ -231,23 +251,6 @@ class TileShardedRenderer:
             ev = torch.cuda.Event()
             ev.record(st)
             self.done_ev[k] = ev
-            return self.frame[k]
-        if self.mode == "peer":
-            # every rank renders its tiles locally, then pushes them into rank 0's framebuffer k over NVLink (16-byte
-            # coalesced stores); the all_reduce is only the "everybody has written" barrier
-            be.render_tiles(k, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
-            be.push_tiles(k, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], self.peer_bufs[k].ptr,
-                          self.layout_flags)
-            ev = torch.cuda.Event()
-            ev.record(st)
-            comm = be.comm_stream
-            comm.wait_event(ev)
-            with torch.cuda.stream(comm):
-                if not _NO_BARRIER:
-                    dist.all_reduce(self.flag, group=self.group)
-                done = torch.cuda.Event()
-                done.record(comm)
-            self.done_ev[k] = done
             return self.frame[k]
         be.render_tiles(k, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
         ev = torch.cuda.Event()
@@ -276,7 +279,10 @@ class TileShardedRenderer:
         # device->host copy on rank 0, the copy of frame f sits between the barriers of f and f+1 on rank 0's communication
         # stream, so "barrier of frame f+1 has completed" (a collective: it needs rank 0) tells EVERY rank that rank 0 has
         # finished reading slot k -- hence the wait on the next slot's event.
-        gate = self.done_ev[(k + 1) % self.S] if (to_host and self.S > 1) else self.done_ev[k]
+        if self.n_ranks > 1 and self.mode == "peer":
+            gate = None                                      # slot streams are in order; cross-rank reuse is gated by the consumed flag
+        else:
+            gate = self.done_ev[(k + 1) % self.S] if (to_host and self.S > 1) else self.done_ev[k]
         if gate is not None:
             st.wait_event(gate)
         if self.n_ranks == 1:
@@ -289,11 +295,28 @@ class TileShardedRenderer:
             ev.record(st)
             self.done_ev[k] = ev
             return self._host_frames()[k] if to_host else self.frame[k]
-        if self.mode != "peer":
-            raise RuntimeError("FrameState fast path is implemented for the peer mode")
+        if self.mode == "gather":
+            raise RuntimeError("FrameState fast path is implemented for the peer modes")
+        ev, done = self._events[k]
+        if self.mode == "peer":
+            # ONE stream, no collective: render -> push (waits for "slot consumed", publishes "arrived") [-> rank 0: complete
+            # (waits for every rank's arrival) -> consumer -> release]
+            self.slot_seq[k] += 1
+            seq = self.slot_seq[k] & 0x7fffffff
+            slot_ptr = self.ctrl.ptr + k * _lib.SYNC_SLOT_BYTES
+            be.render_push_tiles(k, frame, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], self.peer_bufs[k].ptr,
+                                 flags | self.layout_flags, slot_ptr, seq)
+            if self.rank == 0:
+                be.frame_complete(k, slot_ptr, seq, self.n_ranks, release=not to_host)
+                if to_host:
+                    with torch.cuda.stream(st):
+                        self._host_frames()[k].copy_(self.frame[k], non_blocking=True)
+                    be.frame_release(k, slot_ptr, seq)
+            done.record(st)
+            self.done_ev[k] = done
+            return self._host_frames()[k] if to_host else self.frame[k]
         be.render_push_tiles(k, frame, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], self.peer_bufs[k].ptr,
                              flags | self.layout_flags)
-        ev, done = self._events[k]
         ev.record(st)
         comm = be.comm_stream
         comm.wait_event(ev)
@@ -307,6 +330,15 @@ class TileShardedRenderer:
         if to_host:
             return self._host_frames()[k]
         return self.frame[k]
+
+    def check_sync(self):
+        """Raises if a device-side wait of the frame hand-off timed out (a rank died or fell > RT_B200_SYNC_TIMEOUT_MS behind)."""
+        if self.ctrl is None:
+            return
+        err = self.ctrl_view[:, 33].cpu()
+        if int(err.abs().max()) != 0:
+            raise RuntimeError("frame hand-off timed out: error words per slot = %s (0x100+r: rank r never arrived; 0x200+r: "
+                               "rank r never saw the slot released)" % [hex(int(e)) for e in err])
 
     def _single_local(self):
         if not self.local:

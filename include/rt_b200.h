@@ -174,7 +174,9 @@ int rt_render_region_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_
                             uint32_t w, uint32_t h, void *d_out_rgb, void *stream, uint32_t flags);
 
 /* Multi-GPU screen-tile sharding (master/main.go:54-91 partition(), re-designed as interleaved
- * tiles): the full screen is cut into tile_w x tile_h tiles numbered row-major; this call renders
+ * tiles): the full screen is cut into tile_w x tile_h tiles; the tile at column X, row Y has id
+ * t = Y*tiles_x + (X - 3*Y) mod tiles_x (each tile row rotated by 3 more positions, so that the
+ * owners form diagonals, not column stripes, when n_ranks divides tiles_x); this call renders the
  * tiles t with t % n_ranks == rank and packs them, in increasing t, into d_out_tiles (DEVICE,
  * n_local_tiles * tile_w*tile_h*3 bytes, each tile row-major, edge tiles padded with zeros). */
 int rt_render_tiles_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w,
@@ -194,10 +196,23 @@ int rt_push_tiles_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, 
                          uint32_t rank, uint32_t n_ranks, const void *d_tiles, void *d_framebuffer, void *stream,
                          uint32_t flags);
 /* rt_frame_set + rt_render_tiles_device + rt_push_tiles_device in ONE call (the per-frame call of a rank in the multi-GPU
- * pipeline: at 8 GPUs a frame is ~0.12 ms, so host crossings matter).  Asynchronous: `stream` must not be NULL. */
+ * pipeline: at 8 GPUs a frame is ~0.12 ms, so host crossings matter).  Asynchronous: `stream` must not be NULL.
+ *
+ * Frame hand-off without a collective: d_sync_slot (may be NULL = no hand-off) points at the RT_SYNC_SLOT_BYTES record of
+ * the framebuffer slot, in the gathering rank's memory like the framebuffer itself (zeroed once; opened with rt_ipc_open
+ * by the others).  Frames of a slot are numbered seq = 1, 2, ...  The push kernel first waits -- on the device -- until the
+ * gathering rank has released frame seq-1 of the slot, stores its tiles over NVLink, and its last CTA then publishes
+ * arrive[rank] = seq with a system-scope release.  A wait gives up after RT_B200_SYNC_TIMEOUT_MS (2000) and records
+ * 0x200+rank (push) or 0x100+rank (complete) in the record's error word instead of hanging the GPU. */
+#define RT_SYNC_SLOT_BYTES 256u   /* uint32 arrive[32]; uint32 consumed; uint32 error; padding */
 int rt_render_push_tiles(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos,
                          uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
-                         void *d_tiles, void *d_framebuffer, void *stream, uint32_t flags);
+                         void *d_tiles, void *d_framebuffer, void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags);
+/* Gathering rank, in stream order on `stream`: waits (on the device) until all n_ranks ranks have pushed frame `seq` of the
+ * slot; everything enqueued on `stream` afterwards sees the complete frame.  release != 0 hands the slot back at once;
+ * otherwise call rt_frame_release_device after the consumer (e.g. the device->host copy) on the same stream. */
+int rt_frame_complete_device(rt_scene *scene, void *d_sync_slot, uint32_t seq, uint32_t n_ranks, uint32_t release, void *stream);
+int rt_frame_release_device(rt_scene *scene, void *d_sync_slot, uint32_t seq, void *stream);
 /* Device buffers shareable between the one-process-per-GPU ranks of a box (CUDA IPC; 64-byte opaque handles) */
 int rt_device_alloc(int device, size_t bytes, void **out);
 int rt_device_free(int device, void *p);

@@ -140,7 +140,8 @@ def numpy_untile(all_tiles, W, H, tw, th, n_ranks):
     per_rank = rt.tiles_per_rank(W, H, tw, th, n_ranks)
     tiles = all_tiles.reshape(n_ranks, per_rank, th, tw, 3)
     jj, ii = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
-    t = (jj // th) * tiles_x + ii // tw
+    ty = jj // th
+    t = ty * tiles_x + (ii // tw - 3 * ty) % tiles_x          # csrc/rt_types.h: tile_id()
     return tiles[t % n_ranks, t // n_ranks, jj % th, ii % tw]
 
 

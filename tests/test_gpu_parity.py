@@ -15,6 +15,13 @@ LSB_TOL = 1          # FP32_FAST: max |delta| per 8-bit channel ...
 LSB_FRAC = 0.999     # ... on at least this fraction of the pixels
 
 
+def tile_owner(i, j, W, tw, th, n):
+    """csrc/rt_types.h tile_id(): tile row Y is rotated by 3*Y positions; owner = id % n_ranks."""
+    tiles_x = (W + tw - 1) // tw
+    ty = j // th
+    return (ty * tiles_x + (i // tw - 3 * ty) % tiles_x) % n
+
+
 @pytest.fixture(scope="module")
 def rt(built):
     import distributed_raytracer_b200 as rt
@@ -201,7 +208,7 @@ def test_fast_peer_writer_equals_region_render(rt, example_scene, W, H, tw, th, 
     g.render_tiles_peer(W, H, tw, th, 1, n, buf.ptr, None, flags)           # one rank only: the rest must keep the fill value
     one = fb.cpu().numpy().reshape(-1, 3).copy()
     i, j = (np.arange(W * H) % W, np.arange(W * H) // W) if layout == "row" else (np.arange(W * H) // H, np.arange(W * H) % H)
-    owner = ((j // th) * ((W + tw - 1) // tw) + i // tw) % n
+    owner = tile_owner(i, j, W, tw, th, n)
     assert (one[owner != 1] == 77).all() and np.array_equal(one[owner == 1], ref[owner == 1])
     for r in range(n):
         g.render_tiles_peer(W, H, tw, th, r, n, buf.ptr, None, flags)
@@ -228,7 +235,7 @@ def test_fast_push_tiles_equals_region_render(rt, example_scene, W, H, tw, th, n
     per = rt.tiles_per_rank(W, H, tw, th, n)
     tiles = torch.zeros(per * tw * th * 3, dtype=torch.uint8, device="cuda")
     i, j = (np.arange(W * H) % W, np.arange(W * H) // W) if layout == "row" else (np.arange(W * H) // H, np.arange(W * H) % H)
-    owner = ((j // th) * ((W + tw - 1) // tw) + i // tw) % n
+    owner = tile_owner(i, j, W, tw, th, n)
     for r in [1] + [q for q in range(n) if q != 1]:
         g.render_tiles_device(W, H, tw, th, r, n, tiles.data_ptr(), None)
         g.push_tiles_device(W, H, tw, th, r, n, tiles.data_ptr(), buf.ptr, None, flags)
@@ -239,6 +246,73 @@ def test_fast_push_tiles_equals_region_render(rt, example_scene, W, H, tw, th, n
     g.close()
     del fb
     buf.close()
+
+
+def test_frame_handoff_flags_two_ranks_on_one_gpu(rt, example_scene):
+    """Device-side frame hand-off (rt_render_push_tiles with a sync record + rt_frame_complete_device): two "ranks" (two scene
+    handles, two streams) on one GPU push into one framebuffer slot.  Rank 0's complete kernel is enqueued BEFORE rank 1 has
+    even been asked to render, so it really waits on the device for rank 1's arrive flag; rank 1's next frame really waits for
+    the slot to be released (the release is enqueued after a consumer copy).  Every consumed frame must equal the region render."""
+    import torch
+    from distributed_raytracer_b200 import workloads
+    W, H, tw, th, n = 352, 192, 32, 16, 2
+    flags = rt.LAYOUT_COLMAJOR
+    scenes = [rt.GpuScene(example_scene, precision=rt.FP32_FAST) for _ in range(n)]
+    streams = [torch.cuda.Stream() for _ in range(n)]
+    fbuf, ctrl = rt.DeviceBuffer(0, W * H * 3), rt.DeviceBuffer(0, 256)
+    fb = torch.as_tensor(fbuf, device="cuda")
+    cw = torch.as_tensor(ctrl, device="cuda").view(torch.int32)
+    fb.zero_(); cw.zero_()
+    per = rt.tiles_per_rank(W, H, tw, th, n)
+    tiles = [torch.zeros(per * tw * th * 3, dtype=torch.uint8, device="cuda") for _ in range(n)]
+    cams = [workloads.orbit_camera([1.0, 1.0, -1.0], 6.0, np.deg2rad(20.0 * f), 0.05 * f, 1.04719755) for f in range(5)]
+    consumed = [torch.zeros(W * H * 3, dtype=torch.uint8, device="cuda") for _ in cams]
+    for r in range(n):      # first use of a lane allocates its scratch (cudaMalloc waits for the device): not under a spinning kernel
+        scenes[r].render_tiles_device(W, H, tw, th, r, n, tiles[r].data_ptr(), streams[r].cuda_stream)
+    torch.cuda.synchronize()
+    for f, cam in enumerate(cams):
+        fs = rt.FrameState(cam, example_scene["lights"])
+        seq = f + 1
+        scenes[0].render_push_tiles(fs, W, H, tw, th, 0, n, tiles[0].data_ptr(), fbuf.ptr, streams[0].cuda_stream, flags, ctrl.ptr, seq)
+        scenes[0].frame_complete_device(ctrl.ptr, seq, n, False, streams[0].cuda_stream)
+        # Both "ranks" share ONE device here: nothing may be queued behind the waiting kernel in its own stream before the
+        # other rank's work has been submitted (streams can share a hardware queue, and a queue stalls at the first entry
+        # that must wait for the running kernel) -- across real GPUs the ranks' queues are independent.
+        scenes[1].render_push_tiles(fs, W, H, tw, th, 1, n, tiles[1].data_ptr(), fbuf.ptr, streams[1].cuda_stream, flags, ctrl.ptr, seq)
+        with torch.cuda.stream(streams[0]):
+            torch.add(fb, 0, out=consumed[f])                            # the consumer
+        scenes[0].frame_release_device(ctrl.ptr, seq, streams[0].cuda_stream)
+    torch.cuda.synchronize()
+    c = cw.cpu().numpy()
+    assert list(c[:2]) == [5, 5] and c[32] == 5 and c[33] == 0, c[:34]
+    ref = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    for f, cam in enumerate(cams):
+        ref.set_frame(cam, example_scene["lights"])
+        assert np.array_equal(consumed[f].cpu().numpy().reshape(-1, 3), ref.render_region(W, H, flags=flags)), f
+    for g in scenes + [ref]:
+        g.close()
+    del fb, cw
+    fbuf.close(); ctrl.close()
+
+
+def test_frame_handoff_times_out_instead_of_hanging(rt, example_scene, monkeypatch):
+    """A rank that never arrives must not hang the GPU: the wait gives up after RT_B200_SYNC_TIMEOUT_MS and records 0x100+rank."""
+    import torch
+    monkeypatch.setenv("RT_B200_SYNC_TIMEOUT_MS", "50")
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    ctrl = rt.DeviceBuffer(0, 256)
+    cw = torch.as_tensor(ctrl, device="cuda").view(torch.int32)
+    cw.zero_()
+    cw[0] = 1                                                            # rank 0 arrived, rank 1 never does
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    g.frame_complete_device(ctrl.ptr, 1, 2, True, st.cuda_stream)
+    st.synchronize()
+    c = cw.cpu().numpy()
+    assert c[33] == 0x101 and c[32] == 1
+    g.close()
+    del cw
+    ctrl.close()
 
 
 def test_fast_device_output_and_streams(rt, example_scene):
