@@ -376,8 +376,7 @@ __device__ __forceinline__ void push_segments(const uint8_t *s_tile, uint8_t *ou
 }
 
 __device__ __forceinline__ void push_one_tile(const FrameParams &fp, bool rowmajor, const uint8_t *__restrict__ tiles,
-                                              uint8_t *__restrict__ out, uint8_t *s_tile) {
-    const int lt = blockIdx.x;
+                                              uint8_t *__restrict__ out, uint8_t *s_tile, int lt) {
     const uint32_t t = (uint32_t)lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
     const int tw = fp.tile_w, th = fp.tile_h, W = fp.W, H = fp.H;
     uint32_t TX, TY;
@@ -451,14 +450,19 @@ __global__ void k_frame_release(uint32_t *slot, uint32_t seq) { __threadfence_sy
 __global__ void __launch_bounds__(128) k_push_tiles(FrameParams fp, bool rowmajor, const uint8_t *__restrict__ tiles,
                                                      uint8_t *__restrict__ out, PushSync sy) {
     extern __shared__ __align__(16) uint8_t s_tile[];
-    if (sy.slot) {                                  // the slot's previous frame must have been consumed before it is overwritten
+    if (sy.slot && !(sy.debug & 1u)) {              // the slot's previous frame must have been consumed before it is overwritten
         if (threadIdx.x == 0 && !spin_until(sy.slot + RT_SYNC_CONSUMED, sy.seq - 1u, sy.timeout_ms))
             *(volatile uint32_t *)(sy.slot + RT_SYNC_ERROR) = 0x200u + (uint32_t)fp.rank;
         __syncthreads();
     }
-    push_one_tile(fp, rowmajor, tiles, out, s_tile);
+    // with a hand-off the grid is a few CTAs per SM looping over the tiles: the remote flag poll above and the system-scope
+    // fence below (each a NVLink round trip) are paid per CTA, not per tile (per tile they cost 6 % of the N = 2 frame)
+    for (int lt = blockIdx.x; lt < fp.n_local_tiles; lt += gridDim.x) {
+        push_one_tile(fp, rowmajor, tiles, out, s_tile, lt);
+        __syncthreads();                            // s_tile is restaged by the next tile
+    }
     if (sy.slot) {                                  // last CTA to finish publishes "rank has pushed frame seq"
-        __threadfence_system();
+        if (sy.debug & 2u) __threadfence(); else __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned int prev = atomicAdd(sy.blocks_done, 1u);
@@ -645,11 +649,13 @@ cudaError_t rt_launch_clear_tiles(const FrameParams &fp, bool rowmajor, uint8_t 
 }
 
 cudaError_t rt_launch_push_tiles(const FrameParams &fp, bool rowmajor, const uint8_t *d_tiles, uint8_t *d_out, const PushSync &sy,
-                                 cudaStream_t st) {
+                                 int sm_count, cudaStream_t st) {
     if (fp.n_local_tiles <= 0) return cudaSuccess;
     const size_t smem = (size_t)fp.tile_w * fp.tile_h * 3;
     if (smem > 48 * 1024) return cudaErrorInvalidValue;
-    k_push_tiles<<<(unsigned)fp.n_local_tiles, 128, smem, st>>>(fp, rowmajor, d_tiles, d_out, sy);
+    const int per_sm = sy.debug & 8u ? 1024 : 2;
+    const unsigned grid = (unsigned)(sy.slot ? std::min(fp.n_local_tiles, per_sm * sm_count) : fp.n_local_tiles);
+    k_push_tiles<<<grid, 128, smem, st>>>(fp, rowmajor, d_tiles, d_out, sy);
     return cudaGetLastError();
 }
 

@@ -640,7 +640,7 @@ int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
     int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, true);
     if (rc != RT_OK) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : Lp->stream;
-    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, PushSync{}, st));
+    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, PushSync{}, s->sm_count, st));
     if (!stream) CU(s, cudaStreamSynchronize(st));
     return RT_OK;
 }
@@ -667,9 +667,9 @@ int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *ligh
     PushSync sy{};
     if (d_sync_slot) {
         if (n_ranks > 32) return fail(s, RT_ERR_INVALID, "rt_render_push_tiles: the hand-off record holds 32 ranks");
-        sy.slot = (uint32_t *)d_sync_slot; sy.blocks_done = Lp->d_counters + 4; sy.seq = seq; sy.timeout_ms = s->sync_timeout_ms;
+        sy.slot = (uint32_t *)d_sync_slot; sy.blocks_done = Lp->d_counters + 4; sy.seq = seq; sy.timeout_ms = s->sync_timeout_ms; sy.debug = (uint32_t)env_int("RT_B200_SYNC_DEBUG", 0);
     }
-    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, sy, (cudaStream_t)stream));
+    CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, sy, s->sm_count, (cudaStream_t)stream));
     return RT_OK;
 }
 

@@ -72,6 +72,6 @@ cudaError_t rt_launch_untile(const uint8_t *d_tiles, uint8_t *d_out, int W, int 
 cudaError_t rt_fma_peak(bool fp64, int sm_count, double *tflops);
 cudaError_t rt_launch_clear_tiles(const FrameParams &fp, bool rowmajor, uint8_t *d_out, cudaStream_t st);
 cudaError_t rt_launch_push_tiles(const FrameParams &fp, bool rowmajor, const uint8_t *d_tiles, uint8_t *d_out, const PushSync &sy,
-                                 cudaStream_t st);
+                                 int sm_count, cudaStream_t st);
 cudaError_t rt_launch_frame_complete(uint32_t *d_slot, uint32_t seq, int n_ranks, bool release, uint32_t timeout_ms, cudaStream_t st);
 cudaError_t rt_launch_frame_release(uint32_t *d_slot, uint32_t seq, cudaStream_t st);

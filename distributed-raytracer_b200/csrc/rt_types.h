@@ -88,7 +88,7 @@ struct Counters { unsigned long long nodes, tris; };
 #define RT_SYNC_ARRIVE 0        // [0..31]  arrive[rank]
 #define RT_SYNC_CONSUMED 32
 #define RT_SYNC_ERROR 33
-struct PushSync { uint32_t *slot; unsigned int *blocks_done; uint32_t seq, timeout_ms; };
+struct PushSync { uint32_t *slot; unsigned int *blocks_done; uint32_t seq, timeout_ms, debug; };
 
 // ------------------------------------------------------------------------------------------------
 // ray index <-> pixel mapping.  Rays are numbered so that 32 consecutive indices form an 8x4 pixel

@@ -150,7 +150,12 @@ class TileShardedRenderer:
     Frames are pipelined over the backend's slots (scene replicas + streams): frame k renders on slot k % S while the
     gather + de-interleave of earlier frames run on the communication stream.  `render_frame` returns the framebuffer of
     the frame it enqueued (rank 0; None elsewhere); it is complete once `wait()` followed by a synchronize has returned.
-    With one rank there is nothing to gather: the frame is rendered straight into the framebuffer (region mode)."""
+    With one rank there is nothing to gather: the frame is rendered straight into the framebuffer (region mode).
+
+    Lifetime of a device-resident frame: slot k = frame number % S is overwritten by the frame enqueued S frames later -- by any
+    rank, as soon as rank 0 has released the slot.  Rank 0 releases it right after the frame is complete unless the frame has a
+    consumer on the slot's stream (`to_host=True`: the copy into pinned host memory), in which case it is released after the
+    consumer.  A caller that reads `frame[k]` by other means must finish before any rank enqueues frame k + S."""
 
     def __init__(self, scene, W, H, precision=_lib.FP32_FAST, tile=(32, 16), group=None, device_index=0, backend_factory=None,
                  layout_flags=_lib.LAYOUT_ROWMAJOR, replicas=1, mode="peer", shared_scene=False):

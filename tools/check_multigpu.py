@@ -57,6 +57,8 @@ def main():
                 torch.cuda.synchronize(dev)
                 if rank == 0:
                     got += [o.cpu().numpy().reshape(-1, 3).copy() for o in outs]
+                if not to_host:
+                    dist.barrier()      # device-resident frames: a slot may be overwritten (by ANY rank) once the frame S later is enqueued
             # back-to-back frames without collecting in between: only the last S are still resident
             for f in range(F):
                 last = r.render_frame(rt.FrameState(cams[f], sc["lights"]), to_host=to_host) if mode != "gather" else \
