@@ -29,7 +29,7 @@ W, H = 3840, 2160
 SUBDIV = 5
 N_LIGHTS = 2
 METRIC = "Mrays/s (primary+shadow)"
-REPLICAS = 8      # resident scene copies / streams the frames cycle over (see parallel.GpuTileBackend)
+REPLICAS = 8      # frames in flight (lanes of the one resident scene, or scene copies with --replicated-scenes); 12 at N > 1
 TILE = (32, 16)
 SCENE_JSON = os.path.join(ROOT, "tests", "golden", "example", "scene.json")
 
@@ -176,20 +176,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--replicas", type=int, default=0, help="scene replicas / frames in flight (default %d)" % REPLICAS)
+    ap.add_argument("--replicas", type=int, default=0, help="frames in flight (default %d at N = 1, 12 at N > 1)" % REPLICAS)
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e loop (experiments only)")
-    ap.add_argument("--shared-scene", action="store_true", help="frames in flight share ONE resident scene (lanes) instead of replicas")
+    ap.add_argument("--replicated-scenes", action="store_true",
+                    help="every frame in flight renders from its OWN resident copy of the scene (a frame's inputs were last touched "
+                         "that many frames earlier); default: one registered scene, one lane per frame in flight")
     ap.add_argument("--mode", default="peer", choices=["peer", "peer_nccl", "gather"],
                     help="N>1: peer-memory tile push with device-side hand-off flags | same push with an NCCL barrier | NCCL gather")
     ap.add_argument("--persistent", action="store_true", help="use the persistent warp-cooperative primary kernel (RT_FLAG_PERSISTENT)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.replicas > 0:
-        REPLICAS = args.replicas
-
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # frames in flight: 8 saturate one GPU; across GPUs a few more absorb the skew between the ranks (measured at N = 8:
+    # 0.1183 ms/frame with 8, 0.1156 with 12; profiles/r01_n8_sweep.jsonl)
+    REPLICAS = args.replicas if args.replicas > 0 else (REPLICAS if world == 1 else 12)
+    args.shared_scene = not args.replicated_scenes
 
     import __graft_entry__ as ge
     if args.impl == "reference":
@@ -232,8 +235,8 @@ def main():
     stream = torch.cuda.Stream(dev)            # the "main" stream: flushes, timing events, serial passes
     torch.cuda.set_stream(stream)
 
-    # The render pipeline: REPLICAS resident scene copies, one stream each; frame k goes to replica k % REPLICAS, so
-    # several frames are in flight and a frame's inputs were last touched REPLICAS frames earlier (> L2).
+    # The render pipeline: REPLICAS frames in flight, one stream each; frame k goes to lane k % REPLICAS of the one resident
+    # scene (--replicated-scenes: to its own copy of the scene).
     r = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=TILE, device_index=local_rank, replicas=REPLICAS,
                                      layout_flags=rt.LAYOUT_COLMAJOR, mode=args.mode, shared_scene=args.shared_scene)
     g = r.backend.scenes[0]
@@ -479,9 +482,16 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_frame": rays_frame, "hit_pixels": hits_frame, "frames_per_s": 1e3 / ms_per_step,
-                   "l2": "frames cycle over %d resident replicas of the scene per GPU, one stream each (inputs last touched %d frames "
-                         "earlier: %d x ~290 MB > 126 MB L2); no flush inside the pipelined region; the per-kernel times of `roofline` "
-                         "come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS, REPLICAS),
+                   "l2": ("inputs larger than L2: the resident scene is ~290 MB (nodes 32 + triangles 48 + fp64 vertices/normals 143 + "
+                          "materials) against 126 MB of L2 and %d frames are in flight on it, one stream each; no flush inside the "
+                          "pipelined region (the top of the BVH stays cached across frames, as it does in a running worker; with "
+                          "--replicated-scenes, %d copies x 290 MB, the frame takes 1.6 %% longer at N = 1); the per-kernel times of "
+                          "`roofline` come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS))
+                         if args.shared_scene else
+                         ("frames cycle over %d resident replicas of the scene per GPU, one stream each (inputs last touched %d frames "
+                          "earlier: %d x ~290 MB > 126 MB L2); no flush inside the pipelined region; the per-kernel times of `roofline` "
+                          "come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS, REPLICAS)),
+                   "scene_copies": 1 if args.shared_scene else REPLICAS,
                    "frames_in_flight": REPLICAS, "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps, "precision": "FP32_FAST traversal, fp64 shading",
                    "parallelism": ("screen tiles 32x16 round-robin over %d rank(s)" % world) + ("" if world == 1 else
                                    {"peer": "; every rank pushes its tiles into rank 0's framebuffer over NVLink peer memory (CUDA IPC, 16-byte stores) and "

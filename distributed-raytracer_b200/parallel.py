@@ -82,9 +82,15 @@ class GpuTileBackend:
         # orders); otherwise n resident copies (benchmarking: a frame's inputs were last touched n frames earlier)
         self.shared = bool(shared_scene)
         if self.shared:
-            import os
-            os.environ.setdefault("RT_B200_LANES", str(n + 1))
-            one = GpuScene(scene, device=device_index, precision=precision)
+            old = _os.environ.get("RT_B200_LANES")
+            _os.environ["RT_B200_LANES"] = str(max(n + 1, int(old or 0)))       # read by rt_scene_create
+            try:
+                one = GpuScene(scene, device=device_index, precision=precision)
+            finally:
+                if old is None:
+                    del _os.environ["RT_B200_LANES"]
+                else:
+                    _os.environ["RT_B200_LANES"] = old
             if one.lane_count() < n + 1:
                 raise RuntimeError("scene has %d lanes, %d frames in flight requested (RT_B200_LANES)" % (one.lane_count(), n))
             self.scenes = [one] * n

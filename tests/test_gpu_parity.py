@@ -499,6 +499,34 @@ def test_device_api_lanes_run_frames_concurrently(rt, example_scene):
     g.close()
 
 
+@pytest.mark.parametrize("shared", [True, False])
+def test_pipelined_renderer_single_gpu_frames_in_flight(rt, example_scene, shared):
+    """TileShardedRenderer at one rank: 7 different cameras pipelined over 3 frames in flight (lanes of ONE scene, or 3 scene
+    copies); every frame, device-resident and through the pinned-host path, equals its own region render."""
+    import torch
+    from distributed_raytracer_b200 import parallel, workloads
+    W, H, S = 400, 224, 3
+    cams = [workloads.orbit_camera([1.0, 1.0, -1.0], 6.0, np.deg2rad(31.0 * f), 0.04 * f, 1.04719755) for f in range(7)]
+    ref = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    want = []
+    for c in cams:
+        ref.set_frame(c, example_scene["lights"])
+        want.append(ref.render_region(W, H))
+    ref.close()
+    r = parallel.TileShardedRenderer(example_scene, W, H, precision=rt.FP32_FAST, replicas=S, layout_flags=rt.LAYOUT_COLMAJOR,
+                                     shared_scene=shared)
+    assert len(set(id(g) for g in r.backend.scenes)) == (1 if shared else S)
+    for to_host in (False, True):
+        for f0 in range(0, len(cams), S):
+            outs = [r.render_frame(rt.FrameState(cams[f], example_scene["lights"]), to_host=to_host) for f in range(f0, min(len(cams), f0 + S))]
+            r.wait()
+            torch.cuda.synchronize()
+            for k, o in enumerate(outs):
+                assert np.array_equal(o.cpu().numpy().reshape(-1, 3), want[f0 + k]), (to_host, f0 + k)
+    for g in set(r.backend.scenes):
+        g.close()
+
+
 def test_host_tracer_bulk_trace_and_draw(rt, example_scene):
     """The reference-facing interface: Tracer.BulkTrace (distributed/main.go:46-91) over partition() rectangles
     (master/main.go:54-91) reassembles into the same screen as draw() (sequential/main.go:15-32)."""
