@@ -288,7 +288,14 @@ def main():
     while time.perf_counter() - t_ramp < 0.4:
         flush.zero_()
         torch.cuda.synchronize(dev)
-    # ---- warm-up ----
+    # ---- lane priming (untimed, not a step): the first frame on a lane allocates its scratch buffers (cudaMalloc waits for
+    # the device), so every frame slot is used once before anything is measured; then the W warm-up steps ----
+    for _ in range(REPLICAS):
+        step()
+    r.wait()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
     for _ in range(args.warmup):
         step()
     r.wait()
