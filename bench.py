@@ -386,6 +386,37 @@ def main():
                "single_call_value": rays_frame / (sum(t_single) / len(t_single)) / 1e6,
                "call": "rt_bulk_trace (what Tracer.BulkTrace issues per WorkOrder) on ONE registered scene handle, %d caller threads, pinned host result buffers" % T,
                "checksum": checksum}
+        # (c) SURVEY s8 f2: the same calls answered as the protobuf wire bytes of comms.TraceResults (encoded on the GPU,
+        # one D2H copy of exactly the message); beside it the C restatement of the encoder on one host core.
+        try:
+            cap = int(L.rt_trace_results_max_bytes(W * H))
+            wpins = [L.rt_host_alloc(cap) for _ in range(T)]
+            wouts = [np.ctypeslib.as_array((ctypes.c_uint8 * cap).from_address(p)) for p in wpins]
+            wire_len = [0] * T
+
+            def wcaller(k):
+                for _ in range(max(1, per_thread // 2)):
+                    wire_len[k] = handles[k].bulk_trace_encoded(cam13, lights, W, H, 0, 0, W, H, out=wouts[k], tan_half_fov=tan_half).size
+            pool = ThreadPoolExecutor(T)
+            list(pool.map(wcaller, range(T)))
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            list(pool.map(wcaller, range(T)))
+            wire_wall = time.perf_counter() - t0
+            pool.shutdown()
+            from oracle import oracle as orc
+            t0 = time.perf_counter()
+            ref_wire = orc.encode_trace_results(outs[0].reshape(-1, 3))
+            cpu_enc_s = time.perf_counter() - t0
+            wire_ms = 1e3 * wire_wall / (max(1, per_thread // 2) * T)
+            e2e["wire"] = {"call": "rt_bulk_trace_encoded: render + GPU protobuf encode of comms.TraceResults + D2H of the message, %d callers" % T,
+                           "ms_per_step": wire_ms, "value": rays_frame / (wire_ms * 1e-3) / 1e6, "message_bytes": int(wire_len[0]),
+                           "identical_to_cpu_encoder": bool(ref_wire.size == wire_len[0] and np.array_equal(ref_wire, wouts[0][:wire_len[0]])),
+                           "cpu_port_encode_ms_1_core": 1e3 * cpu_enc_s}
+            for p in wpins:
+                L.rt_host_free(p)
+        except Exception as ex:                            # the wire leg is additional evidence, never a reason to lose the line
+            e2e["wire"] = {"error": repr(ex)}
         one.close()
         for p in pins:
             L.rt_host_free(p)

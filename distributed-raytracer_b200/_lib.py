@@ -30,7 +30,8 @@ SYNC_SLOT_BYTES = 256            # include/rt_b200.h: RT_SYNC_SLOT_BYTES
 ABI_SYMBOLS = (
     "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set", "rt_frame_set_lane", "rt_lane_count",
     "rt_render_region", "rt_bulk_trace", "rt_render_region_debug", "rt_render_region_device", "rt_render_tiles_device",
-    "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_frame_complete_device", "rt_frame_release_device", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
+    "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_frame_complete_device", "rt_frame_release_device",
+    "rt_trace_results_max_bytes", "rt_encode_trace_results_device", "rt_bulk_trace_encoded", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
     "rt_ipc_close", "rt_measure_fma_peak", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free",
 )
 
@@ -129,6 +130,13 @@ def load():
     L.rt_frame_complete_device.argtypes = [vp, vp, u32, u32, u32, vp]
     L.rt_frame_release_device.restype = C.c_int
     L.rt_frame_release_device.argtypes = [vp, vp, u32, vp]
+    L.rt_trace_results_max_bytes.restype = C.c_uint64
+    L.rt_trace_results_max_bytes.argtypes = [C.c_uint64]
+    L.rt_encode_trace_results_device.restype = C.c_int
+    L.rt_encode_trace_results_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, vp, u32]
+    L.rt_bulk_trace_encoded.restype = C.c_int
+    L.rt_bulk_trace_encoded.argtypes = [vp, C.POINTER(Camera), vp, u32, vp, u32, u32, u32, u32, u32, u32, vp, C.c_uint64,
+                                        C.POINTER(C.c_uint64), u32]
     L.rt_device_alloc.restype = C.c_int
     L.rt_device_alloc.argtypes = [C.c_int, C.c_size_t, C.POINTER(vp)]
     L.rt_device_free.restype = C.c_int

@@ -42,6 +42,10 @@ struct Lane {
     double *d_dbg_colour = nullptr; int32_t *d_dbg_face = nullptr, *d_dbg_obj = nullptr; uint32_t *d_dbg_lit = nullptr;
     size_t cap_dbg = 0;
     uint8_t *h_pinned = nullptr; size_t cap_pinned = 0;
+    // result wire format (wire.cu): encoded message, block-scan scratch, message length (device + pinned host)
+    uint8_t *d_wire = nullptr; size_t cap_wire = 0;
+    void *d_wire_scratch = nullptr; size_t cap_wire_scratch = 0;
+    uint64_t *d_wire_len = nullptr, *h_wire_len = nullptr;
     cudaStream_t last_stream = nullptr;
     bool stats_pending = false;
     rt_stats stats;
@@ -103,6 +107,8 @@ void destroy_lane(Lane &L) {
     cudaFree(L.d_hits); cudaFree(L.d_hit_colour); cudaFree(L.d_hit_lit); cudaFree(L.d_hit_geom); cudaFree(L.d_counters); cudaFree(L.d_stats);
     cudaFree(L.d_rgb); cudaFree(L.d_dbg_colour); cudaFree(L.d_dbg_face); cudaFree(L.d_dbg_obj); cudaFree(L.d_dbg_lit);
     if (L.h_pinned) cudaFreeHost(L.h_pinned);
+    cudaFree(L.d_wire); cudaFree(L.d_wire_scratch); cudaFree(L.d_wire_len);
+    if (L.h_wire_len) cudaFreeHost(L.h_wire_len);
     for (auto &e : L.ev) if (e) cudaEventDestroy(e);
     if (L.stream) cudaStreamDestroy(L.stream);
 }
@@ -564,6 +570,106 @@ int rt_bulk_trace(rt_scene *s, const rt_camera *cam, const rt_light *lights, uin
             s->last_lane.store(idx);
             rc = render_lane(s, *Lp, fp, flags, (size_t)w * h, o);
         }
+    }
+    release_lane(s, Lp);
+    return rc;
+}
+
+// ---- result wire format: comms.TraceResults as proto.Marshal would emit it --------------------
+uint64_t rt_trace_results_max_bytes(uint64_t n_pixels) { return 11ull * n_pixels; }     // 0x0A len + 3 x (tag + 2-byte varint)
+
+static int ensure_wire_scratch(rt_scene *s, Lane &L, uint64_t n_pixels, bool need_out) {
+    const size_t need = rt_wire_scratch_bytes(n_pixels);
+    if (need > L.cap_wire_scratch) {
+        cudaFree(L.d_wire_scratch); L.d_wire_scratch = nullptr; L.cap_wire_scratch = 0;
+        CU(s, cudaMalloc(&L.d_wire_scratch, need));
+        L.cap_wire_scratch = need;
+    }
+    if (!L.d_wire_len) {
+        CU(s, cudaMalloc((void **)&L.d_wire_len, sizeof(uint64_t)));
+        CU(s, cudaMallocHost((void **)&L.h_wire_len, sizeof(uint64_t)));
+    }
+    const size_t out_need = (size_t)rt_trace_results_max_bytes(n_pixels);
+    if (need_out && out_need > L.cap_wire) {
+        cudaFree(L.d_wire); L.d_wire = nullptr; L.cap_wire = 0;
+        CU(s, cudaMalloc((void **)&L.d_wire, out_need ? out_need : 16));
+        L.cap_wire = out_need;
+    }
+    return RT_OK;
+}
+
+int rt_encode_trace_results_device(rt_scene *s, const void *d_rgb, uint64_t n_pixels, void *d_out, uint64_t capacity, uint64_t *d_len,
+                                   void *stream, uint32_t flags) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!d_len || (n_pixels && (!d_rgb || !d_out))) return fail(s, RT_ERR_INVALID, "rt_encode_trace_results_device: NULL argument");
+    if (((uintptr_t)d_rgb & 3u) != 0) return fail(s, RT_ERR_INVALID, "rt_encode_trace_results_device: d_rgb must be 4-byte aligned");
+    int idx = 0;
+    Lane *Lp = device_lane(s, flags, &idx);
+    if (!Lp) return RT_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(Lp->mu);
+    CU(s, cudaSetDevice(s->device));
+    int rc = ensure_wire_scratch(s, *Lp, n_pixels, false);
+    if (rc != RT_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : Lp->stream;
+    CU(s, rt_launch_wire_encode((const uint8_t *)d_rgb, n_pixels, (uint8_t *)d_out, capacity, d_len, Lp->d_wire_scratch, st));
+    if (!stream) CU(s, cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+// One BulkTrace RPC down to the bytes grpc puts on the wire: frame state + render + encode on the device, then ONE
+// device->host copy of exactly the message (the length is read back first, 8 bytes, while the encoder still runs).
+int rt_bulk_trace_encoded(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
+                          uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out, uint64_t capacity, uint64_t *out_len,
+                          uint32_t flags) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!out || !out_len) return fail(s, RT_ERR_INVALID, "rt_bulk_trace_encoded: NULL argument");
+    if (flags & RT_LAYOUT_ROWMAJOR) return fail(s, RT_ERR_INVALID, "TraceResults is in BulkTrace order (i*height + j): RT_LAYOUT_ROWMAJOR does not apply");
+    int idx = 0;
+    Lane *Lp = acquire_lane(s, &idx);
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(Lp->mu);
+        Lane &L = *Lp;
+        if (!obj_pos) L.h_objs = s->h_objs;
+        rc = frame_set_lane(s, L, cam, lights, n_lights, obj_pos);
+        FrameParams fp;
+        if (rc == RT_OK) rc = region_params(s, L, fp, W, H, x, y, w, h);
+        const uint64_t npix = (uint64_t)w * h;
+        if (rc == RT_OK) {
+            RenderOut o; o.async = true;                       // into the lane's own RGB buffer, no copy out
+            s->last_lane.store(idx);
+            rc = render_lane(s, L, fp, flags, (size_t)npix, o);
+        }
+        if (rc == RT_OK) rc = ensure_wire_scratch(s, L, npix, true);
+        auto body = [&]() -> int {
+            cudaStream_t st = L.stream;
+            CU(s, rt_launch_wire_encode(L.d_rgb, npix, L.d_wire, L.cap_wire, L.d_wire_len, L.d_wire_scratch, st));
+            // the length is final after the scan kernel; reading it here only waits for the encoder as well (same stream)
+            CU(s, cudaMemcpyAsync(L.h_wire_len, L.d_wire_len, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+            CU(s, cudaStreamSynchronize(st));
+            *out_len = *L.h_wire_len;
+            if (*out_len > capacity) return fail(s, RT_ERR_INVALID, "rt_bulk_trace_encoded: out buffer too small (see *out_len)");
+            cudaPointerAttributes attr;
+            const bool pinned = cudaPointerGetAttributes(&attr, out) == cudaSuccess &&
+                                (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+            cudaGetLastError();
+            if (pinned) {
+                CU(s, cudaMemcpyAsync(out, L.d_wire, (size_t)*out_len, cudaMemcpyDeviceToHost, st));
+                CU(s, cudaStreamSynchronize(st));
+            } else {
+                if (*out_len > L.cap_pinned) {
+                    if (L.h_pinned) cudaFreeHost(L.h_pinned);
+                    L.h_pinned = nullptr; L.cap_pinned = 0;
+                    CU(s, cudaMallocHost((void **)&L.h_pinned, (size_t)*out_len));
+                    L.cap_pinned = (size_t)*out_len;
+                }
+                CU(s, cudaMemcpyAsync(L.h_pinned, L.d_wire, (size_t)*out_len, cudaMemcpyDeviceToHost, st));
+                CU(s, cudaStreamSynchronize(st));
+                memcpy(out, L.h_pinned, (size_t)*out_len);
+            }
+            return RT_OK;
+        };
+        if (rc == RT_OK) rc = body();
     }
     release_lane(s, Lp);
     return rc;

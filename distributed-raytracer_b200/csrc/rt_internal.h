@@ -75,3 +75,8 @@ cudaError_t rt_launch_push_tiles(const FrameParams &fp, bool rowmajor, const uin
                                  int sm_count, cudaStream_t st);
 cudaError_t rt_launch_frame_complete(uint32_t *d_slot, uint32_t seq, int n_ranks, bool release, uint32_t timeout_ms, cudaStream_t st);
 cudaError_t rt_launch_frame_release(uint32_t *d_slot, uint32_t seq, cudaStream_t st);
+
+// wire.cu : comms.TraceResults protobuf encoder
+size_t rt_wire_scratch_bytes(uint64_t n_pixels);
+cudaError_t rt_launch_wire_encode(const uint8_t *d_rgb, uint64_t n_pixels, uint8_t *d_out, uint64_t capacity, uint64_t *d_len,
+                                  void *d_scratch, cudaStream_t st);

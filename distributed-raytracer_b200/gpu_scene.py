@@ -108,6 +108,23 @@ class GpuScene:
                                           op.ctypes.data if op is not None else None, W, H, x, y, w, h, out.ctypes.data, flags))
         return out
 
+    def bulk_trace_encoded(self, cam13, lights, W, H, x, y, w, h, obj_pos=None, flags=0, out=None, tan_half_fov=float("nan")):
+        """One BulkTrace down to the protobuf bytes of comms.TraceResults (rt_bulk_trace_encoded).  Returns a uint8 view of the
+        message inside `out` (allocated at the worst-case size if not given)."""
+        cam = make_camera(cam13, tan_half_fov)
+        lights = _c(lights, np.float64).reshape(-1, 6)
+        op = None if obj_pos is None else _c(obj_pos, np.float64)
+        if out is None:
+            out = np.empty(int(self._L.rt_trace_results_max_bytes(w * h)), dtype=np.uint8)
+        n = C.c_uint64(0)
+        self._check(self._L.rt_bulk_trace_encoded(self.h, C.byref(cam), lights.ctypes.data if lights.size else None, lights.shape[0],
+                                                  op.ctypes.data if op is not None else None, W, H, x, y, w, h, out.ctypes.data,
+                                                  out.nbytes, C.byref(n), flags))
+        return out.reshape(-1)[:n.value]
+
+    def encode_trace_results_device(self, d_rgb_ptr, n_pixels, d_out_ptr, capacity, d_len_ptr, stream_ptr=None, flags=0):
+        self._check(self._L.rt_encode_trace_results_device(self.h, d_rgb_ptr, n_pixels, d_out_ptr, capacity, d_len_ptr, stream_ptr, flags))
+
     def render_region_debug(self, W, H, x=0, y=0, w=None, h=None, flags=0):
         w = W - x if w is None else w
         h = H - y if h is None else h

@@ -47,6 +47,8 @@ def load():
     H.rth_tracer_handle.argtypes = [vp]
     H.rth_bulk_trace.restype = C.c_int
     H.rth_bulk_trace.argtypes = [vp, vp, u32, u32, u32, u32, vp, u32]
+    H.rth_bulk_trace_encoded.restype = C.c_longlong
+    H.rth_bulk_trace_encoded.argtypes = [vp, vp, u32, u32, u32, u32, vp, u32]
     H.rth_draw.restype = C.c_int
     H.rth_draw.argtypes = [vp, vp, vp, u32]
     H.rth_partition.restype = u32
@@ -146,6 +148,14 @@ class Tracer:
         if load().rth_bulk_trace(self.t, self.env.h, x, y, width, height, out.ctypes.data, flags) != 0:
             raise RuntimeError("BulkTrace: " + _err())
         return out
+
+    def BulkTraceEncoded(self, x, y, width, height, flags=0):
+        """The same order answered as the protobuf wire bytes of comms.TraceResults (comms.proto:34-41), encoded on the GPU."""
+        out = np.empty(11 * width * height, dtype=np.uint8)
+        n = load().rth_bulk_trace_encoded(self.t, self.env.h, x, y, width, height, out.ctypes.data, flags)
+        if n < 0:
+            raise RuntimeError("BulkTraceEncoded: " + _err())
+        return out[:n]
 
     def draw(self, quantiser=_lib.QUANT_RGBA16_SHR8):
         """sequential/main.go:15-32: the whole screen, row-major [H, W, 3]."""

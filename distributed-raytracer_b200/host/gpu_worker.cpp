@@ -39,6 +39,25 @@ bool Tracer::BulkTrace(const comms::WorkOrder &req, comms::TraceResults &results
     return BulkTraceInto(req, results.rgb.data(), e, flags);
 }
 
+bool Tracer::BulkTraceEncoded(const comms::WorkOrder &req, std::vector<uint8_t> &wire, std::string &e, uint32_t flags) {
+    wire.clear();
+    if (!handle) { e = "tracer has no scene: " + err; return false; }
+    if (req.diff) last = *req.diff;
+    if (req.width == 0 || req.height == 0) return true;              // no results: the empty message
+    rt_camera cam;
+    std::vector<rt_light> lights;
+    std::vector<double> obj_pos;
+    state::FrameState(last, cam, lights, obj_pos);
+    wire.resize(size_t(rt_trace_results_max_bytes(uint64_t(req.width) * req.height)));
+    uint64_t len = 0;
+    int rc = rt_bulk_trace_encoded(handle, &cam, lights.data(), uint32_t(lights.size()), obj_pos.empty() ? nullptr : obj_pos.data(),
+                                   screenWidth, screenHeight, req.x, req.y, req.width, req.height, wire.data(), wire.size(), &len,
+                                   (flags & ~RT_LAYOUT_ROWMAJOR) | RT_QUANT_RGB255);
+    if (rc != RT_OK) { e = rt_last_error(handle); wire.clear(); return false; }
+    wire.resize(size_t(len));
+    return true;
+}
+
 bool draw(Tracer &t, const state::EnvMutables &scene, std::vector<uint8_t> &surface, std::string &e, uint32_t quantiser) {
     if (!t.ok()) { e = t.error(); return false; }
     rt_camera cam;

@@ -43,6 +43,9 @@ class Tracer {                              // distributed/main.go:27-32
     // same order, results written straight into caller memory (width*height*3 bytes, e.g. a pinned buffer from
     // rt_host_alloc wrapped as a Go slice): no intermediate TraceResults copy
     bool BulkTraceInto(const comms::WorkOrder &req, uint8_t *out_rgb, std::string &err, uint32_t flags = 0);
+    // same order, answered with the protobuf wire bytes of comms.TraceResults (comms.proto:34-41) encoded on the GPU: what
+    // grpc-go would produce by marshalling the message BulkTrace builds (distributed/main.go:52-54,79-86).  SURVEY s8 f2.
+    bool BulkTraceEncoded(const comms::WorkOrder &req, std::vector<uint8_t> &wire, std::string &err, uint32_t flags = 0);
     // distributed/main.go:94-98 (keeps the worker registered; nothing to do on the GPU side)
     void Heartbeat() {}
     rt_scene *Handle() { return handle; }

@@ -60,6 +60,17 @@ int rth_bulk_trace(void *t, void *h, uint32_t x, uint32_t y, uint32_t w, uint32_
     if (!((worker::Tracer *)t)->BulkTraceInto(req, out, err, flags)) { g_err = err; return -1; }
     return 0;
 }
+// Tracer.BulkTraceEncoded: the order answered as comms.TraceResults wire bytes; out must hold 11*w*h bytes; returns the length or -1
+long long rth_bulk_trace_encoded(void *t, void *h, uint32_t x, uint32_t y, uint32_t w, uint32_t hgt, uint8_t *out, uint32_t flags) {
+    comms::WorkOrder req;
+    req.x = x; req.y = y; req.width = w; req.height = hgt;
+    req.diff = h ? &((EnvBox *)h)->env.mutableState : nullptr;
+    std::string err;
+    std::vector<uint8_t> wire;
+    if (!((worker::Tracer *)t)->BulkTraceEncoded(req, wire, err, flags)) { g_err = err; return -1; }
+    std::memcpy(out, wire.data(), wire.size());
+    return (long long)wire.size();
+}
 // draw(): whole screen, row-major
 int rth_draw(void *t, void *h, uint8_t *surface, uint32_t quantiser) {
     std::vector<uint8_t> s;

@@ -225,6 +225,29 @@ int rt_ipc_close(int device, void *p);
 int rt_untile_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h,
                      uint32_t n_ranks, const void *d_all_tiles, void *d_out_rgb, void *stream, uint32_t flags);
 
+/* ---- result wire format --------------------------------------------------------
+ * The reference worker returns a region as the protobuf message comms.TraceResults
+ * (shared/comms/comms.proto:34-41: repeated Colour{uint32 r=1, g=2, b=3}), one heap-allocated Colour
+ * per pixel (worker/distributed/main.go:52-54,79-86), marshalled by grpc-go.  These calls produce
+ * exactly the bytes proto.Marshal emits for that message -- per pixel 0x0A len [0x08 r] [0x10 g]
+ * [0x18 b], zero-valued fields omitted (proto3), values >= 128 as 2-byte varints -- on the GPU, so a
+ * worker hands grpc a ready payload and an unmodified master decodes it. */
+uint64_t rt_trace_results_max_bytes(uint64_t n_pixels);            /* 11 * n_pixels */
+/* d_rgb: n_pixels*3 bytes in BulkTrace order (DEVICE, 4-byte aligned); d_out: `capacity` bytes
+ * (DEVICE); *d_len (DEVICE, 8 bytes) receives the message length -- if it exceeds `capacity` the
+ * output is incomplete.  Asynchronous on `stream` (NULL: library stream, synchronous).  The lane
+ * (RT_LANE(k) in flags) owns the scan scratch: one encode at a time per lane. */
+int rt_encode_trace_results_device(rt_scene *scene, const void *d_rgb, uint64_t n_pixels, void *d_out,
+                                   uint64_t capacity, uint64_t *d_len, void *stream, uint32_t flags);
+/* rt_bulk_trace down to the wire bytes: frame state + render + encode on the device, one copy of
+ * exactly *out_len bytes into `out` (HOST, `capacity` bytes; rt_host_alloc memory avoids a staging
+ * copy).  RT_ERR_INVALID with *out_len set if `capacity` is too small.  Concurrent calls on one
+ * handle run concurrently (one lane each), like rt_bulk_trace. */
+int rt_bulk_trace_encoded(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights,
+                          const double *obj_pos, uint32_t screen_w, uint32_t screen_h, uint32_t x, uint32_t y,
+                          uint32_t w, uint32_t h, uint8_t *out, uint64_t capacity, uint64_t *out_len,
+                          uint32_t flags);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 int rt_get_stats(rt_scene *scene, rt_stats *out);
 int rt_get_bvh_info(rt_scene *scene, uint32_t mesh, rt_bvh_info *out);

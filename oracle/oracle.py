@@ -69,6 +69,8 @@ def lib():
         L.orc_new_camera.restype = C.c_int
         L.orc_new_camera.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_primary_ray.argtypes = [C.c_int] * 4 + [C.c_void_p] * 2
+        L.orc_encode_trace_results.restype = C.c_uint64
+        L.orc_encode_trace_results.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -83,6 +85,15 @@ def go_tan(x):
 
 def go_pow(x, y):
     return lib().orc_go_pow(float(x), float(y))
+
+
+def encode_trace_results(rgb):
+    """comms.TraceResults wire bytes of an (n,3) uint8 array in BulkTrace order (rt_oracle.h: orc_encode_trace_results)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+    n = rgb.shape[0]
+    out = np.empty(11 * n, dtype=np.uint8)
+    m = lib().orc_encode_trace_results(_p(rgb) if n else None, n, _p(out) if n else None)
+    return out[:m].copy()
 
 
 def triangle_intersection(tri, o, d):

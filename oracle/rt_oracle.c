@@ -780,3 +780,40 @@ int orc_render_region(const orc_scene *s, int mode, int W, int H, int x, int y, 
     if (stats) *stats = total;
     return 0;
 }
+
+/* ---- comms.TraceResults wire bytes (see rt_oracle.h) -------------------------------------------- */
+static uint64_t put_varint(uint8_t *out, uint64_t pos, uint32_t v) {
+    while (v >= 0x80u) {
+        if (out) out[pos] = (uint8_t)((v & 0x7fu) | 0x80u);
+        pos++;
+        v >>= 7;
+    }
+    if (out) out[pos] = (uint8_t)v;
+    return pos + 1;
+}
+
+static uint32_t varint_len(uint32_t v) {
+    uint32_t n = 1;
+    while (v >= 0x80u) { n++; v >>= 7; }
+    return n;
+}
+
+uint64_t orc_encode_trace_results(const uint8_t *rgb, uint64_t n, uint8_t *out) {
+    uint64_t pos = 0;
+    for (uint64_t p = 0; p < n; p++) {
+        uint32_t len = 0;
+        for (int c = 0; c < 3; c++)
+            if (rgb[3 * p + c]) len += 1 + varint_len(rgb[3 * p + c]);     /* proto3: default (0) scalars are not emitted */
+        if (out) out[pos] = 0x0A;                                          /* field 1, wire type 2 */
+        pos++;
+        pos = put_varint(out, pos, len);
+        for (int c = 0; c < 3; c++) {
+            uint32_t v = rgb[3 * p + c];
+            if (!v) continue;
+            if (out) out[pos] = (uint8_t)((c + 1) << 3);                   /* field c+1, wire type 0 */
+            pos++;
+            pos = put_varint(out, pos, v);
+        }
+    }
+    return pos;
+}

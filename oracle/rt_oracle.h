@@ -109,6 +109,17 @@ int orc_render_region(const orc_scene *, int mode, int W, int H, int x, int y, i
                       uint8_t *out_rgb, double *out_colour, int32_t *out_face,
                       orc_stats *stats);
 
+/* Result wire format: the bytes proto.Marshal emits for comms.TraceResults
+ * (shared/comms/comms.proto:34-41), the message BulkTrace fills one Colour per pixel
+ * (worker/distributed/main.go:52-54,79-86).  protobuf (third-party, unpinned in the reference; the
+ * encoding itself is the published proto3 wire format): every element of `repeated Colour results = 1`
+ * is tag 0x0A + varint length + payload; payload = fields r,g,b (tags 0x08,0x10,0x18) in number
+ * order, a zero value is omitted, the value is a base-128 varint.  PINNED: tests/test_wire.py
+ * compares this function with the google.protobuf runtime on the same message (and with the
+ * committed vectors tests/golden/trace_results_*.bin that runtime produced).
+ * rgb: n*3 bytes; out: at least 11*n bytes (may be NULL to only measure).  Returns the length. */
+uint64_t orc_encode_trace_results(const uint8_t *rgb, uint64_t n, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif
