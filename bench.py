@@ -31,6 +31,7 @@ N_LIGHTS = 2
 METRIC = "Mrays/s (primary+shadow)"
 REPLICAS = 8      # frames in flight (lanes of the one resident scene, or scene copies with --replicated-scenes); 12 at N > 1
 TILE = (32, 16)
+E2E_TILE = (8, 16)    # host-mode e2e: stripes of 8 pixel columns x full height (contiguous in the column-major layout)
 SCENE_JSON = os.path.join(ROOT, "tests", "golden", "example", "scene.json")
 
 
@@ -169,7 +170,7 @@ def run_reference(args, rank):
 
 
 def main():
-    global REPLICAS
+    global REPLICAS, E2E_TILE
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -183,6 +184,9 @@ def main():
                          "that many frames earlier); default: one registered scene, one lane per frame in flight")
     ap.add_argument("--mode", default="peer", choices=["peer", "peer_nccl", "gather"],
                     help="N>1: peer-memory tile push with device-side hand-off flags | same push with an NCCL barrier | NCCL gather")
+    ap.add_argument("--e2e-mode", default="host", choices=["host", "peer"],
+                    help="N>1 e2e: every GPU writes its tiles into a host-shared pinned framebuffer | NVLink push + D2H from rank 0")
+    ap.add_argument("--e2e-tile", default="", help="tile WxH of the host-mode e2e renderer (default %dx%d)" % E2E_TILE)
     ap.add_argument("--persistent", action="store_true", help="use the persistent warp-cooperative primary kernel (RT_FLAG_PERSISTENT)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -193,6 +197,8 @@ def main():
     # 0.1183 ms/frame with 8, 0.1156 with 12; profiles/r01_n8_sweep.jsonl)
     REPLICAS = args.replicas if args.replicas > 0 else (REPLICAS if world == 1 else 12)
     args.shared_scene = not args.replicated_scenes
+    if args.e2e_tile:
+        E2E_TILE = tuple(int(v) for v in args.e2e_tile.lower().split("x"))
 
     import __graft_entry__ as ge
     if args.impl == "reference":
@@ -421,20 +427,31 @@ def main():
         for p in pins:
             L.rt_host_free(p)
     else:
-        # N>1: every step = frame state to every rank (kernel parameters) + tiles + NVLink push into rank 0's framebuffer +
-        # barrier + D2H of the 24.9 MB framebuffer into rank 0's pinned host memory.  Frames are pipelined like `value`
-        # (the D2H of frame f overlaps the render of the following frames); the latency of one isolated frame is
-        # reported next to it.
+        # N>1: every step = frame state to every rank (kernel parameters) + tiles rendered on every rank + the frame in rank 0's
+        # HOST memory.  --e2e-mode host (default): the framebuffers live in pinned host shared memory and every GPU moves its
+        # stripes there over its own PCIe link (N links carry the 24.9 MB frame); --e2e-mode peer: NVLink push into rank 0's
+        # device framebuffer + one D2H copy over rank 0's link (52 GB/s: 0.48 ms per frame at every N).  Frames are pipelined
+        # like `value`; the latency of one isolated frame is reported next to it.
         nbytes = W * H * 3
-        e2e_steps = min(args.steps, 100)
+        e2e_steps = min(args.steps, 200)
+        if args.e2e_mode == "host":
+            re = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=E2E_TILE, device_index=local_rank,
+                                              replicas=REPLICAS, layout_flags=rt.LAYOUT_COLMAJOR, mode="host", shared_scene=args.shared_scene)
+        else:
+            re = r
+        for _ in range(2 * REPLICAS):                       # lane priming + first touch of the host buffers (untimed)
+            re.render_frame(frame_state, flags=render_flags, to_host=True)
+        re.wait()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
         t_single = []
         for it in range(3 + min(e2e_steps, 10)):
             flush.zero_()
             torch.cuda.synchronize(dev)
             dist.barrier()
             t0 = time.perf_counter()
-            r.render_frame(frame_state, flags=render_flags, to_host=True)
-            r.wait()
+            re.render_frame(frame_state, flags=render_flags, to_host=True)
+            re.wait()
             torch.cuda.synchronize(dev)
             dist.barrier()
             if it >= 3:
@@ -443,17 +460,26 @@ def main():
         dist.barrier()
         t0 = time.perf_counter()
         for it in range(e2e_steps):
-            hf = r.render_frame(frame_state, flags=render_flags, to_host=True)
-        r.wait()
+            hf = re.render_frame(frame_state, flags=render_flags, to_host=True)
+        re.wait()
         torch.cuda.synchronize(dev)
         dist.barrier()
         tt = torch.tensor([time.perf_counter() - t0, sum(t_single) / len(t_single)], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        re.check_sync()
         e2e_ms = 1e3 * float(tt[0].item()) / e2e_steps
         e2e = {"value": rays_frame / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_ms, "single_call_ms": 1e3 * float(tt[1].item()),
-               "checksum": int(hf[::4097].to(torch.int64).sum().item()) if rank == 0 else None,
-               "call": "TileShardedRenderer.render_frame(to_host=True): pipelined frames, framebuffer D2H into pinned host memory on rank 0"}
+               "checksum": int(hf[::4097].to(torch.int64).sum().item()) if rank == 0 else None, "mode": args.e2e_mode,
+               "tile": list(E2E_TILE) if args.e2e_mode == "host" else list(TILE),
+               "call": ("TileShardedRenderer.render_frame, mode host: pipelined frames; every rank renders its 8-column stripes in place "
+                        "and moves them with one strided copy-engine transfer into the pinned host-shared framebuffer over its own "
+                        "PCIe link; hand-off flags in the same host memory"
+                        if args.e2e_mode == "host" else
+                        "TileShardedRenderer.render_frame(to_host=True): pipelined frames, framebuffer D2H into pinned host memory on rank 0")}
+        if re is not r:
+            dist.barrier()
+            re.close()
 
     if rank != 0:
         if world > 1:

@@ -30,9 +30,9 @@ SYNC_SLOT_BYTES = 256            # include/rt_b200.h: RT_SYNC_SLOT_BYTES
 ABI_SYMBOLS = (
     "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set", "rt_frame_set_lane", "rt_lane_count",
     "rt_render_region", "rt_bulk_trace", "rt_render_region_debug", "rt_render_region_device", "rt_render_tiles_device",
-    "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_frame_complete_device", "rt_frame_release_device",
+    "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_render_stripes_host", "rt_frame_complete_device", "rt_frame_release_device",
     "rt_trace_results_max_bytes", "rt_encode_trace_results_device", "rt_bulk_trace_encoded", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
-    "rt_ipc_close", "rt_measure_fma_peak", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free",
+    "rt_ipc_close", "rt_measure_fma_peak", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free", "rt_host_register", "rt_host_unregister",
 )
 
 
@@ -126,6 +126,8 @@ def load():
     L.rt_push_tiles_device.argtypes = [vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, u32]
     L.rt_render_push_tiles.restype = C.c_int
     L.rt_render_push_tiles.argtypes = [vp, C.POINTER(Camera), vp, u32, vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, u32, vp, u32]
+    L.rt_render_stripes_host.restype = C.c_int
+    L.rt_render_stripes_host.argtypes = [vp, C.POINTER(Camera), vp, u32, vp, u32, u32, u32, u32, u32, vp, vp, vp, u32, vp, u32]
     L.rt_frame_complete_device.restype = C.c_int
     L.rt_frame_complete_device.argtypes = [vp, vp, u32, u32, u32, vp]
     L.rt_frame_release_device.restype = C.c_int
@@ -161,6 +163,10 @@ def load():
     L.rt_cancel.argtypes = [vp]
     L.rt_host_alloc.restype = vp
     L.rt_host_alloc.argtypes = [C.c_size_t]
+    L.rt_host_register.restype = C.c_int
+    L.rt_host_register.argtypes = [C.c_int, vp, C.c_size_t, C.POINTER(vp)]
+    L.rt_host_unregister.restype = C.c_int
+    L.rt_host_unregister.argtypes = [C.c_int, vp]
     L.rt_host_free.restype = None
     L.rt_host_free.argtypes = [vp]
     _LIB = L

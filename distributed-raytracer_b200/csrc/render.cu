@@ -446,6 +446,12 @@ __global__ void k_frame_complete(uint32_t *slot, uint32_t seq, int n_ranks, int 
     if (release && r == 0) { __threadfence_system(); st_release_sys(slot + RT_SYNC_CONSUMED, seq); }
 }
 __global__ void k_frame_release(uint32_t *slot, uint32_t seq) { __threadfence_system(); st_release_sys(slot + RT_SYNC_CONSUMED, seq); }
+// the two halves of the hand-off as stand-alone kernels, for a hand-over that is not a kernel (copy-engine transfer into
+// the host framebuffer): wait for "previous frame of the slot consumed" before it, publish "rank arrived" after it
+__global__ void k_wait_consumed(uint32_t *slot, uint32_t seq, uint32_t rank, uint32_t timeout_ms) {
+    if (!spin_until(slot + RT_SYNC_CONSUMED, seq - 1u, timeout_ms)) *(volatile uint32_t *)(slot + RT_SYNC_ERROR) = 0x200u + rank;
+}
+__global__ void k_signal_arrive(uint32_t *slot, uint32_t seq, uint32_t rank) { __threadfence_system(); st_release_sys(slot + RT_SYNC_ARRIVE + rank, seq); }
 
 __global__ void __launch_bounds__(128) k_push_tiles(FrameParams fp, bool rowmajor, const uint8_t *__restrict__ tiles,
                                                      uint8_t *__restrict__ out, PushSync sy) {
@@ -661,6 +667,16 @@ cudaError_t rt_launch_push_tiles(const FrameParams &fp, bool rowmajor, const uin
 
 cudaError_t rt_launch_frame_complete(uint32_t *d_slot, uint32_t seq, int n_ranks, bool release, uint32_t timeout_ms, cudaStream_t st) {
     k_frame_complete<<<1, 32, 0, st>>>(d_slot, seq, n_ranks, release ? 1 : 0, timeout_ms);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_wait_consumed(uint32_t *d_slot, uint32_t seq, uint32_t rank, uint32_t timeout_ms, cudaStream_t st) {
+    k_wait_consumed<<<1, 1, 0, st>>>(d_slot, seq, rank, timeout_ms);
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_signal_arrive(uint32_t *d_slot, uint32_t seq, uint32_t rank, cudaStream_t st) {
+    k_signal_arrive<<<1, 1, 0, st>>>(d_slot, seq, rank);
     return cudaGetLastError();
 }
 

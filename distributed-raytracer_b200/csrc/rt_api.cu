@@ -779,6 +779,54 @@ int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *ligh
     return RT_OK;
 }
 
+// Multi-GPU end-to-end path: the frame goes to HOST memory over every GPU's own PCIe link.  The screen is cut into stripes
+// that are contiguous in the output layout (column-major BulkTrace layout: `stripe` pixel columns x full height;
+// row-major: `stripe` pixel rows x full width), dealt round-robin; a rank renders its stripes in place into its local
+// device framebuffer (final layout) and ONE strided copy-engine transfer moves them into the host framebuffer (pinned
+// shared memory, rt_host_register); the hand-off flags live in the same host memory.
+int rt_render_stripes_host(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
+                           uint32_t H, uint32_t stripe, uint32_t rank, uint32_t n_ranks, void *d_local_framebuffer, void *h_framebuffer,
+                           void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!d_local_framebuffer || !h_framebuffer || !stream) return fail(s, RT_ERR_INVALID, "rt_render_stripes_host: NULL buffer or stream");
+    if (n_ranks > 32 && d_sync_slot) return fail(s, RT_ERR_INVALID, "rt_render_stripes_host: the hand-off record holds 32 ranks");
+    const bool rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0;
+    if (stripe == 0 || stripe % (rowmajor ? 4u : 8u)) return fail(s, RT_ERR_INVALID, "stripe must be a multiple of 8 columns (4 rows)");
+    int idx = 0;
+    Lane *Lp = device_lane(s, flags, &idx);
+    if (!Lp) return RT_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(Lp->mu);
+    int rc = frame_set_lane(s, *Lp, cam, lights, n_lights, obj_pos);
+    if (rc != RT_OK) return rc;
+    const uint32_t tile_w = rowmajor ? ((W + 7u) / 8u) * 8u : stripe, tile_h = rowmajor ? stripe : ((H + 3u) / 4u) * 4u;
+    FrameParams fp;
+    rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false);
+    if (rc != RT_OK) return rc;
+    fp.tile_final = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    RenderOut o; o.d_rgb = (uint8_t *)d_local_framebuffer; o.ext_stream = st; o.async = true;
+    s->last_lane.store(idx);
+    rc = render_lane(s, *Lp, fp, flags, (size_t)W * H, o);
+    if (rc != RT_OK) return rc;
+    if (d_sync_slot) CU(s, rt_launch_wait_consumed((uint32_t *)d_sync_slot, seq, rank, s->sync_timeout_ms, st));
+    // stripe t = rank + k*n_ranks starts at byte t*run; all but a cut last stripe are `run` bytes long
+    const size_t extent = rowmajor ? H : W, other = rowmajor ? W : H;
+    const size_t run = (size_t)stripe * other * 3;
+    const size_t n_stripes = (extent + stripe - 1) / stripe, n_full = extent / stripe;
+    const size_t mine_full = n_full > rank ? (n_full - rank + n_ranks - 1) / n_ranks : 0;
+    const uint8_t *src = (const uint8_t *)d_local_framebuffer;
+    uint8_t *dst = (uint8_t *)h_framebuffer;
+    if (mine_full)
+        CU(s, cudaMemcpy2DAsync(dst + (size_t)rank * run, (size_t)n_ranks * run, src + (size_t)rank * run, (size_t)n_ranks * run, run, mine_full,
+                                cudaMemcpyDeviceToHost, st));
+    if (n_stripes > n_full && (n_stripes - 1) % n_ranks == rank) {
+        const size_t off = (n_stripes - 1) * run, bytes = (extent - n_full * stripe) * other * 3;
+        CU(s, cudaMemcpyAsync(dst + off, src + off, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (d_sync_slot) CU(s, rt_launch_signal_arrive((uint32_t *)d_sync_slot, seq, rank, st));
+    return RT_OK;
+}
+
 // gathering rank: frame `seq` of the slot is complete when all ranks have pushed it (waits ON THE DEVICE, in stream order)
 int rt_frame_complete_device(rt_scene *s, void *d_sync_slot, uint32_t seq, uint32_t n_ranks, uint32_t release, void *stream) {
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
@@ -903,6 +951,24 @@ void *rt_host_alloc(size_t bytes) {
 
 void rt_host_free(void *p) {
     if (p) cudaFreeHost(p);
+}
+
+// Pins caller-owned host memory (typically a POSIX shared-memory mapping that every per-GPU process of the box has mapped)
+// and returns the address kernels of `device` use for it: each GPU then stores its tiles straight into the host
+// framebuffer over ITS OWN PCIe link (rt_render_push_tiles with d_framebuffer / d_sync_slot = such addresses).
+int rt_host_register(int device, void *ptr, size_t bytes, void **d_ptr) {
+    if (!ptr || !bytes || !d_ptr) return fail(nullptr, RT_ERR_INVALID, "rt_host_register: bad argument");
+    CU(nullptr, cudaSetDevice(device));
+    CU(nullptr, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    cudaError_t e = cudaHostGetDevicePointer(d_ptr, ptr, 0);
+    if (e != cudaSuccess) { cudaHostUnregister(ptr); return fail(nullptr, RT_ERR_CUDA, cudaGetErrorString(e)); }
+    return RT_OK;
+}
+int rt_host_unregister(int device, void *ptr) {
+    if (!ptr) return RT_OK;
+    CU(nullptr, cudaSetDevice(device));
+    CU(nullptr, cudaHostUnregister(ptr));
+    return RT_OK;
 }
 
 }  // extern "C"

@@ -75,6 +75,8 @@ cudaError_t rt_launch_push_tiles(const FrameParams &fp, bool rowmajor, const uin
                                  int sm_count, cudaStream_t st);
 cudaError_t rt_launch_frame_complete(uint32_t *d_slot, uint32_t seq, int n_ranks, bool release, uint32_t timeout_ms, cudaStream_t st);
 cudaError_t rt_launch_frame_release(uint32_t *d_slot, uint32_t seq, cudaStream_t st);
+cudaError_t rt_launch_wait_consumed(uint32_t *d_slot, uint32_t seq, uint32_t rank, uint32_t timeout_ms, cudaStream_t st);
+cudaError_t rt_launch_signal_arrive(uint32_t *d_slot, uint32_t seq, uint32_t rank, cudaStream_t st);
 
 // wire.cu : comms.TraceResults protobuf encoder
 size_t rt_wire_scratch_bytes(uint64_t n_pixels);

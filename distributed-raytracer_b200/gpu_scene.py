@@ -157,6 +157,12 @@ class GpuScene:
         self._check(self._L.rt_render_push_tiles(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr, W, H, tile_w,
                                                  tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, sync_slot_ptr, seq, stream_ptr, flags))
 
+    def render_stripes_host(self, frame, W, H, stripe, rank, n_ranks, d_local_fb_ptr, h_framebuffer_ptr, stream_ptr, flags=0,
+                            sync_slot_ptr=None, seq=0):
+        """The multi-GPU end-to-end call of a rank: render its stripes, one strided D2H transfer into the host framebuffer."""
+        self._check(self._L.rt_render_stripes_host(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr, W, H, stripe,
+                                                   rank, n_ranks, d_local_fb_ptr, h_framebuffer_ptr, sync_slot_ptr, seq, stream_ptr, flags))
+
     def frame_complete_device(self, sync_slot_ptr, seq, n_ranks, release, stream_ptr):
         self._check(self._L.rt_frame_complete_device(self.h, sync_slot_ptr, seq, n_ranks, 1 if release else 0, stream_ptr))
 
@@ -236,3 +242,52 @@ class DeviceBuffer:
         if getattr(self, "ptr", None):
             (self._L.rt_device_free if self.owner else self._L.rt_ipc_close)(self.device, self.ptr)
             self.ptr = None
+
+
+class HostSharedBuffer:
+    """A POSIX shared-memory segment (mapped by every per-GPU process of the box) pinned for this process's GPU: `.ptr` is the
+    address the GPU's kernels use, `.array` the uint8 numpy view the host reads.  rank 0 creates (and finally unlinks) it, the
+    others attach by name."""
+
+    def __init__(self, device, nbytes=None, name=None):
+        from multiprocessing import shared_memory
+        self._L = _lib.load()
+        self.device, self.owner = device, name is None
+        if self.owner:
+            self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+        else:
+            self.shm = shared_memory.SharedMemory(name=name)
+            try:                                   # the creator unlinks; keep Python's resource tracker from doing it at exit
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.nbytes = nbytes if nbytes is not None else self.shm.size
+        self.array = np.ndarray((self.nbytes,), dtype=np.uint8, buffer=self.shm.buf)
+        if self.owner:
+            self.array[:] = 0
+        self._host_ptr = self.array.ctypes.data
+        p = C.c_void_p()
+        rc = self._L.rt_host_register(device, self._host_ptr, self.shm.size, C.byref(p))
+        if rc != 0:
+            raise _lib.RtError(rc, (self._L.rt_last_error(None) or b"").decode())
+        self.ptr = p.value
+
+    @property
+    def name(self):
+        return self.shm.name
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self._L.rt_host_unregister(self.device, self._host_ptr)
+            self.ptr = None
+            self.array = None
+            try:
+                self.shm.close()
+            except BufferError:
+                pass
+            if self.owner:
+                try:
+                    self.shm.unlink()
+                except FileNotFoundError:
+                    pass

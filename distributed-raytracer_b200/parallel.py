@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .gpu_scene import DeviceBuffer, FrameState, GpuScene, tiles_per_rank
+from .gpu_scene import DeviceBuffer, FrameState, GpuScene, HostSharedBuffer, tiles_per_rank
 
 import os as _os
 _NO_BARRIER = bool(int(_os.environ.get("RT_B200_NO_BARRIER", "0")))   # timing experiments only: frames are then unsynchronised
@@ -135,6 +135,10 @@ class GpuTileBackend:
         self.scenes[slot].render_push_tiles(frame, W, H, tw, th, rank, n_ranks, tiles.data_ptr(), frame_ptr,
                                             self.streams[slot].cuda_stream, flags | self.lane_flags[slot], sync_slot_ptr, seq)
 
+    def render_stripes_host(self, slot, frame, W, H, stripe, rank, n_ranks, local_fb, host_fb_ptr, flags=0, sync_slot_ptr=None, seq=0):
+        self.scenes[slot].render_stripes_host(frame, W, H, stripe, rank, n_ranks, local_fb.data_ptr(), host_fb_ptr,
+                                              self.streams[slot].cuda_stream, flags | self.lane_flags[slot], sync_slot_ptr, seq)
+
     def frame_complete(self, slot, sync_slot_ptr, seq, n_ranks, release):
         self.scenes[slot].frame_complete_device(sync_slot_ptr, seq, n_ranks, release, self.streams[slot].cuda_stream)
 
@@ -187,15 +191,28 @@ class TileShardedRenderer:
         # per frame and rank, and a rank only ever waits for rank 0's consumption of the slot, never for its siblings.
         # mode "peer_nccl": same data path, a 4-byte all_reduce per frame as the barrier (kept for comparison).
         # mode "gather": packed tile buffers + all_gather + de-interleave on rank 0 (the NCCL-only baseline).
-        if mode not in ("peer", "peer_nccl", "gather"):
-            raise ValueError("mode must be peer, peer_nccl or gather")
+        # mode "host": the framebuffers and their hand-off records live in HOST shared memory pinned by every rank, and the
+        # screen is cut into stripes that are contiguous in the output layout (tile[0] pixel columns x full height for the
+        # column-major layout, tile[1] pixel rows x full width for the row-major one).  Each rank renders its stripes in place
+        # and moves them with ONE strided copy-engine transfer over its own PCIe link, so a frame reaches host memory at N x
+        # the bandwidth of the single link a device->host copy from rank 0 has (frames are CPU tensors over the shared memory).
+        # (Storing the tiles into host memory from the push kernel works too, rt_host_register, but reaches only ~11 GB/s
+        # per link: profiles/r01_host_mode_kernel_stores_n2.jsonl.)
+        if mode not in ("peer", "peer_nccl", "gather", "host"):
+            raise ValueError("mode must be peer, peer_nccl, gather or host")
         self.mode = mode if (multi and self.pipelined) else "gather"
         self.peer_bufs = []
         self.ctrl = None
         self.slot_seq = [0] * S
         if self.mode in ("peer", "peer_nccl"):
             self._init_peer(device_index)
-        self.local = [self.backend.alloc(self.per_rank * self.tile_bytes) for _ in range(S)] if multi else []
+        elif self.mode == "host":
+            self._init_host(device_index)
+        if self.mode == "host":
+            self.stripe = self.th if (layout_flags & _lib.LAYOUT_ROWMAJOR) else self.tw
+            self.local = [self.backend.alloc(self.W * self.H * 3) for _ in range(S)]
+        else:
+            self.local = [self.backend.alloc(self.per_rank * self.tile_bytes) for _ in range(S)] if multi else []
         for t in self.local:
             t.zero_()
         self.gathered = [self.backend.alloc(self.n_ranks * self.per_rank * self.tile_bytes) for _ in range(S)] \
@@ -227,6 +244,32 @@ class TileShardedRenderer:
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.backend.device)
         torch.cuda.synchronize(self.backend.device)
         dist.barrier(group=self.group)
+
+    def _init_host(self, device_index):
+        nbytes = self.W * self.H * 3
+        cbytes = self.S * _lib.SYNC_SLOT_BYTES
+        names = [None]
+        if self.rank == 0:
+            self.peer_bufs = [HostSharedBuffer(device_index, nbytes) for _ in range(self.S)]
+            self.ctrl = HostSharedBuffer(device_index, cbytes)
+            names = [[b.name for b in self.peer_bufs] + [self.ctrl.name]]
+        dist.broadcast_object_list(names, src=0, group=self.group)
+        if self.rank != 0:
+            self.peer_bufs = [HostSharedBuffer(device_index, name=n) for n in names[0][:-1]]
+            self.ctrl = HostSharedBuffer(device_index, name=names[0][-1])
+        self.frame = [torch.from_numpy(b.array[:nbytes]) if self.rank == 0 else None for b in self.peer_bufs]
+        self.ctrl_view = torch.from_numpy(self.ctrl.array[:cbytes]).view(torch.int32).view(self.S, -1)
+        torch.cuda.synchronize(self.backend.device)
+        dist.barrier(group=self.group)
+
+    def close(self):
+        """Releases the shared framebuffers (host mode: unpins and, on rank 0, unlinks the shared-memory segments)."""
+        if self.mode == "host":
+            torch.cuda.synchronize(self.backend.device)
+            self.frame, self.ctrl_view = [], None
+            for b in self.peer_bufs + ([self.ctrl] if self.ctrl is not None else []):
+                b.close()
+            self.peer_bufs, self.ctrl = [], None
 
     def render_frame(self, cam13, lights=None, obj_pos=None, tan_half_fov=float("nan"), flags=0, to_host=False):
         """Enqueues one frame; asynchronous on CUDA.  `cam13` may be a prebuilt FrameState (then `lights` etc. are ignored).
@@ -290,7 +333,7 @@ class TileShardedRenderer:
         # device->host copy on rank 0, the copy of frame f sits between the barriers of f and f+1 on rank 0's communication
         # stream, so "barrier of frame f+1 has completed" (a collective: it needs rank 0) tells EVERY rank that rank 0 has
         # finished reading slot k -- hence the wait on the next slot's event.
-        if self.n_ranks > 1 and self.mode == "peer":
+        if self.n_ranks > 1 and self.mode in ("peer", "host"):
             gate = None                                      # slot streams are in order; cross-rank reuse is gated by the consumed flag
         else:
             gate = self.done_ev[(k + 1) % self.S] if (to_host and self.S > 1) else self.done_ev[k]
@@ -309,6 +352,18 @@ class TileShardedRenderer:
         if self.mode == "gather":
             raise RuntimeError("FrameState fast path is implemented for the peer modes")
         ev, done = self._events[k]
+        if self.mode == "host":
+            # stripes rendered in place, one strided D2H transfer per rank, flags in the same pinned host shared memory
+            self.slot_seq[k] += 1
+            seq = self.slot_seq[k] & 0x7fffffff
+            slot_ptr = self.ctrl.ptr + k * _lib.SYNC_SLOT_BYTES
+            be.render_stripes_host(k, frame, self.W, self.H, self.stripe, self.rank, self.n_ranks, self.local[k], self.peer_bufs[k].ptr,
+                                   flags | self.layout_flags, slot_ptr, seq)
+            if self.rank == 0:
+                be.frame_complete(k, slot_ptr, seq, self.n_ranks, release=True)
+            done.record(st)
+            self.done_ev[k] = done
+            return self.frame[k]
         if self.mode == "peer":
             # ONE stream, no collective: render -> push (waits for "slot consumed", publishes "arrived") [-> rank 0: complete
             # (waits for every rank's arrival) -> consumer -> release]
@@ -346,7 +401,7 @@ class TileShardedRenderer:
         """Raises if a device-side wait of the frame hand-off timed out (a rank died or fell > RT_B200_SYNC_TIMEOUT_MS behind)."""
         if self.ctrl is None:
             return
-        err = self.ctrl_view[:, 33].cpu()
+        err = self.ctrl_view[:, 33].cpu().clone()
         if int(err.abs().max()) != 0:
             raise RuntimeError("frame hand-off timed out: error words per slot = %s (0x100+r: rank r never arrived; 0x200+r: "
                                "rank r never saw the slot released)" % [hex(int(e)) for e in err])

@@ -208,6 +208,18 @@ int rt_push_tiles_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, 
 int rt_render_push_tiles(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos,
                          uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
                          void *d_tiles, void *d_framebuffer, void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags);
+/* The multi-GPU END-TO-END path: the frame lands in HOST memory over every GPU's own PCIe link.  The screen is cut into
+ * stripes that are contiguous in the output layout (column-major BulkTrace layout: `stripe` pixel columns x full height,
+ * `stripe` a multiple of 8; RT_LAYOUT_ROWMAJOR: `stripe` pixel rows x full width, a multiple of 4), stripe t owned by rank
+ * t % n_ranks.  One call = rt_frame_set + render of the rank's stripes in place into d_local_framebuffer (DEVICE,
+ * screen_w*screen_h*3, final layout) + ONE strided copy-engine transfer of those stripes into h_framebuffer (the address
+ * rt_host_register returned for the shared host framebuffer).  d_sync_slot / seq as in rt_render_push_tiles (the record
+ * may live in registered host memory too): waits for the slot's release before the transfer, publishes arrive[rank]
+ * after it.  Asynchronous on `stream`. */
+int rt_render_stripes_host(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos,
+                           uint32_t screen_w, uint32_t screen_h, uint32_t stripe, uint32_t rank, uint32_t n_ranks,
+                           void *d_local_framebuffer, void *h_framebuffer, void *d_sync_slot, uint32_t seq, void *stream,
+                           uint32_t flags);
 /* Gathering rank, in stream order on `stream`: waits (on the device) until all n_ranks ranks have pushed frame `seq` of the
  * slot; everything enqueued on `stream` afterwards sees the complete frame.  release != 0 hands the slot back at once;
  * otherwise call rt_frame_release_device after the consumer (e.g. the device->host copy) on the same stream. */
@@ -263,6 +275,13 @@ int rt_measure_fma_peak(int device, int fp64, double *out_tflops);
 /* pinned host buffers so out_rgb can be DMA'd without a staging copy (optional) */
 void *rt_host_alloc(size_t bytes);
 void  rt_host_free(void *p);
+/* Pins caller-owned HOST memory -- typically a POSIX shared-memory mapping that every per-GPU process of
+ * the box has mapped -- for `device` and returns in *d_ptr the address its kernels use for it.  A framebuffer
+ * and its hand-off record registered this way can be the d_framebuffer / d_sync_slot of
+ * rt_render_push_tiles: every GPU then stores its tiles straight into the host framebuffer over ITS OWN
+ * PCIe link (the device->host copy of a 4K frame through one link is what bounds e2e at N > 1). */
+int rt_host_register(int device, void *ptr, size_t bytes, void **d_ptr);
+int rt_host_unregister(int device, void *ptr);
 
 #ifdef __cplusplus
 }

@@ -248,6 +248,64 @@ def test_fast_push_tiles_equals_region_render(rt, example_scene, W, H, tw, th, n
     buf.close()
 
 
+def test_push_tiles_into_host_shared_framebuffer(rt, example_scene):
+    """rt_host_register: the framebuffer and its hand-off record live in pinned POSIX shared memory; every "rank" stores its
+    tiles straight into host memory (second mapping of the same segment = what another process sees), flags included."""
+    import torch
+    W, H, tw, th, n = 352, 192, 32, 16, 3
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    ref = g.render_region(W, H)
+    fb, ctrl = rt.HostSharedBuffer(0, W * H * 3), rt.HostSharedBuffer(0, 256)
+    fb2 = rt.HostSharedBuffer(0, name=fb.name)                       # as a peer process would attach
+    per = rt.tiles_per_rank(W, H, tw, th, n)
+    tiles = torch.zeros(per * tw * th * 3, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    fs = rt.FrameState(example_scene["camera"], example_scene["lights"])
+    for r in range(n):
+        g.render_push_tiles(fs, W, H, tw, th, r, n, tiles.data_ptr(), (fb if r else fb2).ptr, st.cuda_stream, rt.LAYOUT_COLMAJOR, ctrl.ptr, 1)
+    g.frame_complete_device(ctrl.ptr, 1, n, True, st.cuda_stream)
+    st.synchronize()
+    words = ctrl.array.view(np.int32)
+    assert list(words[:n]) == [1] * n and words[32] == 1 and words[33] == 0
+    assert np.array_equal(fb.array[:W * H * 3].reshape(-1, 3), ref)
+    g.close()
+    for b in (fb2, ctrl, fb):
+        b.close()
+
+
+@pytest.mark.parametrize("W,H,stripe,n,layout", [(352, 192, 8, 3, "col"), (333, 187, 16, 4, "col"), (352, 190, 8, 8, "row"), (3840, 2160, 8, 8, "col")])
+def test_render_stripes_host_equals_region_render(rt, example_scene, W, H, stripe, n, layout):
+    """rt_render_stripes_host (the multi-GPU end-to-end path): every "rank" renders its stripes in place and moves them with one
+    strided D2H transfer into the pinned shared host framebuffer; all ranks together reproduce the region render, a single
+    rank leaves the other ranks' bytes untouched (cut last stripe, H not a multiple of 4, both layouts, 4K)."""
+    import torch
+    flags = rt.LAYOUT_ROWMAJOR if layout == "row" else rt.LAYOUT_COLMAJOR
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    ref = g.render_region(W, H, flags=flags)
+    fb, ctrl = rt.HostSharedBuffer(0, W * H * 3), rt.HostSharedBuffer(0, 256)
+    fb.array[:] = 77
+    local = torch.full((W * H * 3,), 55, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.Stream()
+    fs = rt.FrameState(example_scene["camera"], example_scene["lights"])
+    pix = np.arange(W * H)
+    along = (pix // W if layout == "row" else pix // H)               # row index (row-major) / column index (column-major)
+    owner = (along // stripe) % n
+    for r in [1] + [q for q in range(n) if q != 1]:
+        g.render_stripes_host(fs, W, H, stripe, r, n, local.data_ptr(), fb.ptr, st.cuda_stream, flags, ctrl.ptr, 1)
+        st.synchronize()
+        if r == 1:
+            one = fb.array[:W * H * 3].reshape(-1, 3)
+            assert (one[owner != 1] == 77).all() and np.array_equal(one[owner == 1], ref[owner == 1])
+    g.frame_complete_device(ctrl.ptr, 1, n, True, st.cuda_stream)
+    st.synchronize()
+    words = ctrl.array.view(np.int32)
+    assert list(words[:n]) == [1] * n and words[32] == 1 and words[33] == 0
+    assert np.array_equal(fb.array[:W * H * 3].reshape(-1, 3), ref)
+    g.close()
+    for b in (ctrl, fb):
+        b.close()
+
+
 def test_frame_handoff_flags_two_ranks_on_one_gpu(rt, example_scene):
     """Device-side frame hand-off (rt_render_push_tiles with a sync record + rt_frame_complete_device): two "ranks" (two scene
     handles, two streams) on one GPU push into one framebuffer slot.  Rank 0's complete kernel is enqueued BEFORE rank 1 has

@@ -1,7 +1,8 @@
 """Multi-GPU correctness check (run under torchrun, one rank per GPU):
    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/check_multigpu.py
 
-Every mode of TileShardedRenderer (peer = NVLink tile push + device-side hand-off flags, peer_nccl = same push + NCCL barrier,
+Every mode of TileShardedRenderer (peer = NVLink tile push + device-side hand-off flags, host = every GPU stores its tiles into a
+pinned host-shared framebuffer, peer_nccl = NVLink push + NCCL barrier,
 gather = NCCL all_gather + de-interleave) must deliver, on rank 0, exactly the frame a single GPU renders with
 rt_render_region -- for a sequence of DIFFERENT cameras pipelined over the frame slots (so a stale or mixed slot shows up),
 device-resident and through the device->host path.  Prints one 'MULTIGPU OK ...' line on success."""
@@ -38,9 +39,9 @@ def main():
             ref.append(g.render_region(W, H))
         g.close()
     checked = 0
-    for mode in ("peer", "peer_nccl", "gather"):
+    for mode in ("peer", "host", "peer_nccl", "gather"):
         for to_host in (False, True):
-            if to_host and mode == "gather":
+            if to_host and mode in ("gather", "host"):
                 continue
             r = parallel.TileShardedRenderer(sc, W, H, precision=rt.FP32_FAST, tile=(32, 16), device_index=lr, replicas=S,
                                              layout_flags=rt.LAYOUT_COLMAJOR, mode=mode)
@@ -72,6 +73,7 @@ def main():
                 assert np.array_equal(last.cpu().numpy().reshape(-1, 3), ref[F - 1]), (mode, to_host, "back-to-back")
                 checked += F + 1
             dist.barrier()
+            r.close()
             del r
     if rank == 0:
         print("MULTIGPU OK world=%d frames_checked=%d" % (world, checked), flush=True)

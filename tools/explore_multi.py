@@ -59,6 +59,7 @@ def main():
             print(json.dumps({"n": world, "mode": mode, "shared": shared, "tile": [tw, tth], "R": R, "steps": K,
                               "ms_per_frame": [x[0] for x in res], "host_enqueue_ms": [x[1] for x in res]}), flush=True)
         dist.barrier()
+        r.close()
         for g in set(r.backend.scenes):
             g.close()
         del r
