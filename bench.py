@@ -434,11 +434,14 @@ def main():
         # like `value`; the latency of one isolated frame is reported next to it.
         nbytes = W * H * 3
         e2e_steps = min(args.steps, 200)
+        re = r
         if args.e2e_mode == "host":
-            re = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=E2E_TILE, device_index=local_rank,
-                                              replicas=REPLICAS, layout_flags=rt.LAYOUT_COLMAJOR, mode="host", shared_scene=args.shared_scene)
-        else:
-            re = r
+            try:
+                re = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=E2E_TILE, device_index=local_rank,
+                                                  replicas=REPLICAS, layout_flags=rt.LAYOUT_COLMAJOR, mode="host", shared_scene=args.shared_scene)
+            except RuntimeError as ex:                    # raised on every rank alike (e.g. /dev/shm too small): one link it is
+                print("[bench] rank %d: host-mode e2e unavailable (%s); using --e2e-mode peer" % (rank, ex), file=sys.stderr, flush=True)
+                args.e2e_mode = "peer"
         for _ in range(2 * REPLICAS):                       # lane priming + first touch of the host buffers (untimed)
             re.render_frame(frame_state, flags=render_flags, to_host=True)
         re.wait()

@@ -250,10 +250,22 @@ class TileShardedRenderer:
         cbytes = self.S * _lib.SYNC_SLOT_BYTES
         names = [None]
         if self.rank == 0:
-            self.peer_bufs = [HostSharedBuffer(device_index, nbytes) for _ in range(self.S)]
-            self.ctrl = HostSharedBuffer(device_index, cbytes)
-            names = [[b.name for b in self.peer_bufs] + [self.ctrl.name]]
+            try:
+                st = _os.statvfs("/dev/shm")
+                need = self.S * nbytes + cbytes
+                if st.f_bavail * st.f_frsize < need + (64 << 20):
+                    raise OSError("/dev/shm has %d MB free, %d MB needed" % (st.f_bavail * st.f_frsize >> 20, need >> 20))
+                self.peer_bufs = [HostSharedBuffer(device_index, nbytes) for _ in range(self.S)]
+                self.ctrl = HostSharedBuffer(device_index, cbytes)
+                names = [[b.name for b in self.peer_bufs] + [self.ctrl.name]]
+            except Exception as ex:                       # every rank must learn about it: the attach below is collective
+                for b in self.peer_bufs:
+                    b.close()
+                self.peer_bufs = []
+                names = ["ERROR: %r" % (ex,)]
         dist.broadcast_object_list(names, src=0, group=self.group)
+        if isinstance(names[0], str):
+            raise RuntimeError("host-shared framebuffers unavailable on rank 0: " + names[0])
         if self.rank != 0:
             self.peer_bufs = [HostSharedBuffer(device_index, name=n) for n in names[0][:-1]]
             self.ctrl = HostSharedBuffer(device_index, name=names[0][-1])
