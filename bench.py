@@ -245,6 +245,14 @@ def main():
     # scene (--replicated-scenes: to its own copy of the scene).
     r = parallel.TileShardedRenderer(sc_r, W, H, precision=rt.FP32_FAST, tile=TILE, device_index=local_rank, replicas=REPLICAS,
                                      layout_flags=rt.LAYOUT_COLMAJOR, mode=args.mode, shared_scene=args.shared_scene)
+    torch.cuda.synchronize(dev)
+    # register() cost, measured on a SECOND handle (the first one also pays CUDA module loading): indexed mesh H2D +
+    # device-side flatten + LBVH build + lane set-up
+    t_create = time.perf_counter()
+    g2 = rt.GpuScene(sc_r, device=local_rank, precision=rt.FP32_FAST)
+    torch.cuda.synchronize(dev)
+    t_create = time.perf_counter() - t_create
+    g2.close()
     g = r.backend.scenes[0]
     bvh = g.bvh_info()
     # K2 K4 K5 (+ push-tiles (+ frame-complete on rank 0) | untile on rank 0); rank 0's count is the one reported
@@ -558,7 +566,7 @@ def main():
                          ("frames cycle over %d resident replicas of the scene per GPU, one stream each (inputs last touched %d frames "
                           "earlier: %d x ~290 MB > 126 MB L2); no flush inside the pipelined region; the per-kernel times of `roofline` "
                           "come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS, REPLICAS)),
-                   "scene_copies": 1 if args.shared_scene else REPLICAS,
+                   "scene_copies": 1 if args.shared_scene else REPLICAS, "scene_create_ms": 1e3 * t_create,
                    "frames_in_flight": REPLICAS, "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps, "precision": "FP32_FAST traversal, fp64 shading",
                    "parallelism": ("screen tiles 32x16 round-robin over %d rank(s)" % world) + ("" if world == 1 else
                                    {"peer": "; every rank pushes its tiles into rank 0's framebuffer over NVLink peer memory (CUDA IPC, 16-byte stores) and "

@@ -117,6 +117,58 @@ struct Scratch {
 }  // namespace
 
 // Builds nodes / tri32 / tri64 of `m` from m.fverts (device, 9 doubles per face).  Returns false + err.
+// K0: the SoA hand-off.  The caller's INDEXED mesh (verts, normals, 7 indices per face: what
+// state.Mesh holds, shared/state/mesh.go:21-27,100-106) is uploaded as it is and gathered into the per-face records on the
+// device -- one thread per face; indices are validated here too (err: 1 vertex, 2 normal, 3 material index out of range).
+__global__ void k_flatten_faces(const double *__restrict__ verts, const double *__restrict__ normals, const uint32_t *__restrict__ faces,
+                                uint32_t n_faces, uint32_t n_verts, uint32_t n_normals, uint32_t n_materials, double *__restrict__ fverts,
+                                double *__restrict__ fnormals, uint32_t *__restrict__ fmat, unsigned int *err) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_faces) return;
+    const uint32_t *fc = faces + 7 * (size_t)f;
+    unsigned int bad = 0;
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+        const uint32_t iv = fc[v];
+        if (iv >= n_verts) { bad = 1; continue; }
+#pragma unroll
+        for (int k = 0; k < 3; k++) fverts[9 * (size_t)f + 3 * v + k] = verts[3 * (size_t)iv + k];
+        if (n_normals) {
+            const uint32_t in = fc[3 + v];
+            if (in >= n_normals) { bad = bad ? bad : 2; continue; }
+#pragma unroll
+            for (int k = 0; k < 3; k++) fnormals[9 * (size_t)f + 3 * v + k] = normals[3 * (size_t)in + k];
+        }
+    }
+    if (fc[6] >= n_materials) bad = bad ? bad : 3;
+    else fmat[f] = fc[6];
+    if (bad) atomicMax(err, 4u - bad);            // report the first kind in the order vertex, normal, material
+}
+
+// d_verts / d_normals / d_faces: the uploaded indexed mesh (device).  Allocates and fills m.fverts / m.fnormals / m.fmat.
+// *bad: 0 ok, 1 vertex, 2 normal, 3 material index out of range.
+cudaError_t rt_flatten_faces(MeshDevice &m, const double *d_verts, uint32_t n_verts, const double *d_normals, uint32_t n_normals,
+                             const uint32_t *d_faces, cudaStream_t st, int *bad) {
+    *bad = 0;
+    const size_t nf = m.n_faces;
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&m.fverts, sizeof(double) * 9 * (nf ? nf : 1))) != cudaSuccess) return e;
+    if (n_normals && (e = cudaMalloc((void **)&m.fnormals, sizeof(double) * 9 * (nf ? nf : 1))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&m.fmat, sizeof(uint32_t) * (nf ? nf : 1))) != cudaSuccess) return e;
+    if (!nf) return cudaSuccess;
+    unsigned int *d_err = nullptr;
+    if ((e = cudaMalloc((void **)&d_err, sizeof(unsigned int))) != cudaSuccess) return e;
+    cudaMemsetAsync(d_err, 0, sizeof(unsigned int), st);
+    k_flatten_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(d_verts, d_normals, d_faces, (uint32_t)nf, n_verts, n_normals, m.n_materials,
+                                                                  m.fverts, m.fnormals, m.fmat, d_err);
+    unsigned int h_err = 0;
+    e = cudaMemcpyAsync(&h_err, d_err, sizeof h_err, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_err);
+    if (e == cudaSuccess && h_err) *bad = 4 - (int)h_err;
+    return e;
+}
+
 bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStream_t st, std::string &err) {
     const uint32_t n = m.n_faces;
     m.nodes = nullptr; m.tri32 = nullptr; m.tri64 = nullptr; m.n_nodes = 0; m.root_ref = 0;

@@ -127,30 +127,12 @@ int env_int(const char *name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-// gather one mesh into per-face arrays (host), validate indices
-int flatten_mesh(const rt_mesh_desc &d, std::vector<double> &fverts, std::vector<double> &fnormals, std::vector<uint32_t> &fmat,
-                 std::string &err) {
-    const size_t nf = d.n_faces;
-    if (nf && (!d.faces || !d.verts)) { err = "mesh: faces/verts pointer is NULL"; return RT_ERR_INVALID; }
-    if (d.n_materials == 0 && nf) { err = "mesh: no materials"; return RT_ERR_INVALID; }
+// pointer / count sanity of one mesh description (the indices themselves are validated on the device, k_flatten_faces)
+int check_mesh_desc(const rt_mesh_desc &d, std::string &err) {
+    if (d.n_faces && (!d.faces || !d.verts)) { err = "mesh: faces/verts pointer is NULL"; return RT_ERR_INVALID; }
+    if (d.n_materials == 0 && d.n_faces) { err = "mesh: no materials"; return RT_ERR_INVALID; }
     if (d.n_materials && !d.materials) { err = "mesh: materials pointer is NULL"; return RT_ERR_INVALID; }
     if (d.n_normals && !d.normals) { err = "mesh: normals pointer is NULL"; return RT_ERR_INVALID; }
-    fverts.resize(9 * nf);
-    fmat.resize(nf);
-    if (d.n_normals) fnormals.resize(9 * nf); else fnormals.clear();
-    for (size_t f = 0; f < nf; f++) {
-        const uint32_t *fc = d.faces + 7 * f;
-        for (int v = 0; v < 3; v++) {
-            if (fc[v] >= d.n_verts) { err = "mesh: vertex index out of range"; return RT_ERR_INVALID; }
-            for (int k = 0; k < 3; k++) fverts[9 * f + 3 * v + k] = d.verts[3 * (size_t)fc[v] + k];
-            if (d.n_normals) {
-                if (fc[3 + v] >= d.n_normals) { err = "mesh: normal index out of range"; return RT_ERR_INVALID; }
-                for (int k = 0; k < 3; k++) fnormals[9 * f + 3 * v + k] = d.normals[3 * (size_t)fc[3 + v] + k];
-            }
-        }
-        if (fc[6] >= d.n_materials) { err = "mesh: material index out of range"; return RT_ERR_INVALID; }
-        fmat[f] = fc[6];
-    }
     return RT_OK;
 }
 
@@ -487,14 +469,22 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     for (uint32_t k = 0; k < desc->n_meshes; k++) {
         const rt_mesh_desc &d = desc->meshes[k];
         MeshDevice &m = s->meshes[k];
-        std::vector<double> fverts, fnormals; std::vector<uint32_t> fmat;
         std::string e;
-        int rc = flatten_mesh(d, fverts, fnormals, fmat, e);
+        int rc = check_mesh_desc(d, e);
         if (rc != RT_OK) return bail(rc, e);
         m.n_faces = d.n_faces; m.n_materials = d.n_materials;
-        CUB_(upload(&m.fverts, fverts.data(), fverts.size(), st0));
-        if (!fnormals.empty()) CUB_(upload(&m.fnormals, fnormals.data(), fnormals.size(), st0));
-        CUB_(upload(&m.fmat, fmat.data(), fmat.size(), st0));
+        // the indexed mesh goes up as it is (C3: 52 MB instead of 147 MB of per-face records) and is gathered on the device
+        double *d_verts = nullptr, *d_normals = nullptr; uint32_t *d_faces = nullptr;
+        auto drop = [&]() { cudaFree(d_verts); cudaFree(d_normals); cudaFree(d_faces); };
+        cudaError_t ue = upload(&d_verts, d.verts, (size_t)3 * d.n_verts, st0);
+        if (ue == cudaSuccess && d.n_normals) ue = upload(&d_normals, d.normals, (size_t)3 * d.n_normals, st0);
+        if (ue == cudaSuccess) ue = upload(&d_faces, d.faces, (size_t)7 * d.n_faces, st0);
+        int bad = 0;
+        if (ue == cudaSuccess) ue = rt_flatten_faces(m, d_verts, d.n_verts, d_normals, d.n_normals, d_faces, st0, &bad);
+        drop();
+        if (ue != cudaSuccess) return bail(ue == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(ue));
+        if (bad) return bail(RT_ERR_INVALID, bad == 1 ? "mesh: vertex index out of range" : bad == 2 ? "mesh: normal index out of range"
+                                                                                                       : "mesh: material index out of range");
         CUB_(upload(&m.materials, d.materials, (size_t)10 * d.n_materials, st0));
         CUB_(cudaStreamSynchronize(st0));
         if (!rt_build_bvh(m, s->precision == RT_FP32_FAST, s->precision == RT_FP64_EXACT, s->max_leaf, st0, e))

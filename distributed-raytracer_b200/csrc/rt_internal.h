@@ -27,6 +27,8 @@ struct MeshDevice {
 };
 
 bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStream_t st, std::string &err);
+cudaError_t rt_flatten_faces(MeshDevice &m, const double *d_verts, uint32_t n_verts, const double *d_normals, uint32_t n_normals,
+                             const uint32_t *d_faces, cudaStream_t st, int *bad);
 
 // Per-render device scratch + launch description
 struct RenderJob {

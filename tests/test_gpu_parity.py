@@ -585,6 +585,21 @@ def test_pipelined_renderer_single_gpu_frames_in_flight(rt, example_scene, share
         g.close()
 
 
+@pytest.mark.parametrize("col,count_key,msg", [(0, "verts", "vertex index"), (4, "normals", "normal index"), (6, "materials", "material index")])
+def test_scene_create_rejects_out_of_range_indices(rt, example_scene, col, count_key, msg):
+    """The indexed mesh is validated where it is gathered -- on the device (k_flatten_faces): one bad index anywhere in the
+    face table fails rt_scene_create with RT_ERR_INVALID and names the kind (like a Go slice index panic would abort register())."""
+    import copy
+    sc = copy.deepcopy({k: example_scene[k] for k in ("meshes", "obj_pos", "obj_mesh")})
+    m = sc["meshes"][0]
+    faces = np.array(m["faces"], dtype=np.uint32).reshape(-1, 7)
+    faces[len(faces) // 2, col] = np.asarray(m[count_key]).reshape(-1, 3 if count_key != "materials" else 10).shape[0]
+    m["faces"] = faces
+    with pytest.raises(rt.RtError) as ei:
+        rt.GpuScene(sc, precision=rt.FP32_FAST)
+    assert ei.value.code == rt._lib.RT_ERR_INVALID and msg in str(ei.value)
+
+
 def test_host_tracer_bulk_trace_and_draw(rt, example_scene):
     """The reference-facing interface: Tracer.BulkTrace (distributed/main.go:46-91) over partition() rectangles
     (master/main.go:54-91) reassembles into the same screen as draw() (sequential/main.go:15-32)."""
