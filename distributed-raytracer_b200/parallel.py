@@ -7,10 +7,16 @@ screen, carry all the shading + shadow work, so big rectangles would not balance
 
   once per scene : rank 0 broadcasts the flattened SoA scene arrays; every rank builds the same
                    (deterministic) LBVH locally                         [dist.broadcast]
-  per frame      : every rank gets the <1 KB camera/lights state from its caller, renders its tiles
-                   into a packed device buffer (rt_render_tiles_device), the buffers are gathered
-                   [dist.all_gather_into_tensor] and rank 0 de-interleaves them into the framebuffer
-                   (rt_untile_device).
+  per frame      : every rank gets the <1 KB camera/lights state from its caller (kernel parameters) and
+                   makes ONE library call; no collective is on the data path:
+      mode "peer"  rt_render_push_tiles: tiles rendered into a packed local buffer, stored into rank 0's
+                   device framebuffer over NVLink (CUDA IPC), frame handed over through arrive/consumed
+                   flags in rank 0's memory                              [device-resident frames]
+      mode "host"  rt_render_stripes_host: stripes contiguous in the output layout rendered in place, one
+                   strided copy-engine transfer per rank into a pinned host-shared framebuffer over the
+                   rank's own PCIe link, flags in the same host memory   [frames in host memory: e2e]
+      mode "peer_nccl" / "gather": the NCCL baselines kept for comparison (4-byte all_reduce barrier;
+                   all_gather of packed tiles + rt_untile_device on rank 0).
 
 The render backend is injectable so that the host-side logic (tile maps, gather, untile) can be
 exercised on CPU with gloo in tests; the default backend is the GPU one and has no CPU fallback.
@@ -157,8 +163,8 @@ class GpuTileBackend:
 class TileShardedRenderer:
     """Renders full frames; with N > 1 ranks the screen tiles are dealt round-robin over the ranks of `group`.
 
-    Frames are pipelined over the backend's slots (scene replicas + streams): frame k renders on slot k % S while the
-    gather + de-interleave of earlier frames run on the communication stream.  `render_frame` returns the framebuffer of
+    Frames are pipelined over the backend's slots (lanes of one scene, or scene copies; one stream each): frame k renders on
+    slot k % S while earlier frames are still being handed over.  `render_frame` returns the framebuffer of
     the frame it enqueued (rank 0; None elsewhere); it is complete once `wait()` followed by a synchronize has returned.
     With one rank there is nothing to gather: the frame is rendered straight into the framebuffer (region mode).
 
@@ -285,8 +291,8 @@ class TileShardedRenderer:
 
     def render_frame(self, cam13, lights=None, obj_pos=None, tan_half_fov=float("nan"), flags=0, to_host=False):
         """Enqueues one frame; asynchronous on CUDA.  `cam13` may be a prebuilt FrameState (then `lights` etc. are ignored).
-        to_host (FrameState path): rank 0 also copies the finished framebuffer into its pinned host buffer
-        `host_frame[slot]` (returned instead of the device tensor); valid after wait() + synchronize."""
+        to_host: rank 0 also copies the finished framebuffer into its pinned host buffer `host_frame[slot]` (returned instead
+        of the device tensor); valid after wait() + synchronize.  In mode "host" the frame is a host tensor anyway."""
         k = self.seq % self.S
         self.seq += 1
         if self.pipelined and not isinstance(cam13, FrameState) and (self.n_ranks == 1 or self.mode != "gather"):
@@ -312,12 +318,7 @@ class TileShardedRenderer:
         be.set_frame(k, cam13, lights, obj_pos, tan_half_fov)
         if self.done_ev[k] is not None:
             st.wait_event(self.done_ev[k])                 # slot k's previous frame (incl. its gather) must be finished
-        if self.n_ranks == 1:
-            be.render_region(k, self.W, self.H, self.frame[k], flags | self.layout_flags)
-            ev = torch.cuda.Event()
-            ev.record(st)
-            self.done_ev[k] = ev
-            return self.frame[k]
+        # (one rank and the peer / host modes went through _render_frame_fast above: this is the pipelined NCCL gather)
         be.render_tiles(k, self.W, self.H, self.tw, self.th, self.rank, self.n_ranks, self.local[k], flags)
         ev = torch.cuda.Event()
         ev.record(st)
