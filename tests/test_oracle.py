@@ -65,6 +65,61 @@ def test_appendix_c_known_answers(kat, example_scene, example_oracle):
     assert hit and list(ip) == kat["hit_point_160_120"] and list(nrm) == kat["normal_160_120"]
 
 
+def test_oracle_equals_independent_python_restatement(example_scene, example_oracle):
+    """tests/pyref.py was written from the Go sources alone (scalar Python floats, brute force over the faces); the C oracle
+    must agree with it bit for bit -- hit flag, face, lit mask, float64 colour, both quantisers -- on a few hundred pixels of
+    C1: a seeded random sample, plus two scan lines and a column through the silhouette (where every branch of the
+    intersection and shadow logic is exercised).  Two restatements by different routes that agree to the last bit leave
+    little room for a transcription error in either; neither is the Go binary (parity stays unpinned)."""
+    import pyref
+    W, H = 320, 240
+    S = pyref.Scene(example_scene)
+    tan_half = orc.go_tan(float(example_scene["camera"][12]) / 2.0)
+    rng = np.random.default_rng(20261018)
+    pix = {(int(i), int(j)) for i, j in zip(rng.integers(0, W, 400), rng.integers(0, H, 400))}
+    pix |= {(i, 120) for i in range(110, 210)} | {(i, 96) for i in range(120, 200, 2)} | {(160, j) for j in range(50, 190)}
+    rgb255 = example_oracle.render_region(W, H, quant=orc.Q_RGB255)[0].reshape(W, H, 3)
+    sdl = example_oracle.render_region(W, H, quant=orc.Q_RGBA16_SHR8)[0].reshape(W, H, 3)
+    n_hit = 0
+    for (i, j) in sorted(pix):
+        hit, col, face, obj, lit = S.trace_pixel(i, j, W, H, tan_half)
+        o_hit, o_col, o_face, o_obj, o_lit = example_oracle.trace_pixel(i, j, W, H, orc.BRUTE)
+        assert (hit, face, lit) == (o_hit, o_face if o_hit else -1, o_lit if o_hit else 0), (i, j)
+        if hit:
+            n_hit += 1
+            assert [hx(c) for c in col] == [hx(c) for c in o_col], (i, j)
+        assert list(pyref.quantise_rgb(col)) == list(rgb255[i, j]), (i, j)
+        assert list(pyref.quantise_rgba16_shr8(col)) == list(sdl[i, j]), (i, j)
+    assert n_hit > 60 and len(pix) - n_hit > 60          # the sample really covers hits and misses
+
+
+@pytest.mark.parametrize("kw", [dict(n_tris=150, seed=3, n_obj=3, n_lights=4), dict(n_tris=200, seed=4, with_normals=True, n_obj=2, n_lights=3)])
+def test_oracle_equals_independent_python_restatement_on_soups(kw):
+    """Same cross-check on random multi-object scenes: overlapping objects (the camera-distance metric of tracer.go:38 decides,
+    also for shadow rays), flat normals (object.go:93-95) and interpolated ones, two materials with Ns = 10 and 3, up to 4
+    lights -- every pixel of a 40x30 screen, all three candidate-enumeration modes of the oracle."""
+    import pyref
+    sc = random_soup_scene(**kw)
+    W, H = 40, 30
+    S = pyref.Scene(sc)
+    O = orc.Scene(sc)
+    O.build_rtrees()
+    tan_half = orc.go_tan(float(sc["camera"][12]) / 2.0)
+    n_hit = n_shadowed = 0
+    for i in range(W):
+        for j in range(H):
+            hit, col, face, obj, lit = S.trace_pixel(i, j, W, H, tan_half)
+            for mode in (orc.BRUTE, orc.CULLED, orc.RTREE):
+                o_hit, o_col, o_face, o_obj, o_lit = O.trace_pixel(i, j, W, H, mode)
+                assert hit == o_hit, (i, j, mode)
+                if hit:
+                    assert (face, obj, lit) == (o_face, o_obj, o_lit) and [hx(c) for c in col] == [hx(c) for c in o_col], (i, j, mode)
+            n_hit += hit
+            n_shadowed += hit and lit != (1 << len(sc["lights"])) - 1
+    assert n_hit > 60 and n_shadowed > 10
+    O.close()
+
+
 def test_hit_count_matches_survey(kat, example_oracle):
     _, _, face, st = example_oracle.render_region(320, 180, mode=orc.CULLED)
     assert st["hit_pixels"] == kat["stats_320x180"]["hit_pixels"] == int((face >= 0).sum())
