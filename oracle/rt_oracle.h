@@ -9,7 +9,11 @@
  * cannot be built here (no Go toolchain; rtreego / gwob / go-sdl2 absent),
  * so this restatement is pinned only by (1) the reference source it follows
  * line by line (citations below) and (2) the known-answer values in
- * SURVEY.md Appendix C, produced by an independent Python restatement.
+ * SURVEY.md Appendix C, produced by an independent Python restatement, and
+ * (3) tests/pyref.py, a second restatement written from the Go sources alone,
+ * which agrees with this one bit for bit (tests/test_oracle.py).  The one
+ * pinned function is orc_encode_trace_results (checked against the
+ * google.protobuf runtime, tests/test_wire.py).
  *
  * All citations are into /root/reference/.
  */
