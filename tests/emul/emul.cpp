@@ -19,6 +19,7 @@
 #include "../../distributed-raytracer_b200/csrc/rt_types.h"
 #include "../../distributed-raytracer_b200/csrc/rt_bvh.cuh"
 #include "../../distributed-raytracer_b200/csrc/rt_traverse.cuh"
+#include "host_builders_experiment.hpp"
 
 struct EmulMesh {
     std::vector<RtNode> nodes;
@@ -63,6 +64,11 @@ static void build_mesh(EmulMesh &m, int max_leaf) {
     std::vector<unsigned long long> skeys(n);
     std::vector<uint32_t> svals(n);
     for (uint32_t i = 0; i < n; i++) { skeys[i] = keys[perm[i]]; svals[i] = vals[perm[i]]; }
+    const char *builder = getenv("RT_B200_BUILDER");
+    const bool use_sweep = builder && !strcmp(builder, "sweep"), use_sah = builder && !strcmp(builder, "sah") && n >= 2;
+    std::vector<KarrasNode> kn_host(n > 1 ? n - 1 : 0);
+    std::vector<int> pint_host(n > 1 ? n - 1 : 0), pleaf_host(n);
+    if (use_sah) rt_sah_build_host(leafbox.data(), (int)n, svals.data(), kn_host.data(), pint_host.data(), pleaf_host.data());
     m.tri32.resize(3 * (size_t)n);
     m.tri64.resize(10 * (size_t)n);
     for (uint32_t i = 0; i < n; i++) gather_tri_thread(i, m.fverts.data(), svals.data(), m.tri32.data(), m.tri64.data());
@@ -73,7 +79,15 @@ static void build_mesh(EmulMesh &m, int max_leaf) {
         const int ni = (int)n - 1;
         std::vector<KarrasNode> kn(ni);
         std::vector<int> pint(ni), pleaf(n);
-        for (int i = 0; i < ni; i++) karras_thread(i, skeys.data(), (int)n, kn.data(), pint.data(), pleaf.data());
+        if (use_sah) {
+            kn = kn_host; pint = pint_host; pleaf = pleaf_host;
+        } else if (use_sweep) {
+            std::vector<BoxF> sbox(n);
+            for (uint32_t i = 0; i < n; i++) sbox[i] = leafbox[svals[i]];
+            rt_sweep_build_host(sbox.data(), (int)n, kn.data(), pint.data(), pleaf.data());
+        } else {
+            for (int i = 0; i < ni; i++) karras_thread(i, skeys.data(), (int)n, kn.data(), pint.data(), pleaf.data());
+        }
         std::vector<BoxF> ibox(ni);
         std::vector<float> icost(ni);
         std::vector<unsigned char> coll(ni);

@@ -19,7 +19,8 @@ def lib():
     if _LIB is None:
         src = os.path.join(_HERE, "emul", "emul.cpp")
         csrc = os.path.join(_HERE, "..", "distributed-raytracer_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("rt_types.h", "rt_bvh.cuh", "rt_traverse.cuh", "rt_exact.cuh")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("rt_types.h", "rt_bvh.cuh", "rt_traverse.cuh", "rt_exact.cuh")] + \
+            [os.path.join(_HERE, "emul", "host_builders_experiment.hpp")]
         if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
                                    "-o", _SO, src])
