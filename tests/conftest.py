@@ -60,3 +60,33 @@ def random_soup_scene(n_tris, seed, with_normals=False, n_obj=1, n_lights=2, ext
     cam = sl.new_camera([0.2, 0.1, 5.0], [-0.05, -0.02, -1.0], 1.0)
     return {"meshes": [{"verts": verts, "normals": normals, "faces": faces, "materials": mats}],
             "obj_pos": obj_pos, "obj_mesh": np.zeros(n_obj, dtype=np.uint32), "lights": lights, "camera": cam}
+
+
+def degenerate_scenes():
+    """Edge-case inputs (name -> scene): what the reference handles without special code must not trip the GPU path either --
+    no objects at all, a mesh without faces (object.go:72 `if m != nil` loop simply finds nothing), a single triangle,
+    zero-area and duplicate-vertex triangles (triangle.go:46 incidence == 0 => never hit), a triangle seen exactly edge-on."""
+    from oracle import scene_loader as sl
+    cam = sl.new_camera([0.0, 0.0, 5.0], [0.0, 0.0, -1.0], 1.0)
+    lights = np.array([[0.0, 0.0, 10.0, 1.0, 1.0, 1.0], [5.0, 5.0, 5.0, 0.5, 0.25, 1.0]])
+    mat = np.array([[0.1, 0.2, 0.3, 0.8, 0.7, 0.6, 0.5, 0.5, 0.5, 4.0]])
+
+    def mesh(verts, faces):
+        f = np.zeros((len(faces), 7), dtype=np.uint32)
+        if len(faces):
+            f[:, 0:3] = np.asarray(faces, dtype=np.uint32)
+        return {"verts": np.asarray(verts, dtype=np.float64).reshape(-1, 3), "normals": np.zeros((0, 3)), "faces": f, "materials": mat}
+
+    def scene(meshes, obj_pos, obj_mesh):
+        return {"meshes": meshes, "obj_pos": np.asarray(obj_pos, dtype=np.float64).reshape(-1, 3),
+                "obj_mesh": np.asarray(obj_mesh, dtype=np.uint32), "lights": lights, "camera": cam}
+    tri = [[-1.0, -1.0, 0.0], [1.0, -1.0, 0.0], [0.0, 1.0, 0.0]]
+    return {
+        "no_objects": scene([], [], []),
+        "mesh_without_faces": scene([mesh(tri, [])], [[0, 0, 0]], [0]),
+        "single_triangle": scene([mesh(tri, [[0, 1, 2]])], [[0.25, 0.0, 0.0]], [0]),
+        "degenerate_triangles": scene([mesh(tri + [[0.5, 0.5, 1.0], [2.0, 2.0, 1.0]],
+                                            [[0, 1, 2], [0, 0, 1], [3, 3, 3], [0, 3, 4], [1, 1, 1]])], [[0, 0, 0]], [0]),
+        "edge_on_triangle": scene([mesh([[0.0, -1.0, 1.0], [0.0, 1.0, 1.0], [0.0, 0.0, -1.0]] + tri, [[0, 1, 2], [3, 4, 5]])],
+                                  [[0, 0, 0], [0.0, 0.0, -2.0]], [0, 0]),
+    }

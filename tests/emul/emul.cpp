@@ -171,6 +171,8 @@ void emul_scene_destroy(void *h) { delete (EmulScene *)h; }
 // one leaf and that every child box contains its subtree.  Returns 0 if valid, else an error code.
 int emul_bvh_check(void *h, uint32_t mesh, uint32_t *out_nodes, uint32_t *out_depth, uint32_t *out_leaves) {
     EmulScene *s = (EmulScene *)h;
+    *out_nodes = 0; *out_depth = 0; *out_leaves = 0;
+    if (mesh >= s->meshes.size()) return 0;          // a scene without meshes has nothing to check
     EmulMesh &m = s->meshes[mesh];
     *out_nodes = m.view.n_nodes; *out_depth = m.max_depth; *out_leaves = m.n_leaves;
     const uint32_t n = m.view.n_faces;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import emul_build as eb
-from conftest import random_soup_scene
+from conftest import degenerate_scenes, random_soup_scene
 from oracle import oracle as orc
 
 import distributed_raytracer_b200 as rt
@@ -96,6 +96,19 @@ def test_exact_replay_soup_flat_normals_eight_lights(example_scene):
     sc = soup_config_scene(5000, example_scene, angle_deg=33.0)
     st = check_exact(sc, 120, 68)
     assert st["hit_pixels"] > 500 and st["shadow_rays"] == 8 * st["hit_pixels"]
+
+
+@pytest.mark.parametrize("name", ["no_objects", "mesh_without_faces", "single_triangle", "degenerate_triangles", "edge_on_triangle"])
+@pytest.mark.parametrize("W,H", [(1, 1), (3, 5), (64, 48)])
+def test_exact_replay_degenerate_inputs(name, W, H):
+    sc = degenerate_scenes()[name]
+    st = check_exact(sc, W, H)
+    if name in ("no_objects", "mesh_without_faces"):
+        assert st["hit_pixels"] == 0
+    if name == "single_triangle" and W == 64:
+        assert st["hit_pixels"] > 50
+    within, same_face = check_fast(sc, W, H)          # fp32 traversal may decide a silhouette pixel differently
+    assert within >= 0.99 and same_face >= 0.99
 
 
 def test_orbit_camera_matches_reference_basis(example_scene):

@@ -6,7 +6,7 @@ pixels and the hit-face index equal on >= 99.9 %."""
 import numpy as np
 import pytest
 
-from conftest import EXAMPLE_SCENE, random_soup_scene
+from conftest import degenerate_scenes, EXAMPLE_SCENE, random_soup_scene
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -598,6 +598,25 @@ def test_scene_create_rejects_out_of_range_indices(rt, example_scene, col, count
     with pytest.raises(rt.RtError) as ei:
         rt.GpuScene(sc, precision=rt.FP32_FAST)
     assert ei.value.code == rt._lib.RT_ERR_INVALID and msg in str(ei.value)
+
+
+@pytest.mark.parametrize("name", ["no_objects", "mesh_without_faces", "single_triangle", "degenerate_triangles", "edge_on_triangle"])
+def test_degenerate_inputs(rt, name):
+    """Edge-case inputs (conftest.degenerate_scenes): no objects, a mesh without faces, a single triangle, zero-area triangles,
+    an edge-on triangle -- at 1x1, 3x5 and 64x48 pixels.  FP64_EXACT bit-identical to the oracle, FP32_FAST within tolerance."""
+    sc = degenerate_scenes()[name]
+    S = orc.Scene(sc)
+    ge = rt.GpuScene(sc, precision=rt.FP64_EXACT)
+    gf = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    for (W, H) in [(1, 1), (3, 5), (64, 48)]:
+        rgb_o, col_o, face_o, st = S.render_region(W, H, mode=orc.CULLED)
+        rgb, col, face, obj, lit = ge.render_region_debug(W, H)
+        assert np.array_equal(face, face_o) and np.array_equal(col.view(np.uint64), col_o.view(np.uint64)) and np.array_equal(rgb, rgb_o)
+        if name in ("no_objects", "mesh_without_faces"):
+            assert not rgb.any()
+        fast = gf.render_region(W, H)
+        assert (np.abs(fast.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= 1).mean() >= 0.99
+    ge.close(); gf.close(); S.close()
 
 
 def test_host_tracer_bulk_trace_and_draw(rt, example_scene):
