@@ -174,7 +174,7 @@ k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, floa
 // ---------------------------------------------------------------------------------------------
 // K4: fused shadow rays + Phong shading, one thread per primary hit; warps claim 32 hits at a time
 // ---------------------------------------------------------------------------------------------
-template <bool EXACT, bool COUNT, int MINB>
+template <bool EXACT, bool COUNT, int MINB, bool SHADE32 = false>
 __global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr, bool brute,
                                                       const HitRec *__restrict__ hits, unsigned int *counters,
                                                       double *__restrict__ hit_colour, uint32_t *__restrict__ hit_lit,
@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView s
         HitRec hr = hits[h];
         PixMap pm = map_ray(hr.pix, fp, false);
         double col[3];
-        uint32_t lit = shade_hit<EXACT>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, (COUNT && valid) ? &c : nullptr);
+        uint32_t lit = SHADE32 ? shade_hit_fast32(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, col, (COUNT && valid) ? &c : nullptr)
+                               : shade_hit<EXACT>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, (COUNT && valid) ? &c : nullptr);
         if (valid) {
             hit_colour[3 * (size_t)h] = col[0]; hit_colour[3 * (size_t)h + 1] = col[1]; hit_colour[3 * (size_t)h + 2] = col[2];
             hit_lit[h] = lit;
@@ -618,6 +619,9 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
 #define LAUNCH_SHADE(EX, CN, MB) k_shade<EX, CN, MB><<<g, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats)
     if (job.precision == RT_FP64_EXACT) {
         if (count) LAUNCH_SHADE(true, true, 1); else LAUNCH_SHADE(true, false, 1);
+    } else if (job.shade32) {          // opt-in fp32 shading (RT_B200_SHADE32=1): see shade_hit_fast32
+        if (count) k_shade<false, true, 1, true><<<g, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
+        else k_shade<false, false, 8, true><<<g, 128, 0, st>>>(fp, sc, job.fr, brute, job.d_hits, job.d_counters, job.d_hit_colour, job.d_hit_lit, job.d_stats);
     } else if (count) {
         LAUNCH_SHADE(false, true, 1);
     } else {

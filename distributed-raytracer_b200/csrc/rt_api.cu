@@ -64,6 +64,7 @@ struct rt_scene {
     int shade_minb = 8;
     bool primary_persistent = false;
     bool split_shade = false;
+    bool shade32 = false;              // RT_B200_SHADE32=1: FP32_FAST shades in fp32 too (opt-in)
     uint32_t sync_timeout_ms = 2000;   // device-side wait on a peer's hand-off flag gives up after this (master/main.go:35: 2 s per order)
 
     // immutable after rt_scene_create
@@ -281,7 +282,7 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp, uint32_t flags, siz
     job.fr = L.inline_frame;
     job.precision = s->precision; job.flags = flags & 0x00ffffffu;
     job.d_hits = L.d_hits; job.d_hit_colour = L.d_hit_colour; job.d_hit_lit = L.d_hit_lit;
-    job.d_hit_geom = L.d_hit_geom; job.split_shade = s->split_shade;
+    job.d_hit_geom = L.d_hit_geom; job.split_shade = s->split_shade && !s->shade32; job.shade32 = s->shade32;
     job.d_counters = L.d_counters; job.d_stats = L.d_stats;
     job.d_out_rgb = d_rgb;
     job.d_out_colour = out.h_colour ? L.d_dbg_colour : nullptr;
@@ -432,6 +433,7 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->shade_minb = env_int("RT_B200_SHADE_MINB", 8);
     s->primary_persistent = env_int("RT_B200_PERSISTENT", 0) != 0;
     s->split_shade = env_int("RT_B200_SPLIT_SHADE", 0) != 0;
+    s->shade32 = env_int("RT_B200_SHADE32", 0) != 0 && desc->precision == RT_FP32_FAST;
     s->top_in_smem = env_int("RT_B200_TOP_SMEM", 0) != 0;
     s->refill_below = env_int("RT_B200_REFILL", 1);
     s->sync_timeout_ms = (uint32_t)std::max(1, env_int("RT_B200_SYNC_TIMEOUT_MS", 2000));

@@ -45,6 +45,7 @@ struct RenderJob {
     uint32_t *d_hit_lit;      // per hit
     double   *d_hit_geom;     // split K4: 6 per hit (P, N) or nullptr
     bool      split_shade;
+    bool      shade32;        // FP32_FAST: opt-in fp32 shading (RT_B200_SHADE32=1)
     unsigned int *d_counters; // [0]=next ray (primary), [1]=hit count, [2]=next hit (shade), [3]=next hit (write)
     Counters *d_stats;        // [0] = K2 primary, [1] = K4 shadow rays (filled with RT_FLAG_COUNT)
     // outputs (device)

@@ -401,6 +401,109 @@ RT_HD void phong_from_mask(const SceneView &sc, const FrameParams &fp, const Hit
     col[0] = c[0]; col[1] = c[1]; col[2] = c[2];
 }
 
+// ------------------------------------------------------------------------------------------------
+// OPT-IN (RT_B200_SHADE32=1, FP32_FAST only; default off, unmeasured on the GPU so far): the whole of tracer.go:53-77 in
+// fp32.  The default FAST path keeps geometry + Phong in fp64 in the reference's operation order (bit-identical colours
+// wherever face and lit mask agree); fp64 is ~15 % of K4's instructions (21 divisions + 8 square roots per hit with two
+// lights).  The tolerance of north_star (<= 1 LSB on >= 99.9 % of the pixels) does not need it: an fp32 colour is within
+// ~1e-6 of the fp64 one, which moves uint8(255 c) by one step on ~0.05 % of the channels (tests/test_emul.py).
+// ------------------------------------------------------------------------------------------------
+struct fv3 { float x, y, z; };
+RT_HD fv3 fv_make(float x, float y, float z) { fv3 r; r.x = x; r.y = y; r.z = z; return r; }
+RT_HD fv3 fv_sub(fv3 a, fv3 b) { return fv_make(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_HD float fv_dot(fv3 a, fv3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+RT_HD fv3 fv_scale(fv3 a, float s) { return fv_make(a.x * s, a.y * s, a.z * s); }
+RT_HD fv3 fv_norm(fv3 a) { return fv_scale(a, 1.0f / sqrtf(fv_dot(a, a))); }
+RT_HD fv3 fv_ldd(const double *p) { return fv_make((float)p[0], (float)p[1], (float)p[2]); }
+RT_HD float clamp01f(float v) { return fmaxf(0.0f, fminf(v, 1.0f)); }
+// x^ns for x in [0,1]; integral exponents (every MTL file of the BASELINE configs) by square-and-multiply
+RT_HD float pow_ns32(float x, float ns) {
+    if (ns == 0.0f) return 1.0f;
+    const float fl = floorf(ns);
+    if (fl == ns && ns > 0.0f && ns <= 1024.0f) {
+        float r = 1.0f, b = x;
+        for (int e = (int)ns; e; e >>= 1) { if (e & 1) r *= b; b *= b; }
+        return r;
+    }
+    return x > 0.0f ? powf(x, ns) : (ns > 0.0f ? 0.0f : 1.0f / 0.0f);
+}
+
+RT_HD uint32_t shade_hit_fast32(const SceneView &sc, const FrameParams &fp, int i, int j, int obj, int face, float t32,
+                                double col[3], Counters *cnt) {
+    const ObjRec &ob = sc.objs[obj];
+    const MeshView &m = sc.meshes[ob.mesh];
+    // the primary ray exactly as K2 shot it (fp32), object space
+    const int hw = fp.W / 2, hh = fp.H / 2;
+    const float phw = (float)fp.tan_half, phh = phw * (float)fp.H / (float)fp.W;
+    const float si = phw * ((float)(hw - i) - 0.5f) / (float)hw, sj = phh * ((float)(hh - j) - 0.5f) / (float)hh;
+    const fv3 d = fv_norm(fv_make((float)fp.fwd[0] + (float)fp.left[0] * si + (float)fp.up[0] * sj,
+                                  (float)fp.fwd[1] + (float)fp.left[1] * si + (float)fp.up[1] * sj,
+                                  (float)fp.fwd[2] + (float)fp.left[2] * si + (float)fp.up[2] * sj));
+    const fv3 cam = fv_ldd(fp.cam_pos), pos = fv_ldd(ob.pos);
+    const fv3 ol = fv_sub(cam, pos);                                                // object.go:71
+    const double *pv = m.fverts + 9 * (size_t)face;
+    const fv3 P1 = fv_ldd(pv), P2 = fv_ldd(pv + 3), P3 = fv_ldd(pv + 6);
+    // barycentric coordinates of the hit (triangle.go:50-60) from the fp32 intersection; t32 is K2's distance
+    float r1 = 1.0f, r2 = 0.0f, r3 = 0.0f, t = t32;
+    {
+        rt_f4 a, b, c;
+        a.x = P1.x; a.y = P1.y; a.z = P1.z; a.w = 0.0f; b.x = P2.x; b.y = P2.y; b.z = P2.z; b.w = 0.0f; c.x = P3.x; c.y = P3.y; c.z = P3.z; c.w = 0.0f;
+        float tt, u, v;
+        if (tri_test32(a, b, c, make_rayf(ol.x, ol.y, ol.z, d.x, d.y, d.z), tt, u, v)) { t = tt; r2 = u; r3 = v; r1 = 1.0f - u - v; }
+    }
+    const fv3 Pl = fv_make(fmaf(d.x, t, ol.x), fmaf(d.y, t, ol.y), fmaf(d.z, t, ol.z));     // triangle.go:69
+    const fv3 P = fv_make(Pl.x + pos.x, Pl.y + pos.y, Pl.z + pos.z);                         // object.go:109
+    fv3 N;
+    if (m.fnormals) {                                                                          // object.go:90-92
+        const double *pn = m.fnormals + 9 * (size_t)face;
+        const fv3 N1 = fv_ldd(pn), N2 = fv_ldd(pn + 3), N3 = fv_ldd(pn + 6);
+        N = fv_norm(fv_make(N1.x * r1 + N2.x * r2 + N3.x * r3, N1.y * r1 + N2.y * r2 + N3.y * r3, N1.z * r1 + N2.z * r2 + N3.z * r3));
+    } else {                                                                                   // object.go:93-95
+        const fv3 e1 = fv_sub(P2, P1), e2 = fv_sub(P3, P1);
+        N = fv_norm(fv_make(e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x));
+    }
+    const double *mat = hit_material(sc, obj, face);
+    float c[3] = { (float)mat[0], (float)mat[1], (float)mat[2] };                             // tracer.go:56
+    const float ns = (float)mat[9];
+    const fv3 V = fv_norm(fv_sub(cam, P));                                                     // tracer.go:66 (light-independent)
+    uint32_t lit_mask = 0;
+    for (int l = 0; l < fp.n_lights; l++) {
+        RT_SYNCWARP();
+        const LightRec &L = sc.lights[l];
+        const fv3 Lv = fv_sub(fv_ldd(L.pos), P);
+        const float lightLen = sqrtf(fv_dot(Lv, Lv));
+        const fv3 Ld = fv_scale(Lv, 1.0f / lightLen);                                          // tracer.go:61
+        const float bias = (float)RT_SHADOW_BIAS;
+        bool lit;
+        if (fp.n_obj == 1) {
+            RayF r = make_rayf(fmaf(Ld.x, bias, Pl.x), fmaf(Ld.y, bias, Pl.y), fmaf(Ld.z, bias, Pl.z), Ld.x, Ld.y, Ld.z);
+            float tmax = lightLen - bias;
+            int f = -1;
+            lit = !mesh_trace_fast<true>(m, r, tmax, f, cnt);
+        } else {
+            TraceFast s;
+            dv so = dv_make((double)fmaf(Ld.x, bias, P.x), (double)fmaf(Ld.y, bias, P.y), (double)fmaf(Ld.z, bias, P.z));
+            bool shaded = trace_fast_nearest(sc, fp, so, dv_make((double)Ld.x, (double)Ld.y, (double)Ld.z), false, s, cnt);
+            lit = !shaded || lightLen < s.t + bias;
+        }
+        RT_SYNCWARP();
+        if (lit) {
+            lit_mask |= 1u << (l & 31);
+            const float ldn = fv_dot(Ld, N);
+            const fv3 R = fv_sub(fv_scale(N, 2.0f * ldn), Ld);                                 // tracer.go:65
+            const float diff = fmaxf(ldn, 0.0f);                                               // tracer.go:69
+            const float spec = pow_ns32(fmaxf(fv_dot(R, V), 0.0f), ns);                        // tracer.go:72
+            for (int k = 0; k < 3; k++) {
+                const float lc = (float)L.col[k];
+                c[k] = fminf(c[k] + clamp01f(diff * (float)mat[3 + k]) * lc, 1.0f);            // colour.go:38-50
+                c[k] = fminf(c[k] + clamp01f(spec * (float)mat[6 + k]) * lc, 1.0f);
+            }
+        }
+    }
+    col[0] = (double)c[0]; col[1] = (double)c[1]; col[2] = (double)c[2];
+    return lit_mask;
+}
+
 // fused form: geometry, one shadow query per light, Phong accumulation (both modes).  Returns the lit mask.
 template <bool EXACT>
 RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int j, int obj, int face, float t32,

@@ -298,13 +298,16 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
         hits.push_back(hr);
     }
     // K4 + K5
+    const char *s32 = getenv("RT_B200_SHADE32");
+    const bool shade32 = s32 && atoi(s32) != 0;        // opt-in fp32 shading of FP32_FAST (rt_traverse.cuh: shade_hit_fast32)
     for (const HitRec &hr : hits) {
         PixMap pm = map_ray(hr.pix, fp, rowmajor);
         double col[3];
         Counters before = c;
         uint32_t lit = s->precision == RT_FP64_EXACT
                            ? shade_hit<true>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, &c)
-                           : shade_hit<false>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, false, col, &c);
+                           : (shade32 ? shade_hit_fast32(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, col, &c)
+                                      : shade_hit<false>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, false, col, &c));
         size_t o = pm.out;
         if (g_cost_shade) g_cost_shade[o] = (uint32_t)((c.nodes - before.nodes) + (c.tris - before.tris));
         if (out_rgb) for (int k = 0; k < 3; k++) out_rgb[3 * o + k] = quantise_exact(col[k], sdl);

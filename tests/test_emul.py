@@ -131,6 +131,23 @@ def test_fast_replay_random_scenes(kw):
     assert within >= 0.995 and same_face >= 0.995       # tiny random soups have many silhouette pixels
 
 
+def test_fast_replay_with_fp32_shading_option(example_scene, monkeypatch):
+    """RT_B200_SHADE32=1 (opt-in): FP32_FAST with the shading in fp32 too still meets the tolerance of north_star (<= 1 LSB
+    on >= 99.9 % of the pixels); what it gives up is the bit-identical colours of the default fp64 shading."""
+    monkeypatch.setenv("RT_B200_SHADE32", "1")
+    within, same_face = check_fast(example_scene, 320, 240)
+    assert within >= 0.999 and same_face >= 0.999
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 2)]
+    within, same_face = check_fast(sc, 480, 270)
+    assert within >= 0.999 and same_face >= 0.999
+    for kw in (dict(n_tris=400, seed=31, with_normals=True), dict(n_tris=150, seed=32, n_obj=3, n_lights=4)):
+        within, same_face = check_fast(random_soup_scene(**kw), 160, 120)
+        assert within >= 0.99 and same_face >= 0.99
+    monkeypatch.setenv("RT_B200_SHADE32", "0")
+    assert check_fast(example_scene, 320, 240)[0] == 1.0          # the default stays bit-identical on C1
+
+
 def test_region_layout_quantiser(example_scene):
     W, H, x, y, w, h = 96, 72, 30, 20, 41, 33
     S = orc.Scene(example_scene)
