@@ -81,7 +81,23 @@ def degenerate_scenes():
         return {"meshes": meshes, "obj_pos": np.asarray(obj_pos, dtype=np.float64).reshape(-1, 3),
                 "obj_mesh": np.asarray(obj_mesh, dtype=np.uint32), "lights": lights, "camera": cam}
     tri = [[-1.0, -1.0, 0.0], [1.0, -1.0, 0.0], [0.0, 1.0, 0.0]]
+    # an axis-aligned cube on a 1/8 grid seen by an axis-aligned camera with tan(fov/2) = 1: at 16x16 pixels the pixel centres
+    # are odd multiples of 1/16 on the plane one unit ahead, so with the front face 1 unit away rays pass EXACTLY through
+    # the shared diagonal, the cube's edges and (for the larger cube) its corners: equal-distance ties between the two
+    # triangles of a face (lowest index wins, object.go:97) and zero-thickness boxes in the BVH
+    def cube(h):
+        v = [[sx * h, sy * h, sz * h] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]
+        q = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+        return mesh(v, [t for a, b, c, d in q for t in ((a, b, c), (c, d, a))])
+    cam90 = sl.new_camera([0.0, 0.0, 5.0], [0.0, 0.0, -1.0], 2.0 * np.arctan(1.0))
+
+    def with_cam(sc, c):
+        sc = dict(sc)
+        sc["camera"] = c
+        return sc
     return {
+        "cube_edges_and_diagonals": with_cam(scene([cube(0.4375)], [[0.0, 0.0, 3.5625]], [0]), cam90),
+        "two_cubes_coplanar_fronts": with_cam(scene([cube(0.3125)], [[-0.3125, 0.0, 3.6875], [0.3125, 0.0, 3.6875]], [0, 0]), cam90),
         "no_objects": scene([], [], []),
         "mesh_without_faces": scene([mesh(tri, [])], [[0, 0, 0]], [0]),
         "single_triangle": scene([mesh(tri, [[0, 1, 2]])], [[0.25, 0.0, 0.0]], [0]),

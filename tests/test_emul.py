@@ -98,6 +98,19 @@ def test_exact_replay_soup_flat_normals_eight_lights(example_scene):
     assert st["hit_pixels"] > 500 and st["shadow_rays"] == 8 * st["hit_pixels"]
 
 
+@pytest.mark.parametrize("name", ["cube_edges_and_diagonals", "two_cubes_coplanar_fronts"])
+def test_exact_replay_exact_edge_and_corner_hits(name):
+    """Rays through shared edges, face diagonals and corners of axis-aligned cubes (equal-distance ties, zero-thickness BVH
+    boxes, two objects whose front faces are coplanar and touch): the replayed kernels pick the same face as the oracle."""
+    sc = degenerate_scenes()[name]
+    for (W, H) in [(16, 16), (32, 32), (17, 13)]:
+        st = check_exact(sc, W, H)
+        assert st["hit_pixels"] > 0
+    S = orc.Scene(sc)
+    assert S.render_region(16, 16, mode=orc.BRUTE)[3]["nearest_ties"] > 0      # the scene really produces exact ties
+    S.close()
+
+
 @pytest.mark.parametrize("name", ["no_objects", "mesh_without_faces", "single_triangle", "degenerate_triangles", "edge_on_triangle"])
 @pytest.mark.parametrize("W,H", [(1, 1), (3, 5), (64, 48)])
 def test_exact_replay_degenerate_inputs(name, W, H):

@@ -7,7 +7,7 @@ import struct
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, random_soup_scene
+from conftest import GOLDEN, degenerate_scenes, random_soup_scene
 from oracle import oracle as orc
 from oracle import scene_loader as sl
 
@@ -117,6 +117,27 @@ def test_oracle_equals_independent_python_restatement_on_soups(kw):
             n_hit += hit
             n_shadowed += hit and lit != (1 << len(sc["lights"])) - 1
     assert n_hit > 60 and n_shadowed > 10
+    O.close()
+
+
+@pytest.mark.parametrize("name", ["cube_edges_and_diagonals", "two_cubes_coplanar_fronts", "degenerate_triangles", "edge_on_triangle"])
+def test_oracle_equals_independent_python_restatement_on_ties_and_degenerates(name):
+    """Equal-distance ties (rays through shared edges, diagonals, corners: the first candidate in face order must win in both
+    restatements), coplanar touching objects, zero-area triangles: every pixel, all three enumeration modes."""
+    import pyref
+    sc = degenerate_scenes()[name]
+    S, O = pyref.Scene(sc), orc.Scene(sc)
+    O.build_rtrees()
+    tan_half = orc.go_tan(float(sc["camera"][12]) / 2.0)
+    for (W, H) in [(16, 16), (17, 13)]:
+        for i in range(W):
+            for j in range(H):
+                hit, col, face, obj, lit = S.trace_pixel(i, j, W, H, tan_half)
+                for mode in (orc.BRUTE, orc.CULLED, orc.RTREE):
+                    o_hit, o_col, o_face, o_obj, o_lit = O.trace_pixel(i, j, W, H, mode)
+                    assert hit == o_hit, (i, j, mode)
+                    if hit:
+                        assert (face, obj, lit) == (o_face, o_obj, o_lit) and [hx(c) for c in col] == [hx(c) for c in o_col], (i, j, mode)
     O.close()
 
 
