@@ -15,6 +15,11 @@
  * pinned function is orc_encode_trace_results (checked against the
  * google.protobuf runtime, tests/test_wire.py).
  *
+ * Modes: the R-tree mode is the reference-shaped one (candidates = faces whose rectangle the
+ * ray pierces, object.go:76).  Brute force over all faces gives the same result EXCEPT for
+ * zero-area faces, whose `incidence` (triangle.go:42) is a rounding residue and which can then
+ * "hit" at t ~ 0 for rays nowhere near them (profiles/r01_fuzz_cpu_replay.txt).
+ *
  * All citations are into /root/reference/.
  */
 #ifndef RT_ORACLE_H
