@@ -51,6 +51,101 @@ def test_oracle_encoder_decodes_back_with_protobuf(orc, example_oracle):
     assert np.array_equal(back, rgb.reshape(-1, 3))
 
 
+# ------------------------------------------------------------------------------------------------ master-side decoder (CPU)
+def varint(v):
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7f) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def test_decoder_library_exports_declared_symbols(built):
+    import ctypes as C
+    import re
+    from conftest import ROOT
+    from distributed_raytracer_b200 import wire
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rt_wire.h")).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(rt_wire_[a-z_0-9]+)\s*\(", src)))
+    assert set(names) == set(wire.WIRE_SYMBOLS)
+    for path in (wire.LIB_PATH, os.path.join(os.path.dirname(wire.LIB_PATH), "librt_host.so")):
+        lib = C.CDLL(path)
+        for n in names:
+            assert getattr(lib, n) is not None
+
+
+def test_decoder_inverts_protobuf_and_oracle_encoders(built, orc):
+    """decode(protobuf.SerializeToString(m)) == m.results and decode(oracle encoder(x)) == x, incl. every byte value."""
+    from distributed_raytracer_b200 import wire
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 300, 4097):
+        rgb = rng.integers(0, 256, size=(n, 3), dtype=np.uint8)
+        rgb[rng.random(n) < 0.5] = 0
+        assert np.array_equal(wire.decode_trace_results(orc.encode_trace_results(rgb)), rgb)
+        try:
+            enc = mtr.protobuf_encode(rgb)
+        except ImportError:
+            continue
+        assert np.array_equal(wire.decode_trace_results(enc), rgb)
+    for name in ("edge", "random", "sparse"):
+        rgb = np.fromfile(os.path.join(GOLDEN, "trace_results_%s.rgb" % name), dtype=np.uint8).reshape(-1, 3)
+        enc = np.fromfile(os.path.join(GOLDEN, "trace_results_%s.bin" % name), dtype=np.uint8)
+        assert np.array_equal(wire.decode_trace_results(enc), rgb)
+
+
+def test_decoder_accepts_any_valid_encoding_like_protobuf_does():
+    """Non-canonical but valid encodings: fields out of order, repeated scalars (last wins), unknown fields of every wire
+    type at both levels, non-minimal varints, values above 255 (the master truncates: uint8(pixel.GetR()), main.go:172).
+    Each is also parsed with the protobuf runtime to make sure the expectation is protobuf's, not ours."""
+    from distributed_raytracer_b200 import wire
+    sub1 = b"\x18\x07" + b"\x08\x05" + b"\x10\x06"                           # b, r, g out of order
+    sub2 = b"\x08\x01" + b"\x08\x09"                                          # r twice: last wins
+    sub3 = b"\x08" + varint(300) + b"\x10" + varint(2 ** 32 - 1)                # 300 -> 44, 0xffffffff -> 255
+    sub4 = b"\x08\x83\x80\x00" + b"\x20\x05" + b"\x2a\x02hi" + b"\x35\x01\x02\x03\x04" + b"\x39" + bytes(8) + b"\x18\x04"
+    msg = b"".join(b"\x0a" + varint(len(s)) + s for s in (sub1, sub2, sub3, sub4))
+    msg = b"\x10\x2a" + msg + b"\x1a\x03abc" + b"\x0a\x00"                     # unknown top-level fields + an empty Colour
+    want = np.array([[5, 6, 7], [9, 0, 0], [44, 255, 0], [3, 0, 4], [0, 0, 0]], dtype=np.uint8)
+    assert np.array_equal(wire.decode_trace_results(msg), want)
+    try:
+        m = mtr.trace_results_class()()
+    except ImportError:
+        return
+    m.ParseFromString(msg)
+    assert np.array_equal(np.array([[c.r & 255, c.g & 255, c.b & 255] for c in m.results], dtype=np.uint8), want)
+
+
+def test_decoder_rejects_malformed_input_and_respects_capacity():
+    from distributed_raytracer_b200 import wire
+    good = b"\x0a\x02\x08\x01" * 3
+    assert wire.decode_trace_results(good).shape == (3, 3)
+    for bad in (good[:-1], b"\x0a\x05\x08\x01", b"\x0a", b"\x0b\x00", b"\x08" + b"\xff" * 11, b"\x0a\x02\x08\x80", b"\x00\x00"):
+        with pytest.raises(wire.WireError) as ei:
+            wire.decode_trace_results(bad)
+        assert ei.value.code == wire.ERR_MALFORMED, bad
+    with pytest.raises(wire.WireError) as ei:
+        wire.decode_trace_results(good, max_results=2)
+    assert ei.value.code == wire.ERR_CAPACITY
+
+
+def test_blit_is_the_masters_frame_assembly(orc, example_oracle):
+    """rt_wire_blit_trace_results == the loop of master/main.go:166-176: two orders (partition rectangles) of one frame
+    assembled into a 32-bit surface; equals the frame rendered in one piece, row-major."""
+    from distributed_raytracer_b200 import wire
+    W, H = 96, 64
+    whole = example_oracle.render_region(W, H, layout=orc.L_ROWMAJOR)[0].reshape(H, W, 3).astype(np.uint32)
+    want = (whole[..., 0] << 16) | (whole[..., 1] << 8) | whole[..., 2] | 0xFF000000
+    surface = np.zeros((H, W + 5), dtype=np.uint32)[:, :W]                  # a pitch larger than the width
+    for (x, y, w, h) in [(0, 0, 40, H), (40, 0, W - 40, H)]:
+        rgb = example_oracle.render_region(W, H, x, y, w, h)[0]             # BulkTrace order i*h + j
+        wire.blit_trace_results(orc.encode_trace_results(rgb), x, y, w, h, surface, amask=0xFF000000)
+    assert np.array_equal(surface, want)
+    with pytest.raises(wire.WireError):                                     # a reply with too few results for its order
+        wire.blit_trace_results(orc.encode_trace_results(np.zeros((10, 3), np.uint8)), 0, 0, 4, 4, surface)
+    with pytest.raises(wire.WireError):
+        wire.blit_trace_results(b"", 90, 0, 10, 10, surface)                # region outside the surface
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def rt(built):
