@@ -113,6 +113,9 @@ def parse_obj(path):
 def _go_norm(v):
     # vector.go:50-53 ; Python floats are IEEE binary64 and never fused
     mag = math.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+    if mag == 0.0:        # Go divides without trapping: 0/0 = NaN, x/0 = +-Inf (a zero `vn` line in the OBJ file)
+        with np.errstate(all="ignore"):                      # the hardware's own NaN / Inf (DIVSD), as in the Go binary
+            return tuple(float(np.float64(c) / np.float64(mag)) for c in v)
     return (v[0] / mag, v[1] / mag, v[2] / mag)
 
 
