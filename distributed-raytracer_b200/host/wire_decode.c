@@ -16,8 +16,19 @@ static uint64_t get_varint(const uint8_t *p, uint64_t pos, uint64_t end, uint64_
     return 0;
 }
 
-/* skips one field of wire type wt; returns the new position or 0 on error */
-static uint64_t skip_field(const uint8_t *p, uint64_t pos, uint64_t end, unsigned wt) {
+/* a field tag is a 32-bit varint with a non-zero field number (field numbers are at most 2^29 - 1) */
+static uint64_t get_tag(const uint8_t *p, uint64_t pos, uint64_t end, uint64_t *field, unsigned *wt) {
+    uint64_t tag;
+    pos = get_varint(p, pos, end, &tag);
+    if (!pos || tag > 0xFFFFFFFFull || (tag >> 3) == 0) return 0;
+    *field = tag >> 3;
+    *wt = (unsigned)(tag & 7);
+    return pos;
+}
+
+/* skips one field of wire type wt (field number `field`, needed to match the end of a group); returns the new position
+ * or 0 on error.  Unknown groups (wire types 3 / 4, proto2 leftovers) are skipped like protobuf runtimes do. */
+static uint64_t skip_field(const uint8_t *p, uint64_t pos, uint64_t end, uint64_t field, unsigned wt, int depth) {
     uint64_t v;
     switch (wt) {
     case 0: return get_varint(p, pos, end, &v);
@@ -26,8 +37,18 @@ static uint64_t skip_field(const uint8_t *p, uint64_t pos, uint64_t end, unsigne
         pos = get_varint(p, pos, end, &v);
         if (!pos || v > end - pos) return 0;
         return pos + v;
+    case 3:
+        if (depth > 64) return 0;
+        for (;;) {
+            uint64_t f; unsigned w;
+            pos = get_tag(p, pos, end, &f, &w);
+            if (!pos) return 0;
+            if (w == 4) return f == field ? pos : 0;
+            pos = skip_field(p, pos, end, f, w, depth + 1);
+            if (!pos) return 0;
+        }
     case 5: return end - pos >= 4 ? pos + 4 : 0;
-    default: return 0;               /* groups (3, 4) do not occur in proto3 messages */
+    default: return 0;               /* a stray end-group, wire types 6 and 7 */
     }
 }
 
@@ -35,18 +56,16 @@ static uint64_t skip_field(const uint8_t *p, uint64_t pos, uint64_t end, unsigne
 static int parse_colour(const uint8_t *p, uint64_t pos, uint64_t end, uint8_t out[3]) {
     out[0] = out[1] = out[2] = 0;                         /* proto3 default */
     while (pos < end) {
-        uint64_t tag, v;
-        pos = get_varint(p, pos, end, &tag);
+        uint64_t field, v;
+        unsigned wt;
+        pos = get_tag(p, pos, end, &field, &wt);
         if (!pos) return -1;
-        const uint64_t field = tag >> 3;
-        const unsigned wt = (unsigned)(tag & 7);
         if (field >= 1 && field <= 3 && wt == 0) {
             pos = get_varint(p, pos, end, &v);
             if (!pos) return -1;
             out[field - 1] = (uint8_t)v;                  /* uint8(uint32(v)): master/main.go:172 */
-        } else {
-            if (field == 0) return -1;
-            pos = skip_field(p, pos, end, wt);
+        } else {                                          /* unknown field, or a known one with another wire type */
+            pos = skip_field(p, pos, end, field, wt, 0);
             if (!pos) return -1;
         }
     }
@@ -97,12 +116,10 @@ static int64_t walk(const uint8_t *wire, uint64_t len, struct pack_ctx *pc, stru
                 continue;
             }
         }
-        uint64_t tag, n;
-        pos = get_varint(wire, pos, len, &tag);
+        uint64_t field, n;
+        unsigned wt;
+        pos = get_tag(wire, pos, len, &field, &wt);
         if (!pos) return RT_WIRE_ERR_MALFORMED;
-        const uint64_t field = tag >> 3;
-        const unsigned wt = (unsigned)(tag & 7);
-        if (field == 0) return RT_WIRE_ERR_MALFORMED;
         if (field == 1 && wt == 2) {
             pos = get_varint(wire, pos, len, &n);
             if (!pos || n > len - pos) return RT_WIRE_ERR_MALFORMED;
@@ -113,7 +130,7 @@ static int64_t walk(const uint8_t *wire, uint64_t len, struct pack_ctx *pc, stru
             k++;
             pos += n;
         } else {
-            pos = skip_field(wire, pos, len, wt);
+            pos = skip_field(wire, pos, len, field, wt, 0);
             if (!pos) return RT_WIRE_ERR_MALFORMED;
         }
     }

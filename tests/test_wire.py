@@ -104,8 +104,10 @@ def test_decoder_accepts_any_valid_encoding_like_protobuf_does():
     sub3 = b"\x08" + varint(300) + b"\x10" + varint(2 ** 32 - 1)                # 300 -> 44, 0xffffffff -> 255
     sub4 = b"\x08\x83\x80\x00" + b"\x20\x05" + b"\x2a\x02hi" + b"\x35\x01\x02\x03\x04" + b"\x39" + bytes(8) + b"\x18\x04"
     msg = b"".join(b"\x0a" + varint(len(s)) + s for s in (sub1, sub2, sub3, sub4))
+    sub5 = b"\x08\x02" + b"\x43" + b"\x08\x63" + b"\x44" + b"\x1d\x01\x02\x03\x04" + b"\x10\x03"   # an unknown group (proto2 leftover) is
+    msg = b"".join(b"\x0a" + varint(len(s)) + s for s in (sub1, sub2, sub3, sub4, sub5))              # skipped; b as fixed32 = unknown
     msg = b"\x10\x2a" + msg + b"\x1a\x03abc" + b"\x0a\x00"                     # unknown top-level fields + an empty Colour
-    want = np.array([[5, 6, 7], [9, 0, 0], [44, 255, 0], [3, 0, 4], [0, 0, 0]], dtype=np.uint8)
+    want = np.array([[5, 6, 7], [9, 0, 0], [44, 255, 0], [3, 0, 4], [2, 3, 0], [0, 0, 0]], dtype=np.uint8)
     assert np.array_equal(wire.decode_trace_results(msg), want)
     try:
         m = mtr.trace_results_class()()
@@ -119,7 +121,10 @@ def test_decoder_rejects_malformed_input_and_respects_capacity():
     from distributed_raytracer_b200 import wire
     good = b"\x0a\x02\x08\x01" * 3
     assert wire.decode_trace_results(good).shape == (3, 3)
-    for bad in (good[:-1], b"\x0a\x05\x08\x01", b"\x0a", b"\x0b\x00", b"\x08" + b"\xff" * 11, b"\x0a\x02\x08\x80", b"\x00\x00"):
+    for bad in (good[:-1], b"\x0a\x05\x08\x01", b"\x0a", b"\x0b\x00", b"\x08" + b"\xff" * 11, b"\x0a\x02\x08\x80", b"\x00\x00",
+                b"\x88\x80\x80\x80\x10\x00",              # a tag wider than 32 bits
+                b"\x0a\x02\x43\x4c",                        # group closed by another field's end-group
+                b"\x0c"):                                    # stray end-group
         with pytest.raises(wire.WireError) as ei:
             wire.decode_trace_results(bad)
         assert ei.value.code == wire.ERR_MALFORMED, bad
