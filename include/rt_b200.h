@@ -14,8 +14,9 @@
  *  - every entry point returns 0 on success, a negative rt_status otherwise; no exception crosses
  *    the ABI; rt_last_error() returns a message (per handle, or a thread-local one for handle-less
  *    failures when called with NULL).
- *  - handles are internally synchronised (per-handle mutex): BulkTrace may be entered concurrently
- *    from several goroutines (final_report.pdf p.6 s2.3); calls may arrive on any OS thread.
+ *  - handles are internally synchronised: BulkTrace may be entered concurrently from several
+ *    goroutines (final_report.pdf p.6 s2.3) and the calls then run concurrently on the GPU, one
+ *    lane each (see RT_LANE below); calls may arrive on any OS thread.
  *  - there is NO CPU fallback: without a CUDA device / the sm_100a kernels every call fails with
  *    RT_ERR_CUDA.
  */
@@ -52,7 +53,8 @@ typedef enum {
 #define RT_QUANT_RGB255      0x0u  /* uint8(255*c)          -- colour.RGB.RGB(), colour.go:59-61            */
 #define RT_QUANT_RGBA16_SHR8 0x2u  /* uint32(0xFFFF*c) >> 8 -- colour.RGB.RGBA() + go-sdl2 Surface.Set      */
 #define RT_FLAG_COUNT        0x4u  /* accumulate traversal counters (slower; for roofline accounting)       */
-#define RT_FLAG_BRUTE_FORCE  0x8u  /* FP64_EXACT only: ignore the BVH, test every face (debug / parity)     */
+#define RT_FLAG_BRUTE_FORCE  0x8u  /* FP64_EXACT only: ignore the BVH, test every face (debug; NOT the reference's
+                                      semantics for meshes with zero-area faces)               */
 #define RT_FLAG_SIMPLE       0x10u /* FP32_FAST only: one-thread-per-ray primary kernel (the default: fastest measured) */
 #define RT_FLAG_PERSISTENT   0x20u /* FP32_FAST only: persistent warp-cooperative primary kernel (ballot/shuffle refill) */
 
