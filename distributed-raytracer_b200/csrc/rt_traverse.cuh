@@ -23,7 +23,9 @@ struct SceneView {
     const LightRec *lights;
 };
 
+#ifndef RT_COUNT   // (tests/emul redefines it to log the node / leaf visit sequence of a ray: tools/simulate_warp_divergence_cpu.py)
 #define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); } while (0)
+#endif
 
 // Measured on B200 (profiles/r01_ab_traversal_shape_mt_sync_minmax.txt), config 3:
 //  * loop shape: the plain "if internal node ... else leaf" loop below beats a while-while loop with postponed
@@ -32,7 +34,7 @@ struct SceneView {
 //    reconverge after the first shadow ray and the rest of the kernel runs at ~4 active lanes.
 #if defined(__CUDA_ARCH__)
 #define RT_SYNCWARP() __syncwarp()
-#else
+#elif !defined(RT_SYNCWARP)
 #define RT_SYNCWARP() do { } while (0)
 #endif
 

@@ -15,6 +15,14 @@
 #include <numeric>
 #include <vector>
 
+// Event log (tools/simulate_warp_divergence_cpu.py): the counting hooks of the traversal code double as a recorder of the order
+// in which one ray visits nodes (code 0) and leaves (code = triangles in the leaf); RT_SYNCWARP marks the start / end of a
+// light's shadow query (code 254).  Off (nullptr) unless emul_shade_events is running.
+static std::vector<uint8_t> *g_events = nullptr;
+enum { EV_nodes = 0, EV_tris = 1 };
+#define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); if (g_events) g_events->push_back(EV_##field == EV_nodes ? (uint8_t)0 : (uint8_t)(n)); } while (0)
+#define RT_SYNCWARP() do { if (g_events) g_events->push_back((uint8_t)254); } while (0)
+
 #include "../../include/rt_b200.h"
 #include "../../distributed-raytracer_b200/csrc/rt_types.h"
 #include "../../distributed-raytracer_b200/csrc/rt_bvh.cuh"
@@ -318,6 +326,52 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
     }
     if (counters) { counters[0] = c.nodes; counters[1] = c.tris; counters[2] = hits.size(); }
     return 0;
+}
+
+// K4 event log of one frame (FP32_FAST): for every primary hit, in hit-list order (32 consecutive hits = one warp of k_shade),
+// the byte sequence  254 <visits of light 0's shadow ray> 254 254 <light 1> 254 ... 255.  Returns the number of bytes
+// (written up to `cap`), *n_hits = number of hits.
+long long emul_shade_events(void *h, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, uint32_t W, uint32_t H,
+                            uint8_t *out, unsigned long long cap, uint32_t *n_hits) {
+    EmulScene *s = (EmulScene *)h;
+    if (s->precision != RT_FP32_FAST) return -1;
+    FrameParams fp = frame_of(s, cam, n_lights, W, H);
+    fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
+    SceneView sc;
+    sc.meshes = s->views.data(); sc.objs = s->objs.data(); sc.lights = reinterpret_cast<const LightRec *>(lights);
+    std::vector<HitRec> hits;
+    Counters c; c.nodes = 0; c.tris = 0;
+    const uint32_t nrays = ray_count(fp);
+    for (uint32_t ray = 0; ray < nrays; ray++) {
+        PixMap pm = map_ray(ray, fp, false);
+        if (!pm.valid) continue;
+        int hw = fp.W / 2, hh2 = fp.H / 2;
+        float phw = (float)fp.tan_half, phh = phw * (float)fp.H / (float)fp.W;
+        float si = phw * ((float)(hw - pm.i) - 0.5f) / (float)hw, sj = phh * ((float)(hh2 - pm.j) - 0.5f) / (float)hh2;
+        float dx = (float)fp.fwd[0] + (float)fp.left[0] * si + (float)fp.up[0] * sj;
+        float dy = (float)fp.fwd[1] + (float)fp.left[1] * si + (float)fp.up[1] * sj;
+        float dz = (float)fp.fwd[2] + (float)fp.left[2] * si + (float)fp.up[2] * sj;
+        float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        TraceFast tr;
+        if (!trace_fast_nearest(sc, fp, dv_ld(fp.cam_pos), dv_make((double)(dx * inv), (double)(dy * inv), (double)(dz * inv)), true, tr, nullptr))
+            continue;
+        HitRec hr; hr.pix = ray; hr.obj = tr.obj; hr.face = tr.face; hr.t = tr.t;
+        hits.push_back(hr);
+    }
+    *n_hits = (uint32_t)hits.size();
+    std::vector<uint8_t> ev;
+    unsigned long long total = 0;
+    for (const HitRec &hr : hits) {
+        PixMap pm = map_ray(hr.pix, fp, false);
+        double col[3];
+        ev.clear();
+        g_events = &ev;
+        shade_hit<false>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, false, col, &c);
+        g_events = nullptr;
+        ev.push_back((uint8_t)255);
+        for (uint8_t b : ev) { if (total < cap) out[total] = b; total++; }
+    }
+    return (long long)total;
 }
 
 void emul_set_cost_buffers(uint32_t *primary, uint32_t *shade) { g_cost_primary = primary; g_cost_shade = shade; }
