@@ -14,7 +14,7 @@ consecutive hits, one light at a time) and counts warp-level issue slots for dif
 Costs in issue slots: node body 100, leaf entry 15 + 60 per triangle, loop overhead 10 per iteration (counted once per warp
 iteration).  The absolute numbers are a model; the RATIOS between organisations are what it is for.
 
-   python tools/simulate_warp_divergence_cpu.py [width height]      (default 960 540)
+   python tools/simulate_warp_divergence_cpu.py [width height [max_leaf]]      (default 960 540 4)
 """
 import ctypes as C
 import json
@@ -29,12 +29,12 @@ import numpy as np  # noqa: E402
 C_NODE, C_LEAF, C_TRI, C_LOOP = 100, 15, 60, 10
 
 
-def ray_sequences(W, H):
+def ray_sequences(W, H, max_leaf=4):
     import bench
     import distributed_raytracer_b200 as rt
     import emul_build
     sc = bench.build_workload()
-    E = emul_build.EmulScene(sc, rt.FP32_FAST)
+    E = emul_build.EmulScene(sc, rt.FP32_FAST, max_leaf)
     L = emul_build.lib()
     L.emul_shade_events.restype = C.c_longlong
     L.emul_shade_events.argtypes = [C.c_void_p, C.POINTER(rt._lib.Camera), C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
@@ -175,7 +175,8 @@ def thread_work(seq):
 
 def main():
     W, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (960, 540)
-    hits, n_lights = ray_sequences(W, H)
+    max_leaf = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    hits, n_lights = ray_sequences(W, H, max_leaf)
     tot = {"A": 0, "B": 0, "C": 0, "D": 0.0, "E_refill_1024": 0}
     THRESH = (2, 4, 6, 8, 12, 16, 24, 32)
     for T in THRESH:
@@ -200,7 +201,7 @@ def main():
         q = [h[l] for h in hits[w0:w0 + 512] for l in range(n_lights)]
         tot["E_refill_1024"] += cost_E(q)
     n_rays = len(hits) * n_lights
-    out = {"screen": [W, H], "hits": len(hits), "shadow_rays": n_rays, "nodes_per_ray": nodes / n_rays, "leaves_per_ray": leaves / n_rays,
+    out = {"screen": [W, H], "max_leaf": max_leaf, "hits": len(hits), "shadow_rays": n_rays, "nodes_per_ray": nodes / n_rays, "leaves_per_ray": leaves / n_rays,
            "issue_slots_per_ray": {k: v / n_rays for k, v in tot.items()},
            "simd_efficiency": {k: tot["D"] / v for k, v in tot.items()},
            "relative_to_product_loop": {k: v / tot["A"] for k, v in tot.items()}}
