@@ -538,6 +538,10 @@ def main():
                 "kernel": {"primary": "k_primary_fast_" + ("persistent" if args.persistent else "simple"), "shade": "k_shade", "write": "k_write"}[dom],
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": avg[dom],
                 "kernels_ms": avg, "algorithmic_bytes": alg,
+                "note": "algorithmic bytes = node + triangle records the rays fetch (counting build of the kernels); `traffic` is ncu's DRAM "
+                        "traffic of the same kernel -- about 24x lower, the working set lives in L1/L2 -- so the byte roofline is an upper "
+                        "bound on useful bandwidth, not the physical limiter: ncu shows the kernel issue-bound at 45 % SIMD efficiency "
+                        "(profiles/r01_ncu_full_summary.txt, profiles/r01_k4_divergence_model.txt)",
                 "per_ray": {"nodes_primary": cnt["nodes_primary"] / max(1, prim_local), "tris_primary": cnt["tris_primary"] / max(1, prim_local),
                             "nodes_shadow": cnt["nodes_shade"] / max(1, cnt["shadow_rays"]), "tris_shadow": cnt["tris_shade"] / max(1, cnt["shadow_rays"])}}
 
