@@ -342,9 +342,12 @@ long long emul_shade_events(void *h, const rt_camera *cam, const rt_light *light
     std::vector<HitRec> hits;
     Counters c; c.nodes = 0; c.tris = 0;
     const uint32_t nrays = ray_count(fp);
+    const bool primary_mode = n_hits == nullptr;        // log K2 instead: every ray index (warp = 32 consecutive), sequence + 255
+    std::vector<uint8_t> ev;
+    unsigned long long total = 0;
     for (uint32_t ray = 0; ray < nrays; ray++) {
         PixMap pm = map_ray(ray, fp, false);
-        if (!pm.valid) continue;
+        if (!pm.valid) { if (primary_mode) { if (total < cap) out[total] = 255; total++; } continue; }
         int hw = fp.W / 2, hh2 = fp.H / 2;
         float phw = (float)fp.tan_half, phh = phw * (float)fp.H / (float)fp.W;
         float si = phw * ((float)(hw - pm.i) - 0.5f) / (float)hw, sj = phh * ((float)(hh2 - pm.j) - 0.5f) / (float)hh2;
@@ -353,14 +356,20 @@ long long emul_shade_events(void *h, const rt_camera *cam, const rt_light *light
         float dz = (float)fp.fwd[2] + (float)fp.left[2] * si + (float)fp.up[2] * sj;
         float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
         TraceFast tr;
-        if (!trace_fast_nearest(sc, fp, dv_ld(fp.cam_pos), dv_make((double)(dx * inv), (double)(dy * inv), (double)(dz * inv)), true, tr, nullptr))
+        if (primary_mode) { ev.clear(); g_events = &ev; }
+        bool hit = trace_fast_nearest(sc, fp, dv_ld(fp.cam_pos), dv_make((double)(dx * inv), (double)(dy * inv), (double)(dz * inv)), true, tr, &c);
+        if (primary_mode) {
+            g_events = nullptr;
+            ev.push_back((uint8_t)255);
+            for (uint8_t b : ev) { if (total < cap) out[total] = b; total++; }
             continue;
+        }
+        if (!hit) continue;
         HitRec hr; hr.pix = ray; hr.obj = tr.obj; hr.face = tr.face; hr.t = tr.t;
         hits.push_back(hr);
     }
+    if (primary_mode) return (long long)total;
     *n_hits = (uint32_t)hits.size();
-    std::vector<uint8_t> ev;
-    unsigned long long total = 0;
     for (const HitRec &hr : hits) {
         PixMap pm = map_ray(hr.pix, fp, false);
         double col[3];
