@@ -16,6 +16,7 @@ FP64_EXACT, FP32_FAST = 0, 1
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0x0, 0x1
 QUANT_RGB255, QUANT_RGBA16_SHR8 = 0x0, 0x2
 FLAG_COUNT, FLAG_BRUTE_FORCE, FLAG_SIMPLE, FLAG_PERSISTENT = 0x4, 0x8, 0x10, 0x20
+FLAG_FUSED, FLAG_PIPELINE, FLAG_NO_CULL = 0x40, 0x80, 0x100
 
 
 def LANE(k):
@@ -71,7 +72,8 @@ class Stats(C.Structure):
 
 class BvhInfo(C.Structure):
     _fields_ = [("n_faces", C.c_uint64), ("n_nodes", C.c_uint64), ("n_leaves", C.c_uint64), ("max_depth", C.c_uint32),
-                ("max_leaf", C.c_uint32), ("ms_build", C.c_float), ("sah_cost", C.c_float)]
+                ("max_leaf", C.c_uint32), ("ms_build", C.c_float), ("sah_cost", C.c_float),
+                ("n_nodes_any", C.c_uint64), ("n_leaves_any", C.c_uint64), ("max_depth_any", C.c_uint32), ("max_leaf_any", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

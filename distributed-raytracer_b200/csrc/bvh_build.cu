@@ -106,8 +106,9 @@ struct Scratch {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (!ok && m) {
+            if (m->nodes_any != m->nodes) cudaFree(m->nodes_any);
             cudaFree(m->nodes); cudaFree(m->tri32); cudaFree(m->tri64);
-            m->nodes = nullptr; m->tri32 = nullptr; m->tri64 = nullptr;
+            m->nodes = nullptr; m->nodes_any = nullptr; m->tri32 = nullptr; m->tri64 = nullptr;
         }
     }
 };
@@ -169,9 +170,9 @@ cudaError_t rt_flatten_faces(MeshDevice &m, const double *d_verts, uint32_t n_ve
     return e;
 }
 
-bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStream_t st, std::string &err) {
+bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max_leaf_any, int sm_count, cudaStream_t st, std::string &err) {
     const uint32_t n = m.n_faces;
-    m.nodes = nullptr; m.tri32 = nullptr; m.tri64 = nullptr; m.n_nodes = 0; m.root_ref = 0;
+    m.nodes = nullptr; m.nodes_any = nullptr; m.tri32 = nullptr; m.tri64 = nullptr; m.n_nodes = 0; m.n_nodes_any = 0; m.root_ref = 0; m.root_ref_any = 0;
     memset(&m.info, 0, sizeof m.info);
     m.info.n_faces = n; m.info.max_leaf = (uint32_t)max_leaf;
     for (int k = 0; k < 3; k++) { m.lo[k] = 0.f; m.hi[k] = 0.f; }
@@ -179,6 +180,9 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStr
     if (n > RT_LEAF_FIRST_MASK) { err = "mesh has too many faces for the 27-bit leaf encoding"; return false; }
     if (max_leaf < 1) max_leaf = 1;
     if (max_leaf > RT_MAX_LEAF) max_leaf = RT_MAX_LEAF;
+    if (max_leaf_any < 1) max_leaf_any = max_leaf;
+    if (max_leaf_any > RT_MAX_LEAF) max_leaf_any = RT_MAX_LEAF;
+    m.info.max_leaf_any = (uint32_t)max_leaf_any;
 
     unsigned int *d_bounds = nullptr; BoxF *d_leafbox = nullptr, *d_ibox = nullptr;
     unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
@@ -201,7 +205,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStr
         unsigned int init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
         CK(cudaMemcpyAsync(d_bounds, init, sizeof init, cudaMemcpyHostToDevice, st));
     }
-    k_mesh_bounds<<<min(nb, 148u * 8u), TB, 0, st>>>(m.fverts, n, d_bounds);
+    k_mesh_bounds<<<min(nb, (unsigned)(sm_count > 0 ? sm_count : 1) * 8u), TB, 0, st>>>(m.fverts, n, d_bounds);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(hb, d_bounds, sizeof hb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -234,7 +238,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStr
     CK(cudaGetLastError());
 
     if (n == 1) {
-        m.root_ref = rt_leaf_ref(0, 1);
+        m.root_ref = m.root_ref_any = rt_leaf_ref(0, 1);
         m.info.n_leaves = 1; m.info.max_depth = 0;
     } else {
         const int ni = (int)n - 1;
@@ -247,29 +251,29 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStr
         CK(sc.alloc(&d_coll, (size_t)ni));
         CK(sc.alloc(&d_flags, sizeof(unsigned int) * (size_t)ni));
         CK(sc.alloc(&d_leafcnt, sizeof(unsigned int)));
-        CK(cudaMemsetAsync(d_flags, 0, sizeof(unsigned int) * (size_t)ni, st));
-        CK(cudaMemsetAsync(d_leafcnt, 0, sizeof(unsigned int), st));
+        CK(sc.alloc(&d_front[0], sizeof(int) * (size_t)ni));
+        CK(sc.alloc(&d_front[1], sizeof(int) * (size_t)ni));
+        CK(sc.alloc(&d_cnt, sizeof(int) * (size_t)(ni + 1)));
+        CK(sc.alloc(&d_off, sizeof(int) * (size_t)(ni + 1)));
         k_karras<<<nbi, TB, 0, st>>>(sorted_keys, (int)n, d_kn, d_pint, d_pleaf);
         CK(cudaGetLastError());
-        k_refit_sah<<<nb, TB, 0, st>>>((int)n, sorted_vals, d_leafbox, d_kn, d_pint, d_pleaf, d_ibox, d_icost, d_coll,
-                                       d_flags, max_leaf);
-        CK(cudaGetLastError());
-        // root
-        unsigned char root_coll = 0; float root_cost = 0.f; BoxF root_box;
-        CK(cudaMemcpyAsync(&root_coll, d_coll, 1, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&root_cost, d_icost, sizeof(float), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&root_box, d_ibox, sizeof(BoxF), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        { float a = box_half_area(root_box); m.info.sah_cost = a > 0.f ? root_cost / a : 0.f; }
-        if (root_coll) {
-            m.root_ref = rt_leaf_ref(0, n);
-            m.info.n_leaves = 1;
-        } else {
-            CK(cudaMalloc(&m.nodes, sizeof(RtNode) * (size_t)ni));
-            CK(sc.alloc(&d_front[0], sizeof(int) * (size_t)ni));
-            CK(sc.alloc(&d_front[1], sizeof(int) * (size_t)ni));
-            CK(sc.alloc(&d_cnt, sizeof(int) * (size_t)(ni + 1)));
-            CK(sc.alloc(&d_off, sizeof(int) * (size_t)(ni + 1)));
+        // One wide hierarchy per leaf size over the one binary radix tree: refit + SAH collapse decision, then BFS emission.
+        auto emit = [&](int leaf_cap, RtNode **out_nodes, uint32_t *out_n_nodes, int *out_root, uint32_t *out_depth, uint64_t *out_leaves,
+                        float *out_sah) -> bool {
+            CK(cudaMemsetAsync(d_flags, 0, sizeof(unsigned int) * (size_t)ni, st));
+            CK(cudaMemsetAsync(d_leafcnt, 0, sizeof(unsigned int), st));
+            k_refit_sah<<<nb, TB, 0, st>>>((int)n, sorted_vals, d_leafbox, d_kn, d_pint, d_pleaf, d_ibox, d_icost, d_coll, d_flags, leaf_cap);
+            CK(cudaGetLastError());
+            unsigned char root_coll = 0; float root_cost = 0.f; BoxF root_box;
+            CK(cudaMemcpyAsync(&root_coll, d_coll, 1, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&root_cost, d_icost, sizeof(float), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&root_box, d_ibox, sizeof(BoxF), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            { float a = box_half_area(root_box); *out_sah = a > 0.f ? root_cost / a : 0.f; }
+            if (root_coll) { *out_root = rt_leaf_ref(0, n); *out_leaves = 1; *out_n_nodes = 0; *out_depth = 0; *out_nodes = nullptr; return true; }
+            RtNode *nodes = nullptr;
+            CK(cudaMalloc(&nodes, sizeof(RtNode) * (size_t)ni));
+            *out_nodes = nodes;                                   // owned by the mesh from here on (freed by the caller on failure)
             int zero = 0;
             CK(cudaMemcpyAsync(d_front[0], &zero, sizeof(int), cudaMemcpyHostToDevice, st));
             int fsize = 1, base = 0, cur = 0, depth = 0;
@@ -280,7 +284,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStr
                 size_t tb = tmp_bytes;
                 CK(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_off, fsize, st));
                 k_emit_write<<<fb, TB, 0, st>>>(d_front[cur], fsize, base, d_kn, d_coll, d_off, sorted_vals, d_leafbox, d_ibox,
-                                                m.nodes, d_front[cur ^ 1], d_leafcnt);
+                                                nodes, d_front[cur ^ 1], d_leafcnt);
                 CK(cudaGetLastError());
                 int last_off = 0, last_cnt = 0;
                 CK(cudaMemcpyAsync(&last_off, d_off + (fsize - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -292,25 +296,36 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStr
                 depth++;
                 if ((RT_W - 1) * depth + 2 > RT_STACK_SIZE) { err = "BVH deeper than the traversal stack"; return false; }
             }
-            m.n_nodes = (uint32_t)base;
+            *out_n_nodes = (uint32_t)base;
             if ((size_t)base < (size_t)ni) {
                 // the wide tree has far fewer nodes than the binary one it was collapsed from: shrink the allocation
                 RtNode *tight = nullptr;
                 CK(cudaMalloc(&tight, sizeof(RtNode) * (size_t)base));
-                CK(cudaMemcpyAsync(tight, m.nodes, sizeof(RtNode) * (size_t)base, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(tight, nodes, sizeof(RtNode) * (size_t)base, cudaMemcpyDeviceToDevice, st));
                 CK(cudaStreamSynchronize(st));
-                cudaFree(m.nodes);
-                m.nodes = tight;
+                cudaFree(nodes);
+                *out_nodes = tight;
             }
-            m.root_ref = 0;
-            m.info.max_depth = (uint32_t)depth;
+            *out_root = 0;
+            *out_depth = (uint32_t)depth;
             unsigned int nl = 0;
             CK(cudaMemcpyAsync(&nl, d_leafcnt, sizeof nl, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            m.info.n_leaves = nl;
+            *out_leaves = nl;
+            return true;
+        };
+        if (!emit(max_leaf, &m.nodes, &m.n_nodes, &m.root_ref, &m.info.max_depth, &m.info.n_leaves, &m.info.sah_cost)) return false;
+        if (max_leaf_any != max_leaf) {
+            float sah_any = 0.f;
+            if (!emit(max_leaf_any, &m.nodes_any, &m.n_nodes_any, &m.root_ref_any, &m.info.max_depth_any, &m.info.n_leaves_any, &sah_any)) return false;
         }
     }
+    if (max_leaf_any == max_leaf || n == 1) {
+        m.nodes_any = m.nodes; m.n_nodes_any = m.n_nodes; m.root_ref_any = m.root_ref;
+        m.info.max_depth_any = m.info.max_depth; m.info.n_leaves_any = m.info.n_leaves;
+    }
     m.info.n_nodes = m.n_nodes;
+    m.info.n_nodes_any = m.n_nodes_any;
     CK(cudaEventRecord(sc.ev1, st));
     CK(cudaEventSynchronize(sc.ev1));
     CK(cudaEventElapsedTime(&m.info.ms_build, sc.ev0, sc.ev1));

@@ -30,6 +30,18 @@ __device__ __forceinline__ SceneView bind_frame(SceneView sc, const InlineFrame 
     return sc;
 }
 
+// rt_cancel (ctx.Err() of the reference loop, distributed/main.go:73): the generation in the lane's counter block has moved
+// past the one this frame was launched with.  Wrap-safe; one L2-resident word.
+__device__ __forceinline__ bool frame_cancelled(const unsigned int *counters, const FrameParams &fp) {
+    return (int)(*(const volatile unsigned int *)(counters + RT_CNT_CANCEL) - fp.cancel_gen) > 0;
+}
+// the same, decided by lane 0 for the whole warp
+__device__ __forceinline__ bool warp_cancelled(const unsigned int *counters, const FrameParams &fp) {
+    int c = 0;
+    if ((threadIdx.x & 31) == 0) c = frame_cancelled(counters, fp);
+    return __shfl_sync(FULL, c, 0) != 0;
+}
+
 // append this lane's hit (if any) to the compact hit list; all 32 lanes must call
 __device__ __forceinline__ void append_hit(bool hit, uint32_t ray, int obj, int face, float t, HitRec *hits,
                                            unsigned int *hit_count) {
@@ -57,9 +69,9 @@ __global__ void __launch_bounds__(128) k_primary_exact(FrameParams fp, SceneView
     Counters c; c.nodes = 0; c.tris = 0;
     bool hit = false;
     TraceExact tr; tr.face = -1; tr.obj = -1;
-    if (ray < nrays) {
+    if (ray < nrays && !frame_cancelled(counters, fp)) {
         PixMap pm = map_ray(ray, fp, false);
-        if (pm.valid) {
+        if (pm.valid && !(fp.tile_w > 0 && !brute && block_culled(fp, pm.i & ~7, pm.j & ~3))) {
             dv d = primary_dir_exact(pm.i, pm.j, fp);
             hit = trace_exact(sc, fp, dv_ld(fp.cam_pos), d, brute, tr, COUNT ? &c : nullptr);
         }
@@ -94,9 +106,9 @@ __global__ void __launch_bounds__(128) k_primary_fast_simple(FrameParams fp, Sce
     Counters c; c.nodes = 0; c.tris = 0;
     bool hit = false;
     TraceFast tr; tr.face = -1; tr.obj = -1; tr.t = 0.f;
-    if (ray < nrays) {
+    if (ray < nrays && !frame_cancelled(counters, fp)) {
         PixMap pm = map_ray(ray, fp, false);
-        if (pm.valid) {
+        if (pm.valid && !(fp.tile_w > 0 && block_culled(fp, pm.i & ~7, pm.j & ~3))) {
             float dx, dy, dz;
             primary_dir32(pm.i, pm.j, fp, dx, dy, dz);
             dv d = dv_make((double)dx, (double)dy, (double)dz);
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView s
     Counters c; c.nodes = 0; c.tris = 0;
     for (;;) {
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&counters[2], 32u);
+        if (lane == 0) base = frame_cancelled(counters, fp) ? 0xffffffffu : atomicAdd(&counters[2], 32u);
         base = __shfl_sync(FULL, base, 0);
         if (base >= nhits) break;
         // every lane runs shade_hit (its light loop reconverges with __syncwarp); lanes past the end redo the last hit
@@ -268,6 +280,62 @@ __global__ void __launch_bounds__(128) k_phong(FrameParams fp, SceneView sc_in, 
         phong_from_mask(sc, fp, g, hit_material(sc, hr.obj, hr.face), hit_lit[h], col);
         hit_colour[3 * (size_t)h] = col[0]; hit_colour[3 * (size_t)h + 1] = col[1]; hit_colour[3 * (size_t)h + 2] = col[2];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused frame kernel (FP32_FAST; RT_FLAG_FUSED / RT_B200_FUSED): K2 + K4 + K5 in ONE launch.  A warp owns an 8x4 pixel
+// block: it traces the 32 primary rays, and if any lane hit something, the hit lanes shade their pixel (fp64
+// re-intersection, one shadow ray per light, Phong; lanes without a hit shadow the first hit lane so that the warp stays
+// converged through shade_hit's per-light __syncwarp) and write the three bytes of their pixel.  No hit list, no colour
+// buffer, no second and third launch: a frame is one kernel, so its latency is one kernel tail instead of three -- what a
+// rank of an 8-GPU box needs when its share of a 4K frame is 0.1 ms of work.  Blocks outside the projected
+// root boxes are never launched (region mode) or exit at once (tile mode).
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_frame_fused(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
+                                                            bool rowmajor, bool sdl, unsigned int *counters,
+                                                            uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour,
+                                                            int32_t *__restrict__ out_face, int32_t *__restrict__ out_obj,
+                                                            uint32_t *__restrict__ out_lit, Counters *gstats) {
+    const SceneView sc = bind_frame(sc_in, fr);
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nrays = ray_count(fp);
+    const unsigned lane = threadIdx.x & 31;
+    if ((ray & ~31u) >= nrays) return;                        // warp-uniform
+    if (warp_cancelled(counters, fp)) return;
+    Counters c0, c1; c0.nodes = c0.tris = c1.nodes = c1.tris = 0;
+    const PixMap pm = map_ray(ray, fp, rowmajor);
+    if (fp.tile_w > 0 && block_culled(fp, pm.i & ~7, pm.j & ~3)) return;      // warp-uniform: a warp is one 8x4 block
+    bool hit = false;
+    TraceFast tr; tr.face = -1; tr.obj = -1; tr.t = 0.f;
+    if (pm.valid) {
+        float dx, dy, dz;
+        primary_dir32(pm.i, pm.j, fp, dx, dy, dz);
+        hit = trace_fast_nearest(sc, fp, dv_ld(fp.cam_pos), dv_make((double)dx, (double)dy, (double)dz), true, tr, COUNT ? &c0 : nullptr);
+    }
+    const unsigned m = __ballot_sync(FULL, hit);
+    if (m != 0) {
+        if (lane == 0) atomicAdd(&counters[1], (unsigned)__popc(m));          // hit pixels of the frame (rt_stats, ray accounting)
+        const int src = hit ? (int)lane : __ffs(m) - 1;
+        const int si = __shfl_sync(FULL, pm.i, src), sj = __shfl_sync(FULL, pm.j, src);
+        const int sobj = __shfl_sync(FULL, tr.obj, src), sface = __shfl_sync(FULL, tr.face, src);
+        const float st = __shfl_sync(FULL, tr.t, src);
+        double col[3];
+        const uint32_t lit = shade_hit<false>(sc, fp, si, sj, sobj, sface, st, false, col, (COUNT && hit) ? &c1 : nullptr);
+        if (hit) {
+            const size_t o = pm.out;
+            if (out_rgb) {
+                out_rgb[3 * o] = quantise_exact(col[0], sdl);
+                out_rgb[3 * o + 1] = quantise_exact(col[1], sdl);
+                out_rgb[3 * o + 2] = quantise_exact(col[2], sdl);
+            }
+            if (out_colour) { out_colour[3 * o] = col[0]; out_colour[3 * o + 1] = col[1]; out_colour[3 * o + 2] = col[2]; }
+            if (out_face) out_face[o] = tr.face;
+            if (out_obj) out_obj[o] = tr.obj;
+            if (out_lit) out_lit[o] = lit;
+        }
+    }
+    if (COUNT) { flush_counters(gstats, c0); flush_counters(gstats ? gstats + 1 : nullptr, c1); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -631,6 +699,24 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
         else LAUNCH_SHADE(false, false, 1);
     }
 #undef LAUNCH_SHADE
+    return cudaGetLastError();
+}
+
+cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
+    const FrameParams &fp = job.fp;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights;
+    const uint32_t nrays = ray_count(fp);
+    if (nrays == 0) return cudaSuccess;
+    const bool count = (job.flags & RT_FLAG_COUNT) != 0;
+    const bool rowmajor = (job.flags & RT_LAYOUT_ROWMAJOR) != 0, sdl = (job.flags & RT_QUANT_RGBA16_SHR8) != 0;
+    const unsigned nblk = (nrays + 127) / 128;
+#define LAUNCH_FUSED(CN, MB) k_frame_fused<CN, MB><<<nblk, 128, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_out_rgb, \
+                                                                          job.d_out_colour, job.d_out_face, job.d_out_obj, job.d_out_lit, job.d_stats)
+    if (count) LAUNCH_FUSED(true, 1);
+    else if (job.shade_minb >= 8) LAUNCH_FUSED(false, 8);
+    else if (job.shade_minb >= 6) LAUNCH_FUSED(false, 6);
+    else LAUNCH_FUSED(false, 1);
+#undef LAUNCH_FUSED
     return cudaGetLastError();
 }
 

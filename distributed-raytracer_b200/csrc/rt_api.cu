@@ -8,6 +8,7 @@
 // No CPU fallback exists: every path below needs a CUDA device and the sm_100a kernels.
 #include "rt_internal.h"
 #include "go_math.h"
+#include "rt_cull.h"
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
@@ -59,8 +60,9 @@ struct rt_scene {
     uint32_t precision = RT_FP32_FAST;
     int sm_count = 148;
     int max_leaf = 4;
-    bool top_in_smem = false;
-    int refill_below = 1;
+    int max_leaf_any = 4;              // leaf size of the any-hit (shadow-ray) hierarchy, RT_B200_MAX_LEAF_SHADE
+    bool fused = false;                // FP32_FAST default: one fused kernel per frame (RT_B200_FUSED)
+    bool cull = true;                  // projected-root-box culling of primary rays (RT_B200_CULL)
     int shade_minb = 8;
     bool primary_persistent = false;
     bool split_shade = false;
@@ -75,18 +77,32 @@ struct rt_scene {
 
     std::vector<std::unique_ptr<Lane>> lanes;
     std::atomic<int> last_lane{ 0 };   // lane of the most recent call (rt_get_stats)
-    std::atomic<int> cancel{ 0 };
+    // Cancellation (ctx.Err(), distributed/main.go:73): a generation counter.  Every render captures the generation when it
+    // starts; rt_cancel bumps it and writes the new value into word RT_CNT_CANCEL of every lane's counter block, which the
+    // kernels poll.  A call is cancelled iff the generation moved while it was in flight: calls that start later are unaffected,
+    // nothing is ever reset.
+    std::atomic<unsigned int> cancel_gen{ 0 };
+    cudaStream_t cancel_stream = nullptr;
+    unsigned int *h_cancel_word = nullptr;   // pinned staging word of rt_cancel
 };
 
 namespace {
 
+// Error text.  Every entry point clears the calling thread's message on entry, so rt_last_error() describes the thread's LAST
+// call: with a handle it returns this thread's failure on that handle if there is one (concurrent callers do not see each
+// other's errors), else the handle's most recent message; with NULL the thread's message (handle-less failures).
 thread_local std::string g_err;
+thread_local const rt_scene *g_err_scene = nullptr;
+thread_local std::string g_err_ret;
 
 int fail(rt_scene *s, int code, const std::string &msg) {
     if (s) { std::lock_guard<std::mutex> lk(s->mu); s->err = msg; }
     g_err = msg;
+    g_err_scene = s;
     return code;
 }
+struct ApiEnter { ApiEnter() { g_err.clear(); g_err_scene = nullptr; } };
+#define API_ENTER() ApiEnter api_enter_guard_
 #define CU(s, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail((s), e_ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 template <class T> cudaError_t upload(T **d, const T *h, size_t n, cudaStream_t st) {
@@ -97,6 +113,7 @@ template <class T> cudaError_t upload(T **d, const T *h, size_t n, cudaStream_t 
 }
 
 void free_mesh(MeshDevice &m) {
+    if (m.nodes_any != m.nodes) cudaFree(m.nodes_any);
     cudaFree(m.nodes); cudaFree(m.tri32); cudaFree(m.tri64); cudaFree(m.fverts); cudaFree(m.fnormals); cudaFree(m.fmat);
     cudaFree(m.materials);
     m = MeshDevice();
@@ -121,6 +138,8 @@ void destroy_all(rt_scene *s) {
     for (auto &m : s->meshes) free_mesh(m);
     cudaFree(s->d_meshes);
     s->d_meshes = nullptr;
+    if (s->cancel_stream) { cudaStreamDestroy(s->cancel_stream); s->cancel_stream = nullptr; }
+    if (s->h_cancel_word) { cudaFreeHost(s->h_cancel_word); s->h_cancel_word = nullptr; }
 }
 
 int env_int(const char *name, int dflt) {
@@ -162,8 +181,11 @@ Lane *device_lane(rt_scene *s, uint32_t flags, int *index) {
 
 int ensure_scratch(rt_scene *s, Lane &L, size_t nrays, size_t out_bytes, bool need_rgb, bool dbg, size_t npix_out) {
     if (!L.d_counters) {
-        CU(s, cudaMalloc((void **)&L.d_counters, 8 * sizeof(unsigned int)));     // [0..3] per-frame counters, [4] CTAs-done counter of k_push_tiles
-        CU(s, cudaMemset(L.d_counters, 0, 8 * sizeof(unsigned int)));
+        // [0..3] per-frame counters, [RT_CNT_CANCEL] cancel generation (rt_cancel), [RT_CNT_PUSH_DONE] CTAs-done counter of k_push_tiles
+        unsigned int *cnt = nullptr;
+        CU(s, cudaMalloc((void **)&cnt, 8 * sizeof(unsigned int)));
+        CU(s, cudaMemset(cnt, 0, 8 * sizeof(unsigned int)));
+        { std::lock_guard<std::mutex> lk(s->mu); L.d_counters = cnt; }           // rt_cancel walks the lanes under s->mu
         CU(s, cudaMalloc((void **)&L.d_stats, 2 * sizeof(Counters)));
     }
     if (nrays > L.cap_rays) {
@@ -262,10 +284,12 @@ void collect_stats(rt_scene *s, Lane &L) {
 }
 
 // the whole render path on one lane: clear -> K2 -> K4 -> K5 -> (copy out).  Caller holds L.mu.
-int render_lane(rt_scene *s, Lane &L, const FrameParams &fp, uint32_t flags, size_t npix_out, const RenderOut &out) {
+int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, size_t npix_out, const RenderOut &out) {
     if (!L.have_frame) return fail(s, RT_ERR_STATE, "render before rt_frame_set");
     CU(s, cudaSetDevice(s->device));
-    s->cancel.store(0);   // stats of earlier frames are collected lazily (rt_get_stats): no per-frame host sync
+    const unsigned int my_gen = s->cancel_gen.load();     // rt_cancel during this call bumps it (stats of earlier frames are collected lazily)
+    FrameParams fp = fp_in;
+    fp.cancel_gen = my_gen;
     const size_t nrays = ray_count(fp);
     const size_t out_bytes = npix_out * 3;
     const bool dbg = out.h_colour || out.h_face || out.h_obj || out.h_lit;
@@ -295,10 +319,11 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp, uint32_t flags, siz
         job.h_mesh0 = s->h_views[L.h_objs[0].mesh];
         for (int k = 0; k < 3; k++) job.h_obj0_pos[k] = L.h_objs[0].pos[k];
     }
-    job.top_in_smem = s->top_in_smem;
-    job.refill_below = s->refill_below;
     job.shade_minb = s->shade_minb;
     job.primary_persistent = s->primary_persistent;
+    // one fused kernel per frame (FP32_FAST): the scene's default, RT_FLAG_FUSED / RT_FLAG_PIPELINE per call
+    job.fused = s->precision == RT_FP32_FAST && !s->shade32 && !(flags & (RT_FLAG_PIPELINE | RT_FLAG_PERSISTENT)) &&
+                (s->fused || (flags & RT_FLAG_FUSED));
 
     CU(s, cudaMemsetAsync(L.d_counters, 0, 4 * sizeof(unsigned int), st));
     CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), st));
@@ -310,13 +335,21 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp, uint32_t flags, siz
     if (job.d_out_obj) CU(s, cudaMemsetAsync(job.d_out_obj, 0xff, sizeof(int32_t) * npix_out, st));
     if (job.d_out_lit) CU(s, cudaMemsetAsync(job.d_out_lit, 0, sizeof(uint32_t) * npix_out, st));
 
+    auto cancelled = [&]() { return s->cancel_gen.load() != my_gen; };
     CU(s, cudaEventRecord(L.ev[0], st));
-    CU(s, rt_launch_primary(job, st));
-    CU(s, cudaEventRecord(L.ev[1], st));
-    if (s->cancel.load()) { cudaStreamSynchronize(st); return fail(s, RT_ERR_CANCELLED, "cancelled"); }
-    CU(s, rt_launch_shade(job, st));
-    CU(s, cudaEventRecord(L.ev[2], st));
-    CU(s, rt_launch_write(job, st));
+    if (job.fused) {
+        CU(s, rt_launch_fused(job, st));
+        CU(s, cudaEventRecord(L.ev[1], st));
+        CU(s, cudaEventRecord(L.ev[2], st));
+    } else {
+        CU(s, rt_launch_primary(job, st));
+        CU(s, cudaEventRecord(L.ev[1], st));
+        if (cancelled()) { cudaStreamSynchronize(st); return fail(s, RT_ERR_CANCELLED, "cancelled"); }
+        CU(s, rt_launch_shade(job, st));
+        CU(s, cudaEventRecord(L.ev[2], st));
+        if (cancelled()) { cudaStreamSynchronize(st); return fail(s, RT_ERR_CANCELLED, "cancelled"); }
+        CU(s, rt_launch_write(job, st));
+    }
     CU(s, cudaEventRecord(L.ev[3], st));
 
     L.stats.primary_rays = (uint64_t)fp.w * (uint64_t)fp.h;
@@ -351,23 +384,33 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp, uint32_t flags, siz
     if (out.h_obj) CU(s, cudaMemcpyAsync(out.h_obj, job.d_out_obj, sizeof(int32_t) * npix_out, cudaMemcpyDeviceToHost, st));
     if (out.h_lit) CU(s, cudaMemcpyAsync(out.h_lit, job.d_out_lit, sizeof(uint32_t) * npix_out, cudaMemcpyDeviceToHost, st));
     CU(s, cudaStreamSynchronize(st));
+    // the kernels poll the cancel word and give up early: whatever is in the buffers then is not a frame
+    if (cancelled()) return fail(s, RT_ERR_CANCELLED, "cancelled");
     // counters and event times are read lazily by rt_get_stats: two blocking device->host copies per call would be on
     // the critical path of concurrent BulkTrace callers
     return RT_OK;
 }
 
-int region_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h) {
+// fills the culling fields of fp (rt_cull.h) from the lane's object positions
+void cull_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t flags) {
+    if (!s->cull || (flags & (RT_FLAG_NO_CULL | RT_FLAG_BRUTE_FORCE))) { rt_cull_full(fp); return; }
+    rt_cull_frame(fp, s->h_views.data(), L.h_objs.data(), (int)L.h_objs.size());
+}
+
+int region_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h,
+                  uint32_t flags) {
     if (W == 0 || H == 0 || w == 0 || h == 0) return fail(s, RT_ERR_INVALID, "empty screen or region");
     if (W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "screen larger than 65536 pixels on a side");
     if ((uint64_t)x + w > W || (uint64_t)y + h > H) return fail(s, RT_ERR_INVALID, "region exceeds the screen");
     fp = L.frame;
     fp.W = (int)W; fp.H = (int)H; fp.x = (int)x; fp.y = (int)y; fp.w = (int)w; fp.h = (int)h;
     fp.tile_w = fp.tile_h = fp.tiles_x = fp.rank = fp.n_ranks = fp.n_local_tiles = fp.tile_final = 0;
+    cull_params(s, L, fp, flags);
     return RT_OK;
 }
 
 int tile_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank,
-                uint32_t n_ranks, bool need_smem_fit) {
+                uint32_t n_ranks, bool need_smem_fit, uint32_t flags) {
     if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "bad screen size");
     if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4");
     if (need_smem_fit && (size_t)tile_w * tile_h * 3 > 48 * 1024) return fail(s, RT_ERR_INVALID, "tile larger than 16384 pixels");
@@ -380,6 +423,7 @@ int tile_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_
     fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
     fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
     fp.tile_final = 0;
+    cull_params(s, L, fp, flags);
     return RT_OK;
 }
 
@@ -405,12 +449,14 @@ int rt_device_count(void) {
 }
 
 const char *rt_last_error(const rt_scene *scene) {
-    // the calling thread's last message (concurrent callers do not see each other's errors)
-    if (!g_err.empty() || !scene) return g_err.c_str();
-    return scene->err.c_str();
+    if (!scene) return g_err.c_str();
+    if (!g_err.empty() && g_err_scene == scene) return g_err.c_str();       // this thread's last call failed on this handle
+    { std::lock_guard<std::mutex> lk(const_cast<rt_scene *>(scene)->mu); g_err_ret = scene->err; }
+    return g_err_ret.c_str();
 }
 
 int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
+    API_ENTER();
     if (!desc || !out) return fail(nullptr, RT_ERR_INVALID, "rt_scene_create: NULL argument");
     *out = nullptr;
     if (desc->precision != RT_FP64_EXACT && desc->precision != RT_FP32_FAST) return fail(nullptr, RT_ERR_INVALID, "unknown precision mode");
@@ -434,8 +480,9 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->primary_persistent = env_int("RT_B200_PERSISTENT", 0) != 0;
     s->split_shade = env_int("RT_B200_SPLIT_SHADE", 0) != 0;
     s->shade32 = env_int("RT_B200_SHADE32", 0) != 0 && desc->precision == RT_FP32_FAST;
-    s->top_in_smem = env_int("RT_B200_TOP_SMEM", 0) != 0;
-    s->refill_below = env_int("RT_B200_REFILL", 1);
+    s->max_leaf_any = env_int("RT_B200_MAX_LEAF_SHADE", RT_DEFAULT_MAX_LEAF_SHADE);
+    s->fused = env_int("RT_B200_FUSED", RT_DEFAULT_FUSED) != 0;
+    s->cull = env_int("RT_B200_CULL", 1) != 0;
     s->sync_timeout_ms = (uint32_t)std::max(1, env_int("RT_B200_SYNC_TIMEOUT_MS", 2000));
     int n_lanes = env_int("RT_B200_LANES", 9);      // lane 0 + a pool of 8 for concurrent BulkTrace calls / frames in flight
     if (n_lanes < 1) n_lanes = 1;
@@ -465,6 +512,8 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
         CUB_(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
         for (auto &e : L.ev) CUB_(cudaEventCreate(&e));
     }
+    CUB_(cudaStreamCreateWithFlags(&s->cancel_stream, cudaStreamNonBlocking));
+    CUB_(cudaMallocHost((void **)&s->h_cancel_word, sizeof(unsigned int)));
     cudaStream_t st0 = s->lanes[0]->stream;
     s->meshes.resize(desc->n_meshes);
     s->h_views.resize(desc->n_meshes);
@@ -489,11 +538,14 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
                                                                                                        : "mesh: material index out of range");
         CUB_(upload(&m.materials, d.materials, (size_t)10 * d.n_materials, st0));
         CUB_(cudaStreamSynchronize(st0));
-        if (!rt_build_bvh(m, s->precision == RT_FP32_FAST, s->precision == RT_FP64_EXACT, s->max_leaf, st0, e))
+        // the any-hit hierarchy is only walked by FP32_FAST shadow rays
+        if (!rt_build_bvh(m, s->precision == RT_FP32_FAST, s->precision == RT_FP64_EXACT, s->max_leaf,
+                          s->precision == RT_FP32_FAST ? s->max_leaf_any : s->max_leaf, s->sm_count, st0, e))
             return bail(RT_ERR_CUDA, "BVH build: " + e);
         MeshView &v = s->h_views[k];
         v.nodes = m.nodes; v.tri32 = m.tri32; v.tri64 = m.tri64; v.fverts = m.fverts; v.fnormals = m.fnormals; v.fmat = m.fmat;
         v.materials = m.materials; v.n_faces = m.n_faces; v.n_nodes = m.n_nodes; v.root_ref = m.root_ref;
+        v.nodes_any = m.nodes_any; v.root_ref_any = m.root_ref_any; v.n_nodes_any = m.n_nodes_any;
         for (int c = 0; c < 3; c++) { v.lo[c] = m.lo[c]; v.hi[c] = m.hi[c]; }
     }
     CUB_(upload(&s->d_meshes, s->h_views.data(), s->h_views.size(), st0));
@@ -513,10 +565,12 @@ void rt_scene_destroy(rt_scene *scene) {
 int rt_lane_count(rt_scene *s) { return s ? (int)s->lanes.size() : 0; }
 
 int rt_frame_set(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos) {
+    API_ENTER();
     return rt_frame_set_lane(s, 0, cam, lights, n_lights, obj_pos);
 }
 
 int rt_frame_set_lane(rt_scene *s, uint32_t lane, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (lane >= s->lanes.size()) return fail(s, RT_ERR_INVALID, "lane index out of range");
     Lane &L = *s->lanes[lane];
@@ -526,11 +580,12 @@ int rt_frame_set_lane(rt_scene *s, uint32_t lane, const rt_camera *cam, const rt
 
 int rt_render_region_debug(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb,
                            double *out_colour, int32_t *out_face, int32_t *out_obj, uint32_t *out_lit, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     Lane &L = *s->lanes[0];
     std::lock_guard<std::mutex> lk(L.mu);
     FrameParams fp;
-    int rc = region_params(s, L, fp, W, H, x, y, w, h);
+    int rc = region_params(s, L, fp, W, H, x, y, w, h, flags);
     if (rc != RT_OK) return rc;
     RenderOut o; o.h_rgb = out_rgb; o.h_colour = out_colour; o.h_face = out_face; o.h_obj = out_obj; o.h_lit = out_lit;
     s->last_lane.store(0);
@@ -539,12 +594,14 @@ int rt_render_region_debug(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uint
 
 int rt_render_region(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb,
                      uint32_t flags) {
+    API_ENTER();
     if (!out_rgb) return fail(s, RT_ERR_INVALID, "out_rgb is NULL");
     return rt_render_region_debug(s, W, H, x, y, w, h, out_rgb, nullptr, nullptr, nullptr, nullptr, flags);
 }
 
 int rt_bulk_trace(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
                   uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!out_rgb) return fail(s, RT_ERR_INVALID, "out_rgb is NULL");
     int idx = 0;
@@ -556,7 +613,7 @@ int rt_bulk_trace(rt_scene *s, const rt_camera *cam, const rt_light *lights, uin
         if (!obj_pos) Lp->h_objs = s->h_objs;
         rc = frame_set_lane(s, *Lp, cam, lights, n_lights, obj_pos);
         FrameParams fp;
-        if (rc == RT_OK) rc = region_params(s, *Lp, fp, W, H, x, y, w, h);
+        if (rc == RT_OK) rc = region_params(s, *Lp, fp, W, H, x, y, w, h, flags);
         if (rc == RT_OK) {
             RenderOut o; o.h_rgb = out_rgb;
             s->last_lane.store(idx);
@@ -592,6 +649,7 @@ static int ensure_wire_scratch(rt_scene *s, Lane &L, uint64_t n_pixels, bool nee
 
 int rt_encode_trace_results_device(rt_scene *s, const void *d_rgb, uint64_t n_pixels, void *d_out, uint64_t capacity, uint64_t *d_len,
                                    void *stream, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_len || (n_pixels && (!d_rgb || !d_out))) return fail(s, RT_ERR_INVALID, "rt_encode_trace_results_device: NULL argument");
     if (((uintptr_t)d_rgb & 3u) != 0) return fail(s, RT_ERR_INVALID, "rt_encode_trace_results_device: d_rgb must be 4-byte aligned");
@@ -613,6 +671,7 @@ int rt_encode_trace_results_device(rt_scene *s, const void *d_rgb, uint64_t n_pi
 int rt_bulk_trace_encoded(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
                           uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out, uint64_t capacity, uint64_t *out_len,
                           uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!out || !out_len) return fail(s, RT_ERR_INVALID, "rt_bulk_trace_encoded: NULL argument");
     if (flags & RT_LAYOUT_ROWMAJOR) return fail(s, RT_ERR_INVALID, "TraceResults is in BulkTrace order (i*height + j): RT_LAYOUT_ROWMAJOR does not apply");
@@ -625,7 +684,7 @@ int rt_bulk_trace_encoded(rt_scene *s, const rt_camera *cam, const rt_light *lig
         if (!obj_pos) L.h_objs = s->h_objs;
         rc = frame_set_lane(s, L, cam, lights, n_lights, obj_pos);
         FrameParams fp;
-        if (rc == RT_OK) rc = region_params(s, L, fp, W, H, x, y, w, h);
+        if (rc == RT_OK) rc = region_params(s, L, fp, W, H, x, y, w, h, flags);
         const uint64_t npix = (uint64_t)w * h;
         if (rc == RT_OK) {
             RenderOut o; o.async = true;                       // into the lane's own RGB buffer, no copy out
@@ -669,6 +728,7 @@ int rt_bulk_trace_encoded(rt_scene *s, const rt_camera *cam, const rt_light *lig
 
 int rt_render_region_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, void *d_out_rgb,
                             void *stream, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_out_rgb) return fail(s, RT_ERR_INVALID, "d_out_rgb is NULL");
     int idx = 0;
@@ -677,7 +737,7 @@ int rt_render_region_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uin
     std::lock_guard<std::mutex> lk(Lp->mu);
     inherit_frame(s, *Lp, idx);
     FrameParams fp;
-    int rc = region_params(s, *Lp, fp, W, H, x, y, w, h);
+    int rc = region_params(s, *Lp, fp, W, H, x, y, w, h, flags);
     if (rc != RT_OK) return rc;
     RenderOut o; o.d_rgb = (uint8_t *)d_out_rgb; o.ext_stream = (cudaStream_t)stream; o.async = stream != nullptr;
     s->last_lane.store(idx);
@@ -688,6 +748,7 @@ int rt_render_region_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uin
 
 int rt_render_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
                            void *d_out_tiles, void *stream, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_out_tiles) return fail(s, RT_ERR_INVALID, "d_out_tiles is NULL");
     int idx = 0;
@@ -696,7 +757,7 @@ int rt_render_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w,
     std::lock_guard<std::mutex> lk(Lp->mu);
     inherit_frame(s, *Lp, idx);
     FrameParams fp;
-    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false);
+    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false, flags);
     if (rc != RT_OK) return rc;
     RenderOut o; o.d_rgb = (uint8_t *)d_out_tiles; o.ext_stream = (cudaStream_t)stream; o.async = stream != nullptr;
     s->last_lane.store(idx);
@@ -707,6 +768,7 @@ int rt_render_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w,
 
 int rt_render_tiles_peer(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
                          void *d_framebuffer, void *stream, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_framebuffer) return fail(s, RT_ERR_INVALID, "d_framebuffer is NULL");
     int idx = 0;
@@ -715,7 +777,7 @@ int rt_render_tiles_peer(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
     std::lock_guard<std::mutex> lk(Lp->mu);
     inherit_frame(s, *Lp, idx);
     FrameParams fp;
-    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false);
+    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false, flags);
     if (rc != RT_OK) return rc;
     fp.tile_final = 1;
     RenderOut o; o.d_rgb = (uint8_t *)d_framebuffer; o.ext_stream = (cudaStream_t)stream; o.async = stream != nullptr;
@@ -727,6 +789,7 @@ int rt_render_tiles_peer(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
 
 int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks,
                          const void *d_tiles, void *d_framebuffer, void *stream, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_tiles || !d_framebuffer) return fail(s, RT_ERR_INVALID, "rt_push_tiles_device: bad argument");
     int idx = 0;
@@ -735,7 +798,7 @@ int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
     std::lock_guard<std::mutex> lk(Lp->mu);
     CU(s, cudaSetDevice(s->device));
     FrameParams fp;
-    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, true);
+    int rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, true, flags);
     if (rc != RT_OK) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : Lp->stream;
     CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, PushSync{}, s->sm_count, st));
@@ -747,6 +810,7 @@ int rt_push_tiles_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, u
 int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
                          uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks, void *d_tiles, void *d_framebuffer,
                          void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_tiles || !d_framebuffer || !stream) return fail(s, RT_ERR_INVALID, "rt_render_push_tiles: NULL buffer or stream");
     int idx = 0;
@@ -756,7 +820,7 @@ int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *ligh
     int rc = frame_set_lane(s, *Lp, cam, lights, n_lights, obj_pos);
     if (rc != RT_OK) return rc;
     FrameParams fp;
-    rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, true);
+    rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, true, flags);
     if (rc != RT_OK) return rc;
     RenderOut o; o.d_rgb = (uint8_t *)d_tiles; o.ext_stream = (cudaStream_t)stream; o.async = true;
     s->last_lane.store(idx);
@@ -765,7 +829,7 @@ int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *ligh
     PushSync sy{};
     if (d_sync_slot) {
         if (n_ranks > 32) return fail(s, RT_ERR_INVALID, "rt_render_push_tiles: the hand-off record holds 32 ranks");
-        sy.slot = (uint32_t *)d_sync_slot; sy.blocks_done = Lp->d_counters + 4; sy.seq = seq; sy.timeout_ms = s->sync_timeout_ms; sy.debug = (uint32_t)env_int("RT_B200_SYNC_DEBUG", 0);
+        sy.slot = (uint32_t *)d_sync_slot; sy.blocks_done = Lp->d_counters + RT_CNT_PUSH_DONE; sy.seq = seq; sy.timeout_ms = s->sync_timeout_ms; sy.debug = (uint32_t)env_int("RT_B200_SYNC_DEBUG", 0);
     }
     CU(s, rt_launch_push_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, (const uint8_t *)d_tiles, (uint8_t *)d_framebuffer, sy, s->sm_count, (cudaStream_t)stream));
     return RT_OK;
@@ -779,6 +843,7 @@ int rt_render_push_tiles(rt_scene *s, const rt_camera *cam, const rt_light *ligh
 int rt_render_stripes_host(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
                            uint32_t H, uint32_t stripe, uint32_t rank, uint32_t n_ranks, void *d_local_framebuffer, void *h_framebuffer,
                            void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_local_framebuffer || !h_framebuffer || !stream) return fail(s, RT_ERR_INVALID, "rt_render_stripes_host: NULL buffer or stream");
     if (n_ranks > 32 && d_sync_slot) return fail(s, RT_ERR_INVALID, "rt_render_stripes_host: the hand-off record holds 32 ranks");
@@ -792,7 +857,7 @@ int rt_render_stripes_host(rt_scene *s, const rt_camera *cam, const rt_light *li
     if (rc != RT_OK) return rc;
     const uint32_t tile_w = rowmajor ? ((W + 7u) / 8u) * 8u : stripe, tile_h = rowmajor ? stripe : ((H + 3u) / 4u) * 4u;
     FrameParams fp;
-    rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false);
+    rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false, flags);
     if (rc != RT_OK) return rc;
     fp.tile_final = 1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -821,6 +886,7 @@ int rt_render_stripes_host(rt_scene *s, const rt_camera *cam, const rt_light *li
 
 // gathering rank: frame `seq` of the slot is complete when all ranks have pushed it (waits ON THE DEVICE, in stream order)
 int rt_frame_complete_device(rt_scene *s, void *d_sync_slot, uint32_t seq, uint32_t n_ranks, uint32_t release, void *stream) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_sync_slot || !stream || n_ranks == 0 || n_ranks > 32) return fail(s, RT_ERR_INVALID, "rt_frame_complete_device: bad argument");
     CU(s, cudaSetDevice(s->device));
@@ -829,6 +895,7 @@ int rt_frame_complete_device(rt_scene *s, void *d_sync_slot, uint32_t seq, uint3
 }
 
 int rt_frame_release_device(rt_scene *s, void *d_sync_slot, uint32_t seq, void *stream) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_sync_slot || !stream) return fail(s, RT_ERR_INVALID, "rt_frame_release_device: bad argument");
     CU(s, cudaSetDevice(s->device));
@@ -838,18 +905,21 @@ int rt_frame_release_device(rt_scene *s, void *d_sync_slot, uint32_t seq, void *
 
 // ---- device buffers shareable between the per-GPU processes of one box (CUDA IPC over NVLink / NVSwitch) ----
 int rt_device_alloc(int device, size_t bytes, void **out) {
+    API_ENTER();
     if (!out || bytes == 0) return fail(nullptr, RT_ERR_INVALID, "rt_device_alloc: bad argument");
     CU(nullptr, cudaSetDevice(device));
     CU(nullptr, cudaMalloc(out, bytes));
     return RT_OK;
 }
 int rt_device_free(int device, void *p) {
+    API_ENTER();
     if (!p) return RT_OK;
     CU(nullptr, cudaSetDevice(device));
     CU(nullptr, cudaFree(p));
     return RT_OK;
 }
 int rt_ipc_export(void *d_ptr, unsigned char handle[64]) {
+    API_ENTER();
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (!d_ptr || !handle) return fail(nullptr, RT_ERR_INVALID, "rt_ipc_export: NULL argument");
     cudaIpcMemHandle_t h;
@@ -858,6 +928,7 @@ int rt_ipc_export(void *d_ptr, unsigned char handle[64]) {
     return RT_OK;
 }
 int rt_ipc_open(int device, const unsigned char handle[64], void **out) {
+    API_ENTER();
     if (!handle || !out) return fail(nullptr, RT_ERR_INVALID, "rt_ipc_open: NULL argument");
     CU(nullptr, cudaSetDevice(device));
     cudaIpcMemHandle_t h;
@@ -866,6 +937,7 @@ int rt_ipc_open(int device, const unsigned char handle[64], void **out) {
     return RT_OK;
 }
 int rt_ipc_close(int device, void *p) {
+    API_ENTER();
     if (!p) return RT_OK;
     CU(nullptr, cudaSetDevice(device));
     CU(nullptr, cudaIpcCloseMemHandle(p));
@@ -874,6 +946,7 @@ int rt_ipc_close(int device, void *p) {
 
 int rt_untile_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t n_ranks, const void *d_all_tiles,
                      void *d_out_rgb, void *stream, uint32_t flags) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     if (!d_all_tiles || !d_out_rgb || !tile_w || !tile_h || !n_ranks || !W || !H) return fail(s, RT_ERR_INVALID, "rt_untile_device: bad argument");
     if (tile_w % 8 || tile_h % 4 || (size_t)tile_w * tile_h * 3 > 48 * 1024) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4 and at most 16384 pixels");
@@ -891,6 +964,7 @@ int rt_untile_device(rt_scene *s, uint32_t W, uint32_t H, uint32_t tile_w, uint3
 }
 
 int rt_get_stats(rt_scene *s, rt_stats *out) {
+    API_ENTER();
     if (!s || !out) return fail(s, RT_ERR_INVALID, "NULL argument");
     Lane &L = *s->lanes[s->last_lane.load()];
     std::lock_guard<std::mutex> lk(L.mu);
@@ -901,6 +975,7 @@ int rt_get_stats(rt_scene *s, rt_stats *out) {
 }
 
 int rt_get_bvh_info(rt_scene *s, uint32_t mesh, rt_bvh_info *out) {
+    API_ENTER();
     if (!s || !out) return fail(s, RT_ERR_INVALID, "NULL argument");
     if (mesh >= s->meshes.size()) return fail(s, RT_ERR_INVALID, "mesh index out of range");
     *out = s->meshes[mesh].info;
@@ -908,6 +983,7 @@ int rt_get_bvh_info(rt_scene *s, uint32_t mesh, rt_bvh_info *out) {
 }
 
 int rt_synchronize(rt_scene *s) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
     CU(s, cudaSetDevice(s->device));
     for (auto &lp : s->lanes) {
@@ -919,12 +995,22 @@ int rt_synchronize(rt_scene *s) {
 }
 
 int rt_cancel(rt_scene *s) {
+    API_ENTER();
     if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
-    s->cancel.store(1);
+    CU(s, cudaSetDevice(s->device));
+    std::lock_guard<std::mutex> lk(s->mu);
+    const unsigned int gen = s->cancel_gen.fetch_add(1u) + 1u;
+    // tell the kernels in flight (they poll this word; calls that start from now on carry the new generation and ignore it)
+    *s->h_cancel_word = gen;
+    for (auto &lp : s->lanes)
+        if (lp->d_counters)
+            CU(s, cudaMemcpyAsync(lp->d_counters + RT_CNT_CANCEL, s->h_cancel_word, sizeof(unsigned int), cudaMemcpyHostToDevice, s->cancel_stream));
+    CU(s, cudaStreamSynchronize(s->cancel_stream));
     return RT_OK;
 }
 
 int rt_measure_fma_peak(int device, int fp64, double *out_tflops) {
+    API_ENTER();
     if (!out_tflops) return fail(nullptr, RT_ERR_INVALID, "NULL argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return fail(nullptr, RT_ERR_CUDA, "no such CUDA device"); }
@@ -949,6 +1035,7 @@ void rt_host_free(void *p) {
 // and returns the address kernels of `device` use for it: each GPU then stores its tiles straight into the host
 // framebuffer over ITS OWN PCIe link (rt_render_push_tiles with d_framebuffer / d_sync_slot = such addresses).
 int rt_host_register(int device, void *ptr, size_t bytes, void **d_ptr) {
+    API_ENTER();
     if (!ptr || !bytes || !d_ptr) return fail(nullptr, RT_ERR_INVALID, "rt_host_register: bad argument");
     CU(nullptr, cudaSetDevice(device));
     CU(nullptr, cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
@@ -957,6 +1044,7 @@ int rt_host_register(int device, void *ptr, size_t bytes, void **d_ptr) {
     return RT_OK;
 }
 int rt_host_unregister(int device, void *ptr) {
+    API_ENTER();
     if (!ptr) return RT_OK;
     CU(nullptr, cudaSetDevice(device));
     CU(nullptr, cudaHostUnregister(ptr));

@@ -14,19 +14,20 @@
 // Device-resident mesh (owned by rt_scene)
 struct MeshDevice {
     RtNode   *nodes = nullptr;
+    RtNode   *nodes_any = nullptr;   // any-hit hierarchy (== nodes when both leaf sizes agree)
     rt_f4    *tri32 = nullptr;
     double   *tri64 = nullptr;
     double   *fverts = nullptr;
     double   *fnormals = nullptr;
     uint32_t *fmat = nullptr;
     double   *materials = nullptr;
-    uint32_t  n_faces = 0, n_nodes = 0, n_materials = 0;
-    int       root_ref = 0;
+    uint32_t  n_faces = 0, n_nodes = 0, n_nodes_any = 0, n_materials = 0;
+    int       root_ref = 0, root_ref_any = 0;
     float     lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
     rt_bvh_info info;
 };
 
-bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, cudaStream_t st, std::string &err);
+bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max_leaf_any, int sm_count, cudaStream_t st, std::string &err);
 cudaError_t rt_flatten_faces(MeshDevice &m, const double *d_verts, uint32_t n_verts, const double *d_normals, uint32_t n_normals,
                              const uint32_t *d_faces, cudaStream_t st, int *bad);
 
@@ -58,16 +59,16 @@ struct RenderJob {
     bool      single_mesh;    // exactly one object => the persistent kernel takes its mesh by value
     MeshView  h_mesh0;        // host copy of object 0's mesh view
     double    h_obj0_pos[3];
-    bool      top_in_smem;    // keep the first levels of the BVH in shared memory (single-mesh scenes)
     bool      primary_persistent;  // default primary kernel of FP32_FAST (RT_B200_PERSISTENT=1), overridable per call
     int       shade_minb;     // K4 occupancy experiment: min resident CTAs per SM (register cap)
-    int       refill_below;   // persistent kernel: refill a warp when fewer lanes than this are live
+    bool      fused;          // FP32_FAST: one fused kernel per frame instead of K2 -> K4 -> K5
 };
 
 // render.cu : enqueue K2 (primary) / K4 (shadow+shade) / K5 (framebuffer) on `st`
 cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st);
 cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st);
 cudaError_t rt_launch_write(const RenderJob &job, cudaStream_t st);
+cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st);
 cudaError_t rt_launch_untile(const uint8_t *d_tiles, uint8_t *d_out, int W, int H, int tile_w, int tile_h, int n_ranks,
                              int tiles_per_rank_max, bool rowmajor, cudaStream_t st);
 

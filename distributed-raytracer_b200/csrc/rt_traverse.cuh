@@ -245,8 +245,45 @@ RT_HD bool tri_test32(rt_f4 v0, rt_f4 v1, rt_f4 v2, const RayF &r, float &t, flo
     return true;
 }
 
+// The 4 slab tests of one node visit.  RT_OCTANT (default): the sign of each direction component says which of the two planes
+// of an axis the ray enters through, so the near / far plane arrays are picked by ADDRESS (the node keeps lo and hi of an axis in
+// adjacent 16-byte vectors) and the per-child min/max pair of the classic slab test disappears: 6 FFMA + 2 three-input min/max
+// per child instead of 6 FFMA + 6 min/max + 2.  Bit-identical to slab32: lo <= hi and x -> fma(x, i, -a) is monotone, so
+// min(x0, x1) is x0 for i >= 0 and x1 for i < 0.
+#ifndef RT_OCTANT
+#define RT_OCTANT 1
+#endif
+struct NodeHits { float t[RT_W]; int ref[RT_W]; bool hit[RT_W]; };
+RT_HD void node_test32(const RtNode *nd, const RayF &r, float tbest, NodeHits &h) {
+#if RT_OCTANT && RT_W == 4
+    const rt_f4 *q = reinterpret_cast<const rt_f4 *>(nd);
+    const int sx = r.ix < 0.0f, sy = r.iy < 0.0f, sz = r.iz < 0.0f;
+    const rt_f4 nx = ld_f4(q + sx), fx = ld_f4(q + (sx ^ 1));
+    const rt_f4 ny = ld_f4(q + 2 + sy), fy = ld_f4(q + 2 + (sy ^ 1));
+    const rt_f4 nz = ld_f4(q + 4 + sz), fz = ld_f4(q + 4 + (sz ^ 1));
+    const rt_i4 rf = ld_i4(reinterpret_cast<const rt_i4 *>(q + 6));
+#define RT_CHILD(k, c)                                                                                                     \
+    {                                                                                                                      \
+        const float tn = fmaxf(fmaxf(fmaf(nx.c, r.ix, -r.ax), fmaf(ny.c, r.iy, -r.ay)), fmaxf(fmaf(nz.c, r.iz, -r.az), 0.0f)); \
+        const float tf = fminf(fminf(fmaf(fx.c, r.ix, -r.ax), fmaf(fy.c, r.iy, -r.ay)), fminf(fmaf(fz.c, r.iz, -r.az), tbest)); \
+        h.t[k] = tn; h.ref[k] = rf.c; h.hit[k] = tn <= tf && rf.c != RT_EMPTY;                                             \
+    }
+    RT_CHILD(0, x) RT_CHILD(1, y) RT_CHILD(2, z) RT_CHILD(3, w)
+#undef RT_CHILD
+#else
+    NodeRegs n;
+    ld_node(nd, n);
+#pragma unroll
+    for (int k = 0; k < RT_W; k++) {
+        h.ref[k] = n.ref[k];
+        h.hit[k] = slab32(n.lox[k], n.hix[k], n.loy[k], n.hiy[k], n.loz[k], n.hiz[k], r, tbest, h.t[k]) && n.ref[k] != RT_EMPTY;
+    }
+#endif
+}
+
 // Simple per-ray traversal of one mesh (object space).  ANY: stop at the first hit with t <= tbest.
 // Nearest: winner = min t, ties -> lowest face index.  Returns true if something was accepted.
+// ANY rays walk the mesh's any-hit hierarchy (nodes_any: same triangles, its own leaf size).
 template <bool ANY>
 RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &face, Counters *cnt) {
     if (m.n_faces == 0) return false;
@@ -256,19 +293,19 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
     int stack[RT_STACK_SIZE];
     float stack_t[ANY ? 1 : RT_STACK_SIZE];
     int sp = 0;
-    int ref = m.root_ref;
+    const RtNode *nodes = ANY ? m.nodes_any : m.nodes;
+    int ref = ANY ? m.root_ref_any : m.root_ref;
     for (;;) {
         if (ref >= 0) {
-            NodeRegs n;
-            ld_node(m.nodes + ref, n);
+            NodeHits n;
+            node_test32(nodes + ref, r, tbest, n);
             RT_COUNT(cnt, nodes, 1);
             int next = RT_EMPTY;
             float tnext = 0.0f;
 #pragma unroll
             for (int k = 0; k < RT_W; k++) {
-                float t;
-                bool h = slab32(n.lox[k], n.hix[k], n.loy[k], n.hiy[k], n.loz[k], n.hiz[k], r, tbest, t) && n.ref[k] != RT_EMPTY;
-                if (h) {
+                if (n.hit[k]) {
+                    const float t = n.t[k];
                     if (next == RT_EMPTY) { next = n.ref[k]; tnext = t; }
                     else if (!ANY && t < tnext) { stack[sp] = next; stack_t[sp] = tnext; sp++; next = n.ref[k]; tnext = t; }
                     else { stack[sp] = n.ref[k]; if (!ANY) stack_t[sp] = t; sp++; }

@@ -28,6 +28,16 @@
 #define RT_TRI32_BYTES 48
 #define RT_TRI64_BYTES 80
 #define RT_SHADOW_BIAS 0.0001     // tracer.go:64
+// words of a lane's counter block (unsigned int[8]): [0] next ray (persistent K2), [1] hit count, [2] next hit (K4), [3] spare
+#define RT_CNT_CANCEL 4           // cancel generation written by rt_cancel; a kernel gives up when it exceeds FrameParams.cancel_gen
+#define RT_CNT_PUSH_DONE 5        // CTAs-done counter of k_push_tiles
+// measured defaults (profiles/r02_*): leaf size of the any-hit hierarchy, fused frame kernel
+#ifndef RT_DEFAULT_MAX_LEAF_SHADE
+#define RT_DEFAULT_MAX_LEAF_SHADE 4
+#endif
+#ifndef RT_DEFAULT_FUSED
+#define RT_DEFAULT_FUSED 0
+#endif
 
 struct alignas(16) rt_f4 { float x, y, z, w; };
 struct alignas(16) rt_i4 { int x, y, z, w; };
@@ -57,6 +67,11 @@ struct MeshView {
     uint32_t n_faces, n_nodes;
     int      root_ref;         // ref encoding; meaningful iff n_faces > 0
     float    lo[3], hi[3];     // padded mesh bounds (object space)
+    // second hierarchy over the SAME triangle array for any-hit (shadow) rays: its leaves may be smaller (a warp pays for its
+    // largest leaf; RT_B200_MAX_LEAF_SHADE).  Equal to nodes / root_ref when both leaf sizes agree.
+    const RtNode  *nodes_any;
+    int      root_ref_any;
+    uint32_t n_nodes_any;
 };
 
 struct ObjRec { double pos[3]; uint32_t mesh; uint32_t pad; };
@@ -71,6 +86,13 @@ struct FrameParams {
     // tile mode (multi-GPU): if tile_w > 0 the region-linear pixel index maps through interleaved tiles
     int tile_w, tile_h, tiles_x, rank, n_ranks, n_local_tiles;
     int tile_final;      // tile mode: output index = position in the FULL framebuffer (peer-memory writer), not in the packed tiles
+    // Primary-ray culling (rt_cull.h): no primary ray outside the absolute pixel rectangle [cull_i0, cull_i1) x [cull_j0, cull_j1)
+    // can meet an object's root box.  Region mode traces only the 8x4 blocks rbx0 .. rbx0+rnbx-1, rby0 .. rby0+rnby-1 (relative to
+    // the region origin); rnbx == 0 means "every block of the region" (no culling information).  Tile mode keeps its ray
+    // numbering and skips the blocks that lie outside the rectangle (cull_on).
+    int cull_on, cull_i0, cull_j0, cull_i1, cull_j1;
+    int rbx0, rby0, rnbx, rnby;
+    unsigned int cancel_gen;   // generation of the call (rt_cancel): the kernels stop when counters[RT_CNT_CANCEL] has moved past it
 };
 
 // Per-frame mutable state small enough to travel BY VALUE as a __grid_constant__ kernel parameter: no device
@@ -111,8 +133,15 @@ RT_HD uint32_t tile_id(uint32_t X, uint32_t Y, uint32_t tiles_x) {
 
 RT_HD uint32_t ray_count(const FrameParams &fp) {
     if (fp.tile_w > 0) return (uint32_t)fp.n_local_tiles * (uint32_t)(fp.tile_w * fp.tile_h);
+    if (fp.rnbx > 0) return (uint32_t)fp.rnbx * (uint32_t)fp.rnby * 32u;
+    if (fp.cull_on) return 0u;                                   // culling found no block that can be hit
     uint32_t nbx = (uint32_t)(fp.w + 7) / 8, nby = (uint32_t)(fp.h + 3) / 4;
     return nbx * nby * 32u;
+}
+
+// tile mode: can the 8x4 block whose first pixel is (i0, j0) be skipped?
+RT_HD bool block_culled(const FrameParams &fp, int i0, int j0) {
+    return fp.cull_on && (i0 + 8 <= fp.cull_i0 || i0 >= fp.cull_i1 || j0 + 4 <= fp.cull_j0 || j0 >= fp.cull_j1);
 }
 
 RT_HD PixMap map_ray(uint32_t r, const FrameParams &fp, bool rowmajor) {
@@ -135,8 +164,8 @@ RT_HD PixMap map_ray(uint32_t r, const FrameParams &fp, bool rowmajor) {
             p.out = rowmajor ? (uint32_t)p.j * (uint32_t)fp.W + (uint32_t)p.i : (uint32_t)p.i * (uint32_t)fp.H + (uint32_t)p.j;
         return p;
     }
-    uint32_t nbx = (uint32_t)(fp.w + 7) / 8;
-    int ri = (int)(blk % nbx) * 8 + lx, rj = (int)(blk / nbx) * 4 + ly;
+    uint32_t nbx = fp.rnbx > 0 ? (uint32_t)fp.rnbx : (uint32_t)(fp.w + 7) / 8;
+    int ri = ((int)(blk % nbx) + fp.rbx0) * 8 + lx, rj = ((int)(blk / nbx) + fp.rby0) * 4 + ly;
     p.valid = ri < fp.w && rj < fp.h;
     p.i = fp.x + ri; p.j = fp.y + rj;
     p.out = rowmajor ? (uint32_t)rj * (uint32_t)fp.w + (uint32_t)ri        // image order

@@ -62,6 +62,11 @@ class FrameState:
         self._obj = None if obj_pos is None else _c(obj_pos, np.float64)
         self.obj_ptr = self._obj.ctypes.data if self._obj is not None else None
 
+    def check(self, n_objects):
+        """The ABI reads 3 * n_objects doubles behind obj_pos (it carries no length): refuse anything else here."""
+        if self._obj is not None and self._obj.size != 3 * n_objects:
+            raise ValueError("obj_pos holds %d values, the scene has %d objects (3 each)" % (self._obj.size, n_objects))
+
 
 class GpuScene:
     def __init__(self, scene, device=0, precision=_lib.FP32_FAST, flags=0):
@@ -83,10 +88,19 @@ class GpuScene:
         if rc != 0:
             raise _lib.RtError(rc, (self._L.rt_last_error(self.h) or b"").decode())
 
+    def _obj_pos(self, obj_pos):
+        """obj_pos -> contiguous float64 array of exactly 3 * n_objects values (the ABI carries no length) or None."""
+        if obj_pos is None:
+            return None
+        op = _c(obj_pos, np.float64)
+        if op.size != 3 * self.n_objects:
+            raise ValueError("obj_pos holds %d values, the scene has %d objects (3 each)" % (op.size, self.n_objects))
+        return op
+
     def set_frame(self, cam13, lights, obj_pos=None, tan_half_fov=float("nan")):
         cam = make_camera(cam13, tan_half_fov)
         lights = _c(lights, np.float64).reshape(-1, 6)
-        op = None if obj_pos is None else _c(obj_pos, np.float64)
+        op = self._obj_pos(obj_pos)
         self._check(self._L.rt_frame_set(self.h, C.byref(cam), lights.ctypes.data if lights.size else None, lights.shape[0],
                                          op.ctypes.data if op is not None else None))
 
@@ -101,7 +115,7 @@ class GpuScene:
     def bulk_trace(self, cam13, lights, W, H, x, y, w, h, obj_pos=None, flags=0, out=None, tan_half_fov=float("nan")):
         cam = make_camera(cam13, tan_half_fov)
         lights = _c(lights, np.float64).reshape(-1, 6)
-        op = None if obj_pos is None else _c(obj_pos, np.float64)
+        op = self._obj_pos(obj_pos)
         if out is None:
             out = np.empty((w * h, 3), dtype=np.uint8)
         self._check(self._L.rt_bulk_trace(self.h, C.byref(cam), lights.ctypes.data if lights.size else None, lights.shape[0],
@@ -113,7 +127,7 @@ class GpuScene:
         message inside `out` (allocated at the worst-case size if not given)."""
         cam = make_camera(cam13, tan_half_fov)
         lights = _c(lights, np.float64).reshape(-1, 6)
-        op = None if obj_pos is None else _c(obj_pos, np.float64)
+        op = self._obj_pos(obj_pos)
         if out is None:
             out = np.empty(int(self._L.rt_trace_results_max_bytes(w * h)), dtype=np.uint8)
         n = C.c_uint64(0)
@@ -154,12 +168,14 @@ class GpuScene:
                           sync_slot_ptr=None, seq=0):
         """frame = FrameState (prebuilt ctypes camera + lights): one C call per frame.  sync_slot_ptr/seq: device-side frame
         hand-off through the slot's record in the gathering rank's memory (include/rt_b200.h)."""
+        frame.check(self.n_objects)
         self._check(self._L.rt_render_push_tiles(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr, W, H, tile_w,
                                                  tile_h, rank, n_ranks, d_tiles_ptr, d_framebuffer_ptr, sync_slot_ptr, seq, stream_ptr, flags))
 
     def render_stripes_host(self, frame, W, H, stripe, rank, n_ranks, d_local_fb_ptr, h_framebuffer_ptr, stream_ptr, flags=0,
                             sync_slot_ptr=None, seq=0):
         """The multi-GPU end-to-end call of a rank: render its stripes, one strided D2H transfer into the host framebuffer."""
+        frame.check(self.n_objects)
         self._check(self._L.rt_render_stripes_host(self.h, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr, W, H, stripe,
                                                    rank, n_ranks, d_local_fb_ptr, h_framebuffer_ptr, sync_slot_ptr, seq, stream_ptr, flags))
 
@@ -170,6 +186,7 @@ class GpuScene:
         self._check(self._L.rt_frame_release_device(self.h, sync_slot_ptr, seq, stream_ptr))
 
     def set_frame_state(self, frame, lane=0):
+        frame.check(self.n_objects)
         self._check(self._L.rt_frame_set_lane(self.h, lane, C.byref(frame.cam), frame.lights_ptr, frame.n_lights, frame.obj_ptr))
 
     def lane_count(self):
@@ -192,7 +209,7 @@ class GpuScene:
         self._check(self._L.rt_synchronize(self.h))
 
     def cancel(self):
-        self._L.rt_cancel(self.h)
+        self._check(self._L.rt_cancel(self.h))
 
     def close(self):
         if getattr(self, "h", None):

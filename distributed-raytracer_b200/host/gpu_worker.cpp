@@ -19,14 +19,22 @@ Tracer::Tracer(const state::Environment &scene, uint32_t w, uint32_t h, int devi
 
 Tracer::~Tracer() { rt_scene_destroy(handle); }
 
+// The frame state of ONE order, as a per-call value: the reference decodes the gob diff into a local of the RPC
+// (distributed/main.go:56-64), and several BulkTrace calls run concurrently on one Tracer (a goroutine each).  An order
+// without a diff renders the state of the most recent order that had one; that shared copy is only touched under the mutex.
+state::EnvMutables Tracer::frameState(const comms::WorkOrder &req) {
+    std::lock_guard<std::mutex> lk(lastMu);
+    if (req.diff) last = *req.diff;
+    return last;
+}
+
 bool Tracer::BulkTraceInto(const comms::WorkOrder &req, uint8_t *out_rgb, std::string &e, uint32_t flags) {
     if (!handle) { e = "tracer has no scene: " + err; return false; }
-    if (req.diff) last = *req.diff;                                   // distributed/main.go:56-64
-    if (req.width == 0 || req.height == 0) return true;              // empty order: empty results, like the Go loop
+    if (req.width == 0 || req.height == 0) { (void)frameState(req); return true; }   // empty order: empty results, like the Go loop
     rt_camera cam;
     std::vector<rt_light> lights;
     std::vector<double> obj_pos;
-    state::FrameState(last, cam, lights, obj_pos);
+    state::FrameState(frameState(req), cam, lights, obj_pos);
     int rc = rt_bulk_trace(handle, &cam, lights.data(), uint32_t(lights.size()), obj_pos.empty() ? nullptr : obj_pos.data(),
                            screenWidth, screenHeight, req.x, req.y, req.width, req.height, out_rgb,
                            (flags & ~RT_LAYOUT_ROWMAJOR) | RT_LAYOUT_COLMAJOR | RT_QUANT_RGB255);   // :79 RGB(), :82 i*height+j
@@ -42,12 +50,11 @@ bool Tracer::BulkTrace(const comms::WorkOrder &req, comms::TraceResults &results
 bool Tracer::BulkTraceEncoded(const comms::WorkOrder &req, std::vector<uint8_t> &wire, std::string &e, uint32_t flags) {
     wire.clear();
     if (!handle) { e = "tracer has no scene: " + err; return false; }
-    if (req.diff) last = *req.diff;
-    if (req.width == 0 || req.height == 0) return true;              // no results: the empty message
+    if (req.width == 0 || req.height == 0) { (void)frameState(req); return true; }   // no results: the empty message
     rt_camera cam;
     std::vector<rt_light> lights;
     std::vector<double> obj_pos;
-    state::FrameState(last, cam, lights, obj_pos);
+    state::FrameState(frameState(req), cam, lights, obj_pos);
     wire.resize(size_t(rt_trace_results_max_bytes(uint64_t(req.width) * req.height)));
     uint64_t len = 0;
     int rc = rt_bulk_trace_encoded(handle, &cam, lights.data(), uint32_t(lights.size()), obj_pos.empty() ? nullptr : obj_pos.data(),

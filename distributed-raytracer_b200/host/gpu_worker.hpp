@@ -8,6 +8,7 @@
 // Error behaviour: like BulkTrace returning (nil, err) (distributed/main.go:60,74), BulkTrace returns
 // false and fills `err`; the caller (master) then skips the frame (pool.go:172-174).
 #pragma once
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -52,8 +53,10 @@ class Tracer {                              // distributed/main.go:27-32
     uint32_t screenWidth, screenHeight;
 
   private:
+    state::EnvMutables frameState(const comms::WorkOrder &req);   // per-call copy (BulkTrace is entered concurrently)
     rt_scene *handle = nullptr;
-    state::EnvMutables last;                // frame state used when a WorkOrder carries no diff
+    std::mutex lastMu;
+    state::EnvMutables last;                // frame state used when a WorkOrder carries no diff (guarded by lastMu)
     std::string err;
 };
 

@@ -12,8 +12,9 @@
  *  - plain C, no torch / C++ types; every pointer argument is caller-owned and is not retained
  *    after the call returns (cgo rule: C may not keep Go pointers) -- the library copies.
  *  - every entry point returns 0 on success, a negative rt_status otherwise; no exception crosses
- *    the ABI; rt_last_error() returns a message (per handle, or a thread-local one for handle-less
- *    failures when called with NULL).
+ *    the ABI.  rt_last_error(handle): the calling thread's failure on that handle if its last call
+ *    failed (concurrent callers do not see each other's errors), else the handle's most recent
+ *    message; rt_last_error(NULL): the calling thread's last call ("" after a success).
  *  - handles are internally synchronised: BulkTrace may be entered concurrently from several
  *    goroutines (final_report.pdf p.6 s2.3) and the calls then run concurrently on the GPU, one
  *    lane each (see RT_LANE below); calls may arrive on any OS thread.
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef enum {
     RT_OK            = 0,
@@ -57,6 +58,10 @@ typedef enum {
                                       semantics for meshes with zero-area faces)               */
 #define RT_FLAG_SIMPLE       0x10u /* FP32_FAST only: one-thread-per-ray primary kernel (the default: fastest measured) */
 #define RT_FLAG_PERSISTENT   0x20u /* FP32_FAST only: persistent warp-cooperative primary kernel (ballot/shuffle refill) */
+#define RT_FLAG_FUSED        0x40u /* FP32_FAST only: ONE kernel per frame -- a warp traces its 8x4 pixel block, shades the
+                                      hits (shadow rays + Phong) and writes the pixels; no hit list, no K4/K5 launches */
+#define RT_FLAG_PIPELINE     0x80u /* the three-kernel pipeline K2 -> K4 -> K5 even if the scene's default is the fused kernel */
+#define RT_FLAG_NO_CULL      0x100u /* trace every pixel block of the region: no projected-root-box culling (A/B, tests) */
 
 /* Lanes.  A scene handle owns one immutable copy of the geometry (+ BVH) and several LANES -- per-call resources: stream,
  * hit-list scratch, staging buffers, frame state -- the way the reference worker serves every BulkTrace RPC on its own
@@ -132,6 +137,9 @@ typedef struct {
     uint32_t max_depth, max_leaf;
     float    ms_build;         /* CUDA-event time of the whole on-GPU build of this mesh            */
     float    sah_cost;
+    /* the any-hit (shadow-ray) hierarchy over the same triangles; equals the fields above when both leaf sizes agree */
+    uint64_t n_nodes_any, n_leaves_any;
+    uint32_t max_depth_any, max_leaf_any;
 } rt_bvh_info;
 
 /* ---- lifecycle (register(): distributed/main.go:101-129 => create; re-register => destroy+create) */
@@ -141,7 +149,10 @@ const char *rt_last_error(const rt_scene *scene);
 int  rt_abi_version(void);
 int  rt_device_count(void);
 
-/* ---- per-frame mutable state (the gob `diff`: distributed/main.go:56-64, environment.go:65-69) -- */
+/* ---- per-frame mutable state (the gob `diff`: distributed/main.go:56-64, environment.go:65-69) --
+ * obj_pos, wherever it appears below, must hold exactly 3 * n_objects doubles (n_objects of rt_scene_create): like a Go
+ * slice header passed through cgo as a bare pointer, the ABI carries no length for it.  n_lights is unbounded; the lit
+ * mask of the debug outputs has one bit per light modulo 32. */
 int rt_frame_set(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights,
                  const double *obj_pos /* n_objects*3 or NULL = unchanged */);
 /* the same for an explicit lane of the device API */
@@ -266,7 +277,10 @@ int rt_bulk_trace_encoded(rt_scene *scene, const rt_camera *cam, const rt_light 
 int rt_get_stats(rt_scene *scene, rt_stats *out);
 int rt_get_bvh_info(rt_scene *scene, uint32_t mesh, rt_bvh_info *out);
 int rt_synchronize(rt_scene *scene);
-/* ask an in-flight render on this handle to stop (checked between kernels) */
+/* ctx.Err() of the reference loop (distributed/main.go:73): stops the renders that are IN FLIGHT on this handle when it is
+ * called -- their kernels poll a cancel generation and give up, the blocking calls return RT_ERR_CANCELLED (their output
+ * buffers then hold no frame).  Calls that start afterwards are not affected, and with nothing in flight it is a no-op:
+ * nothing needs to be reset. */
 int rt_cancel(rt_scene *scene);
 
 /* Register-resident FMA micro-benchmark (roofline denominator of the flop side): runs `iters`

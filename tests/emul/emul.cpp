@@ -27,10 +27,11 @@ enum { EV_nodes = 0, EV_tris = 1 };
 #include "../../distributed-raytracer_b200/csrc/rt_types.h"
 #include "../../distributed-raytracer_b200/csrc/rt_bvh.cuh"
 #include "../../distributed-raytracer_b200/csrc/rt_traverse.cuh"
+#include "../../distributed-raytracer_b200/csrc/rt_cull.h"
 #include "host_builders_experiment.hpp"
 
 struct EmulMesh {
-    std::vector<RtNode> nodes;
+    std::vector<RtNode> nodes, nodes_any;
     std::vector<rt_f4> tri32;
     std::vector<double> tri64, fverts, fnormals, materials;
     std::vector<uint32_t> fmat;
@@ -45,7 +46,7 @@ struct EmulScene {
     uint32_t precision;
 };
 
-static void build_mesh(EmulMesh &m, int max_leaf) {
+static void build_mesh(EmulMesh &m, int max_leaf, int max_leaf_any) {
     const uint32_t n = (uint32_t)(m.fverts.size() / 9);
     MeshView &v = m.view;
     memset(&v, 0, sizeof v);
@@ -81,7 +82,7 @@ static void build_mesh(EmulMesh &m, int max_leaf) {
     m.tri64.resize(10 * (size_t)n);
     for (uint32_t i = 0; i < n; i++) gather_tri_thread(i, m.fverts.data(), svals.data(), m.tri32.data(), m.tri64.data());
     if (n == 1) {
-        v.root_ref = rt_leaf_ref(0, 1);
+        v.root_ref = v.root_ref_any = rt_leaf_ref(0, 1);
         m.n_leaves = 1;
     } else {
         const int ni = (int)n - 1;
@@ -96,18 +97,22 @@ static void build_mesh(EmulMesh &m, int max_leaf) {
         } else {
             for (int i = 0; i < ni; i++) karras_thread(i, skeys.data(), (int)n, kn.data(), pint.data(), pleaf.data());
         }
-        std::vector<BoxF> ibox(ni);
-        std::vector<float> icost(ni);
-        std::vector<unsigned char> coll(ni);
-        std::vector<unsigned int> flags(ni, 0u);
-        for (int i = 0; i < (int)n; i++)
-            refit_sah_thread(i, svals.data(), leafbox.data(), kn.data(), pint.data(), pleaf.data(), ibox.data(), icost.data(),
-                             coll.data(), flags.data(), max_leaf);
-        if (coll[0]) {
-            v.root_ref = rt_leaf_ref(0, n);
-            m.n_leaves = 1;
-        } else {
-            m.nodes.resize(ni);
+        // one wide hierarchy per leaf size over the one binary tree (bvh_build.cu: emit)
+        auto emit = [&](int leaf_cap, std::vector<RtNode> &nodes, int &root_ref, uint32_t &n_nodes, uint32_t &max_depth, uint32_t &n_leaves) {
+            std::vector<BoxF> ibox(ni);
+            std::vector<float> icost(ni);
+            std::vector<unsigned char> coll(ni);
+            std::vector<unsigned int> flags(ni, 0u);
+            n_leaves = 0; n_nodes = 0; max_depth = 0;
+            for (int i = 0; i < (int)n; i++)
+                refit_sah_thread(i, svals.data(), leafbox.data(), kn.data(), pint.data(), pleaf.data(), ibox.data(), icost.data(),
+                                 coll.data(), flags.data(), leaf_cap);
+            if (coll[0]) {
+                root_ref = rt_leaf_ref(0, n);
+                n_leaves = 1;
+                return;
+            }
+            nodes.resize(ni);
             std::vector<int> front[2] = { std::vector<int>(ni), std::vector<int>(ni) };
             std::vector<int> cnt(ni + 1), off(ni + 1);
             front[0][0] = 0;
@@ -117,26 +122,35 @@ static void build_mesh(EmulMesh &m, int max_leaf) {
                 int acc = 0;
                 for (int p = 0; p < fsize; p++) { off[p] = acc; acc += cnt[p]; }
                 for (int p = 0; p < fsize; p++)
-                    m.n_leaves += emit_write_thread(p, front[cur].data(), fsize, base, kn.data(), coll.data(), off.data(),
-                                                    svals.data(), leafbox.data(), ibox.data(), m.nodes.data(),
-                                                    front[cur ^ 1].data());
+                    n_leaves += emit_write_thread(p, front[cur].data(), fsize, base, kn.data(), coll.data(), off.data(),
+                                                  svals.data(), leafbox.data(), ibox.data(), nodes.data(), front[cur ^ 1].data());
                 base += fsize;
                 fsize = acc;
                 cur ^= 1;
                 depth++;
             }
-            m.nodes.resize(base);
-            v.n_nodes = (uint32_t)base;
-            v.root_ref = 0;
-            m.max_depth = (uint32_t)depth;
+            nodes.resize(base);
+            n_nodes = (uint32_t)base;
+            root_ref = 0;
+            max_depth = (uint32_t)depth;
+        };
+        emit(max_leaf, m.nodes, v.root_ref, v.n_nodes, m.max_depth, m.n_leaves);
+        if (max_leaf_any != max_leaf) {
+            uint32_t d_any = 0, l_any = 0;
+            emit(max_leaf_any, m.nodes_any, v.root_ref_any, v.n_nodes_any, d_any, l_any);
         }
     }
+    if (max_leaf_any == max_leaf || n == 1) { v.root_ref_any = v.root_ref; v.n_nodes_any = v.n_nodes; }
     v.nodes = m.nodes.data(); v.tri32 = m.tri32.data(); v.tri64 = m.tri64.data();
+    v.nodes_any = (max_leaf_any == max_leaf || n == 1) ? m.nodes.data() : m.nodes_any.data();
 }
 
 extern "C" {
 
-void *emul_scene_create(const rt_scene_desc *desc, int max_leaf) {
+void *emul_scene_create2(const rt_scene_desc *desc, int max_leaf, int max_leaf_any);
+void *emul_scene_create(const rt_scene_desc *desc, int max_leaf) { return emul_scene_create2(desc, max_leaf, max_leaf); }
+void *emul_scene_create2(const rt_scene_desc *desc, int max_leaf, int max_leaf_any) {
+    if (max_leaf_any < 1) max_leaf_any = max_leaf;
     EmulScene *s = new EmulScene();
     s->precision = desc->precision;
     s->meshes.resize(desc->n_meshes);
@@ -157,7 +171,7 @@ void *emul_scene_create(const rt_scene_desc *desc, int max_leaf) {
             m.fmat[f] = fc[6];
         }
         m.materials.assign(d.materials, d.materials + 10 * (size_t)d.n_materials);
-        build_mesh(m, max_leaf);
+        build_mesh(m, max_leaf, max_leaf_any);
         m.view.fverts = m.fverts.data();
         m.view.fnormals = d.n_normals ? m.fnormals.data() : nullptr;
         m.view.fmat = m.fmat.data();
@@ -274,12 +288,15 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
     if (out_obj) for (size_t k = 0; k < npix; k++) out_obj[k] = -1;
     if (out_lit) memset(out_lit, 0, sizeof(uint32_t) * npix);
     Counters c; c.nodes = 0; c.tris = 0;
+    // primary-ray culling exactly as rt_api.cu applies it (cull_params): RT_FLAG_NO_CULL / brute force switch it off
+    if ((flags & (RT_FLAG_NO_CULL | RT_FLAG_BRUTE_FORCE)) == 0) rt_cull_frame(fp, s->views.data(), s->objs.data(), (int)s->objs.size());
     const uint32_t nrays = ray_count(fp);
     std::vector<HitRec> hits;
     // K2
     for (uint32_t ray = 0; ray < nrays; ray++) {
         PixMap pm = map_ray(ray, fp, false);
         if (!pm.valid) continue;
+        if (fp.tile_w > 0 && block_culled(fp, pm.i & ~7, pm.j & ~3)) continue;
         HitRec hr; hr.pix = ray; hr.t = 0.f;
         Counters before = c;
         struct CostNote { Counters &c; Counters b; uint32_t *dst; size_t o; ~CostNote() { if (dst) dst[o] = (uint32_t)((c.nodes - b.nodes) + (c.tris - b.tris)); } } note{ c, before, g_cost_primary, pm.out };

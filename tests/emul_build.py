@@ -19,7 +19,7 @@ def lib():
     if _LIB is None:
         src = os.path.join(_HERE, "emul", "emul.cpp")
         csrc = os.path.join(_HERE, "..", "distributed-raytracer_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("rt_types.h", "rt_bvh.cuh", "rt_traverse.cuh", "rt_exact.cuh")] + \
+        deps = [src] + [os.path.join(csrc, f) for f in ("rt_types.h", "rt_bvh.cuh", "rt_traverse.cuh", "rt_exact.cuh", "rt_cull.h")] + \
             [os.path.join(_HERE, "emul", "host_builders_experiment.hpp")]
         if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
@@ -27,6 +27,8 @@ def lib():
         L = C.CDLL(_SO)
         L.emul_scene_create.restype = C.c_void_p
         L.emul_scene_create.argtypes = [C.POINTER(_lib.SceneDesc), C.c_int]
+        L.emul_scene_create2.restype = C.c_void_p
+        L.emul_scene_create2.argtypes = [C.POINTER(_lib.SceneDesc), C.c_int, C.c_int]
         L.emul_scene_destroy.argtypes = [C.c_void_p]
         L.emul_bvh_check.restype = C.c_int
         L.emul_bvh_check.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 3
@@ -44,9 +46,9 @@ def lib():
 
 
 class EmulScene:
-    def __init__(self, scene, precision, max_leaf=4):
+    def __init__(self, scene, precision, max_leaf=4, max_leaf_any=0):
         desc, keep = rt.make_scene_desc(scene, 0, precision)
-        self.h = lib().emul_scene_create(C.byref(desc), max_leaf)
+        self.h = lib().emul_scene_create2(C.byref(desc), max_leaf, max_leaf_any)
         self.scene = scene
 
     def bvh_check(self, mesh=0):

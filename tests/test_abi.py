@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(built):
     assert set(names) == set(rt._lib.ABI_SYMBOLS)
     for n in names:
         assert getattr(lib, n) is not None
-    assert rt._lib.load().rt_abi_version() == 1
+    assert rt._lib.load().rt_abi_version() == 2
 
 
 def test_argument_validation_without_compute(built, example_scene):

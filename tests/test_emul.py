@@ -248,3 +248,84 @@ def test_go_math_device_functions_match_oracle():
     for x in rng.uniform(0, 1.0000001, 300):
         for n in (0.0, 1.0, 2.0, 10.0, 33.0, 0.5, 200.0):
             assert bits(L.emul_go_pow(x, n)) == bits(O.orc_go_pow(x, n))
+
+
+# ---- round 2: primary-ray culling rectangle (csrc/rt_cull.h) and the separate any-hit hierarchy ----------------------
+@pytest.mark.parametrize("precision", [rt.FP64_EXACT, rt.FP32_FAST])
+def test_cull_rectangle_never_changes_a_pixel(example_scene, precision):
+    """The projected-root-box rectangle may only skip rays that cannot hit: frames with and without it are identical, for
+    the example view, for cameras orbiting the object (incl. views where the object is cut by the screen edge or lies
+    behind the camera), for sub-regions and for tile mode."""
+    E = eb.EmulScene(example_scene, precision)
+    lights = example_scene["lights"]
+    views = [(example_scene["camera"], 160, 120)]
+    for k, (radius, elev) in enumerate([(6.0, 0.3), (2.5, -0.4), (1.2, 0.9), (0.4, 0.0), (9.0, 1.2)]):
+        views.append((workloads.orbit_camera([1.0, 1.0, -1.0], radius, np.deg2rad(40.0 * k + 10.0), elev, 1.0), 96 + 8 * k, 72 + 5 * k))
+    # looking away from the object: every corner behind the camera -> no culling information, still an all-black frame
+    away = np.array(example_scene["camera"], dtype=np.float64).copy()
+    away[3:6] = -away[3:6]
+    from oracle import scene_loader as sl
+    views.append((sl.new_camera(away[0:3], away[3:6], float(away[12])), 64, 48))
+    for cam, W, H in views:
+        a = E.render(cam, lights, W, H, flags=rt.FLAG_NO_CULL)
+        b = E.render(cam, lights, W, H)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64))
+        assert int(a[5][2]) == int(b[5][2])                                     # same number of hit pixels
+        x, y, w, h = W // 3, H // 4, W // 2, H // 2
+        a = E.render(cam, lights, W, H, x, y, w, h, flags=rt.FLAG_NO_CULL)
+        b = E.render(cam, lights, W, H, x, y, w, h)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    cam = example_scene["camera"]
+    per = rt.tiles_per_rank(96, 72, 16, 8, 3)
+    for r in range(3):
+        t0, t1 = np.zeros(per * 16 * 8 * 3, dtype=np.uint8), np.zeros(per * 16 * 8 * 3, dtype=np.uint8)
+        E.render_tiles(cam, lights, 96, 72, 16, 8, r, 3, t0, flags=rt.FLAG_NO_CULL)
+        E.render_tiles(cam, lights, 96, 72, 16, 8, r, 3, t1)
+        assert np.array_equal(t0, t1)
+    E.close()
+
+
+def test_cull_rectangle_skips_most_of_the_example_frame(example_scene):
+    """C1/C3 view: ~10 % of the pixels hit; the rectangle must cut the primary-ray work accordingly (node visits counted by
+    the replay: rays outside the rectangle are never generated)."""
+    E = eb.EmulScene(example_scene, rt.FP32_FAST)
+    a = E.render(example_scene["camera"], example_scene["lights"], 320, 240, flags=rt.FLAG_NO_CULL)
+    b = E.render(example_scene["camera"], example_scene["lights"], 320, 240)
+    assert np.array_equal(a[0], b[0])
+    assert int(b[5][0]) <= int(a[5][0])                 # never more node visits
+    E.close()
+
+
+def test_cull_rectangle_multi_object_and_degenerate():
+    for kw in (dict(n_tris=150, seed=13, n_obj=3, n_lights=4), dict(n_tris=1, seed=14, half=1.2, extent=0.2)):
+        sc = random_soup_scene(**kw)
+        E = eb.EmulScene(sc, rt.FP64_EXACT)
+        a = E.render(sc["camera"], sc["lights"], 96, 72, flags=rt.FLAG_NO_CULL)
+        b = E.render(sc["camera"], sc["lights"], 96, 72)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+        E.close()
+    for name, sc in degenerate_scenes().items():
+        E = eb.EmulScene(sc, rt.FP64_EXACT)
+        a = E.render(sc["camera"], sc["lights"], 64, 48, flags=rt.FLAG_NO_CULL)
+        b = E.render(sc["camera"], sc["lights"], 64, 48)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]), name
+        E.close()
+
+
+@pytest.mark.parametrize("leaf_any", [1, 2, 8])
+def test_any_hit_hierarchy_with_its_own_leaf_size(example_scene, leaf_any):
+    """FP32_FAST shadow rays walk a second hierarchy over the same triangles (RT_B200_MAX_LEAF_SHADE): the lit masks and
+    colours must not depend on its leaf size."""
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 1)]
+    E0 = eb.EmulScene(sc, rt.FP32_FAST, 4, 4)
+    E1 = eb.EmulScene(sc, rt.FP32_FAST, 4, leaf_any)
+    assert E1.bvh_check()[0] == 0
+    a = E0.render(sc["camera"], sc["lights"], 240, 180)
+    b = E1.render(sc["camera"], sc["lights"], 240, 180)
+    assert np.array_equal(a[2], b[2])                                            # primary hits: same hierarchy
+    assert (a[4] == b[4]).mean() >= 0.9999                                       # lit masks
+    assert (a[0] == b[0]).all(axis=1).mean() >= 0.9999
+    rgb_o, _, face_o, _ = oracle_render(sc, 240, 180)
+    assert (np.abs(b[0].astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= 1).mean() >= 0.999
+    E0.close(); E1.close()

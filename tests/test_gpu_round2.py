@@ -1,0 +1,163 @@
+"""GPU (-m gpu), round 2: the fused frame kernel, the primary-ray culling rectangle, the separate any-hit hierarchy and
+the per-call cancellation, all through the C ABI.  Every variant must produce the frame of the three-kernel pipeline
+bit for bit (it is the same device code in another launch shape) and meet the oracle bars of test_gpu_parity.py."""
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from conftest import random_soup_scene
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt(built):
+    import distributed_raytracer_b200 as rt
+    if rt._lib.load().rt_device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests cannot run (there is no CPU fallback)")
+    return rt
+
+
+def subdivided(example_scene, levels, n_lights=2):
+    from distributed_raytracer_b200 import workloads
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], levels)]
+    sc["lights"] = example_scene["lights"][:n_lights]
+    return sc
+
+
+@pytest.mark.parametrize("scene_kind", ["example", "subdiv3", "three_objects"])
+def test_fused_kernel_equals_pipeline(rt, example_scene, scene_kind):
+    sc = {"example": lambda: example_scene, "subdiv3": lambda: subdivided(example_scene, 3),
+          "three_objects": lambda: random_soup_scene(n_tris=150, seed=13, n_obj=3, n_lights=4)}[scene_kind]()
+    W, H = (480, 270) if scene_kind != "three_objects" else (160, 120)
+    g = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    a = g.render_region_debug(W, H, flags=rt.FLAG_PIPELINE)
+    na = g.stats()["hit_pixels"]
+    b = g.render_region_debug(W, H, flags=rt.FLAG_FUSED)
+    nb = g.stats()["hit_pixels"]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert na == nb == int((a[2] >= 0).sum())
+    # sub-region, row-major, SDL quantiser
+    x0, y0, w, h = W // 5, H // 7, W // 2 + 3, H // 2 + 1
+    for flags in (0, rt.LAYOUT_ROWMAJOR, rt.QUANT_RGBA16_SHR8):
+        p = g.render_region(W, H, x0, y0, w, h, flags=flags | rt.FLAG_PIPELINE)
+        f = g.render_region(W, H, x0, y0, w, h, flags=flags | rt.FLAG_FUSED)
+        assert np.array_equal(p, f)
+    g.close()
+
+
+def test_fused_kernel_meets_the_oracle_bar(rt, example_scene):
+    S = orc.Scene(example_scene)
+    rgb_o, _, face_o, _ = S.render_region(320, 240, mode=orc.CULLED)
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    rgb, col, face, obj, lit = g.render_region_debug(320, 240, flags=rt.FLAG_FUSED)
+    g.close()
+    assert (np.abs(rgb.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= 1).mean() >= 0.999
+    assert (face == face_o).mean() >= 0.999
+
+
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_cull_rectangle_never_changes_a_pixel(rt, example_scene, precision):
+    from distributed_raytracer_b200 import workloads
+    prec = rt.FP64_EXACT if precision == "exact" else rt.FP32_FAST
+    g = rt.GpuScene(example_scene, precision=prec)
+    lights = example_scene["lights"]
+    views = [(example_scene["camera"], 320, 240)]
+    for k, (radius, elev) in enumerate([(6.0, 0.3), (2.5, -0.4), (1.2, 0.9), (0.4, 0.0), (9.0, 1.2)]):
+        views.append((workloads.orbit_camera([1.0, 1.0, -1.0], radius, np.deg2rad(40.0 * k + 10.0), elev, 1.0), 200 + 8 * k, 150 + 5 * k))
+    for cam, W, H in views:
+        g.set_frame(cam, lights)
+        a = g.render_region_debug(W, H, flags=rt.FLAG_NO_CULL | rt.FLAG_PIPELINE)
+        b = g.render_region_debug(W, H, flags=rt.FLAG_PIPELINE)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        if precision == "fast":
+            c = g.render_region_debug(W, H, flags=rt.FLAG_FUSED)
+            for x, y in zip(a, c):
+                assert np.array_equal(x, y)
+        x0, y0, w, h = W // 3, H // 4, W // 2, H // 2
+        assert np.array_equal(g.render_region(W, H, x0, y0, w, h, flags=rt.FLAG_NO_CULL), g.render_region(W, H, x0, y0, w, h))
+    g.close()
+
+
+def test_cull_rectangle_in_tile_mode(rt, example_scene):
+    import torch
+    W, H, tw, th, n = 320, 240, 32, 16, 3
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    g.set_frame(example_scene["camera"], example_scene["lights"])
+    per = rt.tiles_per_rank(W, H, tw, th, n)
+    for rank in range(n):
+        outs = []
+        for flags in (rt.FLAG_NO_CULL | rt.FLAG_PIPELINE, rt.FLAG_PIPELINE, rt.FLAG_FUSED):
+            t = torch.zeros(per * tw * th * 3, dtype=torch.uint8, device="cuda")
+            g.render_tiles_device(W, H, tw, th, rank, n, t.data_ptr(), None, flags)
+            outs.append(t.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+        assert outs[0].any()
+    g.close()
+
+
+@pytest.mark.parametrize("leaf_any", [1, 2])
+def test_any_hit_hierarchy_leaf_size(rt, example_scene, monkeypatch, leaf_any):
+    sc = subdivided(example_scene, 3)
+    monkeypatch.setenv("RT_B200_MAX_LEAF_SHADE", "4")
+    g0 = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    monkeypatch.setenv("RT_B200_MAX_LEAF_SHADE", str(leaf_any))
+    g1 = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    info = g1.bvh_info()
+    assert info["max_leaf_any"] == leaf_any and info["max_leaf"] == 4 and info["n_nodes_any"] > info["n_nodes"]
+    a = g0.render_region_debug(480, 270)
+    b = g1.render_region_debug(480, 270)
+    g0.close(); g1.close()
+    assert np.array_equal(a[2], b[2])
+    assert (a[4] == b[4]).mean() >= 0.9999 and (a[0] == b[0]).all(axis=1).mean() >= 0.9999
+
+
+def test_cancel_is_per_call_and_does_not_stick(rt, example_scene):
+    """rt_cancel stops the calls in flight (ctx.Err(), distributed/main.go:73) and nothing else: a call that starts after
+    it renders normally; with nothing in flight it is a no-op."""
+    sc = subdivided(example_scene, 4)
+    g = rt.GpuScene(sc, precision=rt.FP64_EXACT)          # exact mode at 4K: a call long enough to be hit by the cancel
+    ref = g.bulk_trace(sc["camera"], sc["lights"], 640, 360, 0, 0, 640, 360)
+    L = rt._lib.load()
+    assert L.rt_cancel(g.h) == 0                          # nothing in flight
+    again = g.bulk_trace(sc["camera"], sc["lights"], 640, 360, 0, 0, 640, 360)
+    assert np.array_equal(ref, again)
+    result = {}
+
+    def long_call():
+        try:
+            g.bulk_trace(sc["camera"], sc["lights"], 3840, 2160, 0, 0, 3840, 2160)
+            result["rc"] = 0
+        except rt.RtError as ex:
+            result["rc"] = ex.code
+    th = threading.Thread(target=long_call)
+    t0 = time.perf_counter()
+    th.start()
+    time.sleep(0.002)
+    assert L.rt_cancel(g.h) == 0
+    th.join()
+    result["dt"] = time.perf_counter() - t0
+    assert result["rc"] in (0, -5)                        # RT_ERR_CANCELLED unless the frame had already finished
+    after = g.bulk_trace(sc["camera"], sc["lights"], 640, 360, 0, 0, 640, 360)
+    assert np.array_equal(ref, after)                     # the cancellation did not leak into the next call
+    g.close()
+
+
+def test_last_error_follows_the_last_call(rt, example_scene):
+    import ctypes as C
+    L = rt._lib.load()
+    L.rt_last_error.restype = C.c_char_p
+    g = rt.GpuScene(example_scene, precision=rt.FP32_FAST)
+    with pytest.raises(rt.RtError):
+        g.render_region(64, 48, 0, 0, 65, 48)             # region exceeds the screen
+    assert b"region" in L.rt_last_error(g.h)
+    g.render_region(64, 48)                               # a successful call clears the thread's message ...
+    assert L.rt_last_error(None) == b""
+    assert b"region" in L.rt_last_error(g.h)              # ... the handle keeps its most recent failure
+    g.close()
