@@ -713,7 +713,10 @@ cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
 #define LAUNCH_FUSED(CN, MB) k_frame_fused<CN, MB><<<nblk, 128, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_out_rgb, \
                                                                           job.d_out_colour, job.d_out_face, job.d_out_obj, job.d_out_lit, job.d_stats)
     if (count) LAUNCH_FUSED(true, 1);
+    else if (job.shade_minb >= 10) LAUNCH_FUSED(false, 10);
+    else if (job.shade_minb >= 9) LAUNCH_FUSED(false, 9);
     else if (job.shade_minb >= 8) LAUNCH_FUSED(false, 8);
+    else if (job.shade_minb >= 7) LAUNCH_FUSED(false, 7);
     else if (job.shade_minb >= 6) LAUNCH_FUSED(false, 6);
     else LAUNCH_FUSED(false, 1);
 #undef LAUNCH_FUSED

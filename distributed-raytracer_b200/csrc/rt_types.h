@@ -31,12 +31,13 @@
 // words of a lane's counter block (unsigned int[8]): [0] next ray (persistent K2), [1] hit count, [2] next hit (K4), [3] spare
 #define RT_CNT_CANCEL 4           // cancel generation written by rt_cancel; a kernel gives up when it exceeds FrameParams.cancel_gen
 #define RT_CNT_PUSH_DONE 5        // CTAs-done counter of k_push_tiles
-// measured defaults (profiles/r02_*): leaf size of the any-hit hierarchy, fused frame kernel
+// measured defaults (profiles/r02_kernel_ab.txt, C3 at N = 1): any-hit hierarchy with leaves of <= 2 triangles (K4 -2.8 %,
+// +15 % node memory; single-triangle leaves are no faster and cost +93 %), fused frame kernel (-6.5 % pipelined, -12 % latency)
 #ifndef RT_DEFAULT_MAX_LEAF_SHADE
-#define RT_DEFAULT_MAX_LEAF_SHADE 4
+#define RT_DEFAULT_MAX_LEAF_SHADE 2
 #endif
 #ifndef RT_DEFAULT_FUSED
-#define RT_DEFAULT_FUSED 0
+#define RT_DEFAULT_FUSED 1
 #endif
 
 struct alignas(16) rt_f4 { float x, y, z, w; };

@@ -63,9 +63,11 @@ def test_c1_exact_bit_identical(rt, example_scene):
 
 
 def test_c1_exact_matches_golden_fixture(rt, example_scene):
+    """GPU FP64_EXACT against the golden frame of the INDEPENDENT restatement (tests/golden/make_golden_pyref.py), every pixel:
+    face map, float64 colour bits, lit masks, both quantisers."""
     import os
     from conftest import GOLDEN
-    gold = np.load(os.path.join(GOLDEN, "c1_320x240.npz"))
+    gold = np.load(os.path.join(GOLDEN, "c1_320x240_pyref.npz"))
     g = rt.GpuScene(example_scene, precision=rt.FP64_EXACT)
     rgb, col, face, obj, lit = g.render_region_debug(320, 240)
     sdl = g.render_region(320, 240, flags=rt.QUANT_RGBA16_SHR8)
@@ -73,8 +75,32 @@ def test_c1_exact_matches_golden_fixture(rt, example_scene):
     hit = gold["hit_index"]
     assert np.array_equal(face, gold["face"].astype(np.int32))
     assert np.array_equal(col[hit].view(np.uint64), gold["colour_bits"])
+    assert np.array_equal(lit[hit], gold["lit"].astype(np.uint32))
     assert np.array_equal(rgb[hit], gold["rgb"]) and np.array_equal(sdl[hit], gold["sdl"])
     assert not rgb[face < 0].any() and (obj[face >= 0] == 0).all() and (obj[face < 0] == -1).all()
+
+
+def test_c2_exact_matches_golden_sample(rt, example_scene):
+    """C2 (1920x1080, lights[0]): every 97th pixel of the GPU FP64_EXACT frame against the independent restatement; FP32_FAST on
+    the same sample: same face on >= 99.9 %, within 1 LSB on >= 99.9 %."""
+    import os
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "c2_1080p_sample_pyref.npz"))
+    sc = dict(example_scene)
+    sc["lights"] = example_scene["lights"][:1]
+    idx = gold["index"]
+    g = rt.GpuScene(sc, precision=rt.FP64_EXACT)
+    rgb, col, face, obj, lit = g.render_region_debug(1920, 1080)
+    g.close()
+    assert np.array_equal(face[idx], gold["face"].astype(np.int32))
+    assert np.array_equal(col[idx].view(np.uint64), gold["colour_bits"])
+    assert np.array_equal(lit[idx], gold["lit"].astype(np.uint32))
+    assert np.array_equal(rgb[idx], gold["rgb"])
+    g = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    rgb, col, face, obj, lit = g.render_region_debug(1920, 1080)
+    g.close()
+    assert (face[idx] == gold["face"]).mean() >= LSB_FRAC
+    assert (np.abs(rgb[idx].astype(np.int32) - gold["rgb"].astype(np.int32)).max(axis=1) <= LSB_TOL).mean() >= LSB_FRAC
 
 
 def test_c1_exact_brute_force_kernel(rt, example_scene):

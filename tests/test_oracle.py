@@ -147,16 +147,56 @@ def test_hit_count_matches_survey(kat, example_oracle):
     assert st["shadow_rays"] == 3 * st["hit_pixels"] and st["primary_rays"] == 320 * 180
 
 
-def test_c1_golden_image(example_oracle):
-    g = np.load(os.path.join(GOLDEN, "c1_320x240.npz"))
-    rgb, col, face, st = example_oracle.render_region(320, 240, mode=orc.CULLED)
+@pytest.mark.parametrize("mode", ["CULLED", "BRUTE", "RTREE"])
+def test_c1_golden_image_from_independent_restatement(example_oracle, mode):
+    """The WHOLE C1 frame against tests/golden/c1_320x240_pyref.npz, which was produced by tests/golden/make_golden_pyref.py:
+    its own scene/OBJ/MTL reader, its own math.Tan, the scalar Python arithmetic of tests/pyref.py -- nothing of the oracle
+    or of the product.  Face map, float64 colour bits, lit masks and both quantisations must agree on every pixel."""
+    g = np.load(os.path.join(GOLDEN, "c1_320x240_pyref.npz"))
+    rgb, col, face, st = example_oracle.render_region(320, 240, mode=getattr(orc, mode))
     assert np.array_equal(face, g["face"].astype(np.int32))
     hit = g["hit_index"]
+    assert st["hit_pixels"] == len(hit) == 5820
     assert np.array_equal(col[hit].view(np.uint64), g["colour_bits"])
     assert np.array_equal(rgb[hit], g["rgb"]) and not rgb[face < 0].any()
-    sdl, _, _, _ = example_oracle.render_region(320, 240, mode=orc.CULLED, quant=orc.Q_RGBA16_SHR8, want_colour=False)
+    sdl, _, _, _ = example_oracle.render_region(320, 240, mode=getattr(orc, mode), quant=orc.Q_RGBA16_SHR8, want_colour=False)
     assert np.array_equal(sdl[hit], g["sdl"])
     assert (sdl != rgb).any()          # the two quantisers differ (SURVEY Appendix B-6)
+
+
+def test_c2_golden_sample_from_independent_restatement(example_scene):
+    """C2 (1920x1080, lights[0] only): every 97th pixel of the BulkTrace order against the independent restatement."""
+    g = np.load(os.path.join(GOLDEN, "c2_1080p_sample_pyref.npz"))
+    sc = dict(example_scene)
+    sc["lights"] = example_scene["lights"][:1]
+    S = orc.Scene(sc)
+    rgb, col, face, st = S.render_region(1920, 1080, mode=orc.CULLED, n_threads=0)
+    S.close()
+    idx = g["index"]
+    assert np.array_equal(face[idx], g["face"].astype(np.int32))
+    assert np.array_equal(col[idx].view(np.uint64), g["colour_bits"])
+    assert np.array_equal(rgb[idx], g["rgb"])
+    assert (g["face"] >= 0).sum() > 2000
+
+
+def test_golden_generator_loader_agrees_with_the_oracle_loader(example_scene):
+    """The golden generator reads scene.json / suzanne.obj / suzanne.mtl with its own code; the per-face geometry it feeds
+    its renderer must be the geometry the oracle's loader produces (different indexing: it does not deduplicate)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_pyref", os.path.join(GOLDEN, "make_golden_pyref.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    sc = mg.read_obj_scene(os.path.join(GOLDEN, "example", "scene.json"))
+    m, mo = sc["meshes"][0], example_scene["meshes"][0]
+    v, n, f = np.array(m["verts"]), np.array(m["normals"]), np.array(m["faces"])
+    vo, no, fo = np.asarray(mo["verts"]).reshape(-1, 3), np.asarray(mo["normals"]).reshape(-1, 3), np.asarray(mo["faces"]).reshape(-1, 7)
+    assert f.shape == fo.shape == (968, 7)
+    assert np.array_equal(v[f[:, 0:3]].view(np.uint64), vo[fo[:, 0:3]].view(np.uint64))
+    assert np.array_equal(n[f[:, 3:6]].view(np.uint64), no[fo[:, 3:6]].view(np.uint64))
+    assert np.array_equal(np.array(m["materials"])[f[:, 6]].view(np.uint64), np.asarray(mo["materials"]).reshape(-1, 10)[fo[:, 6]].view(np.uint64))
+    assert np.array_equal(np.array(sc["camera"]).view(np.uint64), np.asarray(example_scene["camera"], dtype=np.float64).view(np.uint64))
+    assert np.array_equal(np.array(sc["lights"]).view(np.uint64), np.asarray(example_scene["lights"], dtype=np.float64).reshape(-1, 6).view(np.uint64))
+    assert mg.go_tan(sc["camera"][12] / 2.0) == orc.go_tan(sc["camera"][12] / 2.0)
 
 
 @pytest.mark.parametrize("kw", [dict(n_tris=60, seed=3), dict(n_tris=200, seed=4, with_normals=True),
