@@ -8,8 +8,8 @@ The directory name carries a hyphen (it mirrors the reference's repository name)
 from . import _lib
 from ._lib import (FP32_FAST, FP64_EXACT, LANE, FLAG_BRUTE_FORCE, FLAG_COUNT, FLAG_PERSISTENT, FLAG_SIMPLE, FLAG_FUSED, FLAG_PIPELINE, FLAG_NO_CULL, LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR,
                    QUANT_RGB255, QUANT_RGBA16_SHR8, RtError)
-from .gpu_scene import DeviceBuffer, FrameState, GpuScene, HostSharedBuffer, make_camera, make_scene_desc, tiles_per_rank
+from .gpu_scene import DeviceBuffer, FrameState, GpuGroup, GpuScene, HostSharedBuffer, make_camera, make_scene_desc, tiles_per_rank
 
-__all__ = ["GpuScene", "DeviceBuffer", "HostSharedBuffer", "FrameState", "RtError", "FP32_FAST", "FP64_EXACT", "LANE", "FLAG_BRUTE_FORCE", "FLAG_COUNT", "FLAG_SIMPLE", "FLAG_PERSISTENT", "FLAG_FUSED", "FLAG_PIPELINE", "FLAG_NO_CULL",
+__all__ = ["GpuScene", "GpuGroup", "DeviceBuffer", "HostSharedBuffer", "FrameState", "RtError", "FP32_FAST", "FP64_EXACT", "LANE", "FLAG_BRUTE_FORCE", "FLAG_COUNT", "FLAG_SIMPLE", "FLAG_PERSISTENT", "FLAG_FUSED", "FLAG_PIPELINE", "FLAG_NO_CULL",
            "LAYOUT_COLMAJOR", "LAYOUT_ROWMAJOR", "QUANT_RGB255", "QUANT_RGBA16_SHR8", "make_camera", "make_scene_desc",
            "tiles_per_rank", "_lib"]

@@ -34,6 +34,7 @@ ABI_SYMBOLS = (
     "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_render_stripes_host", "rt_frame_complete_device", "rt_frame_release_device",
     "rt_trace_results_max_bytes", "rt_encode_trace_results_device", "rt_bulk_trace_encoded", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
     "rt_ipc_close", "rt_measure_fma_peak", "rt_get_stats", "rt_get_bvh_info", "rt_synchronize", "rt_cancel", "rt_host_alloc", "rt_host_free", "rt_host_register", "rt_host_unregister",
+    "rt_group_create", "rt_group_destroy", "rt_group_device_count", "rt_group_scene", "rt_group_last_error", "rt_group_bulk_trace",
 )
 
 
@@ -171,5 +172,17 @@ def load():
     L.rt_host_unregister.argtypes = [C.c_int, vp]
     L.rt_host_free.restype = None
     L.rt_host_free.argtypes = [vp]
+    L.rt_group_create.restype = C.c_int
+    L.rt_group_create.argtypes = [C.POINTER(SceneDesc), vp, u32, C.POINTER(vp)]
+    L.rt_group_destroy.restype = None
+    L.rt_group_destroy.argtypes = [vp]
+    L.rt_group_device_count.restype = C.c_int
+    L.rt_group_device_count.argtypes = [vp]
+    L.rt_group_scene.restype = vp
+    L.rt_group_scene.argtypes = [vp, u32]
+    L.rt_group_last_error.restype = C.c_char_p
+    L.rt_group_last_error.argtypes = [vp]
+    L.rt_group_bulk_trace.restype = C.c_int
+    L.rt_group_bulk_trace.argtypes = [vp, C.POINTER(Camera), vp, u32, vp, u32, u32, u32, u32, u32, u32, vp, u32]
     _LIB = L
     return L

@@ -232,7 +232,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
         CK(cub::DeviceRadixSort::SortPairs(d_tmp, tb, kb, vb, (int)n, 0, 63, st));
         sorted_keys = kb.Current(); sorted_vals = vb.Current();
     }
-    if (want32) CK(cudaMalloc(&m.tri32, sizeof(rt_f4) * 3 * (size_t)n));
+    if (want32) CK(cudaMalloc(&m.tri32, sizeof(rt_f4) * RT_TRI32_F4 * (size_t)n));
     if (want64) CK(cudaMalloc(&m.tri64, sizeof(double) * 10 * (size_t)n));
     k_gather_tris<<<nb, TB, 0, st>>>(m.fverts, sorted_vals, n, m.tri32, m.tri64);
     CK(cudaGetLastError());

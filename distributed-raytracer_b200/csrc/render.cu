@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) k_primary_exact(FrameParams fp, SceneView
     TraceExact tr; tr.face = -1; tr.obj = -1;
     if (ray < nrays && !frame_cancelled(counters, fp)) {
         PixMap pm = map_ray(ray, fp, false);
-        if (pm.valid && !(fp.tile_w > 0 && !brute && block_culled(fp, pm.i & ~7, pm.j & ~3))) {
+        if (pm.valid && !(fp.tile_w > 0 && !brute && block_culled(fp, pm.i - (int)(ray & 7u), pm.j - (int)((ray >> 3) & 3u)))) {
             dv d = primary_dir_exact(pm.i, pm.j, fp);
             hit = trace_exact(sc, fp, dv_ld(fp.cam_pos), d, brute, tr, COUNT ? &c : nullptr);
         }
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) k_primary_fast_simple(FrameParams fp, Sce
     TraceFast tr; tr.face = -1; tr.obj = -1; tr.t = 0.f;
     if (ray < nrays && !frame_cancelled(counters, fp)) {
         PixMap pm = map_ray(ray, fp, false);
-        if (pm.valid && !(fp.tile_w > 0 && block_culled(fp, pm.i & ~7, pm.j & ~3))) {
+        if (pm.valid && !(fp.tile_w > 0 && block_culled(fp, pm.i - (int)(ray & 7u), pm.j - (int)((ray >> 3) & 3u)))) {
             float dx, dy, dz;
             primary_dir32(pm.i, pm.j, fp, dx, dy, dz);
             dv d = dv_make((double)dx, (double)dy, (double)dz);
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(128, MINB) k_frame_fused(FrameParams fp, Scene
     if (warp_cancelled(counters, fp)) return;
     Counters c0, c1; c0.nodes = c0.tris = c1.nodes = c1.tris = 0;
     const PixMap pm = map_ray(ray, fp, rowmajor);
-    if (fp.tile_w > 0 && block_culled(fp, pm.i & ~7, pm.j & ~3)) return;      // warp-uniform: a warp is one 8x4 block
+    if (fp.tile_w > 0 && block_culled(fp, pm.i - (int)(ray & 7u), pm.j - (int)((ray >> 3) & 3u))) return;      // warp-uniform: a warp is one 8x4 block
     bool hit = false;
     TraceFast tr; tr.face = -1; tr.obj = -1; tr.t = 0.f;
     if (pm.valid) {
@@ -447,7 +447,7 @@ __device__ __forceinline__ void push_segments(const uint8_t *s_tile, uint8_t *ou
 __device__ __forceinline__ void push_one_tile(const FrameParams &fp, bool rowmajor, const uint8_t *__restrict__ tiles,
                                               uint8_t *__restrict__ out, uint8_t *s_tile, int lt) {
     const uint32_t t = (uint32_t)lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
-    const int tw = fp.tile_w, th = fp.tile_h, W = fp.W, H = fp.H;
+    const int tw = fp.tile_w, th = fp.tile_h, W = fp.w, H = fp.h;      // the framebuffer is the region's (full frame: the screen)
     uint32_t TX, TY;
     tile_pos(t, (uint32_t)fp.tiles_x, TX, TY);
     const int tx0 = (int)TX * tw, ty0 = (int)TY * th;
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(128) k_push_tiles(FrameParams fp, bool rowmajo
 __global__ void __launch_bounds__(128) k_clear_tiles(FrameParams fp, bool rowmajor, uint8_t *__restrict__ out) {
     const int lt = blockIdx.x;
     const uint32_t t = (uint32_t)lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
-    const int tw = fp.tile_w, th = fp.tile_h, W = fp.W, H = fp.H;
+    const int tw = fp.tile_w, th = fp.tile_h, W = fp.w, H = fp.h;      // region-relative, like map_ray
     uint32_t TX, TY;
     tile_pos(t, (uint32_t)fp.tiles_x, TX, TY);
     const int tx0 = (int)TX * tw, ty0 = (int)TY * th;

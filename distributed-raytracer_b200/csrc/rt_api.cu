@@ -409,22 +409,28 @@ int region_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint3
     return RT_OK;
 }
 
-int tile_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank,
-                uint32_t n_ranks, bool need_smem_fit, uint32_t flags) {
+// tile mode over the region (x, y, w, h) of the W x H screen: the tiles are cut from the region
+int tile_params_region(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h,
+                       uint32_t tile_w, uint32_t tile_h, uint32_t rank, uint32_t n_ranks, bool need_smem_fit, uint32_t flags) {
     if (W == 0 || H == 0 || W > 65536 || H > 65536) return fail(s, RT_ERR_INVALID, "bad screen size");
+    if (w == 0 || h == 0 || (uint64_t)x + w > W || (uint64_t)y + h > H) return fail(s, RT_ERR_INVALID, "empty region or region exceeds the screen");
     if (tile_w == 0 || tile_h == 0 || tile_w % 8 || tile_h % 4) return fail(s, RT_ERR_INVALID, "tile size must be a multiple of 8x4");
     if (need_smem_fit && (size_t)tile_w * tile_h * 3 > 48 * 1024) return fail(s, RT_ERR_INVALID, "tile larger than 16384 pixels");
     if (n_ranks == 0 || rank >= n_ranks) return fail(s, RT_ERR_INVALID, "bad rank / n_ranks");
     fp = L.frame;
-    fp.W = (int)W; fp.H = (int)H; fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
+    fp.W = (int)W; fp.H = (int)H; fp.x = (int)x; fp.y = (int)y; fp.w = (int)w; fp.h = (int)h;
     fp.tile_w = (int)tile_w; fp.tile_h = (int)tile_h;
-    fp.tiles_x = (int)((W + tile_w - 1) / tile_w);
-    const uint32_t n_tiles = (uint32_t)fp.tiles_x * ((H + tile_h - 1) / tile_h);
+    fp.tiles_x = (int)((w + tile_w - 1) / tile_w);
+    const uint32_t n_tiles = (uint32_t)fp.tiles_x * ((h + tile_h - 1) / tile_h);
     fp.rank = (int)rank; fp.n_ranks = (int)n_ranks;
     fp.n_local_tiles = (int)((n_tiles > rank) ? (n_tiles - rank + n_ranks - 1) / n_ranks : 0);
     fp.tile_final = 0;
     cull_params(s, L, fp, flags);
     return RT_OK;
+}
+int tile_params(rt_scene *s, const Lane &L, FrameParams &fp, uint32_t W, uint32_t H, uint32_t tile_w, uint32_t tile_h, uint32_t rank,
+                uint32_t n_ranks, bool need_smem_fit, uint32_t flags) {
+    return tile_params_region(s, L, fp, W, H, 0, 0, W, H, tile_w, tile_h, rank, n_ranks, need_smem_fit, flags);
 }
 
 // the device API on a lane other than 0 inherits lane 0's frame state until it is given its own (rt_frame_set_lane)
@@ -438,6 +444,55 @@ void inherit_frame(rt_scene *s, Lane &L, int idx) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+int rt_internal_fail(rt_scene *s, int code, const std::string &msg) { return fail(s, code, msg); }
+
+// The stripes of rank `rank` of the REGION (x, y, w, h): rendered in place into d_local_framebuffer (w*h*3, the region's final layout), then
+// moved with ONE strided copy-engine transfer into h_framebuffer (the same layout in host memory).  rt_render_stripes_host is the
+// full-screen case; rt_group_bulk_trace (rt_group.cu) drives one such call per GPU of the box for one BulkTrace order.
+int rt_internal_render_stripes(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
+                               uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t stripe, uint32_t rank, uint32_t n_ranks,
+                               void *d_local_framebuffer, void *h_framebuffer, void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags) {
+    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
+    if (!d_local_framebuffer || !h_framebuffer || !stream) return fail(s, RT_ERR_INVALID, "rt_render_stripes_host: NULL buffer or stream");
+    if (n_ranks > 32 && d_sync_slot) return fail(s, RT_ERR_INVALID, "rt_render_stripes_host: the hand-off record holds 32 ranks");
+    const bool rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0;
+    if (stripe == 0 || stripe % (rowmajor ? 4u : 8u)) return fail(s, RT_ERR_INVALID, "stripe must be a multiple of 8 columns (4 rows)");
+    int idx = 0;
+    Lane *Lp = device_lane(s, flags, &idx);
+    if (!Lp) return RT_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(Lp->mu);
+    int rc = frame_set_lane(s, *Lp, cam, lights, n_lights, obj_pos);
+    if (rc != RT_OK) return rc;
+    const uint32_t tile_w = rowmajor ? ((w + 7u) / 8u) * 8u : stripe, tile_h = rowmajor ? stripe : ((h + 3u) / 4u) * 4u;
+    FrameParams fp;
+    rc = tile_params_region(s, *Lp, fp, W, H, x, y, w, h, tile_w, tile_h, rank, n_ranks, false, flags);
+    if (rc != RT_OK) return rc;
+    fp.tile_final = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    RenderOut o; o.d_rgb = (uint8_t *)d_local_framebuffer; o.ext_stream = st; o.async = true;
+    s->last_lane.store(idx);
+    rc = render_lane(s, *Lp, fp, flags, (size_t)w * h, o);
+    if (rc != RT_OK) return rc;
+    if (d_sync_slot) CU(s, rt_launch_wait_consumed((uint32_t *)d_sync_slot, seq, rank, s->sync_timeout_ms, st));
+    // stripe t = rank + k*n_ranks starts at byte t*run; all but a cut last stripe are `run` bytes long
+    const size_t extent = rowmajor ? h : w, other = rowmajor ? w : h;
+    const size_t run = (size_t)stripe * other * 3;
+    const size_t n_stripes = (extent + stripe - 1) / stripe, n_full = extent / stripe;
+    const size_t mine_full = n_full > rank ? (n_full - rank + n_ranks - 1) / n_ranks : 0;
+    const uint8_t *src = (const uint8_t *)d_local_framebuffer;
+    uint8_t *dst = (uint8_t *)h_framebuffer;
+    if (mine_full)
+        CU(s, cudaMemcpy2DAsync(dst + (size_t)rank * run, (size_t)n_ranks * run, src + (size_t)rank * run, (size_t)n_ranks * run, run, mine_full,
+                                cudaMemcpyDeviceToHost, st));
+    if (n_stripes > n_full && (n_stripes - 1) % n_ranks == rank) {
+        const size_t off = (n_stripes - 1) * run, bytes = (extent - n_full * stripe) * other * 3;
+        CU(s, cudaMemcpyAsync(dst + off, src + off, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (d_sync_slot) CU(s, rt_launch_signal_arrive((uint32_t *)d_sync_slot, seq, rank, st));
+    return RT_OK;
+}
+
+
 extern "C" {
 
 int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
@@ -476,7 +531,7 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     s->device = desc->device;
     s->precision = desc->precision;
     s->max_leaf = env_int("RT_B200_MAX_LEAF", 4);
-    s->shade_minb = env_int("RT_B200_SHADE_MINB", 8);
+    s->shade_minb = env_int("RT_B200_SHADE_MINB", 9);   // fused kernel: 9 CTAs/SM = 56 registers (measured best); K4 of the pipeline caps at 8
     s->primary_persistent = env_int("RT_B200_PERSISTENT", 0) != 0;
     s->split_shade = env_int("RT_B200_SPLIT_SHADE", 0) != 0;
     s->shade32 = env_int("RT_B200_SHADE32", 0) != 0 && desc->precision == RT_FP32_FAST;
@@ -844,44 +899,8 @@ int rt_render_stripes_host(rt_scene *s, const rt_camera *cam, const rt_light *li
                            uint32_t H, uint32_t stripe, uint32_t rank, uint32_t n_ranks, void *d_local_framebuffer, void *h_framebuffer,
                            void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags) {
     API_ENTER();
-    if (!s) return fail(nullptr, RT_ERR_INVALID, "NULL scene");
-    if (!d_local_framebuffer || !h_framebuffer || !stream) return fail(s, RT_ERR_INVALID, "rt_render_stripes_host: NULL buffer or stream");
-    if (n_ranks > 32 && d_sync_slot) return fail(s, RT_ERR_INVALID, "rt_render_stripes_host: the hand-off record holds 32 ranks");
-    const bool rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0;
-    if (stripe == 0 || stripe % (rowmajor ? 4u : 8u)) return fail(s, RT_ERR_INVALID, "stripe must be a multiple of 8 columns (4 rows)");
-    int idx = 0;
-    Lane *Lp = device_lane(s, flags, &idx);
-    if (!Lp) return RT_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(Lp->mu);
-    int rc = frame_set_lane(s, *Lp, cam, lights, n_lights, obj_pos);
-    if (rc != RT_OK) return rc;
-    const uint32_t tile_w = rowmajor ? ((W + 7u) / 8u) * 8u : stripe, tile_h = rowmajor ? stripe : ((H + 3u) / 4u) * 4u;
-    FrameParams fp;
-    rc = tile_params(s, *Lp, fp, W, H, tile_w, tile_h, rank, n_ranks, false, flags);
-    if (rc != RT_OK) return rc;
-    fp.tile_final = 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    RenderOut o; o.d_rgb = (uint8_t *)d_local_framebuffer; o.ext_stream = st; o.async = true;
-    s->last_lane.store(idx);
-    rc = render_lane(s, *Lp, fp, flags, (size_t)W * H, o);
-    if (rc != RT_OK) return rc;
-    if (d_sync_slot) CU(s, rt_launch_wait_consumed((uint32_t *)d_sync_slot, seq, rank, s->sync_timeout_ms, st));
-    // stripe t = rank + k*n_ranks starts at byte t*run; all but a cut last stripe are `run` bytes long
-    const size_t extent = rowmajor ? H : W, other = rowmajor ? W : H;
-    const size_t run = (size_t)stripe * other * 3;
-    const size_t n_stripes = (extent + stripe - 1) / stripe, n_full = extent / stripe;
-    const size_t mine_full = n_full > rank ? (n_full - rank + n_ranks - 1) / n_ranks : 0;
-    const uint8_t *src = (const uint8_t *)d_local_framebuffer;
-    uint8_t *dst = (uint8_t *)h_framebuffer;
-    if (mine_full)
-        CU(s, cudaMemcpy2DAsync(dst + (size_t)rank * run, (size_t)n_ranks * run, src + (size_t)rank * run, (size_t)n_ranks * run, run, mine_full,
-                                cudaMemcpyDeviceToHost, st));
-    if (n_stripes > n_full && (n_stripes - 1) % n_ranks == rank) {
-        const size_t off = (n_stripes - 1) * run, bytes = (extent - n_full * stripe) * other * 3;
-        CU(s, cudaMemcpyAsync(dst + off, src + off, bytes, cudaMemcpyDeviceToHost, st));
-    }
-    if (d_sync_slot) CU(s, rt_launch_signal_arrive((uint32_t *)d_sync_slot, seq, rank, st));
-    return RT_OK;
+    return rt_internal_render_stripes(s, cam, lights, n_lights, obj_pos, W, H, 0, 0, W, H, stripe, rank, n_ranks, d_local_framebuffer, h_framebuffer,
+                                      d_sync_slot, seq, stream, flags);
 }
 
 // gathering rank: frame `seq` of the slot is complete when all ranks have pushed it (waits ON THE DEVICE, in stream order)

@@ -305,7 +305,9 @@ RT_HD void gather_tri_thread(uint32_t i, const double *fverts, const uint32_t *v
         a.x = (float)v[0]; a.y = (float)v[1]; a.z = (float)v[2]; a.w = rt_int_as_float((int)f);
         b.x = (float)v[3]; b.y = (float)v[4]; b.z = (float)v[5]; b.w = 0.0f;
         c.x = (float)v[6]; c.y = (float)v[7]; c.z = (float)v[8]; c.w = 0.0f;
-        tri32[3 * (size_t)i] = a; tri32[3 * (size_t)i + 1] = b; tri32[3 * (size_t)i + 2] = c;
+        rt_f4 *q = tri32 + RT_TRI32_F4 * (size_t)i;
+        q[0] = a; q[1] = b; q[2] = c;
+        if (RT_TRI32_F4 > 3) { rt_f4 z; z.x = z.y = z.z = z.w = 0.0f; q[3] = z; }
     }
     if (tri64) {
         double *q = tri64 + 10 * (size_t)i;

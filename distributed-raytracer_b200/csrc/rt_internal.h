@@ -82,6 +82,12 @@ cudaError_t rt_launch_frame_release(uint32_t *d_slot, uint32_t seq, cudaStream_t
 cudaError_t rt_launch_wait_consumed(uint32_t *d_slot, uint32_t seq, uint32_t rank, uint32_t timeout_ms, cudaStream_t st);
 cudaError_t rt_launch_signal_arrive(uint32_t *d_slot, uint32_t seq, uint32_t rank, cudaStream_t st);
 
+// rt_api.cu : region form of rt_render_stripes_host (used by the multi-GPU group handle, rt_group.cu)
+int rt_internal_render_stripes(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
+                               uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t stripe, uint32_t rank, uint32_t n_ranks,
+                               void *d_local_framebuffer, void *h_framebuffer, void *d_sync_slot, uint32_t seq, void *stream, uint32_t flags);
+int rt_internal_fail(rt_scene *s, int code, const std::string &msg);
+
 // wire.cu : comms.TraceResults protobuf encoder
 size_t rt_wire_scratch_bytes(uint64_t n_pixels);
 cudaError_t rt_launch_wire_encode(const uint8_t *d_rgb, uint64_t n_pixels, uint8_t *d_out, uint64_t capacity, uint64_t *d_len,

@@ -46,6 +46,17 @@ RT_HD rt_f4 ld_f4(const rt_f4 *p) {
     return *p;
 #endif
 }
+// one 32-byte vector through the read-only path: LDG.E.256 on sm_100a (needs 32-byte alignment)
+RT_HD rt_f8 ld_f8(const rt_f4 *p) {
+#if defined(__CUDA_ARCH__) && RT_LD256
+    rt_f8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+#else
+    rt_f8 r; r.a = ld_f4(p); r.b = ld_f4(p + 1); return r;
+#endif
+}
 RT_HD rt_i4 ld_i4(const rt_i4 *p) {
 #if defined(__CUDA_ARCH__)
     int4 v = __ldg(reinterpret_cast<const int4 *>(p));
@@ -69,9 +80,10 @@ RT_HD void ld_node(const RtNode *n, NodeRegs &r) {
     const rt_f4 *q = reinterpret_cast<const rt_f4 *>(n);
     float *dst = r.lox;                       // the six box arrays are contiguous in both structs
 #pragma unroll
-    for (int k = 0; k < 6 * RT_W / 4; k++) {
-        rt_f4 v = ld_f4(q + k);
-        dst[4 * k] = v.x; dst[4 * k + 1] = v.y; dst[4 * k + 2] = v.z; dst[4 * k + 3] = v.w;
+    for (int k = 0; k < 6 * RT_W / 4; k += 2) {
+        rt_f8 v = ld_f8(q + k);
+        dst[4 * k] = v.a.x; dst[4 * k + 1] = v.a.y; dst[4 * k + 2] = v.a.z; dst[4 * k + 3] = v.a.w;
+        dst[4 * k + 4] = v.b.x; dst[4 * k + 5] = v.b.y; dst[4 * k + 6] = v.b.z; dst[4 * k + 7] = v.b.w;
     }
     const rt_i4 *qi = reinterpret_cast<const rt_i4 *>(n->ref);
 #pragma unroll
@@ -255,7 +267,23 @@ RT_HD bool tri_test32(rt_f4 v0, rt_f4 v1, rt_f4 v2, const RayF &r, float &t, flo
 #endif
 struct NodeHits { float t[RT_W]; int ref[RT_W]; bool hit[RT_W]; };
 RT_HD void node_test32(const RtNode *nd, const RayF &r, float tbest, NodeHits &h) {
-#if RT_OCTANT && RT_W == 4
+#if RT_LD256 && RT_W == 4
+    // lo[4] and hi[4] of an axis are one 32-byte vector: 3 x LDG.256 + the refs = 4 load instructions per visit
+    const rt_f4 *q = reinterpret_cast<const rt_f4 *>(nd);
+    const rt_f8 bx = ld_f8(q), by = ld_f8(q + 2), bz = ld_f8(q + 4);
+    const rt_i4 rf = ld_i4(reinterpret_cast<const rt_i4 *>(q + 6));
+#define RT_CHILD(k, c)                                                                                                     \
+    {                                                                                                                      \
+        const float x0 = fmaf(bx.a.c, r.ix, -r.ax), x1 = fmaf(bx.b.c, r.ix, -r.ax);                                        \
+        const float y0 = fmaf(by.a.c, r.iy, -r.ay), y1 = fmaf(by.b.c, r.iy, -r.ay);                                        \
+        const float z0 = fmaf(bz.a.c, r.iz, -r.az), z1 = fmaf(bz.b.c, r.iz, -r.az);                                        \
+        const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));                           \
+        const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tbest));                          \
+        h.t[k] = tn; h.ref[k] = rf.c; h.hit[k] = tn <= tf && rf.c != RT_EMPTY;                                             \
+    }
+    RT_CHILD(0, x) RT_CHILD(1, y) RT_CHILD(2, z) RT_CHILD(3, w)
+#undef RT_CHILD
+#elif RT_OCTANT && RT_W == 4
     const rt_f4 *q = reinterpret_cast<const rt_f4 *>(nd);
     const int sx = r.ix < 0.0f, sy = r.iy < 0.0f, sz = r.iz < 0.0f;
     const rt_f4 nx = ld_f4(q + sx), fx = ld_f4(q + (sx ^ 1));
@@ -316,8 +344,13 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
             uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
             RT_COUNT(cnt, tris, count);
             for (uint32_t k = first; k < first + count; k++) {
-                const rt_f4 *p = m.tri32 + 3 * (size_t)k;
+                const rt_f4 *p = m.tri32 + RT_TRI32_F4 * (size_t)k;
+#if RT_LD256
+                const rt_f8 t01 = ld_f8(p), t2x = ld_f8(p + 2);
+                const rt_f4 v0 = t01.a, v1 = t01.b, v2 = t2x.a;
+#else
                 rt_f4 v0 = ld_f4(p), v1 = ld_f4(p + 1), v2 = ld_f4(p + 2);
+#endif
                 float t, u, v;
                 if (tri_test32(v0, v1, v2, r, t, u, v)) {
 #if defined(__CUDA_ARCH__)

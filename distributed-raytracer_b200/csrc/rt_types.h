@@ -25,7 +25,15 @@
 #define RT_MAX_LEAF 16
 #define RT_EMPTY 0x7fffffff       // unused child slot / "no node" sentinel (never a valid index)
 #define RT_NODE_BYTES (28 * RT_W) // bytes fetched per node visit: 6 box arrays + refs, RT_W x 4 B each
-#define RT_TRI32_BYTES 48
+// 256-bit loads (sm_100a: LDG.E.256).  The traversal is bound by the L1 data pipe (ncu: l1tex wavefronts 68 % of peak, the
+// highest unit, while issue slots are half empty -- profiles/r02_ncu_c3_summary.txt), and a divergent warp pays one wavefront per
+// lane and LOAD INSTRUCTION whatever its width: fetching a node with 3 x 32 B + 16 B instead of 7 x 16 B, and a triangle with
+// 2 x 32 B (64-byte records) instead of 3 x 16 B, cuts the wavefronts of a ray by ~40 %.
+#ifndef RT_LD256
+#define RT_LD256 1
+#endif
+#define RT_TRI32_F4 (RT_LD256 ? 4 : 3)          // float4 slots per FP32_FAST triangle record
+#define RT_TRI32_BYTES (16 * RT_TRI32_F4)
 #define RT_TRI64_BYTES 80
 #define RT_SHADOW_BIAS 0.0001     // tracer.go:64
 // words of a lane's counter block (unsigned int[8]): [0] next ray (persistent K2), [1] hit count, [2] next hit (K4), [3] spare
@@ -41,13 +49,14 @@
 #endif
 
 struct alignas(16) rt_f4 { float x, y, z, w; };
+struct alignas(32) rt_f8 { rt_f4 a, b; };
 struct alignas(16) rt_i4 { int x, y, z, w; };
 
 // One wide-BVH node: the boxes of its RT_W children in SoA form (each array is RT_W/4 16-byte vectors, fetched with
 // LDG.128 through the read-only path) + the child refs.  ref >= 0: node index, ref < 0: leaf (see below),
 // ref == RT_EMPTY: unused slot.  A ray visits a node once and tests all children with independent instructions, so the
 // dependent chain per ray is the tree depth (log_W), ~2.2x shorter than with a binary tree for RT_W = 4.
-struct alignas(16) RtNode {
+struct alignas(32) RtNode {
     float lox[RT_W], hix[RT_W], loy[RT_W], hiy[RT_W], loz[RT_W], hiz[RT_W];
     int ref[RT_W];
     int pad[RT_W];
@@ -59,7 +68,7 @@ RT_HD uint32_t rt_leaf_count(int ref) { return (((uint32_t)~ref) >> RT_LEAF_FIRS
 
 struct MeshView {
     const RtNode  *nodes;
-    const rt_f4   *tri32;      // 3 per triangle: (P1,faceidx) (P2,-) (P3,-)
+    const rt_f4   *tri32;      // RT_TRI32_F4 per triangle: (P1,faceidx) (P2,-) (P3,-) [(pad)]
     const double  *tri64;      // 10 per triangle: P1 P2 P3, [9] = face index (as double, exact)
     const double  *fverts;     // 9 per face
     const double  *fnormals;   // 9 per face or nullptr
@@ -140,7 +149,8 @@ RT_HD uint32_t ray_count(const FrameParams &fp) {
     return nbx * nby * 32u;
 }
 
-// tile mode: can the 8x4 block whose first pixel is (i0, j0) be skipped?
+// tile mode: can the 8x4 block whose first pixel is (i0, j0) be skipped?  (i0, j0) = pixel of the ray minus its lane offsets
+// (lane & 7, lane >> 3): blocks are aligned to the REGION origin, not to the screen
 RT_HD bool block_culled(const FrameParams &fp, int i0, int j0) {
     return fp.cull_on && (i0 + 8 <= fp.cull_i0 || i0 >= fp.cull_i1 || j0 + 4 <= fp.cull_j0 || j0 >= fp.cull_j1);
 }
@@ -150,6 +160,7 @@ RT_HD PixMap map_ray(uint32_t r, const FrameParams &fp, bool rowmajor) {
     uint32_t lane = r & 31u, blk = r >> 5;
     int lx = (int)(lane & 7u), ly = (int)(lane >> 3);
     if (fp.tile_w > 0) {
+        // tiles are cut from the REGION (x, y, w, h); a full-screen frame is the region (0, 0, W, H)
         uint32_t bpt = (uint32_t)(fp.tile_w * fp.tile_h) / 32u;       // blocks per tile
         uint32_t lt = blk / bpt, b = blk % bpt;
         uint32_t bx = b % (uint32_t)(fp.tile_w / 8), by = b / (uint32_t)(fp.tile_w / 8);
@@ -157,12 +168,13 @@ RT_HD PixMap map_ray(uint32_t r, const FrameParams &fp, bool rowmajor) {
         uint32_t t = lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;
         uint32_t TX, TY;
         tile_pos(t, (uint32_t)fp.tiles_x, TX, TY);
-        p.i = (int)TX * fp.tile_w + tx;
-        p.j = (int)TY * fp.tile_h + ty;
+        const int ri = (int)TX * fp.tile_w + tx, rj = (int)TY * fp.tile_h + ty;
+        p.i = fp.x + ri;
+        p.j = fp.y + rj;
         p.out = lt * (uint32_t)(fp.tile_w * fp.tile_h) + (uint32_t)(ty * fp.tile_w + tx);
-        p.valid = p.i < fp.W && p.j < fp.H;
+        p.valid = ri < fp.w && rj < fp.h;
         if (fp.tile_final && p.valid)
-            p.out = rowmajor ? (uint32_t)p.j * (uint32_t)fp.W + (uint32_t)p.i : (uint32_t)p.i * (uint32_t)fp.H + (uint32_t)p.j;
+            p.out = rowmajor ? (uint32_t)rj * (uint32_t)fp.w + (uint32_t)ri : (uint32_t)ri * (uint32_t)fp.h + (uint32_t)rj;
         return p;
     }
     uint32_t nbx = fp.rnbx > 0 ? (uint32_t)fp.rnbx : (uint32_t)(fp.w + 7) / 8;

@@ -223,6 +223,50 @@ class GpuScene:
             pass
 
 
+class GpuGroup:
+    """One worker process, several GPUs (rt_group_*): the scene is registered on every device and ONE bulk_trace call is
+    answered by all of them (stripes of the region dealt round-robin, every GPU copies its stripes into the reply over its own
+    PCIe link).  What master/pool sees is still one worker answering one BulkTrace (pool.go:148-197); no torch.distributed,
+    no second process.  devices=None: every GPU of the box."""
+
+    def __init__(self, scene, devices=None, precision=_lib.FP32_FAST):
+        self._L = _lib.load()
+        desc, keep = make_scene_desc(scene, 0, precision)
+        h = C.c_void_p()
+        devs = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        rc = self._L.rt_group_create(C.byref(desc), devs.ctypes.data if devs is not None else None, 0 if devs is None else devs.size, C.byref(h))
+        if rc != 0:
+            raise _lib.RtError(rc, (self._L.rt_group_last_error(None) or b"").decode())
+        self.h = h
+        self.n_objects = desc.n_objects
+        self.n_devices = self._L.rt_group_device_count(self.h)
+
+    def bulk_trace(self, cam13, lights, W, H, x, y, w, h, obj_pos=None, flags=0, out=None, tan_half_fov=float("nan")):
+        cam = make_camera(cam13, tan_half_fov)
+        lights = _c(lights, np.float64).reshape(-1, 6)
+        op = None if obj_pos is None else _c(obj_pos, np.float64)
+        if op is not None and op.size != 3 * self.n_objects:
+            raise ValueError("obj_pos holds %d values, the scene has %d objects (3 each)" % (op.size, self.n_objects))
+        if out is None:
+            out = np.empty((w * h, 3), dtype=np.uint8)
+        rc = self._L.rt_group_bulk_trace(self.h, C.byref(cam), lights.ctypes.data if lights.size else None, lights.shape[0],
+                                         op.ctypes.data if op is not None else None, W, H, x, y, w, h, out.ctypes.data, flags)
+        if rc != 0:
+            raise _lib.RtError(rc, (self._L.rt_group_last_error(self.h) or b"").decode())
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.rt_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def tiles_per_rank(W, H, tile_w, tile_h, n_ranks):
     n_tiles = ((W + tile_w - 1) // tile_w) * ((H + tile_h - 1) // tile_h)
     return (n_tiles + n_ranks - 1) // n_ranks

@@ -250,6 +250,28 @@ int rt_ipc_close(int device, void *p);
 int rt_untile_device(rt_scene *scene, uint32_t screen_w, uint32_t screen_h, uint32_t tile_w, uint32_t tile_h,
                      uint32_t n_ranks, const void *d_all_tiles, void *d_out_rgb, void *stream, uint32_t flags);
 
+/* ---- one worker process, several GPUs (master/pool dispatches ONE BulkTrace per worker: pool.go:148-197 ->
+ * worker/distributed/main.go:46-91) -----------------------------------------------------------------------------------------
+ * rt_group_create registers the scene on every listed device (devices == NULL or n_devices == 0: every GPU of the box); it is
+ * register() (distributed/main.go:101-129) for a worker that owns the whole box.  rt_group_bulk_trace answers ONE order with all
+ * of them: the region is cut into stripes that are contiguous in the reply's layout (8 pixel columns x region height in
+ * BulkTrace's layout, 4 pixel rows x region width with RT_LAYOUT_ROWMAJOR), stripe t is rendered by device t mod N, and every
+ * device moves its stripes with one strided copy over its own PCIe link into out_rgb (directly if out_rgb is pinned memory from
+ * rt_host_alloc, else through a pinned staging frame).  No collective, no torch.distributed, no second process: the calling
+ * thread enqueues N command sequences and waits for N streams.  Same arguments, result bytes and error behaviour as
+ * rt_bulk_trace on one device (the frame is byte-identical); thread-safe and concurrent (RT_B200_GROUP_LANES calls in flight,
+ * default 8).  A device may be listed more than once (it then holds that many copies of the scene and renders that many
+ * shares of the stripes).  The per-device scene handles stay owned by the group (rt_group_scene: introspection only). */
+typedef struct rt_group rt_group;
+int  rt_group_create(const rt_scene_desc *desc /* .device ignored */, const int32_t *devices, uint32_t n_devices, rt_group **out);
+void rt_group_destroy(rt_group *group);
+int  rt_group_device_count(const rt_group *group);
+rt_scene *rt_group_scene(rt_group *group, uint32_t k);
+const char *rt_group_last_error(const rt_group *group);
+int  rt_group_bulk_trace(rt_group *group, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos,
+                         uint32_t screen_w, uint32_t screen_h, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb,
+                         uint32_t flags);
+
 /* ---- result wire format --------------------------------------------------------
  * The reference worker returns a region as the protobuf message comms.TraceResults
  * (shared/comms/comms.proto:34-41: repeated Colour{uint32 r=1, g=2, b=3}), one heap-allocated Colour

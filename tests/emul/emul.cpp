@@ -78,7 +78,7 @@ static void build_mesh(EmulMesh &m, int max_leaf, int max_leaf_any) {
     std::vector<KarrasNode> kn_host(n > 1 ? n - 1 : 0);
     std::vector<int> pint_host(n > 1 ? n - 1 : 0), pleaf_host(n);
     if (use_sah) rt_sah_build_host(leafbox.data(), (int)n, svals.data(), kn_host.data(), pint_host.data(), pleaf_host.data());
-    m.tri32.resize(3 * (size_t)n);
+    m.tri32.resize(RT_TRI32_F4 * (size_t)n);
     m.tri64.resize(10 * (size_t)n);
     for (uint32_t i = 0; i < n; i++) gather_tri_thread(i, m.fverts.data(), svals.data(), m.tri32.data(), m.tri64.data());
     if (n == 1) {
@@ -296,7 +296,7 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
     for (uint32_t ray = 0; ray < nrays; ray++) {
         PixMap pm = map_ray(ray, fp, false);
         if (!pm.valid) continue;
-        if (fp.tile_w > 0 && block_culled(fp, pm.i & ~7, pm.j & ~3)) continue;
+        if (fp.tile_w > 0 && block_culled(fp, pm.i - (int)(ray & 7u), pm.j - (int)((ray >> 3) & 3u))) continue;
         HitRec hr; hr.pix = ray; hr.t = 0.f;
         Counters before = c;
         struct CostNote { Counters &c; Counters b; uint32_t *dst; size_t o; ~CostNote() { if (dst) dst[o] = (uint32_t)((c.nodes - b.nodes) + (c.tris - b.tris)); } } note{ c, before, g_cost_primary, pm.out };

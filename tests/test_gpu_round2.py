@@ -161,3 +161,73 @@ def test_last_error_follows_the_last_call(rt, example_scene):
     assert L.rt_last_error(None) == b""
     assert b"region" in L.rt_last_error(g.h)              # ... the handle keeps its most recent failure
     g.close()
+
+
+# ---- rt_group_*: one process, several GPUs, ONE BulkTrace (no torch.distributed) ------------------------------------
+def _group_devices(rt):
+    n = rt._lib.load().rt_device_count()
+    return list(range(n)) if n >= 2 else [0, 0, 0]        # one GPU: three shares on the same device exercise the same code
+
+
+@pytest.mark.parametrize("scene_kind", ["c1", "subdiv4"])
+def test_group_bulk_trace_equals_single_device(rt, example_scene, scene_kind):
+    sc = example_scene if scene_kind == "c1" else subdivided(example_scene, 4)
+    W, H = (320, 240) if scene_kind == "c1" else (1920, 1080)
+    one = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    grp = rt.GpuGroup(sc, devices=_group_devices(rt), precision=rt.FP32_FAST)
+    assert grp.n_devices == len(_group_devices(rt))
+    L = rt._lib.load()
+    for (x, y, w, h) in [(0, 0, W, H), (W // 5 + 3, H // 7 + 1, W // 2 + 5, H // 2 + 3), (W - 9, H - 5, 9, 5)]:
+        for flags in (0, rt.LAYOUT_ROWMAJOR, rt.QUANT_RGBA16_SHR8):
+            ref = one.bulk_trace(sc["camera"], sc["lights"], W, H, x, y, w, h, flags=flags)
+            got = grp.bulk_trace(sc["camera"], sc["lights"], W, H, x, y, w, h, flags=flags)
+            assert np.array_equal(ref, got), (x, y, w, h, flags)
+    # pinned destination: the GPUs copy straight into the caller's buffer
+    import ctypes
+    nbytes = W * H * 3
+    p = L.rt_host_alloc(nbytes)
+    out = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(p)).reshape(-1, 3)
+    out[:] = 7
+    grp.bulk_trace(sc["camera"], sc["lights"], W, H, 0, 0, W, H, out=out)
+    assert np.array_equal(out, one.bulk_trace(sc["camera"], sc["lights"], W, H, 0, 0, W, H))
+    L.rt_host_free(p)
+    with pytest.raises(rt.RtError):
+        grp.bulk_trace(sc["camera"], sc["lights"], W, H, 0, 0, W + 1, H)
+    one.close(); grp.close()
+
+
+def test_group_bulk_trace_exact_and_concurrent_callers(rt, example_scene):
+    """FP64_EXACT through the group is bit-identical to the oracle's bytes; concurrent orders (a goroutine each in the reference
+    worker) with DIFFERENT cameras do not disturb each other."""
+    from concurrent.futures import ThreadPoolExecutor
+    from distributed_raytracer_b200 import workloads
+    sc = example_scene
+    S = orc.Scene(sc)
+    grp = rt.GpuGroup(sc, devices=_group_devices(rt), precision=rt.FP64_EXACT)
+    cams = [sc["camera"]] + [workloads.orbit_camera([1.0, 1.0, -1.0], 6.0, np.deg2rad(25.0 * k), 0.2, 1.0) for k in range(1, 6)]
+    refs = []
+    for cam in cams:
+        S.set_frame(cam, sc["lights"])
+        refs.append(S.render_region(200, 150, mode=orc.CULLED)[0])
+    S.close()
+
+    def order(k):
+        return [grp.bulk_trace(cams[k], sc["lights"], 200, 150, 0, 0, 200, 150) for _ in range(5)]
+    with ThreadPoolExecutor(6) as pool:
+        outs = list(pool.map(order, range(len(cams))))
+    for k, frames in enumerate(outs):
+        for f in frames:
+            assert np.array_equal(f, refs[k]), k
+    grp.close()
+
+
+def test_group_object_positions_follow_the_order(rt):
+    sc = random_soup_scene(n_tris=150, seed=13, n_obj=3, n_lights=4)
+    one = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    grp = rt.GpuGroup(sc, devices=_group_devices(rt), precision=rt.FP32_FAST)
+    moved = np.asarray(sc["obj_pos"], dtype=np.float64) + [[0.3, -0.2, 0.1]]
+    for pos in (None, moved, None):                       # an order without positions renders the registered ones again
+        ref = one.bulk_trace(sc["camera"], sc["lights"], 160, 120, 0, 0, 160, 120, obj_pos=pos)
+        got = grp.bulk_trace(sc["camera"], sc["lights"], 160, 120, 0, 0, 160, 120, obj_pos=pos)
+        assert np.array_equal(ref, got)
+    one.close(); grp.close()

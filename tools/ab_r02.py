@@ -18,22 +18,17 @@ sys.path.insert(0, ROOT)
 CACHE = "/tmp/c3_workload.npz"
 
 VARIANTS = {
-    # name: (env, render flags by name)
-    "r01_like_nooct_nocull": ({"RT_B200_LIB": "build_variants/librt_b200_nooct.so", "RT_B200_CULL": "0"}, []),
-    "nooct": ({"RT_B200_LIB": "build_variants/librt_b200_nooct.so"}, []),
-    "oct_nocull": ({"RT_B200_CULL": "0"}, []),
-    "oct": ({}, []),
-    "oct_leaf_any2": ({"RT_B200_MAX_LEAF_SHADE": "2"}, []),
-    "oct_leaf_any1": ({"RT_B200_MAX_LEAF_SHADE": "1"}, []),
-    "oct_leaf2_any1": ({"RT_B200_MAX_LEAF": "2", "RT_B200_MAX_LEAF_SHADE": "1"}, []),
-    "oct_leaf1_any1": ({"RT_B200_MAX_LEAF": "1", "RT_B200_MAX_LEAF_SHADE": "1"}, []),
-    "oct_leaf8_any1": ({"RT_B200_MAX_LEAF": "8", "RT_B200_MAX_LEAF_SHADE": "1"}, []),
-    "oct_any1_minb6": ({"RT_B200_MAX_LEAF_SHADE": "1", "RT_B200_SHADE_MINB": "6"}, []),
-    "fused": ({}, ["FUSED"]),
-    "fused_any1": ({"RT_B200_MAX_LEAF_SHADE": "1"}, ["FUSED"]),
-    "fused_any1_minb6": ({"RT_B200_MAX_LEAF_SHADE": "1", "RT_B200_SHADE_MINB": "6"}, ["FUSED"]),
-    "fused_any1_minb1": ({"RT_B200_MAX_LEAF_SHADE": "1", "RT_B200_SHADE_MINB": "1"}, ["FUSED"]),
-    "fused_leaf2_any1": ({"RT_B200_MAX_LEAF": "2", "RT_B200_MAX_LEAF_SHADE": "1"}, ["FUSED"]),
+    # name: (env, render flags by name).  build_variants/*.so: see tools/build_variants.sh
+    "r01_like": ({"RT_B200_LIB": "build_variants/librt_b200_nooct.so", "RT_B200_CULL": "0", "RT_B200_MAX_LEAF_SHADE": "4", "RT_B200_SHADE_MINB": "8"}, ["PIPELINE"]),
+    "pipeline_ld128": ({"RT_B200_LIB": "build_variants/librt_b200_ld128.so"}, ["PIPELINE"]),
+    "pipeline": ({}, ["PIPELINE"]),
+    "fused_ld128": ({"RT_B200_LIB": "build_variants/librt_b200_ld128.so"}, []),
+    "fused": ({}, []),
+    "fused_minb8": ({"RT_B200_SHADE_MINB": "8"}, []),
+    "fused_minb10": ({"RT_B200_SHADE_MINB": "10"}, []),
+    "fused_any4": ({"RT_B200_MAX_LEAF_SHADE": "4"}, []),
+    "fused_any1": ({"RT_B200_MAX_LEAF_SHADE": "1"}, []),
+    "fused_leaf2_any2": ({"RT_B200_MAX_LEAF": "2"}, []),
 }
 
 
