@@ -24,10 +24,18 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "C3: Suzanne subdivided x5 (991232 tris) @3840x2160, 2 lights, example camera, FP32_FAST"
+# BASELINE.json configs that are bench workloads: C3 is the configuration the metric is quoted on (the default); C4 is the
+# BVH-build / traversal stress (--config c4), the one scene whose working set (~2 GB) is HBM-sized.
+CONFIGS = {
+    "c3": "C3: Suzanne subdivided x5 (991232 tris) @3840x2160, 2 lights, example camera, FP32_FAST",
+    "c4": "C4: 10000000-triangle random soup (seed 0x5EED, flat normals) @3840x2160, 8 white lights on a ring, example camera, FP32_FAST",
+}
+WORKLOAD = CONFIGS["c3"]
+CONFIG = "c3"
 W, H = 3840, 2160
 SUBDIV = 5
 N_LIGHTS = 2
+C4_TRIS = 10_000_000
 METRIC = "Mrays/s (primary+shadow)"
 REPLICAS = 8      # frames in flight (lanes of the one resident scene, or scene copies with --replicated-scenes); 12 at N > 1
 TILE = (32, 16)
@@ -35,15 +43,52 @@ E2E_TILE = (8, 16)    # host-mode e2e: stripes of 8 pixel columns x full height 
 SCENE_JSON = os.path.join(ROOT, "tests", "golden", "example", "scene.json")
 
 
-def build_workload():
-    """Scene arrays of config 3, produced through the product's own loader (C++ host mirror) + workloads.subdivide."""
+def build_workload(config=None):
+    """Scene arrays of the bench configuration, produced through the product's own loader (C++ host mirror) + workloads."""
     from distributed_raytracer_b200 import host, workloads
     env = host.Environment(SCENE_JSON)
     sc = env.scene_arrays()
-    sc["meshes"] = [workloads.subdivide(sc["meshes"][0], SUBDIV)]
-    sc["lights"] = sc["lights"][:N_LIGHTS]
+    if (config or CONFIG) == "c4":
+        sc["meshes"] = [workloads.triangle_soup(C4_TRIS)]
+        sc["lights"] = workloads.ring_lights(8)
+    else:
+        sc["meshes"] = [workloads.subdivide(sc["meshes"][0], SUBDIV)]
+        sc["lights"] = sc["lights"][:N_LIGHTS]
     env.close()
     return sc
+
+
+def build_workload_reference_arm(config):
+    """The same scene arrays WITHOUT touching the product: the oracle's own loader (oracle/scene_loader.py) and the numpy
+    generators of workloads.py loaded by file path (importing the package would not load a native library either, but the
+    reference arm keeps clear of it altogether)."""
+    import importlib.util
+    from oracle import scene_loader as sl
+    spec = importlib.util.spec_from_file_location("rt_workloads", os.path.join(ROOT, "distributed-raytracer_b200", "workloads.py"))
+    workloads = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(workloads)
+    sc = sl.environment_from_file(SCENE_JSON)
+    if config == "c4":
+        sc["meshes"] = [workloads.triangle_soup(C4_TRIS)]
+        sc["lights"] = workloads.ring_lights(8)
+    else:
+        sc["meshes"] = [workloads.subdivide(sc["meshes"][0], SUBDIV)]
+        sc["lights"] = sc["lights"][:N_LIGHTS]
+    if "tan_half_fov" not in sc:
+        from oracle import oracle as orc
+        sc["tan_half_fov"] = orc.go_tan(float(sc["camera"][12]) / 2.0)
+    return sc
+
+
+def config_dict(**kw):
+    """The `config` object of the JSON line: the SAME keys on the repo's arm and on the reference arm (values that do not apply
+    to an arm are null)."""
+    keys = ("workload", "rays_per_frame", "hit_pixels", "frames_per_s", "l2", "scene_copies", "scene_create_ms", "frames_in_flight",
+            "host_enqueue_ms_per_step", "precision", "parallelism", "bvh", "render_kernel", "note")
+    d = {k: None for k in keys}
+    d.update(kw)
+    assert set(d) == set(keys), sorted(set(d) ^ set(keys))
+    return d
 
 
 class ClockSampler:
@@ -140,7 +185,9 @@ def run_reference(args, rank):
     box.go's predicate, no tmax, full nearest-hit shadow queries), run on all host threads."""
     if rank != 0:
         return
-    sc = build_workload()
+    # only the oracle is built and loaded here: no CUDA library of the repo is mapped into this process
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], env=dict(os.environ, CC="gcc", CXX="g++"))
+    sc = build_workload_reference_arm(args.config)
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
     S = orc.Scene(sc)
@@ -174,15 +221,18 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "C restatement of worker/sequential's Go path (oracle port), not the Go binary"},
+        "config": config_dict(workload=WORKLOAD, precision="float64 (the reference's arithmetic)",
+                              parallelism="%d host threads, each a band of pixel columns (one reference worker per thread)" % cores,
+                              note="C restatement of worker/sequential's Go path (oracle port), not the Go binary"),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
 def main():
-    global REPLICAS, E2E_TILE
+    global REPLICAS, E2E_TILE, WORKLOAD, CONFIG
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="bench workload (default: c3, the configuration the metric is quoted on)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
@@ -199,7 +249,9 @@ def main():
                     help="N>1 e2e: every GPU writes its tiles into a host-shared pinned framebuffer | NVLink push + D2H from rank 0")
     ap.add_argument("--e2e-tile", default="", help="tile WxH of the host-mode e2e renderer (default %dx%d)" % E2E_TILE)
     ap.add_argument("--persistent", action="store_true", help="use the persistent warp-cooperative primary kernel (RT_FLAG_PERSISTENT)")
+    ap.add_argument("--pipeline", action="store_true", help="three kernels per frame (K2 -> K4 -> K5, RT_FLAG_PIPELINE) instead of the fused frame kernel")
     args = ap.parse_args()
+    CONFIG, WORKLOAD = args.config, CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -211,12 +263,10 @@ def main():
     if args.e2e_tile:
         E2E_TILE = tuple(int(v) for v in args.e2e_tile.lower().split("x"))
 
-    import __graft_entry__ as ge
     if args.impl == "reference":
-        if rank == 0:
-            ge.build()
         run_reference(args, rank)
         return
+    import __graft_entry__ as ge
 
     import numpy as np
     import torch
@@ -236,7 +286,7 @@ def main():
     import distributed_raytracer_b200 as rt
     from distributed_raytracer_b200 import host, parallel
 
-    render_flags = rt.FLAG_PERSISTENT if args.persistent else 0
+    render_flags = rt.FLAG_PERSISTENT if args.persistent else (rt.FLAG_PIPELINE if args.pipeline else 0)
     sc = build_workload() if rank == 0 else None
     if world > 1:
         # scene broadcast once over NCCL/NVLink; every rank builds the same LBVH locally
@@ -266,8 +316,10 @@ def main():
     g2.close()
     g = r.backend.scenes[0]
     bvh = g.bvh_info()
-    # K2 K4 K5 (+ push-tiles (+ frame-complete on rank 0) | untile on rank 0); rank 0's count is the one reported
-    launches_per_step = 3 if world == 1 else ((5 if rank == 0 else 4) if args.mode == "peer" else 4)
+    # kernels of the repo per frame: the fused frame kernel (--pipeline: K2 K4 K5) (+ push-tiles (+ frame-complete on rank 0) |
+    # untile on rank 0); rank 0's count is the one reported
+    render_kernels = 3 if args.pipeline else 1
+    launches_per_step = render_kernels if world == 1 else render_kernels + ((2 if rank == 0 else 1) if args.mode == "peer" else 1)
 
     frame_state = rt.FrameState(cam13, lights, tan_half_fov=tan_half)   # camera + lights marshalled once; handed over per frame
 
@@ -295,15 +347,40 @@ def main():
     rays_frame = W * H + hits_frame * len(lights)         # tile padding beyond the screen is not a ray
 
     # ---- per-kernel durations (serial frames, L2 flushed before each, CUDA events on the launching stream) ----
-    kern_ms = {"primary": [], "shade": [], "write": []}
+    # both launch shapes are timed: the frame kernel that runs by default and the three-kernel pipeline it replaced
+    kern_ms = {"frame": [], "primary": [], "shade": [], "write": []}
+    fused_default = not (args.pipeline or args.persistent)
     for _ in range(3 + min(args.steps, 20)):
         flush.zero_()
         torch.cuda.synchronize(dev)
-        serial_frame(render_flags)
+        serial_frame(rt.FLAG_PIPELINE | (rt.FLAG_PERSISTENT if args.persistent else 0))
         st = g.stats()
-        for name in kern_ms:
+        for name in ("primary", "shade", "write"):
             kern_ms[name].append(st["ms_" + name])
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        serial_frame(rt.FLAG_FUSED)
+        kern_ms["frame"].append(g.stats()["ms_total"])
     kern_ms = {k: v[3:] for k, v in kern_ms.items()}
+
+    # ---- N > 1: the sharded frame must BE the single-GPU frame, byte for byte (both the device-resident path of `value` and the
+    # host path of `e2e`); checked before anything is timed, the run aborts otherwise ----
+    frame_identical = None
+    ref_frame = None
+    if world > 1:
+        if rank == 0:
+            ref_frame = torch.empty(W * H * 3, dtype=torch.uint8, device=dev)
+            g.render_region_device(W, H, 0, 0, W, H, ref_frame.data_ptr(), None, render_flags | rt.LAYOUT_COLMAJOR)
+            torch.cuda.synchronize(dev)
+        f = r.render_frame(frame_state, flags=render_flags)
+        r.wait()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        ok = torch.tensor([1 if (rank != 0 or torch.equal(f, ref_frame)) else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        frame_identical = {"value_path_" + args.mode: bool(ok.item())}
+        if not ok.item():
+            raise SystemExit("bench: the %d-GPU frame differs from the single-GPU frame (mode %s)" % (world, args.mode))
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -462,10 +539,15 @@ def main():
                 print("[bench] rank %d: host-mode e2e unavailable (%s); using --e2e-mode peer" % (rank, ex), file=sys.stderr, flush=True)
                 args.e2e_mode = "peer"
         for _ in range(2 * REPLICAS):                       # lane priming + first touch of the host buffers (untimed)
-            re.render_frame(frame_state, flags=render_flags, to_host=True)
+            hf = re.render_frame(frame_state, flags=render_flags, to_host=True)
         re.wait()
         torch.cuda.synchronize(dev)
         dist.barrier()
+        ok = torch.tensor([1 if (rank != 0 or torch.equal(hf, ref_frame.cpu())) else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        frame_identical["e2e_path_" + args.e2e_mode] = bool(ok.item())
+        if not ok.item():
+            raise SystemExit("bench: the %d-GPU host frame differs from the single-GPU frame (e2e mode %s)" % (world, args.e2e_mode))
         t_single = []
         for it in range(3 + min(e2e_steps, 10)):
             flush.zero_()
@@ -525,23 +607,38 @@ def main():
         # K5: per hit HitRec 16 + colour 24 + lit 4 read, 3 bytes written
         "write": hits_local * (16 + 24 + 4 + 3),
     }
-    dom = max(avg, key=lambda k: avg[k])
+    # fused frame kernel: the same records, no hit list / colour buffer in between, 3 bytes written per hit pixel
+    alg["frame"] = (cnt["nodes_primary"] + cnt["nodes_shade"]) * nb + (cnt["tris_primary"] + cnt["tris_shade"]) * tb + hits_local * (72 + 72 + 4 + 80 + 3)
+    dom = "frame" if fused_default else max(("primary", "shade", "write"), key=lambda k: avg[k])
+    kernel_name = {"frame": "k_frame_fused", "primary": "k_primary_fast_" + ("persistent" if args.persistent else "simple"), "shade": "k_shade",
+                   "write": "k_write"}[dom]
     achieved = alg[dom] / (avg[dom] * 1e-3) / 1e9 if avg[dom] > 0 else 0.0
-    traffic = None
+    # what ncu measured for this kernel on this workload (profiles/traffic.json, filled from the committed ncu captures): DRAM and L2
+    # bytes per launch, issue-slot and L1-pipe utilisation
+    physical = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            physical = json.load(open(tpath)).get(CONFIG, {}).get(kernel_name)
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": {"primary": "k_primary_fast_" + ("persistent" if args.persistent else "simple"), "shade": "k_shade", "write": "k_write"}[dom],
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": avg[dom],
+            physical = None
+    traffic = physical.get("dram_bytes") if physical else None
+    dram_frac = (traffic / (avg[dom] * 1e-3) / 1e9 / peak) if traffic else None
+    # Which roof binds?  If the kernel's measured DRAM traffic moved at more than half of the HBM peak it is an HBM kernel and `frac`
+    # is measured DRAM bytes / time / peak; otherwise the working set is cache-resident and the byte figure is algorithmic (records
+    # the rays fetch, served by L1/L2): the kernel is then bound by the latency of dependent loads, and `frac` only says how the
+    # algorithmic byte rate compares with HBM -- the physical numbers are in `physical`.
+    hbm_bound = dram_frac is not None and dram_frac >= 0.5
+    roofline = {"bound": "hbm" if hbm_bound else "latency (dependent L1/L2 loads of the traversal; DRAM is idle)",
+                "achieved": (traffic / (avg[dom] * 1e-3) / 1e9) if hbm_bound else achieved, "peak": peak, "unit": "GB/s",
+                "frac": dram_frac if hbm_bound else achieved / peak, "frac_numerator": "measured DRAM bytes (ncu)" if hbm_bound else "algorithmic bytes",
+                "traffic": traffic, "dram_frac_of_peak": dram_frac, "physical": physical,
+                "kernel": kernel_name, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": avg[dom],
                 "kernels_ms": avg, "algorithmic_bytes": alg,
-                "note": "algorithmic bytes = node + triangle records the rays fetch (counting build of the kernels); `traffic` is ncu's DRAM "
-                        "traffic of the same kernel -- about 24x lower, the working set lives in L1/L2 -- so the byte roofline is an upper "
-                        "bound on useful bandwidth, not the physical limiter: ncu shows the kernel issue-bound at 45 % SIMD efficiency "
-                        "(profiles/r01_ncu_full_summary.txt, profiles/r01_k4_divergence_model.txt)",
+                "note": "algorithmic bytes = node (112 B) + triangle (64 B) records the rays fetch, from the counting build of the kernels; "
+                        "`traffic` / `physical` are ncu's DRAM and L2 bytes, issue-slot and L1-pipe utilisation of one launch of the same kernel "
+                        "(profiles/r02_ncu_*_summary.txt).  On C3 the scene is cache-resident (DRAM ~3 % of peak): the limiter is the dependent "
+                        "L1/L2 load latency of a BVH visit at the occupancy the registers allow, not bytes and not issue slots",
                 "per_ray": {"nodes_primary": cnt["nodes_primary"] / max(1, prim_local), "tris_primary": cnt["tris_primary"] / max(1, prim_local),
                             "nodes_shadow": cnt["nodes_shade"] / max(1, cnt["shadow_rays"]), "tris_shadow": cnt["tris_shade"] / max(1, cnt["shadow_rays"])}}
 
@@ -557,11 +654,15 @@ def main():
     roofline["fma_peak_tflops_measured"] = {"fp32": fp32_peak.value, "fp64": fp64_peak.value}
     roofline["flop_side"] = {"fp32_flops": flops32, "fp64_flops": flops64,
                              "t_flops_ms": 1e3 * (flops32 / max(fp32_peak.value, 1e-9) + flops64 / max(fp64_peak.value, 1e-9)) / 1e12,
-                             "t_bytes_ms": 1e3 * sum(alg.values()) / (peak * 1e9),
-                             "t_measured_ms": sum(avg.values())}
+                             "t_bytes_ms": 1e3 * alg["frame"] / (peak * 1e9),
+                             "t_measured_ms": avg["frame"] if fused_default else avg["primary"] + avg["shade"] + avg["write"]}
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and CONFIG == "c4":
+        cpu_baseline = {"value": None, "unit": "Mrays/s", "cores": 1, "kind": "port",
+                        "sample": "not timed for C4: the reference-shaped R-tree of 10 M faces alone takes minutes to insert on one core; "
+                                  "see the C3 line (python bench.py) for the CPU arm"}
+    elif world == 1 and not args.no_cpu_baseline:
         v, rays, dt, stride = oracle_cpu_rate(sc, n_threads=1, budget_s=15.0)
         cpu_baseline = {"value": v, "unit": "Mrays/s", "cores": 1, "kind": "port",
                         "sample": "every %d-th band of 16 pixel columns of the same 4K frame (%d rays, %.1f s), single thread like worker/sequential, "
@@ -571,24 +672,25 @@ def main():
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_frame": rays_frame, "hit_pixels": hits_frame, "frames_per_s": 1e3 / ms_per_step,
-                   "l2": ("inputs larger than L2: the resident scene is ~290 MB (nodes 32 + triangles 48 + fp64 vertices/normals 143 + "
-                          "materials) against 126 MB of L2 and %d frames are in flight on it, one stream each; no flush inside the "
-                          "pipelined region (the top of the BVH stays cached across frames, as it does in a running worker; with "
-                          "--replicated-scenes, %d copies x 290 MB, the frame takes 1.6 %% longer at N = 1); the per-kernel times of "
-                          "`roofline` come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS))
-                         if args.shared_scene else
-                         ("frames cycle over %d resident replicas of the scene per GPU, one stream each (inputs last touched %d frames "
-                          "earlier: %d x ~290 MB > 126 MB L2); no flush inside the pipelined region; the per-kernel times of `roofline` "
-                          "come from a serial pass with a 256 MiB memset before each frame" % (REPLICAS, REPLICAS, REPLICAS)),
-                   "scene_copies": 1 if args.shared_scene else REPLICAS, "scene_create_ms": 1e3 * t_create,
-                   "frames_in_flight": REPLICAS, "host_enqueue_ms_per_step": 1e3 * t_enqueue / args.steps, "precision": "FP32_FAST traversal, fp64 shading",
-                   "parallelism": ("screen tiles 32x16 round-robin over %d rank(s)" % world) + ("" if world == 1 else
-                                   {"peer": "; every rank pushes its tiles into rank 0's framebuffer over NVLink peer memory (CUDA IPC, 16-byte stores) and "
-                                            "the push kernel hands the frame over through arrive/consumed flags in rank 0's memory (no collective)",
-                                    "peer_nccl": "; tiles pushed into rank 0's framebuffer over NVLink peer memory, 4-byte all_reduce as barrier",
-                                    "gather": "; NCCL all_gather of packed tiles + de-interleave on rank 0"}[args.mode]), "bvh": bvh,
-                   "primary_kernel": "persistent" if args.persistent else "simple"},
+        "config": config_dict(
+            workload=WORKLOAD, rays_per_frame=rays_frame, hit_pixels=hits_frame, frames_per_s=1e3 / ms_per_step,
+            l2=("inputs larger than L2: the resident scene (%s) against 126 MB of L2 and %d frames are in flight on it, one stream each; "
+                "no flush inside the pipelined region (the top of the BVH stays cached across frames, as it does in a running worker); the "
+                "per-kernel times of `roofline` come from a serial pass with a 256 MiB memset before each frame"
+                % ("~300 MB: nodes 32 + 37, triangles 63, fp64 vertices/normals 143" if CONFIG == "c3" else "~2.8 GB", REPLICAS))
+            if args.shared_scene else
+            ("frames cycle over %d resident replicas of the scene per GPU, one stream each; no flush inside the pipelined region; the "
+             "per-kernel times of `roofline` come from a serial pass with a 256 MiB memset before each frame" % REPLICAS),
+            scene_copies=1 if args.shared_scene else REPLICAS, scene_create_ms=1e3 * t_create, frames_in_flight=REPLICAS,
+            host_enqueue_ms_per_step=1e3 * t_enqueue / args.steps, precision="FP32_FAST traversal, fp64 shading",
+            parallelism=("screen tiles 32x16 round-robin over %d rank(s)" % world) + ("" if world == 1 else
+                        {"peer": "; every rank pushes its tiles into rank 0's framebuffer over NVLink peer memory (CUDA IPC, 16-byte stores) and "
+                                 "the push kernel hands the frame over through arrive/consumed flags in rank 0's memory (no collective)",
+                         "peer_nccl": "; tiles pushed into rank 0's framebuffer over NVLink peer memory, 4-byte all_reduce as barrier",
+                         "gather": "; NCCL all_gather of packed tiles + de-interleave on rank 0"}[args.mode]),
+            bvh=bvh, render_kernel="persistent K2 + K4 + K5" if args.persistent else ("K2 + K4 + K5" if args.pipeline else "k_frame_fused"),
+            note="frame_identical_to_single_gpu is checked before the timed region at N > 1"),
+        "frame_identical_to_single_gpu": (all(frame_identical.values()) if frame_identical else None), "frame_identity_checks": frame_identical,
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "clocks": clocks, "wall_s_timed_region": wall,
     }

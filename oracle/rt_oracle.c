@@ -281,18 +281,45 @@ static void face_bounds(const omesh *m, uint32_t f, vec *lo, vec *hi) {
     lo->z = fmin(a.z, fmin(b.z, c.z)); hi->z = fmax(a.z, fmax(b.z, c.z));
 }
 
-static const double *g_sortkey;
-static int cmp_key(const void *a, const void *b) {
-    double ka = g_sortkey[*(const int32_t *)a], kb = g_sortkey[*(const int32_t *)b];
-    if (ka < kb) return -1;
-    if (ka > kb) return 1;
-    int32_t ia = *(const int32_t *)a, ib = *(const int32_t *)b;
-    return (ia > ib) - (ia < ib);
+/* Median partition of order[first .. first+count) by (key, index): after the call every entry of the lower half compares
+ * <= every entry of the upper half.  Quickselect (median of three, Hoare partition) -- O(n) per level instead of a full sort;
+ * the tree may only CULL (padded boxes, no tmax), so any split is a valid one: only build time depends on it (a 10 M-face soup
+ * took 116 s with qsort at every level). */
+static inline int key_less(const double *key, int32_t a, int32_t b) { return key[a] < key[b] || (key[a] == key[b] && a < b); }
+static void median_partition(int32_t *v, int32_t n, int32_t k, const double *key) {
+    int32_t lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int32_t mid = lo + (hi - lo) / 2;
+        /* median of three -> pivot value */
+        int32_t a = v[lo], b = v[mid], c = v[hi], p;
+        if (key_less(key, a, b)) p = key_less(key, b, c) ? b : (key_less(key, a, c) ? c : a);
+        else p = key_less(key, a, c) ? a : (key_less(key, b, c) ? c : b);
+        int32_t i = lo, j = hi;
+        while (i <= j) {
+            while (key_less(key, v[i], p)) i++;
+            while (key_less(key, p, v[j])) j--;
+            if (i <= j) { int32_t t = v[i]; v[i] = v[j]; v[j] = t; i++; j--; }
+        }
+        if (k <= j) hi = j;
+        else if (k >= i) lo = i;
+        else return;
+    }
+}
+
+/* Subtrees of more than CBVH_PAR faces are built by their own thread (the node array is preallocated, ids come from an atomic
+ * counter): the tree only culls, so the order in which ids are handed out is irrelevant to every result. */
+#define CBVH_PAR 400000
+typedef struct { omesh *m; const vec *flo, *fhi; double **cent; int32_t first, count; double pad; int32_t id; } cbvh_job;
+static int32_t cbvh_build(omesh *m, const vec *flo, const vec *fhi, double *cent[3], int32_t first, int32_t count, double pad);
+static void *cbvh_thread(void *arg) {
+    cbvh_job *j = (cbvh_job *)arg;
+    j->id = cbvh_build(j->m, j->flo, j->fhi, j->cent, j->first, j->count, j->pad);
+    return NULL;
 }
 
 static int32_t cbvh_build(omesh *m, const vec *flo, const vec *fhi, double *cent[3], int32_t first, int32_t count,
                           double pad) {
-    int32_t id = m->n_nodes++;
+    int32_t id = __atomic_fetch_add(&m->n_nodes, 1, __ATOMIC_RELAXED);
     cnode *n = &m->nodes[id];
     vec lo = { DBL_MAX, DBL_MAX, DBL_MAX }, hi = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
     vec clo = lo, chi = hi;
@@ -309,12 +336,19 @@ static int32_t cbvh_build(omesh *m, const vec *flo, const vec *fhi, double *cent
     if (count <= 4) return id;
     double ex = chi.x - clo.x, ey = chi.y - clo.y, ez = chi.z - clo.z;
     int ax = (ex >= ey && ex >= ez) ? 0 : (ey >= ez ? 1 : 2);
-    g_sortkey = cent[ax];
-    qsort(m->order + first, (size_t)count, sizeof(int32_t), cmp_key);
     int32_t half = count / 2;
-    int32_t l = cbvh_build(m, flo, fhi, cent, first, half, pad);
-    int32_t r = cbvh_build(m, flo, fhi, cent, first + half, count - half, pad);
-    n = &m->nodes[id];
+    median_partition(m->order + first, count, half, cent[ax]);
+    int32_t l, r;
+    pthread_t th;
+    cbvh_job job = { m, flo, fhi, cent, first, half, pad, -1 };
+    if (count > CBVH_PAR && pthread_create(&th, NULL, cbvh_thread, &job) == 0) {
+        r = cbvh_build(m, flo, fhi, cent, first + half, count - half, pad);
+        pthread_join(th, NULL);
+        l = job.id;
+    } else {
+        l = cbvh_build(m, flo, fhi, cent, first, half, pad);
+        r = cbvh_build(m, flo, fhi, cent, first + half, count - half, pad);
+    }
     n->left = l; n->right = r; n->count = 0;
     return id;
 }

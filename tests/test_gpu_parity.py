@@ -465,7 +465,7 @@ def test_counting_build_reports_traversal_work(rt, example_scene):
     g.close()
     assert np.array_equal(a, b)
     assert s0["nodes_fetched"] == 0 and s1["nodes_fetched"] > 0 and s1["tris_fetched"] > 0
-    assert s1["node_bytes"] == 112 and s1["tri_bytes"] == 48 and s1["primary_rays"] == 320 * 240 and s1["ms_total"] > 0
+    assert s1["node_bytes"] == 112 and s1["tri_bytes"] == 64 and s1["primary_rays"] == 320 * 240 and s1["ms_total"] > 0
 
 
 def test_errors_and_lifecycle(rt, example_scene):

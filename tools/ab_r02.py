@@ -29,6 +29,10 @@ VARIANTS = {
     "fused_any4": ({"RT_B200_MAX_LEAF_SHADE": "4"}, []),
     "fused_any1": ({"RT_B200_MAX_LEAF_SHADE": "1"}, []),
     "fused_leaf2_any2": ({"RT_B200_MAX_LEAF": "2"}, []),
+    "fused_w8": ({"RT_B200_LIB": "build_variants/librt_b200_w8.so"}, []),
+    "fused_w8_minb8": ({"RT_B200_LIB": "build_variants/librt_b200_w8.so", "RT_B200_SHADE_MINB": "8"}, []),
+    "fused_w8_minb7": ({"RT_B200_LIB": "build_variants/librt_b200_w8.so", "RT_B200_SHADE_MINB": "7"}, []),
+    "pipeline_w8": ({"RT_B200_LIB": "build_variants/librt_b200_w8.so"}, ["PIPELINE"]),
 }
 
 

@@ -8,3 +8,4 @@ SRC="rt_api.cu rt_group.cu render.cu bvh_build.cu wire.cu"
 $NV -DRT_LD256=0 -o ../../build_variants/librt_b200_ld128.so $SRC &
 $NV -DRT_LD256=0 -DRT_OCTANT=0 -o ../../build_variants/librt_b200_nooct.so $SRC &
 wait
+$NV -DRT_W=8 -o ../../build_variants/librt_b200_w8.so $SRC
