@@ -38,6 +38,7 @@ inline void rt_cull_frame(FrameParams &fp, const MeshView *meshes, const ObjRec 
     for (int k = 0; k < n_obj; k++) {
         const MeshView &m = meshes[objs[k].mesh];
         if (m.n_faces == 0) continue;
+        if (!(objs[k].pos[0] == objs[k].pos[0])) continue;        // NaN position: absent from this order, can never be hit
         for (int corner = 0; corner < 8; corner++) {
             double v[3];
             for (int d = 0; d < 3; d++)

@@ -191,6 +191,7 @@ RT_HD bool trace_exact(const SceneView &sc, const FrameParams &fp, dv o, dv d, b
     dv cam = dv_ld(fp.cam_pos);
     for (int k = 0; k < fp.n_obj; k++) {
         const ObjRec &ob = sc.objs[k];
+        if (!(ob.pos[0] == ob.pos[0])) continue;          // NaN position: the object is absent from this order (rt_b200.h)
         dv pos = dv_ld(ob.pos);
         BestExact b; b.has = false; b.dist = 0.0; b.face = -1;
         mesh_nearest_exact(sc.meshes[ob.mesh], dv_sub(o, pos), d, b, brute, cnt);       // object.go:71
@@ -382,6 +383,7 @@ RT_HD bool trace_fast_nearest(const SceneView &sc, const FrameParams &fp, dv o, 
     float best_metric = 0.0f;
     for (int k = 0; k < fp.n_obj; k++) {
         const ObjRec &ob = sc.objs[k];
+        if (!(ob.pos[0] == ob.pos[0])) continue;          // NaN position: the object is absent from this order (rt_b200.h)
         RayF r = make_rayf((float)(o.x - ob.pos[0]), (float)(o.y - ob.pos[1]), (float)(o.z - ob.pos[2]), (float)d.x,
                            (float)d.y, (float)d.z);
         float t = 3.0e38f;

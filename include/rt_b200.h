@@ -151,8 +151,10 @@ int  rt_device_count(void);
 
 /* ---- per-frame mutable state (the gob `diff`: distributed/main.go:56-64, environment.go:65-69) --
  * obj_pos, wherever it appears below, must hold exactly 3 * n_objects doubles (n_objects of rt_scene_create): like a Go
- * slice header passed through cgo as a bare pointer, the ABI carries no length for it.  n_lights is unbounded; the lit
- * mask of the debug outputs has one bit per light modulo 32. */
+ * slice header passed through cgo as a bare pointer, the ABI carries no length for it.  An object whose position is NaN
+ * (its x component) is ABSENT from the order and can never be hit: the reference rebuilds the object R-tree from the diff
+ * alone (environment.go:73-98), so a registered object that an order does not list is simply not rendered.  n_lights is
+ * unbounded; the lit mask of the debug outputs has one bit per light modulo 32. */
 int rt_frame_set(rt_scene *scene, const rt_camera *cam, const rt_light *lights, uint32_t n_lights,
                  const double *obj_pos /* n_objects*3 or NULL = unchanged */);
 /* the same for an explicit lane of the device API */

@@ -4,6 +4,7 @@
 package state
 
 import (
+	"math"
 	"sort"
 
 	"github.com/mwindels/rtreego"
@@ -104,7 +105,9 @@ func (em *EnvMutables) Flatten(ids []uint) FlatFrame {
 		if o, ok := pos[id]; ok {
 			ff.ObjPos = append(ff.ObjPos, o.Pos.X, o.Pos.Y, o.Pos.Z)
 		} else {
-			ff.ObjPos = append(ff.ObjPos, 0, 0, 0)
+			// not in this order's diff: LinkTo (environment.go:73-98) rebuilds the object tree from the diff alone, so the
+			// reference does not render it.  A NaN position marks the object absent for the backend (rt_b200.h).
+			ff.ObjPos = append(ff.ObjPos, math.NaN(), math.NaN(), math.NaN())
 		}
 	}
 	return ff

@@ -329,3 +329,22 @@ def test_any_hit_hierarchy_with_its_own_leaf_size(example_scene, leaf_any):
     rgb_o, _, face_o, _ = oracle_render(sc, 240, 180)
     assert (np.abs(b[0].astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= 1).mean() >= 0.999
     E0.close(); E1.close()
+
+
+@pytest.mark.parametrize("precision", [rt.FP64_EXACT, rt.FP32_FAST])
+def test_object_with_nan_position_is_absent(precision):
+    """An order that does not list a registered object (environment.go:73-98 rebuilds the object tree from the diff alone) hands
+    the backend a NaN position for it: the frame must be the frame of the scene WITHOUT that object."""
+    sc = random_soup_scene(n_tris=150, seed=13, n_obj=3, n_lights=4)
+    without = dict(sc, obj_pos=np.asarray(sc["obj_pos"])[[0, 2]], obj_mesh=np.asarray(sc["obj_mesh"])[[0, 2]])
+    rgb_o, col_o, face_o, _ = oracle_render(without, 96, 72)
+    pos = np.asarray(sc["obj_pos"], dtype=np.float64).copy()
+    pos[1] = np.nan
+    E = eb.EmulScene(dict(sc, obj_pos=pos), precision)
+    rgb, col, face, obj, lit, cnt = E.render(sc["camera"], sc["lights"], 96, 72)
+    E.close()
+    assert not (obj == 1).any() and (obj == 2).any()
+    if precision == rt.FP64_EXACT:
+        assert np.array_equal(face, face_o) and np.array_equal(col.view(np.uint64), col_o.view(np.uint64)) and np.array_equal(rgb, rgb_o)
+    else:
+        assert (face == face_o).mean() >= 0.995 and (np.abs(rgb.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= 1).mean() >= 0.995

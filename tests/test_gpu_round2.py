@@ -231,3 +231,25 @@ def test_group_object_positions_follow_the_order(rt):
         got = grp.bulk_trace(sc["camera"], sc["lights"], 160, 120, 0, 0, 160, 120, obj_pos=pos)
         assert np.array_equal(ref, got)
     one.close(); grp.close()
+
+
+def test_object_with_nan_position_is_absent(rt):
+    """A registered object that an order does not list arrives with a NaN position (rt_b200.h): it must not be rendered, and the
+    other objects must render as in the scene without it (environment.go:73-98)."""
+    sc = random_soup_scene(n_tris=150, seed=13, n_obj=3, n_lights=4)
+    without = dict(sc, obj_pos=np.asarray(sc["obj_pos"])[[0, 2]], obj_mesh=np.asarray(sc["obj_mesh"])[[0, 2]])
+    S = orc.Scene(without)
+    rgb_o, col_o, face_o, _ = S.render_region(160, 120, mode=orc.CULLED)
+    S.close()
+    pos = np.asarray(sc["obj_pos"], dtype=np.float64).copy()
+    pos[1] = np.nan
+    g = rt.GpuScene(sc, precision=rt.FP64_EXACT)
+    g.set_frame(sc["camera"], sc["lights"], obj_pos=pos)
+    rgb, col, face, obj, lit = g.render_region_debug(160, 120)
+    g.close()
+    assert not (obj == 1).any() and (obj == 2).any()
+    assert np.array_equal(face, face_o) and np.array_equal(col.view(np.uint64), col_o.view(np.uint64)) and np.array_equal(rgb, rgb_o)
+    g = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    fast = g.bulk_trace(sc["camera"], sc["lights"], 160, 120, 0, 0, 160, 120, obj_pos=pos)
+    g.close()
+    assert (np.abs(fast.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= 1).mean() >= 0.995
