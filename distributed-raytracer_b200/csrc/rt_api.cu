@@ -49,6 +49,7 @@ struct Lane {
     uint64_t *d_wire_len = nullptr, *h_wire_len = nullptr;
     cudaStream_t last_stream = nullptr;
     bool stats_pending = false;
+    bool stats_counted = false;        // the frame whose stats are pending ran with RT_FLAG_COUNT
     rt_stats stats;
 };
 
@@ -267,7 +268,7 @@ void collect_stats(rt_scene *s, Lane &L) {
     cudaMemcpy(counters, L.d_counters, sizeof counters, cudaMemcpyDeviceToHost);
     Counters c[2];
     memset(c, 0, sizeof c);
-    cudaMemcpy(c, L.d_stats, sizeof c, cudaMemcpyDeviceToHost);
+    if (L.stats_counted) cudaMemcpy(c, L.d_stats, sizeof c, cudaMemcpyDeviceToHost);   // traversal counters exist only for RT_FLAG_COUNT frames
     L.stats.hit_pixels = counters[1];
     L.stats.shadow_rays = (uint64_t)counters[1] * (uint64_t)L.frame.n_lights;
     L.stats.nodes_primary = c[0].nodes; L.stats.tris_primary = c[0].tris;
@@ -326,7 +327,7 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
                 (s->fused || (flags & RT_FLAG_FUSED));
 
     CU(s, cudaMemsetAsync(L.d_counters, 0, 4 * sizeof(unsigned int), st));
-    CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), st));
+    if (flags & RT_FLAG_COUNT) CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), st));
     // background: sequential/main.go:17 surface.FillRect(nil, 0); distributed/main.go:70 default 0,0,0
     if (fp.tile_final) CU(s, rt_launch_clear_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, d_rgb, st));   // only this rank's pixels (peer framebuffer)
     else CU(s, cudaMemsetAsync(d_rgb, 0, out_bytes, st));
@@ -353,8 +354,9 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     CU(s, cudaEventRecord(L.ev[3], st));
 
     L.stats.primary_rays = (uint64_t)fp.w * (uint64_t)fp.h;
-    if (fp.tile_w > 0) L.stats.primary_rays = nrays;
+    if (fp.tile_w > 0) L.stats.primary_rays = (uint64_t)fp.n_local_tiles * (uint64_t)(fp.tile_w * fp.tile_h);   // answered pixels, traced or culled
     L.stats_pending = true;
+    L.stats_counted = (flags & RT_FLAG_COUNT) != 0;
     L.last_stream = st;
     if (out.async) return RT_OK;
 

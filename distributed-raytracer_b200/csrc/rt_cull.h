@@ -19,6 +19,7 @@
 inline void rt_cull_full(FrameParams &fp) {
     fp.cull_on = 0; fp.cull_i0 = 0; fp.cull_j0 = 0; fp.cull_i1 = fp.W; fp.cull_j1 = fp.H;
     fp.rbx0 = fp.rby0 = fp.rnbx = fp.rnby = 0;
+    fp.lt0 = fp.lt_n = 0;
 }
 
 // Fills the cull_* / r* fields of fp (whose camera, screen and region / tile fields are final).
@@ -67,7 +68,20 @@ inline void rt_cull_frame(FrameParams &fp, const MeshView *meshes, const ObjRec 
     if (j1 > fp.H) j1 = fp.H;
     if (i1 <= i0 || j1 <= j0) { fp.cull_i0 = fp.cull_i1 = fp.cull_j0 = fp.cull_j1 = 0; return; }
     fp.cull_i0 = i0; fp.cull_i1 = i1; fp.cull_j0 = j0; fp.cull_j1 = j1;
-    if (fp.tile_w > 0) return;                                   // tile mode: per-block test in the kernels (block_culled)
+    if (fp.tile_w > 0) {
+        // tile mode: the kernels test every block against the rectangle (block_culled); here the launch is cut down to the tile
+        // ROWS that meet it.  Tile ids of rows TY0..TY1 are the range [TY0*tiles_x, (TY1+1)*tiles_x); this rank's tiles
+        // t = lt*n_ranks + rank inside it are the contiguous local range [lt_a, lt_b).
+        const int y0 = j0 > fp.y ? j0 : fp.y, y1 = j1 < fp.y + fp.h ? j1 : fp.y + fp.h;
+        if (y1 <= y0 || i1 <= fp.x || i0 >= fp.x + fp.w) { fp.cull_i0 = fp.cull_i1 = fp.cull_j0 = fp.cull_j1 = 0; return; }
+        const long long ta = (long long)((y0 - fp.y) / fp.tile_h) * fp.tiles_x, tb = (long long)((y1 - 1 - fp.y) / fp.tile_h + 1) * fp.tiles_x;
+        const long long n = fp.n_ranks, r = fp.rank;
+        long long lt_a = ta > r ? (ta - r + n - 1) / n : 0, lt_b = tb > r ? (tb - r + n - 1) / n : 0;
+        if (lt_b > fp.n_local_tiles) lt_b = fp.n_local_tiles;
+        if (lt_b <= lt_a) { fp.cull_i0 = fp.cull_i1 = fp.cull_j0 = fp.cull_j1 = 0; return; }
+        fp.lt0 = (int)lt_a; fp.lt_n = (int)(lt_b - lt_a);
+        return;
+    }
     // region mode: the block sub-rectangle of the region that intersects the pixel rectangle
     const int x0 = i0 > fp.x ? i0 : fp.x, x1 = i1 < fp.x + fp.w ? i1 : fp.x + fp.w;
     const int y0 = j0 > fp.y ? j0 : fp.y, y1 = j1 < fp.y + fp.h ? j1 : fp.y + fp.h;

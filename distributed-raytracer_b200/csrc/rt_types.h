@@ -102,6 +102,9 @@ struct FrameParams {
     // numbering and skips the blocks that lie outside the rectangle (cull_on).
     int cull_on, cull_i0, cull_j0, cull_i1, cull_j1;
     int rbx0, rby0, rnbx, rnby;
+    int lt0, lt_n;
+    // ^ tile mode: only the local tiles lt0 .. lt0+lt_n-1 are traced (the tile ROWS that meet the rectangle: the local tiles of a
+    // range of rows are a contiguous range of local indices); lt_n == 0 means all of them
     unsigned int cancel_gen;   // generation of the call (rt_cancel): the kernels stop when counters[RT_CNT_CANCEL] has moved past it
 };
 
@@ -142,7 +145,10 @@ RT_HD uint32_t tile_id(uint32_t X, uint32_t Y, uint32_t tiles_x) {
 }   // i,j = absolute screen pixel; out = index in the output buffer
 
 RT_HD uint32_t ray_count(const FrameParams &fp) {
-    if (fp.tile_w > 0) return (uint32_t)fp.n_local_tiles * (uint32_t)(fp.tile_w * fp.tile_h);
+    if (fp.tile_w > 0) {
+        if (fp.cull_on && fp.cull_i1 <= fp.cull_i0) return 0u;     // nothing can be hit
+        return (uint32_t)(fp.lt_n > 0 ? fp.lt_n : fp.n_local_tiles) * (uint32_t)(fp.tile_w * fp.tile_h);
+    }
     if (fp.rnbx > 0) return (uint32_t)fp.rnbx * (uint32_t)fp.rnby * 32u;
     if (fp.cull_on) return 0u;                                   // culling found no block that can be hit
     uint32_t nbx = (uint32_t)(fp.w + 7) / 8, nby = (uint32_t)(fp.h + 3) / 4;
@@ -162,7 +168,7 @@ RT_HD PixMap map_ray(uint32_t r, const FrameParams &fp, bool rowmajor) {
     if (fp.tile_w > 0) {
         // tiles are cut from the REGION (x, y, w, h); a full-screen frame is the region (0, 0, W, H)
         uint32_t bpt = (uint32_t)(fp.tile_w * fp.tile_h) / 32u;       // blocks per tile
-        uint32_t lt = blk / bpt, b = blk % bpt;
+        uint32_t lt = (uint32_t)fp.lt0 + blk / bpt, b = blk % bpt;
         uint32_t bx = b % (uint32_t)(fp.tile_w / 8), by = b / (uint32_t)(fp.tile_w / 8);
         int tx = (int)bx * 8 + lx, ty = (int)by * 4 + ly;
         uint32_t t = lt * (uint32_t)fp.n_ranks + (uint32_t)fp.rank;

@@ -30,14 +30,30 @@ type Scene struct {
 // NewScene uploads the immutable scene and builds the BVHs on `device` (what register() does once per registration,
 // worker/distributed/main.go:101-129).  fast selects RT_FP32_FAST (fp32 traversal, fp64 shading) over RT_FP64_EXACT.
 func NewScene(env state.Environment, device int, fast bool) (*Scene, error) {
+	var d C.rt_scene_desc
+	release, ids, err := fillSceneDesc(env, fast, &d)
+	if err != nil {
+		return nil, err
+	}
+	defer release()
+	d.device = C.int32_t(device)
+	s := &Scene{ids: ids}
+	if rc := C.rt_scene_create(&d, &s.h); rc != 0 {
+		return nil, fmt.Errorf("rt_scene_create: %d %s", int(rc), C.GoString(C.rt_last_error(nil)))
+	}
+	runtime.SetFinalizer(s, func(s *Scene) { s.Close() })
+	return s, nil
+}
+
+// fillSceneDesc flattens env into an rt_scene_desc.  rt_mesh_desc holds C pointers into Go memory: allowed for the duration
+// of the create call because the slices contain no Go pointers; the descriptor array itself lives in C memory, and the
+// slices stay pinned until release() is called (after rt_scene_create / rt_group_create has copied everything).
+func fillSceneDesc(env state.Environment, fast bool, d *C.rt_scene_desc) (release func(), ids []uint, err error) {
 	flat := env.Flatten()
 	n := len(flat.Meshes)
-	// rt_mesh_desc holds C pointers into Go memory: allowed for the duration of the call because the slices contain no
-	// Go pointers; the descriptor array itself lives in C memory, and the slices are pinned while C reads them.
-	var pin runtime.Pinner
-	defer pin.Unpin()
+	pin := new(runtime.Pinner)
 	descs := (*C.rt_mesh_desc)(C.calloc(C.size_t(maxInt(n, 1)), C.sizeof_rt_mesh_desc))
-	defer C.free(unsafe.Pointer(descs))
+	release = func() { pin.Unpin(); C.free(unsafe.Pointer(descs)); runtime.KeepAlive(flat) }
 	dv := unsafe.Slice(descs, maxInt(n, 1))
 	for i := range flat.Meshes {
 		f := &flat.Meshes[i]
@@ -62,7 +78,6 @@ func NewScene(env state.Environment, device int, fast bool) (*Scene, error) {
 		}
 		dv[i].n_materials = C.uint32_t(len(f.Materials) / 10)
 	}
-	var d C.rt_scene_desc
 	d.meshes, d.n_meshes = descs, C.uint32_t(n)
 	if len(flat.ObjMesh) > 0 {
 		pin.Pin(&flat.ObjPos[0])
@@ -70,17 +85,11 @@ func NewScene(env state.Environment, device int, fast bool) (*Scene, error) {
 		d.obj_pos, d.obj_mesh = (*C.double)(&flat.ObjPos[0]), (*C.uint32_t)(&flat.ObjMesh[0])
 	}
 	d.n_objects = C.uint32_t(len(flat.ObjMesh))
-	d.device = C.int32_t(device)
 	d.precision = C.RT_FP64_EXACT
 	if fast {
 		d.precision = C.RT_FP32_FAST
 	}
-	s := &Scene{ids: flat.ObjIds}
-	if rc := C.rt_scene_create(&d, &s.h); rc != 0 {
-		return nil, fmt.Errorf("rt_scene_create: %d %s", int(rc), C.GoString(C.rt_last_error(nil)))
-	}
-	runtime.SetFinalizer(s, func(s *Scene) { s.Close() })
-	return s, nil
+	return release, flat.ObjIds, nil
 }
 
 // Close releases the GPU scene (re-registration: Close the old scene, NewScene the new one; main.go:146-185).
@@ -171,8 +180,64 @@ func (s *Scene) BulkTraceEncoded(em *state.EnvMutables, screenW, screenH, x, y, 
 	return buf[:n], nil
 }
 
-// Cancel makes renders in flight on this scene return RT_ERR_CANCELLED at their next kernel boundary (ctx.Err(), main.go:73).
+// Cancel stops the renders that are in flight on this scene (ctx.Err(), main.go:73): their kernels poll a cancel generation
+// and give up, the blocked BulkTrace calls return RT_ERR_CANCELLED.  Calls that start afterwards are not affected.
 func (s *Scene) Cancel() { C.rt_cancel(s.h) }
+
+// Group is one registered scene on SEVERAL GPUs of the box (rt_group): one worker process, one BulkTrace per order, all GPUs
+// rendering stripes of it and copying them into the reply over their own PCIe links.  master/pool still sees one worker.
+type Group struct {
+	h   *C.rt_group
+	ids []uint
+}
+
+// NewGroup registers the scene on the listed CUDA devices (nil: every GPU of the box).
+func NewGroup(env state.Environment, devices []int32, fast bool) (*Group, error) {
+	var d C.rt_scene_desc
+	release, ids, err := fillSceneDesc(env, fast, &d) // the body of NewScene up to rt_scene_create, shared by both constructors
+	if err != nil {
+		return nil, err
+	}
+	defer release()
+	g := &Group{ids: ids}
+	var dp *C.int32_t
+	if len(devices) > 0 {
+		dp = (*C.int32_t)(&devices[0])
+	}
+	if rc := C.rt_group_create(&d, dp, C.uint32_t(len(devices)), &g.h); rc != 0 {
+		return nil, fmt.Errorf("rt_group_create: %d %s", int(rc), C.GoString(C.rt_group_last_error(nil)))
+	}
+	runtime.SetFinalizer(g, func(g *Group) { g.Close() })
+	return g, nil
+}
+
+func (g *Group) Close() {
+	if g.h != nil {
+		C.rt_group_destroy(g.h)
+		g.h = nil
+	}
+}
+
+// BulkTrace: same contract as Scene.BulkTrace (bytes identical to the single-GPU frame); safe to call concurrently.
+// Hand it a buffer from rt_host_alloc (pinned) and the GPUs copy their stripes straight into it.
+func (g *Group) BulkTrace(em *state.EnvMutables, screenW, screenH, x, y, w, h uint32, out []byte) error {
+	if uint64(len(out)) < uint64(w)*uint64(h)*3 {
+		return fmt.Errorf("rtb200: out holds %d bytes, %d needed", len(out), uint64(w)*uint64(h)*3)
+	}
+	if w == 0 || h == 0 {
+		return nil
+	}
+	f := (&Scene{ids: g.ids}).frameOf(em)
+	lp, pp := f.ptrs()
+	rc := C.rt_group_bulk_trace(g.h, &f.cam, lp, C.uint32_t(len(f.lights)), pp,
+		C.uint32_t(screenW), C.uint32_t(screenH), C.uint32_t(x), C.uint32_t(y), C.uint32_t(w), C.uint32_t(h),
+		(*C.uint8_t)(&out[0]), C.RT_LAYOUT_COLMAJOR|C.RT_QUANT_RGB255)
+	runtime.KeepAlive(f)
+	if rc != 0 {
+		return fmt.Errorf("rt_group_bulk_trace: %d %s", int(rc), C.GoString(C.rt_group_last_error(g.h)))
+	}
+	return nil
+}
 
 func maxInt(a, b int) int {
 	if a > b {
