@@ -295,7 +295,15 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     const size_t out_bytes = npix_out * 3;
     const bool dbg = out.h_colour || out.h_face || out.h_obj || out.h_lit;
     const bool internal_rgb = out.d_rgb == nullptr;
-    int rc = ensure_scratch(s, L, nrays, out_bytes, internal_rgb, dbg, npix_out);
+    // one fused kernel per frame (FP32_FAST): the scene's default, RT_FLAG_FUSED / RT_FLAG_PIPELINE per call
+    const bool fused = s->precision == RT_FP32_FAST && !s->shade32 && !(flags & (RT_FLAG_PIPELINE | RT_FLAG_PERSISTENT)) &&
+                       (s->fused || (flags & RT_FLAG_FUSED));
+    // The hit-list scratch is sized for the UN-culled ray count of the region / tile set, so that a camera move (another cull
+    // rectangle) never re-allocates: cudaMalloc / cudaFree wait for the device, and in the multi-GPU pipeline a peer's hand-off
+    // kernel may be spinning on this very rank's progress.  The fused kernel needs no hit list at all.
+    size_t full_rays = fp.tile_w > 0 ? (size_t)fp.n_local_tiles * (size_t)(fp.tile_w * fp.tile_h)
+                                     : (size_t)((fp.w + 7) / 8) * (size_t)((fp.h + 3) / 4) * 32u;
+    int rc = ensure_scratch(s, L, fused ? 0 : full_rays, out_bytes, internal_rgb, dbg, npix_out);
     if (rc != RT_OK) return rc;
     cudaStream_t st = out.ext_stream ? out.ext_stream : L.stream;
     uint8_t *d_rgb = internal_rgb ? L.d_rgb : out.d_rgb;
@@ -322,9 +330,7 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     }
     job.shade_minb = s->shade_minb;
     job.primary_persistent = s->primary_persistent;
-    // one fused kernel per frame (FP32_FAST): the scene's default, RT_FLAG_FUSED / RT_FLAG_PIPELINE per call
-    job.fused = s->precision == RT_FP32_FAST && !s->shade32 && !(flags & (RT_FLAG_PIPELINE | RT_FLAG_PERSISTENT)) &&
-                (s->fused || (flags & RT_FLAG_FUSED));
+    job.fused = fused;
 
     CU(s, cudaMemsetAsync(L.d_counters, 0, 4 * sizeof(unsigned int), st));
     if (flags & RT_FLAG_COUNT) CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), st));

@@ -179,6 +179,21 @@ class Tracer:
             pass
 
 
+def partition_balanced(width, height, workers, last_rgb, hit_weight=30.0):
+    """partition() with the cuts placed by the cost of the PREVIOUS frame (`last_rgb`: width*height*3 bytes in
+    BulkTrace order; a hit pixel costs 1 + hit_weight, a miss 1).  List of (x, y, w, h)."""
+    H_ = load()
+    rgb = np.ascontiguousarray(last_rgb, dtype=np.uint8).reshape(-1)
+    if rgb.size != width * height * 3:
+        raise ValueError("last_rgb must hold width*height*3 bytes")
+    cap = max(4 * workers, 16)
+    out = np.zeros((cap, 4), dtype=np.uint32)
+    H_.rth_partition_balanced.restype = C.c_uint32
+    H_.rth_partition_balanced.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_double, C.c_void_p, C.c_uint32]
+    n = H_.rth_partition_balanced(width, height, workers, rgb.ctypes.data, float(hit_weight), out.ctypes.data, cap)
+    return [tuple(int(v) for v in out[k]) for k in range(n)]
+
+
 def partition(width, height, workers):
     """master/main.go:54-91: list of (x, y, w, h)."""
     cap = max(4 * workers, 16)

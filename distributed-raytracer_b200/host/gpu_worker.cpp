@@ -110,4 +110,74 @@ std::vector<comms::WorkOrder> partition(const comms::WorkOrder &area, unsigned w
     return left;
 }
 
+namespace {
+
+// summed-area table of the per-pixel cost (column-major like the frame: index i*(H+1) + j over (W+1) x (H+1))
+struct CostTable {
+    uint32_t W = 0, H = 0;
+    std::vector<double> sat;
+    double sum(uint32_t x, uint32_t y, uint32_t w, uint32_t h) const {
+        auto at = [&](uint32_t i, uint32_t j) { return sat[size_t(i) * (H + 1) + j]; };
+        return at(x + w, y + h) - at(x, y + h) - at(x + w, y) + at(x, y);
+    }
+};
+
+void balanced(const CostTable &ct, const comms::WorkOrder &area, unsigned workers, unsigned dimension, unsigned *leftover,
+              std::vector<comms::WorkOrder> &out) {
+    if (workers / workerRedundancy < 2) {                                            // master/main.go:56-62
+        *leftover = workers > workerRedundancy ? workers % workerRedundancy : 0;
+        out.push_back(area);
+        return;
+    }
+    const uint32_t x = area.x, y = area.y, width = area.width, height = area.height;
+    if (width <= widthKernel && height <= heightKernel) {                            // :66-68
+        *leftover = workers - workerRedundancy;
+        out.push_back(area);
+        return;
+    } else if (width <= widthKernel) dimension = 1;
+    else if (height <= heightKernel) dimension = 0;
+    const unsigned wl = workers / 2 + workers % 2;                                   // workers of the left half (:88)
+    const double want = ct.sum(x, y, width, height) * double(wl) / double(workers);
+    const bool vertical = dimension % 2 == 0;
+    const uint32_t extent = vertical ? width : height;
+    // smallest cut whose left part carries at least its share of the cost (binary search on the monotone prefix cost),
+    // kept at least one pixel away from both ends
+    uint32_t lo = 1, hi = extent - 1;
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        const double c = vertical ? ct.sum(x, y, mid, height) : ct.sum(x, y, width, mid);
+        if (c < want) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t cut = lo;
+    comms::WorkOrder l = area, r = area;
+    if (vertical) { l.width = cut; r.x = x + cut; r.width = width - cut; }
+    else { l.height = cut; r.y = y + cut; r.height = height - cut; }
+    unsigned remainder = 0;
+    balanced(ct, l, wl, (dimension + 1) % 2, &remainder, out);
+    balanced(ct, r, workers / 2 + remainder, (dimension + 1) % 2, &remainder, out);
+    *leftover = remainder;
+}
+
+}  // namespace
+
+std::vector<comms::WorkOrder> partitionBalanced(const comms::WorkOrder &area, unsigned workers, const uint8_t *last_rgb, uint32_t W,
+                                                uint32_t H, double hit_weight) {
+    if (!last_rgb || W == 0 || H == 0) return partition(area, workers, 0, nullptr);
+    CostTable ct;
+    ct.W = W; ct.H = H;
+    ct.sat.assign(size_t(W + 1) * (H + 1), 0.0);
+    for (uint32_t i = 0; i < W; i++) {
+        double col = 0.0;                                        // running cost of pixel column i
+        for (uint32_t j = 0; j < H; j++) {
+            const uint8_t *p = last_rgb + (size_t(i) * H + j) * 3;
+            col += 1.0 + ((p[0] | p[1] | p[2]) ? hit_weight : 0.0);
+            ct.sat[size_t(i + 1) * (H + 1) + (j + 1)] = ct.sat[size_t(i) * (H + 1) + (j + 1)] + col;
+        }
+    }
+    std::vector<comms::WorkOrder> out;
+    unsigned leftover = 0;
+    balanced(ct, area, workers, 0, &leftover, out);
+    return out;
+}
+
 }  // namespace worker

@@ -70,4 +70,13 @@ bool draw(Tracer &t, const state::EnvMutables &scene, std::vector<uint8_t> &surf
 // (widthKernel = heightKernel = 50, workerRedundancy = 1: master/main.go:25-31).
 std::vector<comms::WorkOrder> partition(const comms::WorkOrder &area, unsigned workers, unsigned dimension, unsigned *leftover);
 
+// SURVEY s8 row f4 -- a content-aware partition() for the master.  Same recursion as partition() (alternate axis, the same
+// split of the worker count, the same 50x50 floor), but the cut is placed where the COST of the two halves is in the ratio of
+// their worker counts instead of at the geometric middle.  The cost of a pixel is 1 for a primary ray that missed plus
+// `hit_weight` if the pixel was hit in the PREVIOUS frame (shading + one shadow ray per light): the master already holds that
+// frame (master/main.go:166-176 draws it), so no new data crosses the wire.  last_rgb: the previous frame in BulkTrace order
+// (pixel (i, j) at (i*height + j)*3), nullptr = no history -> identical to partition().
+std::vector<comms::WorkOrder> partitionBalanced(const comms::WorkOrder &area, unsigned workers, const uint8_t *last_rgb, uint32_t screenWidth,
+                                                uint32_t screenHeight, double hit_weight);
+
 }  // namespace worker

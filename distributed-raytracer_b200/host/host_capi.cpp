@@ -94,4 +94,18 @@ uint32_t rth_partition(uint32_t W, uint32_t H, uint32_t workers, uint32_t *out, 
     return n;
 }
 
+// partitionBalanced(): like rth_partition, cut by the cost of the previous frame (last_rgb: W*H*3 bytes in BulkTrace order)
+uint32_t rth_partition_balanced(uint32_t W, uint32_t H, uint32_t workers, const uint8_t *last_rgb, double hit_weight, uint32_t *out, uint32_t cap) {
+    comms::WorkOrder area;
+    area.width = W; area.height = H;
+    std::vector<comms::WorkOrder> v = worker::partitionBalanced(area, workers, last_rgb, W, H, hit_weight);
+    uint32_t n = 0;
+    for (const comms::WorkOrder &o : v) {
+        if (n >= cap) break;
+        out[4 * n] = o.x; out[4 * n + 1] = o.y; out[4 * n + 2] = o.width; out[4 * n + 3] = o.height;
+        n++;
+    }
+    return n;
+}
+
 }  // extern "C"

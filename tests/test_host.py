@@ -93,3 +93,35 @@ def test_partition_known_shapes(host):
     assert host.partition(321, 241, 2) == [(0, 0, 160, 241), (160, 0, 161, 241)]
     assert host.partition(50, 50, 9) == [(0, 0, 50, 50)]              # <= widthKernel x heightKernel: not split (:66)
     assert host.partition(100, 40, 4) == [(0, 0, 50, 40), (50, 0, 50, 40)]   # height <= 50: only vertical cuts (:72)
+
+
+def test_partition_balanced_tiles_the_screen_and_balances_cost():
+    """partitionBalanced cuts by the cost of the previous frame.  The rectangles must tile the screen exactly, and
+    on a frame whose hits sit in the middle (the BASELINE views) the most expensive rectangle must be far cheaper than with
+    partition()'s geometric bisection (master/main.go:54-91)."""
+    from distributed_raytracer_b200 import host
+    W, H = 640, 360
+    last = np.zeros((W, H, 3), dtype=np.uint8)                       # BulkTrace order: [i][j]
+    ii, jj = np.meshgrid(np.arange(W), np.arange(H), indexing="ij")
+    blob = ((ii - 330) / 95.0) ** 2 + ((jj - 170) / 70.0) ** 2 < 1.0   # ~9 % of the pixels hit, off-centre
+    last[blob] = (10, 200, 30)
+    cost = 1.0 + 30.0 * blob
+
+    def worst(rects):
+        c = [cost[x:x + w, y:y + h].sum() for x, y, w, h in rects]
+        return max(c) / (sum(c) / len(c))
+    for workers in (2, 3, 5, 8, 16):
+        rb = host.partition_balanced(W, H, workers, last, 30.0)
+        rp = host.partition(W, H, workers)
+        assert len(rb) == len(rp) == workers
+        cover = np.zeros((W, H), dtype=np.int32)
+        for x, y, w, h in rb:
+            assert w > 0 and h > 0
+            cover[x:x + w, y:y + h] += 1
+        assert (cover == 1).all()
+        assert worst(rb) <= 1.25, (workers, worst(rb))
+        if workers >= 8:
+            assert worst(rp) >= 2.0 * worst(rb), (workers, worst(rp), worst(rb))
+    # without history it IS partition()
+    black = np.zeros((W, H, 3), dtype=np.uint8)
+    assert host.partition_balanced(W, H, 8, black, 30.0) == host.partition(W, H, 8)
