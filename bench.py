@@ -399,16 +399,20 @@ def main():
         torch.cuda.synchronize(dev)
     # ---- lane priming (untimed, not a step): the first frame on a lane allocates its scratch buffers (cudaMalloc waits for
     # the device), so every frame slot is used once before anything is measured; then the W warm-up steps ----
+    if world > 1:
+        dist.barrier()                                    # the ranks enter the frame pipeline together (a rank > 2 s late is a hand-off time-out)
     for _ in range(REPLICAS):
         step()
     r.wait()
     torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
+    r.check_sync(" (lane priming)")
     for _ in range(args.warmup):
         step()
     r.wait()
     torch.cuda.synchronize(dev)
+    r.check_sync(" (warm-up)")
 
     # ---- timed region: exactly K steps, barrier + synchronize on both sides, device timing, max over ranks ----
     if world > 1:
@@ -427,7 +431,7 @@ def main():
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
-    r.check_sync()                                        # a timed-out device-side hand-off would invalidate the run
+    r.check_sync(" (timed region)")                       # a timed-out device-side hand-off would invalidate the run
     dev_ms = ev0.elapsed_time(ev1)
     print("[bench] rank %d: %.3f ms per step on this rank" % (rank, dev_ms / args.steps), file=sys.stderr, flush=True)
     if world > 1:

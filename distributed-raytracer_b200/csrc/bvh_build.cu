@@ -7,7 +7,8 @@
 //   cub radix sort  (key, face) pairs                                  [library plumbing]
 //   k_karras        binary radix tree over the sorted keys (Karras 2012), parent links
 //   k_refit_sah     bottom-up boxes + SAH cost, collapse subtrees of <= max_leaf faces into leaves
-//   k_emit_count / scan / k_emit_write   BFS re-emission into RT_W-wide traversal nodes (greedy surface-area collapse)
+//   k_emit_count_d / scan / k_emit_write_d / k_emit_advance   BFS re-emission into RT_W-wide traversal nodes (greedy
+//                   surface-area collapse), frontier size kept on the device: one host round trip per 8 levels
 //   k_gather_tris   triangle records in leaf order: 48 B fp32 and/or 80 B fp64
 #include "rt_internal.h"
 #include <cub/cub.cuh>
@@ -67,21 +68,35 @@ __global__ void k_refit_sah(int n, const uint32_t *__restrict__ vals, const BoxF
     if (i < n) refit_sah_thread(i, vals, leafbox, kn, parent_int, parent_leaf, ibox, icost, collapsed, flags, max_leaf);
 }
 
-__global__ void k_emit_count(const int *__restrict__ frontier, int fsize, const KarrasNode *__restrict__ kn,
-                             const unsigned char *__restrict__ collapsed, const BoxF *__restrict__ ibox, int *__restrict__ cnt) {
+// ---- BFS emission with the frontier size on the DEVICE ------------------------------------------------------------
+// state[0] = frontier size of the current level, [1] = index of its first node, [2] = levels emitted, [3] = total leaf refs.
+// Every kernel of a level is launched for the widest possible frontier and reads the real size from `state`, so a batch of
+// levels is enqueued without a host round trip (rt_build_bvh reads the state back once per RT_EMIT_BATCH levels).
+#define RT_EMIT_BATCH 8
+__global__ void k_emit_count_d(const int *__restrict__ frontier, const int *__restrict__ state, int n_max, const KarrasNode *__restrict__ kn,
+                               const unsigned char *__restrict__ collapsed, const BoxF *__restrict__ ibox, int *__restrict__ cnt) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < fsize) emit_count_thread(p, frontier, kn, collapsed, ibox, cnt);
+    if (p >= n_max) return;
+    if (p < state[0]) emit_count_thread(p, frontier, kn, collapsed, ibox, cnt);
+    else cnt[p] = 0;                                              // the scan runs over n_max entries
 }
-
-__global__ void k_emit_write(const int *__restrict__ frontier, int fsize, int level_base, const KarrasNode *__restrict__ kn,
-                             const unsigned char *__restrict__ collapsed, const int *__restrict__ off,
-                             const uint32_t *__restrict__ vals, const BoxF *__restrict__ leafbox,
-                             const BoxF *__restrict__ ibox, RtNode *__restrict__ nodes, int *__restrict__ next_frontier,
-                             unsigned int *__restrict__ leaf_counter) {
+__global__ void k_emit_write_d(const int *__restrict__ frontier, const int *__restrict__ state, const KarrasNode *__restrict__ kn,
+                               const unsigned char *__restrict__ collapsed, const int *__restrict__ off, const uint32_t *__restrict__ vals,
+                               const BoxF *__restrict__ leafbox, const BoxF *__restrict__ ibox, RtNode *__restrict__ nodes,
+                               int *__restrict__ next_frontier, unsigned int *__restrict__ leaf_counter) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int fsize = state[0];
     if (p >= fsize) return;
-    unsigned int nleaf = emit_write_thread(p, frontier, fsize, level_base, kn, collapsed, off, vals, leafbox, ibox, nodes, next_frontier);
+    unsigned int nleaf = emit_write_thread(p, frontier, fsize, state[1], kn, collapsed, off, vals, leafbox, ibox, nodes, next_frontier);
     if (nleaf) atomicAdd(leaf_counter, nleaf);
+}
+// next level: base += fsize; fsize = number of internal children just emitted
+__global__ void k_emit_advance(int *state, const int *__restrict__ cnt, const int *__restrict__ off) {
+    const int fsize = state[0];
+    if (fsize <= 0) return;
+    state[1] += fsize;
+    state[0] = off[fsize - 1] + cnt[fsize - 1];
+    state[2] += 1;
 }
 
 __global__ void k_gather_tris(const double *__restrict__ fverts, const uint32_t *__restrict__ vals, uint32_t n,
@@ -188,7 +203,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
     unsigned long long *d_keys = nullptr, *d_keys2 = nullptr; uint32_t *d_vals = nullptr, *d_vals2 = nullptr;
     KarrasNode *d_kn = nullptr; int *d_pint = nullptr, *d_pleaf = nullptr; float *d_icost = nullptr;
     unsigned char *d_coll = nullptr; unsigned int *d_flags = nullptr, *d_leafcnt = nullptr;
-    int *d_front[2] = { nullptr, nullptr }, *d_cnt = nullptr, *d_off = nullptr;
+    int *d_front[2] = { nullptr, nullptr }, *d_cnt = nullptr, *d_off = nullptr, *d_state = nullptr;
     void *d_tmp = nullptr; size_t tmp_bytes = 0, tmp_scan = 0;
     Scratch sc; sc.m = &m;
     const int TB = 256;
@@ -255,6 +270,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
         CK(sc.alloc(&d_front[1], sizeof(int) * (size_t)ni));
         CK(sc.alloc(&d_cnt, sizeof(int) * (size_t)(ni + 1)));
         CK(sc.alloc(&d_off, sizeof(int) * (size_t)(ni + 1)));
+        CK(sc.alloc(&d_state, 4 * sizeof(int)));
         k_karras<<<nbi, TB, 0, st>>>(sorted_keys, (int)n, d_kn, d_pint, d_pleaf);
         CK(cudaGetLastError());
         // One wide hierarchy per leaf size over the one binary radix tree: refit + SAH collapse decision, then BFS emission.
@@ -274,28 +290,30 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
             RtNode *nodes = nullptr;
             CK(cudaMalloc(&nodes, sizeof(RtNode) * (size_t)ni));
             *out_nodes = nodes;                                   // owned by the mesh from here on (freed by the caller on failure)
-            int zero = 0;
-            CK(cudaMemcpyAsync(d_front[0], &zero, sizeof(int), cudaMemcpyHostToDevice, st));
-            int fsize = 1, base = 0, cur = 0, depth = 0;
-            while (fsize > 0) {
-                unsigned int fb = (fsize + TB - 1) / TB;
-                k_emit_count<<<fb, TB, 0, st>>>(d_front[cur], fsize, d_kn, d_coll, d_ibox, d_cnt);
+            int init_state[4] = { 1, 0, 0, 0 };                   // frontier = { root }
+            CK(cudaMemcpyAsync(d_state, init_state, sizeof init_state, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(d_front[0], 0, sizeof(int), st));
+            const unsigned int fb = (ni + TB - 1) / TB;
+            const int max_levels = (RT_STACK_SIZE - 2) / (RT_W - 1);
+            int h_state[4] = { 1, 0, 0, 0 };
+            int cur = 0;
+            while (h_state[0] > 0) {
+                if (h_state[2] >= max_levels) { err = "BVH deeper than the traversal stack"; return false; }
+                for (int b = 0; b < RT_EMIT_BATCH; b++) {
+                    k_emit_count_d<<<fb, TB, 0, st>>>(d_front[cur], d_state, ni, d_kn, d_coll, d_ibox, d_cnt);
+                    size_t tb = tmp_bytes;
+                    CK(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_off, ni, st));
+                    k_emit_write_d<<<fb, TB, 0, st>>>(d_front[cur], d_state, d_kn, d_coll, d_off, sorted_vals, d_leafbox, d_ibox, nodes,
+                                                      d_front[cur ^ 1], d_leafcnt);
+                    k_emit_advance<<<1, 1, 0, st>>>(d_state, d_cnt, d_off);
+                    cur ^= 1;
+                }
                 CK(cudaGetLastError());
-                size_t tb = tmp_bytes;
-                CK(cub::DeviceScan::ExclusiveSum(d_tmp, tb, d_cnt, d_off, fsize, st));
-                k_emit_write<<<fb, TB, 0, st>>>(d_front[cur], fsize, base, d_kn, d_coll, d_off, sorted_vals, d_leafbox, d_ibox,
-                                                nodes, d_front[cur ^ 1], d_leafcnt);
-                CK(cudaGetLastError());
-                int last_off = 0, last_cnt = 0;
-                CK(cudaMemcpyAsync(&last_off, d_off + (fsize - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(&last_cnt, d_cnt + (fsize - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(h_state, d_state, sizeof h_state, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
-                base += fsize;
-                fsize = last_off + last_cnt;
-                cur ^= 1;
-                depth++;
-                if ((RT_W - 1) * depth + 2 > RT_STACK_SIZE) { err = "BVH deeper than the traversal stack"; return false; }
             }
+            const int base = h_state[1], depth = h_state[2];
+            if ((RT_W - 1) * depth + 2 > RT_STACK_SIZE) { err = "BVH deeper than the traversal stack"; return false; }
             *out_n_nodes = (uint32_t)base;
             if ((size_t)base < (size_t)ni) {
                 // the wide tree has far fewer nodes than the binary one it was collapsed from: shrink the allocation

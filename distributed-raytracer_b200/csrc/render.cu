@@ -622,6 +622,16 @@ cudaError_t rt_fma_peak(bool fp64, int sm_count, double *tflops) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+template <class K> static void prefer_l1(K kern) {
+    static thread_local int done_for_device = -1;             // per kernel instantiation (K differs) and calling thread
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev == done_for_device) return;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaGetLastError();
+    done_for_device = dev;
+}
+
 cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
     SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights;
@@ -710,8 +720,10 @@ cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool rowmajor = (job.flags & RT_LAYOUT_ROWMAJOR) != 0, sdl = (job.flags & RT_QUANT_RGBA16_SHR8) != 0;
     const unsigned nblk = (nrays + 127) / 128;
-#define LAUNCH_FUSED(CN, MB) k_frame_fused<CN, MB><<<nblk, 128, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_out_rgb, \
-                                                                          job.d_out_colour, job.d_out_face, job.d_out_obj, job.d_out_lit, job.d_stats)
+    // the traversal kernels use no shared memory: ask for the whole unified L1 / shared array as L1 (once per kernel and device)
+#define LAUNCH_FUSED(CN, MB) do { prefer_l1(k_frame_fused<CN, MB>);                                                                   \
+        k_frame_fused<CN, MB><<<nblk, 128, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_out_rgb, job.d_out_colour,             \
+                                                    job.d_out_face, job.d_out_obj, job.d_out_lit, job.d_stats); } while (0)
     if (count) LAUNCH_FUSED(true, 1);
     else if (job.shade_minb >= 10) LAUNCH_FUSED(false, 10);
     else if (job.shade_minb >= 9) LAUNCH_FUSED(false, 9);

@@ -410,14 +410,17 @@ class TileShardedRenderer:
             return self._host_frames()[k]
         return self.frame[k]
 
-    def check_sync(self):
+    def check_sync(self, where=""):
         """Raises if a device-side wait of the frame hand-off timed out (a rank died or fell > RT_B200_SYNC_TIMEOUT_MS behind)."""
         if self.ctrl is None:
             return
-        err = self.ctrl_view[:, 33].cpu().clone()
+        words = self.ctrl_view.cpu().clone()
+        err = words[:, 33]
         if int(err.abs().max()) != 0:
-            raise RuntimeError("frame hand-off timed out: error words per slot = %s (0x100+r: rank r never arrived; 0x200+r: "
-                               "rank r never saw the slot released)" % [hex(int(e)) for e in err])
+            raise RuntimeError("frame hand-off timed out%s: error words per slot = %s (0x100+r: rank r never arrived; 0x200+r: "
+                               "rank r never saw the slot released); arrive[0..%d] / consumed per slot = %s; frames enqueued per slot here = %s"
+                               % (where, [hex(int(e)) for e in err], self.n_ranks - 1,
+                                  [([int(v) for v in w[:self.n_ranks]], int(w[32])) for w in words], self.slot_seq))
 
     def _single_local(self):
         if not self.local:
