@@ -331,7 +331,7 @@ def main():
     frame_state = rt.FrameState(cam13, lights, tan_half_fov=tan_half)   # camera + lights marshalled once; handed over per frame
 
     def step():
-        r.render_frame(frame_state, flags=render_flags)
+        return r.render_frame(frame_state, flags=render_flags)
 
     # ---- counting pass (outside the timed region, serial): algorithmic traversal work of one frame on this rank ----
     g.set_frame(cam13, lights, tan_half_fov=tan_half)
@@ -415,23 +415,44 @@ def main():
     r.check_sync(" (warm-up)")
 
     # ---- timed region: exactly K steps, barrier + synchronize on both sides, device timing, max over ranks ----
+    # A device-side hand-off wait that timed out (a rank stalled for > 2 s: the run shares its box) invalidates the region: it is
+    # then measured again, at most twice, and the line says so (`handoff_retries`).
+    handoff_retries = 0
+    while True:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        ev0.record(stream)
+        r.start_after(ev0)
+        for k in range(args.steps):
+            last_frame = step()
+        t_enqueue = time.perf_counter() - wall0           # host time to enqueue the K frames (diagnostic: host- vs device-bound)
+        r.wait()                                          # the main stream waits for every frame (incl. gather / untile)
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        wall = time.perf_counter() - wall0
+        try:
+            r.check_sync(" (timed region)")
+            break
+        except RuntimeError as ex:
+            handoff_retries += 1
+            print("[bench] rank %d: %s" % (rank, ex), file=sys.stderr, flush=True)
+            if handoff_retries > 2:
+                raise
+            dist.barrier()
+            r.clear_sync_errors()
+            dist.barrier()
     if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    ev0.record(stream)
-    r.start_after(ev0)
-    for k in range(args.steps):
-        step()
-    t_enqueue = time.perf_counter() - wall0               # host time to enqueue the K frames (diagnostic: host- vs device-bound)
-    r.wait()                                              # the main stream waits for every frame (incl. gather / untile)
-    ev1.record(stream)
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    wall = time.perf_counter() - wall0
-    r.check_sync(" (timed region)")                       # a timed-out device-side hand-off would invalidate the run
+        # the frame the timed region ended with is still the single-GPU frame
+        ok = torch.tensor([1 if (rank != 0 or torch.equal(last_frame, ref_frame)) else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        frame_identical["last_timed_frame"] = bool(ok.item())
+        if not ok.item():
+            raise SystemExit("bench: the last frame of the timed region differs from the single-GPU frame")
     dev_ms = ev0.elapsed_time(ev1)
     print("[bench] rank %d: %.3f ms per step on this rank" % (rank, dev_ms / args.steps), file=sys.stderr, flush=True)
     if world > 1:
@@ -571,17 +592,28 @@ def main():
             dist.barrier()
             if it >= 3:
                 t_single.append(time.perf_counter() - t0)
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        t0 = time.perf_counter()
-        for it in range(e2e_steps):
-            hf = re.render_frame(frame_state, flags=render_flags, to_host=True)
-        re.wait()
-        torch.cuda.synchronize(dev)
-        dist.barrier()
-        tt = torch.tensor([time.perf_counter() - t0, sum(t_single) / len(t_single)], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        re.check_sync()
+        for attempt in range(3):                            # a timed-out hand-off (a rank stalled > 2 s) => measure again
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            t0 = time.perf_counter()
+            for it in range(e2e_steps):
+                hf = re.render_frame(frame_state, flags=render_flags, to_host=True)
+            re.wait()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            tt = torch.tensor([time.perf_counter() - t0, sum(t_single) / len(t_single)], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            try:
+                re.check_sync(" (e2e)")
+                break
+            except RuntimeError as ex:
+                print("[bench] rank %d: %s" % (rank, ex), file=sys.stderr, flush=True)
+                if attempt == 2:
+                    raise
+                handoff_retries += 1
+                dist.barrier()
+                re.clear_sync_errors()
+                dist.barrier()
         e2e_ms = 1e3 * float(tt[0].item()) / e2e_steps
         e2e = {"value": rays_frame / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_ms, "single_call_ms": 1e3 * float(tt[1].item()),
@@ -701,7 +733,7 @@ def main():
                          "gather": "; NCCL all_gather of packed tiles + de-interleave on rank 0"}[args.mode]),
             bvh=bvh, render_kernel="persistent K2 + K4 + K5" if args.persistent else ("K2 + K4 + K5" if args.pipeline else "k_frame_fused"),
             note="frame_identical_to_single_gpu is checked before the timed region at N > 1"),
-        "frame_identical_to_single_gpu": (all(frame_identical.values()) if frame_identical else None), "frame_identity_checks": frame_identical,
+        "frame_identical_to_single_gpu": (all(frame_identical.values()) if frame_identical else None), "frame_identity_checks": frame_identical, "handoff_retries": handoff_retries,
         "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "clocks": clocks, "wall_s_timed_region": wall,
     }

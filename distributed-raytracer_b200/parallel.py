@@ -422,6 +422,13 @@ class TileShardedRenderer:
                                % (where, [hex(int(e)) for e in err], self.n_ranks - 1,
                                   [([int(v) for v in w[:self.n_ranks]], int(w[32])) for w in words], self.slot_seq))
 
+    def clear_sync_errors(self):
+        """Rank 0 zeroes the error words of the hand-off records (callers put a barrier on both sides)."""
+        if self.ctrl is not None and self.rank == 0:
+            self.ctrl_view[:, 33] = 0
+            if self.backend is not None and hasattr(self.backend, "device"):
+                torch.cuda.synchronize(self.backend.device)
+
     def _single_local(self):
         if not self.local:
             self.local = [self.backend.alloc(self.per_rank * self.tile_bytes)]
