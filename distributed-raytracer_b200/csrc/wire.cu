@@ -11,10 +11,17 @@
 // proto3 wire form of one pixel:  0x0A  len  [0x08 varint(r)] [0x10 varint(g)] [0x18 varint(b)]   -- a field whose value is 0
 // is omitted (proto3 default), a value < 128 is a 1-byte varint, 128..255 takes 2 bytes; len <= 9, so 2..11 bytes a pixel.
 //
+// Default (round 2): ONE pass.
+//   k_wire_onepass    per 1024-pixel block: sizes, block-local scan, decoupled look-back over the preceding blocks' aggregates
+//                     (Merrill & Garland's single-pass scan: a block publishes its aggregate, then its inclusive prefix, in one
+//                     64-bit status word), encode into shared memory at the output's 16-byte phase, copy out with uint4 stores.
+//                     The pixels are read once (3 B), 2..11 B are written, the last block writes the message length.
+// Round-1 form, kept for A/B (RT_B200_WIRE_ONEPASS=0):
 //   W1 k_wire_sizes   bytes of every 1024-pixel block                      (reads 3 B / pixel)
 //   W2 k_wire_scan    exclusive scan of the block sizes + total length     (one CTA)
 //   W3 k_wire_encode  block-local scan, encode into shared memory, copy out with 16-byte stores  (3 B read, 2..11 B written)
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "rt_internal.h"
@@ -182,11 +189,100 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_encode(const uint8_t *__r
     }
 }
 
+// ---- single pass ---------------------------------------------------------------------------------------------------------
+// status[b]: bits 63..62 = 0 nothing yet, 1 = aggregate of block b, 2 = inclusive prefix up to and including block b; low 62 bits = bytes
+constexpr unsigned long long WIRE_FLAG_AGG = 1ull << 62, WIRE_FLAG_INC = 2ull << 62, WIRE_VAL_MASK = (1ull << 62) - 1ull;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(WIRE_THREADS) k_wire_onepass(const uint8_t *__restrict__ rgb, uint64_t n, unsigned long long *status,
+                                                                unsigned int *ticket, uint32_t n_blocks, uint8_t *__restrict__ out,
+                                                                uint64_t capacity, uint64_t *__restrict__ total_len) {
+    __shared__ __align__(16) uint8_t s_bytes[16 + WIRE_BLOCK_PIX * 11 + 16];
+    __shared__ uint32_t s_warp[WIRE_THREADS / 32];
+    __shared__ uint32_t s_block;
+    __shared__ unsigned long long s_prefix;
+    // blocks take their index from a ticket in the order they START, so every predecessor a block waits for is already running
+    if (threadIdx.x == 0) s_block = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t b = s_block;
+    uint32_t px[WIRE_PIX_PER_THREAD][3];
+    int count;
+    load_pixels(rgb, (uint64_t)b * WIRE_BLOCK_PIX + (uint64_t)threadIdx.x * WIRE_PIX_PER_THREAD, n, px, count);
+    uint32_t total;
+    const uint32_t off = block_exclusive_scan(thread_bytes(px, count), s_warp, &total);
+    // publish the aggregate, look back for the exclusive prefix (warp 0; one status word per lane and step)
+    if (threadIdx.x < 32) {
+        const unsigned lane = threadIdx.x;
+        if (lane == 0) st_status(status + b, (b == 0 ? WIRE_FLAG_INC : WIRE_FLAG_AGG) | (unsigned long long)total);
+        unsigned long long prefix = 0;
+        if (b > 0) {
+            int64_t look = (int64_t)b - 1 - (int64_t)lane;            // lane k inspects block b-1-k
+            for (;;) {
+                unsigned long long v = look >= 0 ? ld_status(status + look) : WIRE_FLAG_INC;      // before block 0: prefix 0
+                // wait until every inspected block has published something
+                while (__any_sync(0xffffffffu, (v >> 62) == 0ull)) v = look >= 0 ? ld_status(status + look) : WIRE_FLAG_INC;
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+                // sum the aggregates of the lanes in front of the first inclusive prefix, plus that prefix
+                const int first_inc = inc_mask ? __ffs(inc_mask) - 1 : 32;
+                unsigned long long part = (int)lane <= first_inc ? (v & WIRE_VAL_MASK) : 0ull;
+                if ((int)lane > first_inc) part = 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                prefix += part;
+                if (inc_mask) break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (b > 0) st_status(status + b, WIRE_FLAG_INC | (prefix + (unsigned long long)total));
+            if (b == n_blocks - 1) *total_len = prefix + (unsigned long long)total;
+        }
+    }
+    __syncthreads();
+    const uint64_t g0 = s_prefix;
+    if (g0 + total > capacity) return;                       // caller compares the reported length with its capacity
+    const uint32_t pad = (uint32_t)((uintptr_t)(out + g0) & 15u);
+    uint8_t *p = s_bytes + pad + off;
+#pragma unroll
+    for (int q = 0; q < WIRE_PIX_PER_THREAD; q++) {
+        if (q < count) {
+            uint32_t len = 0;
+            len += put_channel(p + 2 + len, 0x08u, px[q][0]);
+            len += put_channel(p + 2 + len, 0x10u, px[q][1]);
+            len += put_channel(p + 2 + len, 0x18u, px[q][2]);
+            p[0] = 0x0Au;
+            p[1] = (uint8_t)len;
+            p += 2 + len;
+        }
+    }
+    __syncthreads();
+    uint8_t *gbase = out + g0 - pad;
+    const uint32_t end = pad + total;
+    const uint32_t n_chunks = (end + 15u) / 16u;
+    for (uint32_t c = threadIdx.x; c < n_chunks; c += WIRE_THREADS) {
+        const uint32_t lo = c * 16u, hi = lo + 16u;
+        if (lo >= pad && hi <= end) {
+            *reinterpret_cast<uint4 *>(gbase + lo) = *reinterpret_cast<const uint4 *>(s_bytes + lo);
+        } else {
+            for (uint32_t k = (lo > pad ? lo : pad); k < (hi < end ? hi : end); k++) gbase[k] = s_bytes[k];
+        }
+    }
+}
+
 }  // namespace
 
 size_t rt_wire_scratch_bytes(uint64_t n_pixels) {
     const uint64_t nb = (n_pixels + WIRE_BLOCK_PIX - 1) / WIRE_BLOCK_PIX;
-    return (size_t)(16 + nb * 4 + 16 + nb * 8);
+    return (size_t)(16 + nb * 4 + 16 + nb * 8 + 16);          // both forms fit: {block_bytes, block_offset} or {status words, ticket}
 }
 
 // d_scratch: rt_wire_scratch_bytes(n) bytes, 16-byte aligned.  d_len receives the message length (also when it exceeds capacity,
@@ -196,6 +292,15 @@ cudaError_t rt_launch_wire_encode(const uint8_t *d_rgb, uint64_t n_pixels, uint8
     if (n_pixels == 0) return cudaMemsetAsync(d_len, 0, sizeof(uint64_t), st);
     const uint64_t nb = (n_pixels + WIRE_BLOCK_PIX - 1) / WIRE_BLOCK_PIX;
     if (nb > 0x7fffffffull) return cudaErrorInvalidValue;
+    static const bool onepass = [] { const char *v = getenv("RT_B200_WIRE_ONEPASS"); return !(v && *v && atoi(v) == 0); }();
+    if (onepass) {
+        unsigned long long *status = reinterpret_cast<unsigned long long *>(d_scratch);            // nb words, then the ticket
+        unsigned int *ticket = reinterpret_cast<unsigned int *>(status + nb);
+        cudaError_t e = cudaMemsetAsync(d_scratch, 0, (size_t)(nb * 8 + 8), st);
+        if (e != cudaSuccess) return e;
+        k_wire_onepass<<<(unsigned)nb, WIRE_THREADS, 0, st>>>(d_rgb, n_pixels, status, ticket, (uint32_t)nb, d_out, capacity, d_len);
+        return cudaGetLastError();
+    }
     uint32_t *block_bytes = reinterpret_cast<uint32_t *>(d_scratch);
     uint64_t *block_offset = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(d_scratch) + ((nb * 4 + 15) / 16) * 16);
     k_wire_sizes<<<(unsigned)nb, WIRE_THREADS, 0, st>>>(d_rgb, n_pixels, block_bytes);
