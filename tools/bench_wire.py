@@ -1,4 +1,4 @@
-"""Times the TraceResults protobuf encoder (csrc/wire.cu: k_wire_sizes, k_wire_scan, k_wire_encode) on a 4K frame of C3-like
+"""Times the TraceResults protobuf encoder (csrc/wire.cu: k_wire_onepass; RT_B200_WIRE_ONEPASS=0: k_wire_sizes, k_wire_scan, k_wire_encode) on a 4K frame of C3-like
 content (example scene rendered at 3840x2160: ~10 % hit pixels), L2 flushed before every launch, CUDA events on the launching
 stream; prints one JSON line with the algorithmic bytes and the fraction of the measured HBM peak."""
 import json, os, sys
@@ -40,8 +40,9 @@ m = int(d_len.item())
 from oracle import oracle as orc                              # checker only
 same = bool(np.array_equal(d_out[:m].cpu().numpy(), orc.encode_trace_results(d_rgb.cpu().numpy().reshape(-1, 3))))
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-alg = 2 * 3 * n + m                                            # RGB read by the size pass and by the encode pass + the message written
+onepass = os.environ.get("RT_B200_WIRE_ONEPASS", "1") != "0"
+alg = (1 if onepass else 2) * 3 * n + m                        # RGB read once (single pass) or by the size pass and the encode pass, + the message written
 t = float(np.median(ms))
-print(json.dumps({"kernels": "k_wire_sizes + k_wire_scan + k_wire_encode", "pixels": n, "message_bytes": m, "ms": t, "ms_min": float(min(ms)),
+print(json.dumps({"kernels": "k_wire_onepass (decoupled look-back)" if onepass else "k_wire_sizes + k_wire_scan + k_wire_encode", "pixels": n, "message_bytes": m, "ms": t, "ms_min": float(min(ms)),
                   "algorithmic_bytes": alg, "achieved_gbs": alg / t / 1e6, "peak_gbs": peak, "frac": alg / t / 1e6 / peak,
                   "identical_to_oracle": same, "hit_fraction": float((d_rgb.view(-1, 3).amax(dim=1) > 0).float().mean().item())}))
