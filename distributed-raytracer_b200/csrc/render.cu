@@ -24,11 +24,18 @@ __device__ __forceinline__ void flush_counters(Counters *g, const Counters &c) {
 }
 
 // lights / object positions come by value (a __grid_constant__ parameter may have its address taken) when they fit
-__device__ __forceinline__ SceneView bind_frame(SceneView sc, const InlineFrame &fr) {
+__device__ __forceinline__ SceneView bind_frame(SceneView sc, const InlineFrame &fr, uint32_t *trav_smem = nullptr) {
     if (fr.use_lights) sc.lights = fr.lights;
     if (fr.use_objs) sc.objs = fr.objs;
+    sc.trav_smem = trav_smem;
     return sc;
 }
+// the shared-memory part of the traversal stacks of a 128-thread CTA (SceneView::trav_smem): 8 KB
+#if RT_SMEM_STACK
+#define RT_DECLARE_TRAV_SMEM() __shared__ uint32_t s_trav[RT_SMEM_STACK_WORDS * RT_SMEM_STACK_STRIDE]; uint32_t *trav_smem = s_trav + threadIdx.x
+#else
+#define RT_DECLARE_TRAV_SMEM() uint32_t *trav_smem = nullptr
+#endif
 
 // rt_cancel (ctx.Err() of the reference loop, distributed/main.go:73): the generation in the lane's counter block has moved
 // past the one this frame was launched with.  Wrap-safe; one L2-resident word.
@@ -100,7 +107,8 @@ __device__ __forceinline__ void primary_dir32(int i, int j, const FrameParams &f
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_primary_fast_simple(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
                                                               HitRec *hits, unsigned int *counters, Counters *gstats) {
-    const SceneView sc = bind_frame(sc_in, fr);
+    RT_DECLARE_TRAV_SMEM();
+    const SceneView sc = bind_frame(sc_in, fr, trav_smem);
     uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t nrays = ray_count(fp);
     Counters c; c.nodes = 0; c.tris = 0;
@@ -138,6 +146,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(128, 4)
 k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, float olz, HitRec *hits, unsigned int *counters,
                           Counters *gstats) {
+    RT_DECLARE_TRAV_SMEM();
     const unsigned lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t nrays = ray_count(fp);
@@ -176,7 +185,7 @@ k_primary_fast_persistent(FrameParams fp, MeshView m, float olx, float oly, floa
         // ---- traverse: same per-ray loop as the default kernel ----
         float tbest = 3.0e38f;
         int face = -1;
-        bool hit = have && mesh_trace_fast<false>(m, r, tbest, face, COUNT ? &c : nullptr);
+        bool hit = have && mesh_trace_fast<false>(m, r, tbest, face, COUNT ? &c : nullptr, trav_smem);
         append_hit(hit, ray, 0, face, tbest, hits, &counters[1]);
         have = false;
     }
@@ -191,7 +200,8 @@ __global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView s
                                                       const HitRec *__restrict__ hits, unsigned int *counters,
                                                       double *__restrict__ hit_colour, uint32_t *__restrict__ hit_lit,
                                                       Counters *gstats) {
-    const SceneView sc = bind_frame(sc_in, fr);
+    RT_DECLARE_TRAV_SMEM();
+    const SceneView sc = bind_frame(sc_in, fr, EXACT ? nullptr : trav_smem);
     const unsigned lane = threadIdx.x & 31;
     const unsigned int nhits = counters[1];
     Counters c; c.nodes = 0; c.tris = 0;
@@ -297,7 +307,8 @@ __global__ void __launch_bounds__(128, MINB) k_frame_fused(FrameParams fp, Scene
                                                             uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour,
                                                             int32_t *__restrict__ out_face, int32_t *__restrict__ out_obj,
                                                             uint32_t *__restrict__ out_lit, Counters *gstats) {
-    const SceneView sc = bind_frame(sc_in, fr);
+    RT_DECLARE_TRAV_SMEM();
+    const SceneView sc = bind_frame(sc_in, fr, trav_smem);
     const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t nrays = ray_count(fp);
     const unsigned lane = threadIdx.x & 31;
@@ -634,7 +645,7 @@ template <class K> static void prefer_l1(K kern) {
 
 cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr;
     const uint32_t nrays = ray_count(fp);
     if (nrays == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
@@ -676,7 +687,7 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
 
 cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr;
     if (ray_count(fp) == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
@@ -714,7 +725,7 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
 
 cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr;
     const uint32_t nrays = ray_count(fp);
     if (nrays == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;

@@ -17,8 +17,13 @@
 // This is the orchestration that round 1 had in Python over torch.distributed (parallel.py, mode "host"); parallel.py's
 // one-process-per-GPU form stays for the torchrun benchmark, where the driver launches one rank per GPU.
 #include "rt_internal.h"
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <deque>
+#include <functional>
 #include <memory>
+#include <thread>
 
 namespace {
 
@@ -33,6 +38,44 @@ struct GroupLane {
 
 thread_local std::string g_group_err;
 
+// One enqueue thread per device: the command sequence of an order (frame state, clear, frame kernel, strided copy) costs
+// ~20 us of host time per device; issued by the calling thread alone that is 8 x 20 us at 8 GPUs, more than the 0.12 ms the
+// GPUs then need.  The workers only ENQUEUE (asynchronous); the caller waits for the streams.  A worker spins briefly after its
+// last task before it sleeps, so a worker that is being fed stays hot and one that is not costs nothing.
+struct DevWorker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    std::atomic<int> pending{ 0 };
+    bool stop = false;
+
+    void post(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); pending.fetch_add(1, std::memory_order_release); }
+        cv.notify_one();
+    }
+    void run() {
+        for (;;) {
+            std::function<void()> f;
+            // spin ~200 us for the next task before sleeping
+            const auto t0 = std::chrono::steady_clock::now();
+            while (pending.load(std::memory_order_acquire) == 0) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+                std::this_thread::yield();
+            }
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (q.empty()) return;                      // stop requested and nothing left
+                f = std::move(q.front());
+                q.pop_front();
+                pending.fetch_sub(1, std::memory_order_relaxed);
+            }
+            f();
+        }
+    }
+};
+
 }  // namespace
 
 struct rt_group {
@@ -43,6 +86,7 @@ struct rt_group {
     std::vector<rt_scene *> scenes;
     std::vector<double> obj_pos;           // registered object positions (an order without positions renders these)
     std::vector<std::unique_ptr<GroupLane>> lanes;
+    std::vector<std::unique_ptr<DevWorker>> workers;   // one per device entry except the first (the caller enqueues that one itself)
     uint32_t stripe_cols = 8, stripe_rows = 4;
 };
 
@@ -55,6 +99,12 @@ int gfail(rt_group *g, int code, const std::string &msg) {
 }
 
 void destroy_group(rt_group *g) {
+    for (auto &wp : g->workers) {
+        { std::lock_guard<std::mutex> lk(wp->mu); wp->stop = true; }
+        wp->cv.notify_all();
+        if (wp->th.joinable()) wp->th.join();
+    }
+    g->workers.clear();
     for (auto &lp : g->lanes) {
         for (size_t d = 0; d < g->devices.size(); d++) {
             cudaSetDevice(g->devices[d]);
@@ -150,6 +200,11 @@ int rt_group_create(const rt_scene_desc *desc, const int32_t *devices, uint32_t 
             }
         }
     }
+    for (size_t d = 1; d < devs.size(); d++) {
+        g->workers.emplace_back(new DevWorker());
+        DevWorker *w = g->workers.back().get();
+        w->th = std::thread([w] { w->run(); });
+    }
     *out = g;
     return RT_OK;
 }
@@ -214,21 +269,39 @@ int rt_group_bulk_trace(rt_group *g, const rt_camera *cam, const rt_light *light
         dst = L->h_stage;
     }
     const double *pos = obj_pos ? obj_pos : (g->obj_pos.empty() ? nullptr : g->obj_pos.data());
-    uint32_t launched = 0;
-    for (uint32_t d = 0; d < n && rc == RT_OK; d++) {
-        if (!cu(cudaSetDevice(g->devices[d]), "cudaSetDevice")) break;
-        if (bytes > L->cap_local[d]) {
+    // per-device enqueue: device 0 by this thread, the others by their workers, all at once
+    std::vector<int> d_rc(n, RT_OK);
+    std::vector<std::string> d_msg(n);
+    std::vector<char> d_launched(n, 0);
+    std::atomic<uint32_t> done{ 0 };
+    auto enqueue = [&](uint32_t d) {
+        cudaError_t e = cudaSetDevice(g->devices[d]);
+        if (e == cudaSuccess && bytes > L->cap_local[d]) {
             cudaFree(L->d_local[d]);
             L->d_local[d] = nullptr; L->cap_local[d] = 0;
-            if (!cu(cudaMalloc((void **)&L->d_local[d], bytes), "cudaMalloc")) break;
-            L->cap_local[d] = bytes;
+            e = cudaMalloc((void **)&L->d_local[d], bytes);
+            if (e == cudaSuccess) L->cap_local[d] = bytes;
         }
-        int r = rt_internal_render_stripes(g->scenes[d], cam, lights, n_lights, pos, W, H, x, y, w, h, stripe, d, n, L->d_local[d], dst, nullptr, 0,
-                                           L->streams[d], (flags & 0x00ffffffu) | RT_LANE((uint32_t)idx + 1u));
-        if (r != RT_OK) { rc = r; msg = std::string("device ") + std::to_string(g->devices[d]) + ": " + rt_last_error(g->scenes[d]); break; }
-        launched = d + 1;
+        if (e != cudaSuccess) {
+            d_rc[d] = e == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA;
+            d_msg[d] = std::string("device ") + std::to_string(g->devices[d]) + ": " + cudaGetErrorString(e);
+        } else {
+            int r = rt_internal_render_stripes(g->scenes[d], cam, lights, n_lights, pos, W, H, x, y, w, h, stripe, d, n, L->d_local[d], dst, nullptr, 0,
+                                               L->streams[d], (flags & 0x00ffffffu) | RT_LANE((uint32_t)idx + 1u));
+            if (r != RT_OK) { d_rc[d] = r; d_msg[d] = std::string("device ") + std::to_string(g->devices[d]) + ": " + rt_last_error(g->scenes[d]); }
+            else d_launched[d] = 1;
+        }
+        done.fetch_add(1, std::memory_order_release);
+    };
+    if (rc == RT_OK) {
+        for (uint32_t d = 1; d < n; d++) g->workers[d - 1]->post([&enqueue, d] { enqueue(d); });
+        enqueue(0);
+        while (done.load(std::memory_order_acquire) < n) std::this_thread::yield();      // ~20 us of enqueue work per device
+        for (uint32_t d = 0; d < n; d++)
+            if (d_rc[d] != RT_OK && rc == RT_OK) { rc = d_rc[d]; msg = d_msg[d]; }
     }
-    for (uint32_t d = 0; d < launched; d++) {               // every stream that got work is drained, error or not
+    for (uint32_t d = 0; d < n; d++) {                      // every stream that got work is drained, error or not
+        if (!d_launched[d]) continue;
         cudaSetDevice(g->devices[d]);
         cu(cudaStreamSynchronize(L->streams[d]), "cudaStreamSynchronize");
     }

@@ -21,7 +21,18 @@ struct SceneView {
     const MeshView *meshes;
     const ObjRec   *objs;
     const LightRec *lights;
+    // Shared-memory column of this thread for the bottom of the traversal stack (device kernels; nullptr = local memory only).
+    // Entry k of the thread lives at trav_smem[k * RT_SMEM_STACK_STRIDE]: lanes with different stack depths still hit 32 different
+    // banks, so a push / pop is ONE shared-memory wavefront per warp instead of up to 32 local-memory wavefronts through L1
+    // (ncu, fused kernel: local loads + stores were 28 % of the LSU wavefronts and 40 % of the L1 sectors).
+    uint32_t *trav_smem;
 };
+
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 1
+#endif
+#define RT_SMEM_STACK_STRIDE 128          // threads per CTA of every traversal kernel
+#define RT_SMEM_STACK_WORDS 16            // 4-byte words per thread: 16 refs (any-hit) or 8 x (ref, t) (nearest-hit)
 
 #ifndef RT_COUNT   // (tests/emul redefines it to log the node / leaf visit sequence of a ray: tools/simulate_warp_divergence_cpu.py)
 #define RT_COUNT(c, field, n) do { if (c) (c)->field += (n); } while (0)
@@ -212,6 +223,21 @@ RT_HD bool trace_exact(const SceneView &sc, const FrameParams &fp, dv o, dv d, b
 // ------------------------------------------------------------------------------------------------
 struct RayF { float ox, oy, oz, dx, dy, dz, ix, iy, iz, ax, ay, az; };   // i = 1/d, a = o/d
 
+RT_HD uint32_t rt_float_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+RT_HD float rt_bits_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
 RT_HD float safe_rcp(float d) {
     const float eps = 8.2718061e-25f;   // 2^-80
     float ad = fabsf(d) > eps ? d : copysignf(eps, d);
@@ -314,7 +340,7 @@ RT_HD void node_test32(const RtNode *nd, const RayF &r, float tbest, NodeHits &h
 // Nearest: winner = min t, ties -> lowest face index.  Returns true if something was accepted.
 // ANY rays walk the mesh's any-hit hierarchy (nodes_any: same triangles, its own leaf size).
 template <bool ANY>
-RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &face, Counters *cnt) {
+RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &face, Counters *cnt, uint32_t *smem = nullptr) {
     if (m.n_faces == 0) return false;
     float tin;
     if (!slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, tbest, tin)) return false;
@@ -322,6 +348,24 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
     int stack[RT_STACK_SIZE];
     float stack_t[ANY ? 1 : RT_STACK_SIZE];
     int sp = 0;
+    // the first SK entries live in shared memory (see SceneView::trav_smem), deeper ones in the local arrays above
+#if RT_SMEM_STACK
+    const int SK = smem ? (ANY ? RT_SMEM_STACK_WORDS : RT_SMEM_STACK_WORDS / 2) : 0;
+#else
+    const int SK = 0;
+    (void)smem;
+#endif
+#define RT_PUSH(REF, T)                                                                                                    \
+    do {                                                                                                                   \
+        if (sp < SK) {                                                                                                     \
+            smem[sp * RT_SMEM_STACK_STRIDE] = (uint32_t)(REF);                                                             \
+            if (!ANY) smem[(SK + sp) * RT_SMEM_STACK_STRIDE] = rt_float_bits(T);                                           \
+        } else {                                                                                                           \
+            stack[sp] = (REF);                                                                                             \
+            if (!ANY) stack_t[sp] = (T);                                                                                   \
+        }                                                                                                                  \
+        sp++;                                                                                                              \
+    } while (0)
     const RtNode *nodes = ANY ? m.nodes_any : m.nodes;
     int ref = ANY ? m.root_ref_any : m.root_ref;
     for (;;) {
@@ -336,8 +380,8 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
                 if (n.hit[k]) {
                     const float t = n.t[k];
                     if (next == RT_EMPTY) { next = n.ref[k]; tnext = t; }
-                    else if (!ANY && t < tnext) { stack[sp] = next; stack_t[sp] = tnext; sp++; next = n.ref[k]; tnext = t; }
-                    else { stack[sp] = n.ref[k]; if (!ANY) stack_t[sp] = t; sp++; }
+                    else if (!ANY && t < tnext) { RT_PUSH(next, tnext); next = n.ref[k]; tnext = t; }
+                    else RT_PUSH(n.ref[k], t);
                 }
             }
             if (next != RT_EMPTY) { ref = next; continue; }
@@ -346,7 +390,7 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
             RT_COUNT(cnt, tris, count);
             for (uint32_t k = first; k < first + count; k++) {
                 const rt_f4 *p = m.tri32 + RT_TRI32_F4 * (size_t)k;
-#if RT_LD256
+#if RT_TRI_LD256
                 const rt_f8 t01 = ld_f8(p), t2x = ld_f8(p + 2);
                 const rt_f4 v0 = t01.a, v1 = t01.b, v2 = t2x.a;
 #else
@@ -365,12 +409,20 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
             }
         }
         // pop (nearest-hit mode skips entries that start beyond the current best hit)
+        float tpop = 0.0f;
         do {
             if (sp == 0) return found;
             --sp;
-            ref = stack[sp];
-        } while (!ANY && stack_t[sp] > tbest);
+            if (sp < SK) {
+                ref = (int)smem[sp * RT_SMEM_STACK_STRIDE];
+                if (!ANY) tpop = rt_bits_float(smem[(SK + sp) * RT_SMEM_STACK_STRIDE]);
+            } else {
+                ref = stack[sp];
+                if (!ANY) tpop = stack_t[sp];
+            }
+        } while (!ANY && tpop > tbest);
     }
+#undef RT_PUSH
 }
 
 struct TraceFast { int face, obj; float t; };
@@ -388,7 +440,7 @@ RT_HD bool trace_fast_nearest(const SceneView &sc, const FrameParams &fp, dv o, 
                            (float)d.y, (float)d.z);
         float t = 3.0e38f;
         int face = -1;
-        if (mesh_trace_fast<false>(sc.meshes[ob.mesh], r, t, face, cnt)) {
+        if (mesh_trace_fast<false>(sc.meshes[ob.mesh], r, t, face, cnt, sc.trav_smem)) {
             float metric = t;
             if (!from_camera) {
                 float px = (float)(o.x + d.x * t - fp.cam_pos[0]), py = (float)(o.y + d.y * t - fp.cam_pos[1]),
@@ -447,7 +499,7 @@ RT_HD bool light_visible(const SceneView &sc, const FrameParams &fp, dv P, int o
                            (float)Ld.y, (float)Ld.z);
         float tmax = (float)(lightLen - RT_SHADOW_BIAS);
         int f = -1;
-        return !mesh_trace_fast<true>(sc.meshes[ob.mesh], r, tmax, f, cnt);
+        return !mesh_trace_fast<true>(sc.meshes[ob.mesh], r, tmax, f, cnt, sc.trav_smem);
     } else {
         TraceFast s;
         bool shaded = trace_fast_nearest(sc, fp, so, Ld, false, s, cnt);
@@ -553,7 +605,7 @@ RT_HD uint32_t shade_hit_fast32(const SceneView &sc, const FrameParams &fp, int 
             RayF r = make_rayf(fmaf(Ld.x, bias, Pl.x), fmaf(Ld.y, bias, Pl.y), fmaf(Ld.z, bias, Pl.z), Ld.x, Ld.y, Ld.z);
             float tmax = lightLen - bias;
             int f = -1;
-            lit = !mesh_trace_fast<true>(m, r, tmax, f, cnt);
+            lit = !mesh_trace_fast<true>(m, r, tmax, f, cnt, sc.trav_smem);
         } else {
             TraceFast s;
             dv so = dv_make((double)fmaf(Ld.x, bias, P.x), (double)fmaf(Ld.y, bias, P.y), (double)fmaf(Ld.z, bias, P.z));

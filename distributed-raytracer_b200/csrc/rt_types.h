@@ -32,7 +32,10 @@
 #ifndef RT_LD256
 #define RT_LD256 1
 #endif
-#define RT_TRI32_F4 (RT_LD256 ? 4 : 3)          // float4 slots per FP32_FAST triangle record
+#ifndef RT_TRI_LD256
+#define RT_TRI_LD256 RT_LD256                   // 64-byte triangle records fetched with 2 x LDG.256 (0: 48 bytes, 3 x LDG.128)
+#endif
+#define RT_TRI32_F4 (RT_TRI_LD256 ? 4 : 3)      // float4 slots per FP32_FAST triangle record
 #define RT_TRI32_BYTES (16 * RT_TRI32_F4)
 #define RT_TRI64_BYTES 80
 #define RT_SHADOW_BIAS 0.0001     // tracer.go:64

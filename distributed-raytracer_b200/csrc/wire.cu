@@ -11,12 +11,13 @@
 // proto3 wire form of one pixel:  0x0A  len  [0x08 varint(r)] [0x10 varint(g)] [0x18 varint(b)]   -- a field whose value is 0
 // is omitted (proto3 default), a value < 128 is a 1-byte varint, 128..255 takes 2 bytes; len <= 9, so 2..11 bytes a pixel.
 //
-// Default (round 2): ONE pass.
+// Round-2 experiment, opt-in (RT_B200_WIRE_ONEPASS=1): ONE pass.  Measured on B200 on the 4K C3 frame: 72.7 us against 57.3 us for
+// the three kernels below -- the look-back chain over 8100 blocks costs more latency than the second read of 25 MB it saves.
 //   k_wire_onepass    per 1024-pixel block: sizes, block-local scan, decoupled look-back over the preceding blocks' aggregates
 //                     (Merrill & Garland's single-pass scan: a block publishes its aggregate, then its inclusive prefix, in one
 //                     64-bit status word), encode into shared memory at the output's 16-byte phase, copy out with uint4 stores.
 //                     The pixels are read once (3 B), 2..11 B are written, the last block writes the message length.
-// Round-1 form, kept for A/B (RT_B200_WIRE_ONEPASS=0):
+// Default:
 //   W1 k_wire_sizes   bytes of every 1024-pixel block                      (reads 3 B / pixel)
 //   W2 k_wire_scan    exclusive scan of the block sizes + total length     (one CTA)
 //   W3 k_wire_encode  block-local scan, encode into shared memory, copy out with 16-byte stores  (3 B read, 2..11 B written)
@@ -292,7 +293,7 @@ cudaError_t rt_launch_wire_encode(const uint8_t *d_rgb, uint64_t n_pixels, uint8
     if (n_pixels == 0) return cudaMemsetAsync(d_len, 0, sizeof(uint64_t), st);
     const uint64_t nb = (n_pixels + WIRE_BLOCK_PIX - 1) / WIRE_BLOCK_PIX;
     if (nb > 0x7fffffffull) return cudaErrorInvalidValue;
-    static const bool onepass = [] { const char *v = getenv("RT_B200_WIRE_ONEPASS"); return !(v && *v && atoi(v) == 0); }();
+    static const bool onepass = [] { const char *v = getenv("RT_B200_WIRE_ONEPASS"); return v && *v && atoi(v) != 0; }();   // opt-in: measured SLOWER than the three kernels (72.7 vs 57.3 us per 4K frame, profiles/r02_wire_encoder_timing.json)
     if (onepass) {
         unsigned long long *status = reinterpret_cast<unsigned long long *>(d_scratch);            // nb words, then the ticket
         unsigned int *ticket = reinterpret_cast<unsigned int *>(status + nb);

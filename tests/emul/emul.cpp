@@ -280,6 +280,10 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
                        double *out_colour, int32_t *out_face, int32_t *out_obj, uint32_t *out_lit, unsigned long long *counters) {
     SceneView sc;
     sc.meshes = s->views.data(); sc.objs = s->objs.data(); sc.lights = reinterpret_cast<const LightRec *>(lights);
+    // the replay runs one "thread" at a time: its shared-memory stack column (SceneView::trav_smem) is this array, so that the
+    // hybrid shared / local stack of mesh_trace_fast (incl. the overflow into the local part) is exercised on the CPU as well
+    static uint32_t s_trav[RT_SMEM_STACK_WORDS * RT_SMEM_STACK_STRIDE];
+    sc.trav_smem = getenv("RT_EMUL_NO_SMEM_STACK") ? nullptr : s_trav;
     const bool brute = (flags & RT_FLAG_BRUTE_FORCE) != 0, rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0,
                sdl = (flags & RT_QUANT_RGBA16_SHR8) != 0;
     if (out_rgb) memset(out_rgb, 0, 3 * npix);
@@ -356,6 +360,10 @@ long long emul_shade_events(void *h, const rt_camera *cam, const rt_light *light
     fp.x = 0; fp.y = 0; fp.w = (int)W; fp.h = (int)H;
     SceneView sc;
     sc.meshes = s->views.data(); sc.objs = s->objs.data(); sc.lights = reinterpret_cast<const LightRec *>(lights);
+    // the replay runs one "thread" at a time: its shared-memory stack column (SceneView::trav_smem) is this array, so that the
+    // hybrid shared / local stack of mesh_trace_fast (incl. the overflow into the local part) is exercised on the CPU as well
+    static uint32_t s_trav[RT_SMEM_STACK_WORDS * RT_SMEM_STACK_STRIDE];
+    sc.trav_smem = getenv("RT_EMUL_NO_SMEM_STACK") ? nullptr : s_trav;
     std::vector<HitRec> hits;
     Counters c; c.nodes = 0; c.tris = 0;
     const uint32_t nrays = ray_count(fp);

@@ -20,19 +20,14 @@ CACHE = "/tmp/c3_workload.npz"
 VARIANTS = {
     # name: (env, render flags by name).  build_variants/*.so: see tools/build_variants.sh
     "r01_like": ({"RT_B200_LIB": "build_variants/librt_b200_nooct.so", "RT_B200_CULL": "0", "RT_B200_MAX_LEAF_SHADE": "4", "RT_B200_SHADE_MINB": "8"}, ["PIPELINE"]),
-    "pipeline_ld128": ({"RT_B200_LIB": "build_variants/librt_b200_ld128.so"}, ["PIPELINE"]),
     "pipeline": ({}, ["PIPELINE"]),
     "fused_ld128": ({"RT_B200_LIB": "build_variants/librt_b200_ld128.so"}, []),
+    "fused_nosmemstack": ({"RT_B200_LIB": "build_variants/librt_b200_nosmemstack.so"}, []),
+    "fused_tri48": ({"RT_B200_LIB": "build_variants/librt_b200_tri48.so"}, []),
     "fused": ({}, []),
     "fused_minb8": ({"RT_B200_SHADE_MINB": "8"}, []),
     "fused_minb10": ({"RT_B200_SHADE_MINB": "10"}, []),
     "fused_any4": ({"RT_B200_MAX_LEAF_SHADE": "4"}, []),
-    "fused_any1": ({"RT_B200_MAX_LEAF_SHADE": "1"}, []),
-    "fused_leaf2_any2": ({"RT_B200_MAX_LEAF": "2"}, []),
-    "fused_w8": ({"RT_B200_LIB": "build_variants/librt_b200_w8.so"}, []),
-    "fused_w8_minb8": ({"RT_B200_LIB": "build_variants/librt_b200_w8.so", "RT_B200_SHADE_MINB": "8"}, []),
-    "fused_w8_minb7": ({"RT_B200_LIB": "build_variants/librt_b200_w8.so", "RT_B200_SHADE_MINB": "7"}, []),
-    "pipeline_w8": ({"RT_B200_LIB": "build_variants/librt_b200_w8.so"}, ["PIPELINE"]),
 }
 
 

@@ -40,7 +40,7 @@ m = int(d_len.item())
 from oracle import oracle as orc                              # checker only
 same = bool(np.array_equal(d_out[:m].cpu().numpy(), orc.encode_trace_results(d_rgb.cpu().numpy().reshape(-1, 3))))
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-onepass = os.environ.get("RT_B200_WIRE_ONEPASS", "1") != "0"
+onepass = os.environ.get("RT_B200_WIRE_ONEPASS", "0") not in ("", "0")
 alg = (1 if onepass else 2) * 3 * n + m                        # RGB read once (single pass) or by the size pass and the encode pass, + the message written
 t = float(np.median(ms))
 print(json.dumps({"kernels": "k_wire_onepass (decoupled look-back)" if onepass else "k_wire_sizes + k_wire_scan + k_wire_encode", "pixels": n, "message_bytes": m, "ms": t, "ms_min": float(min(ms)),
