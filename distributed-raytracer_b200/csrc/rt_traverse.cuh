@@ -28,8 +28,11 @@ struct SceneView {
     uint32_t *trav_smem;
 };
 
+// MEASURED SLOWER (profiles/r02_kernel_ab.txt: fused frame 0.627 -> 0.726 ms pipelined, K2 +15 %, K4 +9 %): the depth test and the
+// second address stream cost more issue slots than the saved L1 wavefronts give back, and 72 KB of shared memory per SM come out
+// of the L1.  Kept as a compile-time experiment (-DRT_SMEM_STACK=1), off by default.
 #ifndef RT_SMEM_STACK
-#define RT_SMEM_STACK 1
+#define RT_SMEM_STACK 0
 #endif
 #define RT_SMEM_STACK_STRIDE 128          // threads per CTA of every traversal kernel
 #define RT_SMEM_STACK_WORDS 16            // 4-byte words per thread: 16 refs (any-hit) or 8 x (ref, t) (nearest-hit)

@@ -22,7 +22,7 @@ VARIANTS = {
     "r01_like": ({"RT_B200_LIB": "build_variants/librt_b200_nooct.so", "RT_B200_CULL": "0", "RT_B200_MAX_LEAF_SHADE": "4", "RT_B200_SHADE_MINB": "8"}, ["PIPELINE"]),
     "pipeline": ({}, ["PIPELINE"]),
     "fused_ld128": ({"RT_B200_LIB": "build_variants/librt_b200_ld128.so"}, []),
-    "fused_nosmemstack": ({"RT_B200_LIB": "build_variants/librt_b200_nosmemstack.so"}, []),
+    "fused_smemstack": ({"RT_B200_LIB": "build_variants/librt_b200_smemstack.so"}, []),
     "fused_tri48": ({"RT_B200_LIB": "build_variants/librt_b200_tri48.so"}, []),
     "fused": ({}, []),
     "fused_minb8": ({"RT_B200_SHADE_MINB": "8"}, []),

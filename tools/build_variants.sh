@@ -8,7 +8,7 @@ SRC="rt_api.cu rt_group.cu render.cu bvh_build.cu wire.cu"
 $NV -DRT_LD256=0 -o ../../build_variants/librt_b200_ld128.so $SRC &
 $NV -DRT_LD256=0 -DRT_OCTANT=0 -o ../../build_variants/librt_b200_nooct.so $SRC &
 wait
-$NV -DRT_SMEM_STACK=0 -o ../../build_variants/librt_b200_nosmemstack.so $SRC &
+$NV -DRT_SMEM_STACK=1 -o ../../build_variants/librt_b200_smemstack.so $SRC &
 $NV -DRT_TRI_LD256=0 -o ../../build_variants/librt_b200_tri48.so $SRC &
 wait
 # $NV -DRT_W=8 -o ../../build_variants/librt_b200_w8.so $SRC      # 8 children per node: measured 35-70 % slower (profiles/r02_kernel_ab.txt)
