@@ -301,8 +301,11 @@ __global__ void __launch_bounds__(128) k_phong(FrameParams fp, SceneView sc_in, 
 // rank of an 8-GPU box needs when its share of a 4K frame is 0.1 ms of work.  Blocks outside the projected
 // root boxes are never launched (region mode) or exit at once (tile mode).
 // ---------------------------------------------------------------------------------------------
+#ifndef RT_FUSED_THREADS
+#define RT_FUSED_THREADS 128      // threads per CTA of the fused kernel (64: measured in profiles/r02_kernel_ab.txt)
+#endif
 template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_frame_fused(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
+__global__ void __launch_bounds__(RT_FUSED_THREADS, MINB * (128 / RT_FUSED_THREADS)) k_frame_fused(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
                                                             bool rowmajor, bool sdl, unsigned int *counters,
                                                             uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour,
                                                             int32_t *__restrict__ out_face, int32_t *__restrict__ out_obj,
@@ -730,10 +733,10 @@ cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
     if (nrays == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool rowmajor = (job.flags & RT_LAYOUT_ROWMAJOR) != 0, sdl = (job.flags & RT_QUANT_RGBA16_SHR8) != 0;
-    const unsigned nblk = (nrays + 127) / 128;
+    const unsigned nblk = (nrays + RT_FUSED_THREADS - 1) / RT_FUSED_THREADS;
     // the traversal kernels use no shared memory: ask for the whole unified L1 / shared array as L1 (once per kernel and device)
 #define LAUNCH_FUSED(CN, MB) do { prefer_l1(k_frame_fused<CN, MB>);                                                                   \
-        k_frame_fused<CN, MB><<<nblk, 128, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_out_rgb, job.d_out_colour,             \
+        k_frame_fused<CN, MB><<<nblk, RT_FUSED_THREADS, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_out_rgb, job.d_out_colour, \
                                                     job.d_out_face, job.d_out_obj, job.d_out_lit, job.d_stats); } while (0)
     if (count) LAUNCH_FUSED(true, 1);
     else if (job.shade_minb >= 10) LAUNCH_FUSED(false, 10);

@@ -24,6 +24,7 @@ VARIANTS = {
     "fused_ld128": ({"RT_B200_LIB": "build_variants/librt_b200_ld128.so"}, []),
     "fused_smemstack": ({"RT_B200_LIB": "build_variants/librt_b200_smemstack.so"}, []),
     "fused_tri48": ({"RT_B200_LIB": "build_variants/librt_b200_tri48.so"}, []),
+    "fused_cta64": ({"RT_B200_LIB": "build_variants/librt_b200_cta64.so"}, []),
     "fused": ({}, []),
     "fused_minb8": ({"RT_B200_SHADE_MINB": "8"}, []),
     "fused_minb10": ({"RT_B200_SHADE_MINB": "10"}, []),

@@ -10,5 +10,6 @@ $NV -DRT_LD256=0 -DRT_OCTANT=0 -o ../../build_variants/librt_b200_nooct.so $SRC 
 wait
 $NV -DRT_SMEM_STACK=1 -o ../../build_variants/librt_b200_smemstack.so $SRC &
 $NV -DRT_TRI_LD256=0 -o ../../build_variants/librt_b200_tri48.so $SRC &
+$NV -DRT_FUSED_THREADS=64 -o ../../build_variants/librt_b200_cta64.so $SRC &
 wait
 # $NV -DRT_W=8 -o ../../build_variants/librt_b200_w8.so $SRC      # 8 children per node: measured 35-70 % slower (profiles/r02_kernel_ab.txt)
