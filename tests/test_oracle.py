@@ -179,6 +179,28 @@ def test_c2_golden_sample_from_independent_restatement(example_scene):
     assert (g["face"] >= 0).sum() > 2000
 
 
+def test_c3_golden_sample_from_independent_restatement(example_scene):
+    """Config 3 (991 232 faces, 3840x2160, lights[0..1]): 404 pixels rendered by tests/golden/make_golden_pyref_c3.py -- its own
+    subdivision of Suzanne, its own reader and math.Tan, tests/pyref.py arithmetic over ALL faces -- against the oracle on the
+    mesh workloads.subdivide makes: the face index (so the two subdivisions number and place the faces alike), the float64
+    colour bits, the lit masks and both quantisations."""
+    from distributed_raytracer_b200 import workloads
+    g = np.load(os.path.join(GOLDEN, "c3_4k_sample_pyref.npz"))
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 5)]
+    sc["lights"] = example_scene["lights"][:2]
+    S = orc.Scene(sc)
+    assert (g["face"] >= 0).sum() >= 200
+    for k, (i, j) in enumerate(zip(g["pixel_i"], g["pixel_j"])):
+        hit, col, face, obj, lit = S.trace_pixel(int(i), int(j), 3840, 2160, mode=orc.CULLED)
+        assert face == int(g["face"][k]), (i, j)
+        if hit:
+            assert np.array_equal(col.view(np.uint64), g["colour_bits"][k]), (i, j)
+            assert lit == int(g["lit"][k])
+            assert tuple(int(255 * c) for c in col) == tuple(int(v) for v in g["rgb"][k])
+    S.close()
+
+
 def test_golden_generator_loader_agrees_with_the_oracle_loader(example_scene):
     """The golden generator reads scene.json / suzanne.obj / suzanne.mtl with its own code; the per-face geometry it feeds
     its renderer must be the geometry the oracle's loader produces (different indexing: it does not deduplicate)."""
