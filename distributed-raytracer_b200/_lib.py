@@ -29,7 +29,7 @@ RT_OK, RT_ERR_INVALID, RT_ERR_CUDA, RT_ERR_OOM, RT_ERR_STATE, RT_ERR_CANCELLED =
 SYNC_SLOT_BYTES = 256            # include/rt_b200.h: RT_SYNC_SLOT_BYTES
 
 ABI_SYMBOLS = (
-    "rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set", "rt_frame_set_lane", "rt_lane_count",
+    "rt_scene_create", "rt_scene_create_obj", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_device_count", "rt_frame_set", "rt_frame_set_lane", "rt_lane_count",
     "rt_render_region", "rt_bulk_trace", "rt_render_region_debug", "rt_render_region_device", "rt_render_tiles_device",
     "rt_untile_device", "rt_render_tiles_peer", "rt_push_tiles_device", "rt_render_push_tiles", "rt_render_stripes_host", "rt_frame_complete_device", "rt_frame_release_device",
     "rt_trace_results_max_bytes", "rt_encode_trace_results_device", "rt_bulk_trace_encoded", "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open",
@@ -43,6 +43,11 @@ class MeshDesc(C.Structure):
                 ("normals", C.c_void_p), ("n_normals", C.c_uint32),
                 ("faces", C.c_void_p), ("n_faces", C.c_uint32),
                 ("materials", C.c_void_p), ("n_materials", C.c_uint32)]
+
+
+class ObjMeshDesc(C.Structure):
+    _fields_ = [("obj_text", C.c_void_p), ("obj_bytes", C.c_uint64), ("materials", C.c_void_p), ("n_materials", C.c_uint32),
+                ("usemtl_offset", C.c_void_p), ("usemtl_material", C.c_void_p), ("n_usemtl", C.c_uint32), ("default_material", C.c_uint32)]
 
 
 class SceneDesc(C.Structure):
@@ -74,7 +79,8 @@ class Stats(C.Structure):
 class BvhInfo(C.Structure):
     _fields_ = [("n_faces", C.c_uint64), ("n_nodes", C.c_uint64), ("n_leaves", C.c_uint64), ("max_depth", C.c_uint32),
                 ("max_leaf", C.c_uint32), ("ms_build", C.c_float), ("sah_cost", C.c_float),
-                ("n_nodes_any", C.c_uint64), ("n_leaves_any", C.c_uint64), ("max_depth_any", C.c_uint32), ("max_leaf_any", C.c_uint32)]
+                ("n_nodes_any", C.c_uint64), ("n_leaves_any", C.c_uint64), ("max_depth_any", C.c_uint32), ("max_leaf_any", C.c_uint32),
+                ("ms_ingest", C.c_float), ("n_verts_ingested", C.c_uint32), ("n_normals_ingested", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -101,6 +107,8 @@ def load():
     u32, vp = C.c_uint32, C.c_void_p
     L.rt_scene_create.restype = C.c_int
     L.rt_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp)]
+    L.rt_scene_create_obj.restype = C.c_int
+    L.rt_scene_create_obj.argtypes = [C.POINTER(ObjMeshDesc), u32, vp, vp, u32, C.c_int32, u32, C.POINTER(vp)]
     L.rt_scene_destroy.restype = None
     L.rt_scene_destroy.argtypes = [vp]
     L.rt_last_error.restype = C.c_char_p

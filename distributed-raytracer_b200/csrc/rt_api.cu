@@ -14,6 +14,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <memory>
 #include <new>
 
@@ -518,31 +519,32 @@ const char *rt_last_error(const rt_scene *scene) {
     return g_err_ret.c_str();
 }
 
-int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
-    API_ENTER();
-    if (!desc || !out) return fail(nullptr, RT_ERR_INVALID, "rt_scene_create: NULL argument");
+// Common part of the two registration entry points.  load_mesh(k, m, st, err) must leave mesh k's per-face records on the device
+// (m.fverts, m.fnormals or nullptr, m.fmat, m.materials, m.n_faces, m.n_materials); the LBVHs are built here.
+static int create_scene_common(uint32_t precision, int32_t device, uint32_t n_meshes, const double *obj_pos, const uint32_t *obj_mesh,
+                               uint32_t n_objects, const std::function<int(uint32_t, MeshDevice &, cudaStream_t, std::string &)> &load_mesh,
+                               rt_scene **out) {
     *out = nullptr;
-    if (desc->precision != RT_FP64_EXACT && desc->precision != RT_FP32_FAST) return fail(nullptr, RT_ERR_INVALID, "unknown precision mode");
-    if (desc->n_meshes && !desc->meshes) return fail(nullptr, RT_ERR_INVALID, "meshes is NULL");
-    if (desc->n_objects && (!desc->obj_pos || !desc->obj_mesh)) return fail(nullptr, RT_ERR_INVALID, "objects are NULL");
-    for (uint32_t k = 0; k < desc->n_objects; k++)
-        if (desc->obj_mesh[k] >= desc->n_meshes) return fail(nullptr, RT_ERR_INVALID, "object refers to a mesh out of range");
+    if (precision != RT_FP64_EXACT && precision != RT_FP32_FAST) return fail(nullptr, RT_ERR_INVALID, "unknown precision mode");
+    if (n_objects && (!obj_pos || !obj_mesh)) return fail(nullptr, RT_ERR_INVALID, "objects are NULL");
+    for (uint32_t k = 0; k < n_objects; k++)
+        if (obj_mesh[k] >= n_meshes) return fail(nullptr, RT_ERR_INVALID, "object refers to a mesh out of range");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0) {
         cudaGetLastError();
         return fail(nullptr, RT_ERR_CUDA, std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(ce));
     }
-    if (desc->device < 0 || desc->device >= ndev) return fail(nullptr, RT_ERR_INVALID, "device ordinal out of range");
+    if (device < 0 || device >= ndev) return fail(nullptr, RT_ERR_INVALID, "device ordinal out of range");
     rt_scene *s = new (std::nothrow) rt_scene();
     if (!s) return fail(nullptr, RT_ERR_OOM, "out of host memory");
-    s->device = desc->device;
-    s->precision = desc->precision;
+    s->device = device;
+    s->precision = precision;
     s->max_leaf = env_int("RT_B200_MAX_LEAF", 4);
     s->shade_minb = env_int("RT_B200_SHADE_MINB", 9);   // fused kernel: 9 CTAs/SM = 56 registers (measured best); K4 of the pipeline caps at 8
     s->primary_persistent = env_int("RT_B200_PERSISTENT", 0) != 0;
     s->split_shade = env_int("RT_B200_SPLIT_SHADE", 0) != 0;
-    s->shade32 = env_int("RT_B200_SHADE32", 0) != 0 && desc->precision == RT_FP32_FAST;
+    s->shade32 = env_int("RT_B200_SHADE32", 0) != 0 && precision == RT_FP32_FAST;
     s->max_leaf_any = env_int("RT_B200_MAX_LEAF_SHADE", RT_DEFAULT_MAX_LEAF_SHADE);
     s->fused = env_int("RT_B200_FUSED", RT_DEFAULT_FUSED) != 0;
     s->cull = env_int("RT_B200_CULL", 1) != 0;
@@ -560,10 +562,10 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
         // the kernels are compiled for sm_100a only: on any other device the first launch fails with
         // cudaErrorNoKernelImageForDevice and the error is returned (no fallback)
     }
-    s->h_objs.resize(desc->n_objects);
-    for (uint32_t k = 0; k < desc->n_objects; k++) {
-        for (int c = 0; c < 3; c++) s->h_objs[k].pos[c] = desc->obj_pos[3 * (size_t)k + c];
-        s->h_objs[k].mesh = desc->obj_mesh[k]; s->h_objs[k].pad = 0;
+    s->h_objs.resize(n_objects);
+    for (uint32_t k = 0; k < n_objects; k++) {
+        for (int c = 0; c < 3; c++) s->h_objs[k].pos[c] = obj_pos[3 * (size_t)k + c];
+        s->h_objs[k].mesh = obj_mesh[k]; s->h_objs[k].pad = 0;
     }
     for (int k = 0; k < n_lanes; k++) {
         s->lanes.emplace_back(new Lane());
@@ -578,33 +580,20 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
     CUB_(cudaStreamCreateWithFlags(&s->cancel_stream, cudaStreamNonBlocking));
     CUB_(cudaMallocHost((void **)&s->h_cancel_word, sizeof(unsigned int)));
     cudaStream_t st0 = s->lanes[0]->stream;
-    s->meshes.resize(desc->n_meshes);
-    s->h_views.resize(desc->n_meshes);
-    for (uint32_t k = 0; k < desc->n_meshes; k++) {
-        const rt_mesh_desc &d = desc->meshes[k];
+    s->meshes.resize(n_meshes);
+    s->h_views.resize(n_meshes);
+    for (uint32_t k = 0; k < n_meshes; k++) {
         MeshDevice &m = s->meshes[k];
         std::string e;
-        int rc = check_mesh_desc(d, e);
+        int rc = load_mesh(k, m, st0, e);
         if (rc != RT_OK) return bail(rc, e);
-        m.n_faces = d.n_faces; m.n_materials = d.n_materials;
-        // the indexed mesh goes up as it is (C3: 52 MB instead of 147 MB of per-face records) and is gathered on the device
-        double *d_verts = nullptr, *d_normals = nullptr; uint32_t *d_faces = nullptr;
-        auto drop = [&]() { cudaFree(d_verts); cudaFree(d_normals); cudaFree(d_faces); };
-        cudaError_t ue = upload(&d_verts, d.verts, (size_t)3 * d.n_verts, st0);
-        if (ue == cudaSuccess && d.n_normals) ue = upload(&d_normals, d.normals, (size_t)3 * d.n_normals, st0);
-        if (ue == cudaSuccess) ue = upload(&d_faces, d.faces, (size_t)7 * d.n_faces, st0);
-        int bad = 0;
-        if (ue == cudaSuccess) ue = rt_flatten_faces(m, d_verts, d.n_verts, d_normals, d.n_normals, d_faces, st0, &bad);
-        drop();
-        if (ue != cudaSuccess) return bail(ue == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(ue));
-        if (bad) return bail(RT_ERR_INVALID, bad == 1 ? "mesh: vertex index out of range" : bad == 2 ? "mesh: normal index out of range"
-                                                                                                       : "mesh: material index out of range");
-        CUB_(upload(&m.materials, d.materials, (size_t)10 * d.n_materials, st0));
         CUB_(cudaStreamSynchronize(st0));
         // the any-hit hierarchy is only walked by FP32_FAST shadow rays
+        const rt_bvh_info ingest = m.info;           // rt_build_bvh resets the record
         if (!rt_build_bvh(m, s->precision == RT_FP32_FAST, s->precision == RT_FP64_EXACT, s->max_leaf,
                           s->precision == RT_FP32_FAST ? s->max_leaf_any : s->max_leaf, s->sm_count, st0, e))
             return bail(RT_ERR_CUDA, "BVH build: " + e);
+        m.info.ms_ingest = ingest.ms_ingest; m.info.n_verts_ingested = ingest.n_verts_ingested; m.info.n_normals_ingested = ingest.n_normals_ingested;
         MeshView &v = s->h_views[k];
         v.nodes = m.nodes; v.tri32 = m.tri32; v.tri64 = m.tri64; v.fverts = m.fverts; v.fnormals = m.fnormals; v.fmat = m.fmat;
         v.materials = m.materials; v.n_faces = m.n_faces; v.n_nodes = m.n_nodes; v.root_ref = m.root_ref;
@@ -616,6 +605,74 @@ int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
 #undef CUB_
     *out = s;
     return RT_OK;
+}
+
+static const char *bad_index_message(int bad) {
+    return bad == 1 ? "mesh: vertex index out of range" : bad == 2 ? "mesh: normal index out of range" : "mesh: material index out of range";
+}
+
+int rt_scene_create(const rt_scene_desc *desc, rt_scene **out) {
+    API_ENTER();
+    if (!desc || !out) return fail(nullptr, RT_ERR_INVALID, "rt_scene_create: NULL argument");
+    *out = nullptr;
+    if (desc->n_meshes && !desc->meshes) return fail(nullptr, RT_ERR_INVALID, "meshes is NULL");
+    auto load = [&](uint32_t k, MeshDevice &m, cudaStream_t st0, std::string &e) -> int {
+        const rt_mesh_desc &d = desc->meshes[k];
+        int rc = check_mesh_desc(d, e);
+        if (rc != RT_OK) return rc;
+        m.n_faces = d.n_faces; m.n_materials = d.n_materials;
+        // the indexed mesh goes up as it is (C3: 52 MB instead of 147 MB of per-face records) and is gathered on the device
+        double *d_verts = nullptr, *d_normals = nullptr; uint32_t *d_faces = nullptr;
+        cudaError_t ue = upload(&d_verts, d.verts, (size_t)3 * d.n_verts, st0);
+        if (ue == cudaSuccess && d.n_normals) ue = upload(&d_normals, d.normals, (size_t)3 * d.n_normals, st0);
+        if (ue == cudaSuccess) ue = upload(&d_faces, d.faces, (size_t)7 * d.n_faces, st0);
+        int bad = 0;
+        if (ue == cudaSuccess) ue = rt_flatten_faces(m, d_verts, d.n_verts, d_normals, d.n_normals, d_faces, st0, &bad);
+        cudaFree(d_verts); cudaFree(d_normals); cudaFree(d_faces);
+        if (ue == cudaSuccess) ue = upload(&m.materials, d.materials, (size_t)10 * d.n_materials, st0);
+        if (ue != cudaSuccess) { e = std::string("scene upload: ") + cudaGetErrorString(ue); return ue == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA; }
+        if (bad) { e = bad_index_message(bad); return RT_ERR_INVALID; }
+        return RT_OK;
+    };
+    return create_scene_common(desc->precision, desc->device, desc->n_meshes, desc->obj_pos, desc->obj_mesh, desc->n_objects, load, out);
+}
+
+// registration straight from the OBJ text.  The file's bytes are parsed ON THE GPU (obj_ingest.cu) into the
+// indexed arrays rt_mesh_desc describes -- no gwob tokenizer, no value-keyed de-duplication maps (mesh.go:146-203), no R-tree
+// Insert per face (mesh.go:208) -- and flow on the device into the same flatten + LBVH build as rt_scene_create.
+int rt_scene_create_obj(const rt_obj_mesh_desc *meshes, uint32_t n_meshes, const double *obj_pos, const uint32_t *obj_mesh, uint32_t n_objects,
+                        int32_t device, uint32_t precision, rt_scene **out) {
+    API_ENTER();
+    if (!out || (n_meshes && !meshes)) return fail(nullptr, RT_ERR_INVALID, "rt_scene_create_obj: NULL argument");
+    *out = nullptr;
+    auto load = [&](uint32_t k, MeshDevice &m, cudaStream_t st0, std::string &e) -> int {
+        const rt_obj_mesh_desc &d = meshes[k];
+        if (d.obj_bytes && !d.obj_text) { e = "mesh: obj_text is NULL"; return RT_ERR_INVALID; }
+        if (d.n_materials == 0 || !d.materials) { e = "mesh: no materials"; return RT_ERR_INVALID; }
+        if (d.n_usemtl && (!d.usemtl_offset || !d.usemtl_material)) { e = "mesh: usemtl table is NULL"; return RT_ERR_INVALID; }
+        if (d.default_material >= d.n_materials) { e = "mesh: material index out of range"; return RT_ERR_INVALID; }
+        for (uint32_t u = 0; u < d.n_usemtl; u++)
+            if (d.usemtl_material[u] >= d.n_materials || (u && d.usemtl_offset[u] < d.usemtl_offset[u - 1])) { e = "mesh: bad usemtl table"; return RT_ERR_INVALID; }
+        double *d_verts = nullptr, *d_normals = nullptr; uint32_t *d_faces = nullptr;
+        uint32_t nv = 0, nn = 0, nf = 0;
+        float ms = 0.f;
+        if (!rt_obj_ingest(d.obj_text, d.obj_bytes, d.usemtl_offset, d.usemtl_material, d.n_usemtl, d.default_material, st0, &d_verts, &nv, &d_normals,
+                           &nn, &d_faces, &nf, &ms, e)) {
+            e = "OBJ ingest: " + e;
+            return RT_ERR_INVALID;
+        }
+        m.n_faces = nf; m.n_materials = d.n_materials;
+        int bad = 0;
+        cudaError_t ue = rt_flatten_faces(m, d_verts, nv, nn ? d_normals : nullptr, nn, d_faces, st0, &bad);
+        cudaFree(d_verts); cudaFree(d_normals); cudaFree(d_faces);
+        if (ue == cudaSuccess) ue = upload(&m.materials, d.materials, (size_t)10 * d.n_materials, st0);
+        if (ue != cudaSuccess) { e = std::string("scene upload: ") + cudaGetErrorString(ue); return ue == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA; }
+        if (bad) { e = bad_index_message(bad); return RT_ERR_INVALID; }
+        m.info.ms_ingest = ms;
+        m.info.n_verts_ingested = nv; m.info.n_normals_ingested = nn;
+        return RT_OK;
+    };
+    return create_scene_common(precision, device, n_meshes, obj_pos, obj_mesh, n_objects, load, out);
 }
 
 void rt_scene_destroy(rt_scene *scene) {

@@ -31,6 +31,11 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
 cudaError_t rt_flatten_faces(MeshDevice &m, const double *d_verts, uint32_t n_verts, const double *d_normals, uint32_t n_normals,
                              const uint32_t *d_faces, cudaStream_t st, int *bad);
 
+// obj_ingest.cu : OBJ text (host) -> indexed mesh arrays on the device
+bool rt_obj_ingest(const char *text, uint64_t n, const uint64_t *usemtl_off, const uint32_t *usemtl_mat, uint32_t n_usemtl, uint32_t default_mat,
+                   cudaStream_t st, double **d_verts, uint32_t *n_verts, double **d_normals, uint32_t *n_normals, uint32_t **d_faces,
+                   uint32_t *n_faces, float *ms, std::string &err);
+
 // Per-render device scratch + launch description
 struct RenderJob {
     FrameParams fp;

@@ -84,6 +84,15 @@ class GpuScene:
         if "camera" in scene and "lights" in scene:
             self.set_frame(scene["camera"], scene["lights"])
 
+    @classmethod
+    def from_handle(cls, handle, n_objects, device=0, precision=_lib.FP32_FAST):
+        """Wraps an rt_scene* created elsewhere (host.gpu_scene_from_file: registration from OBJ text)."""
+        self = cls.__new__(cls)
+        self._L = _lib.load()
+        self.h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+        self.device, self.precision, self.n_objects, self.n_meshes = device, precision, n_objects, None
+        return self
+
     def _check(self, rc):
         if rc != 0:
             raise _lib.RtError(rc, (self._L.rt_last_error(self.h) or b"").decode())

@@ -179,6 +179,41 @@ class Tracer:
             pass
 
 
+def gpu_scene_from_file(scene_path, device=0, precision=_lib.FP32_FAST):
+    """register() straight from the scene file -- every model is handed to the GPU as the TEXT of its OBJ file and
+    parsed there (rt_scene_create_obj); the host reads bytes, scans for mtllib / usemtl lines and parses the MTL file.
+    Returns (GpuScene, cam13, tan_half_fov, lights[n,6], obj_pos[n,3]); the frame state is already set on the scene."""
+    from .gpu_scene import GpuScene
+    H_ = load()
+    H_.rth_gpu_scene_from_file.restype = C.c_void_p
+    H_.rth_gpu_scene_from_file.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    cam = _lib.Camera()
+    lights = np.zeros((64, 6), dtype=np.float64)
+    op = np.zeros((64, 3), dtype=np.float64)
+    nl, nobj = C.c_uint32(0), C.c_uint32(0)
+    h = H_.rth_gpu_scene_from_file(os.fsencode(scene_path), device, precision, C.byref(cam), lights.ctypes.data, 64, C.byref(nl),
+                                   op.ctypes.data, 64, C.byref(nobj))
+    if not h:
+        raise RuntimeError("GpuSceneFromFile: " + _err())
+    g = GpuScene.from_handle(h, nobj.value, device, precision)
+    cam13 = np.array(list(cam.pos) + list(cam.forward) + list(cam.left) + list(cam.up) + [cam.fov])
+    lights, op = lights[:nl.value].copy(), op[:nobj.value].copy()
+    g.set_frame(cam13, lights, tan_half_fov=cam.tan_half_fov)
+    return g, cam13, cam.tan_half_fov, lights, op
+
+
+def obj_text_probe(obj_path):
+    """The host half of the OBJ ingest alone (file read + mtllib / usemtl scan + MTL parse): (bytes, n_materials, n_usemtl)."""
+    H_ = load()
+    H_.rth_obj_text_probe.restype = C.c_longlong
+    H_.rth_obj_text_probe.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p]
+    nm, nu = C.c_uint32(0), C.c_uint32(0)
+    n = H_.rth_obj_text_probe(os.fsencode(obj_path), C.byref(nm), C.byref(nu))
+    if n < 0:
+        raise RuntimeError("ObjTextFromFile: " + _err())
+    return int(n), nm.value, nu.value
+
+
 def partition_balanced(width, height, workers, last_rgb, hit_weight=30.0):
     """partition() with the cuts placed by the cost of the PREVIOUS frame (`last_rgb`: width*height*3 bytes in
     BulkTrace order; a hit pixel costs 1 + hit_weight, a miss 1).  List of (x, y, w, h)."""

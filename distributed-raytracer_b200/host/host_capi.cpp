@@ -1,5 +1,6 @@
 // host_capi.cpp -- C exports of the C++ host mirror so that the Python tests / bench can drive the
 // reference-facing interface (EnvironmentFromFile, Tracer.BulkTrace, partition) through ctypes.
+#include <algorithm>
 #include <cstring>
 
 #include "gpu_worker.hpp"
@@ -92,6 +93,32 @@ uint32_t rth_partition(uint32_t W, uint32_t H, uint32_t workers, uint32_t *out, 
         n++;
     }
     return n;
+}
+
+// register a GPU scene straight from the scene file (every model goes to the device as OBJ text and is parsed there).
+// Returns the scene handle (rt_scene_destroy frees it) or nullptr; cam / lights / obj_pos as rth_environment_frame fills them
+// (lights: up to max_lights * 6 doubles, *n_lights receives the count; obj_pos: up to max_objs * 3 doubles).
+rt_scene *rth_gpu_scene_from_file(const char *scene_path, int device, uint32_t precision, rt_camera *cam, double *lights, uint32_t max_lights,
+                                  uint32_t *n_lights, double *obj_pos, uint32_t max_objs, uint32_t *n_objs) {
+    rt_scene *s = nullptr;
+    state::EnvMutables em;
+    std::string err;
+    if (state::GpuSceneFromFile(scene_path, device, precision, &s, em, err) != RT_OK) { g_err = err; return nullptr; }
+    std::vector<rt_light> l;
+    std::vector<double> p;
+    state::FrameState(em, *cam, l, p);
+    *n_lights = uint32_t(l.size()); *n_objs = uint32_t(p.size() / 3);
+    if (lights) std::memcpy(lights, l.data(), sizeof(rt_light) * std::min<size_t>(l.size(), max_lights));
+    if (obj_pos) std::memcpy(obj_pos, p.data(), sizeof(double) * 3 * std::min<size_t>(p.size() / 3, max_objs));
+    return s;
+}
+// the host half alone (file read + mtllib / usemtl scan + MTL parse), for timing: returns the bytes read, or -1
+long long rth_obj_text_probe(const char *obj_path, uint32_t *n_materials, uint32_t *n_usemtl) {
+    try {
+        state::ObjTextMesh t = state::ObjTextFromFile(obj_path);
+        *n_materials = uint32_t(t.materials.size() / 10); *n_usemtl = uint32_t(t.usemtl_off.size());
+        return (long long)t.text.size();
+    } catch (const std::exception &e) { g_err = e.what(); return -1; }
 }
 
 // partitionBalanced(): like rth_partition, cut by the cost of the previous frame (last_rgb: W*H*3 bytes in BulkTrace order)

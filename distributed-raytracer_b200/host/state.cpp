@@ -302,6 +302,133 @@ static double jnum(const JVal *o, const char *k) {
 }
 static geom::Vector jvec(const JVal *o) { return { jnum(o, "x"), jnum(o, "y"), jnum(o, "z") }; }
 
+rt_obj_mesh_desc ObjTextMesh::desc() const {
+    rt_obj_mesh_desc d;
+    d.obj_text = text.data(); d.obj_bytes = text.size();
+    d.materials = materials.data(); d.n_materials = uint32_t(materials.size() / 10);
+    d.usemtl_offset = usemtl_off.empty() ? nullptr : usemtl_off.data();
+    d.usemtl_material = usemtl_mat.empty() ? nullptr : usemtl_mat.data();
+    d.n_usemtl = uint32_t(usemtl_off.size());
+    d.default_material = default_material;
+    return d;
+}
+
+static void material_doubles(const Material &m, double out[10]) {
+    const double a[10] = { m.Ka.r, m.Ka.g, m.Ka.b, m.Kd.r, m.Kd.g, m.Kd.b, m.Ks.r, m.Ks.g, m.Ks.b, m.Ns };
+    for (int k = 0; k < 10; k++) out[k] = a[k];
+}
+
+ObjTextMesh ObjTextFromFile(const std::string &path) {
+    ObjTextMesh o;
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (!f.good()) throw std::runtime_error("cannot open model " + path);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        o.text = ss.str();
+    }
+    // one pass over the line starts: only `mtllib` and `usemtl` lines are looked at
+    std::string mtllib;
+    std::vector<std::pair<uint64_t, std::string>> uses;
+    const char *base = o.text.data(), *end = base + o.text.size();
+    for (const char *p = base; p < end;) {
+        const char *nl = (const char *)memchr(p, '\n', size_t(end - p));
+        const char *le = nl ? nl : end;
+        const char *q = p;
+        while (q < le && (*q == ' ' || *q == '\t')) q++;
+        if (le - q > 6 && (!memcmp(q, "usemtl", 6) || !memcmp(q, "mtllib", 6)) && (q[6] == ' ' || q[6] == '\t')) {
+            auto t = fields(std::string(q, le));
+            std::string name = t.size() > 1 ? t[1] : "";
+            if (q[0] == 'u') uses.emplace_back(uint64_t(p - base), name); else mtllib = name;
+        }
+        p = nl ? nl + 1 : end;
+    }
+    std::map<std::string, MtlEntry> lib;
+    if (!mtllib.empty()) {                                                           // mesh.go:120-129
+        std::string rel = relativePath(path, mtllib);
+        lib = ReadMaterialLibFromFile(file_exists(rel) ? rel : mtllib);
+    }
+    std::map<Material, unsigned> materialMap;
+    auto index_of = [&](const std::string &name) {
+        Material mat;                                                                // mesh.go:151 default material
+        mat.Ka = colour::NewRGB(0x10, 0x10, 0x10); mat.Kd = colour::NewRGB(0xFF, 0xFF, 0xFF); mat.Ks = colour::NewRGB(0, 0, 0); mat.Ns = 0.0;
+        auto it = lib.find(name);
+        if (it != lib.end()) {                                                       // mesh.go:152-154
+            const MtlEntry &e = it->second;
+            mat.Ka = colour::NewRGBFromFloats(e.Ka[0], e.Ka[1], e.Ka[2]);
+            mat.Kd = colour::NewRGBFromFloats(e.Kd[0], e.Kd[1], e.Kd[2]);
+            mat.Ks = colour::NewRGBFromFloats(e.Ks[0], e.Ks[1], e.Ks[2]);
+            mat.Ns = double(e.Ns);
+        }
+        auto mi = materialMap.find(mat);                                             // mesh.go:157-163
+        if (mi != materialMap.end()) return mi->second;
+        unsigned k = unsigned(o.materials.size() / 10);
+        double d[10];
+        material_doubles(mat, d);
+        o.materials.insert(o.materials.end(), d, d + 10);
+        materialMap[mat] = k;
+        return k;
+    };
+    o.default_material = index_of("");                                               // faces above the first usemtl line
+    for (auto &u : uses) { o.usemtl_off.push_back(u.first); o.usemtl_mat.push_back(index_of(u.second)); }
+    return o;
+}
+
+int GpuSceneFromFile(const std::string &path, int device, uint32_t precision, rt_scene **out, EnvMutables &em, std::string &err) {
+    *out = nullptr;
+    try {
+        std::ifstream f(path);
+        if (!f.good()) throw std::runtime_error("cannot open scene " + path);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        std::string src = ss.str();
+        JParser jp(src);
+        JVal root = jp.parse();
+        std::vector<ObjTextMesh> texts;
+        std::map<std::string, uint32_t> index;
+        std::vector<double> obj_pos;
+        std::vector<uint32_t> obj_mesh;
+        em = EnvMutables();
+        const JVal *objs = root.get("objs");
+        if (objs)
+            for (size_t i = 0; i < objs->arr.size(); i++) {                         // environment.go:190-216
+                const JVal &o = objs->arr[i];
+                const JVal *model = o.get("model");
+                std::string m = model ? model->str : "";
+                auto it = index.find(m);
+                if (it == index.end()) {
+                    std::string rel = relativePath(path, m);
+                    texts.push_back(ObjTextFromFile(file_exists(rel) ? rel : m));
+                    it = index.emplace(m, uint32_t(texts.size() - 1)).first;
+                }
+                Object ob;
+                ob.Pos = jvec(o.get("pos")); ob.id = unsigned(i + 1);
+                em.Objs.push_back(ob);
+                obj_pos.insert(obj_pos.end(), { ob.Pos.X, ob.Pos.Y, ob.Pos.Z });
+                obj_mesh.push_back(it->second);
+            }
+        const JVal *lights = root.get("lights");
+        if (lights)
+            for (const JVal &l : lights->arr) {                                      // environment.go:220-225
+                Light li;
+                li.Pos = jvec(l.get("pos"));
+                const JVal *c = l.get("col");
+                li.Col = colour::NewRGB(uint8_t(jnum(c, "r")), uint8_t(jnum(c, "g")), uint8_t(jnum(c, "b")));
+                em.Lights.push_back(li);
+            }
+        const JVal *cam = root.get("cam");
+        em.Cam = NewCamera(jvec(cam ? cam->get("pos") : nullptr), jvec(cam ? cam->get("dir") : nullptr), jnum(cam, "fov"));
+        std::vector<rt_obj_mesh_desc> descs;
+        for (const ObjTextMesh &t : texts) descs.push_back(t.desc());
+        int rc = rt_scene_create_obj(descs.data(), uint32_t(descs.size()), obj_pos.data(), obj_mesh.data(), uint32_t(obj_mesh.size()), device, precision, out);
+        if (rc != RT_OK) err = rt_last_error(nullptr);
+        return rc;
+    } catch (const std::exception &e) {
+        err = e.what();
+        return RT_ERR_INVALID;
+    }
+}
+
 Environment EnvironmentFromFile(const std::string &path) {                          // environment.go:162-234
     std::ifstream f(path);
     if (!f.good()) throw std::runtime_error("cannot open scene " + path);

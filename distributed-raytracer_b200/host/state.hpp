@@ -132,6 +132,21 @@ class Environment {                                          // environment.go:1
 
 Environment EnvironmentFromFile(const std::string &path);    // environment.go:162-234 (throws)
 
+// a model as the TEXT of its OBJ file + the small tables the GPU ingest needs (rt_obj_mesh_desc): the host only reads
+// the bytes, finds the mtllib / usemtl lines and parses the MTL file -- no tokenizer pass over the geometry, no value-keyed maps.
+struct ObjTextMesh {
+    std::string text;
+    std::vector<double> materials;            // 10 per material, first-use order, de-duplicated by value (mesh.go:151-163)
+    std::vector<uint64_t> usemtl_off;
+    std::vector<uint32_t> usemtl_mat;
+    uint32_t default_material = 0;
+    rt_obj_mesh_desc desc() const;
+};
+ObjTextMesh ObjTextFromFile(const std::string &path);        // throws
+// register() of a GPU worker straight from the scene file: every distinct model goes to the device as OBJ text
+// (rt_scene_create_obj); `em` receives objects, lights and camera exactly as EnvironmentFromFile fills them.
+int GpuSceneFromFile(const std::string &scene_path, int device, uint32_t precision, rt_scene **out, EnvMutables &em, std::string &err);
+
 // frame state for rt_frame_set / rt_bulk_trace from the mutable part
 void FrameState(const EnvMutables &em, rt_camera &cam, std::vector<rt_light> &lights, std::vector<double> &obj_pos);
 

@@ -140,10 +140,33 @@ typedef struct {
     /* the any-hit (shadow-ray) hierarchy over the same triangles; equals the fields above when both leaf sizes agree */
     uint64_t n_nodes_any, n_leaves_any;
     uint32_t max_depth_any, max_leaf_any;
+    /* rt_scene_create_obj only: device time of the OBJ ingest and what it found (0 otherwise) */
+    float    ms_ingest;
+    uint32_t n_verts_ingested, n_normals_ingested;
 } rt_bvh_info;
+
+/* One mesh as the TEXT of its Wavefront OBJ file.  The library parses it on the GPU with gwob's published
+ * semantics (mesh.go:109-133,166-204): v / vn / f lines, coordinates parsed to float32 then widened (mesh.go:176), corners
+ * "v", "v/t", "v//n", "v/t/n" with 1-based or negative indices, triangles and quads (quad -> (0,1,2) + (2,3,0)), faces in file
+ * order; vertex normals stored normalised (mesh.go:202).  What it does NOT do is de-duplicate by value (mesh.go:146-203): that
+ * changes no rendered bit.  The small MTL file stays with the host: it hands over the material table (as in rt_mesh_desc)
+ * and, for every `usemtl` line of the OBJ text, its byte offset and the material index it selects. */
+typedef struct {
+    const char     *obj_text;         /* obj_bytes bytes, HOST memory, need not be NUL-terminated                     */
+    uint64_t        obj_bytes;
+    const double   *materials;        /* n_materials*10: Ka[3] Kd[3] Ks[3] Ns                       mesh.go:94-97,151-154 */
+    uint32_t        n_materials;
+    const uint64_t *usemtl_offset;    /* n_usemtl byte offsets of the `usemtl` lines, ascending                        */
+    const uint32_t *usemtl_material;  /* n_usemtl material indices                                                    */
+    uint32_t        n_usemtl;
+    uint32_t        default_material; /* material of the faces above the first usemtl line          mesh.go:151       */
+} rt_obj_mesh_desc;
 
 /* ---- lifecycle (register(): distributed/main.go:101-129 => create; re-register => destroy+create) */
 int  rt_scene_create(const rt_scene_desc *desc, rt_scene **out);
+/* the same registration from OBJ text: parse on the GPU -> flatten -> LBVH, nothing but the file's bytes crosses PCIe */
+int  rt_scene_create_obj(const rt_obj_mesh_desc *meshes, uint32_t n_meshes, const double *obj_pos, const uint32_t *obj_mesh,
+                         uint32_t n_objects, int32_t device, uint32_t precision, rt_scene **out);
 void rt_scene_destroy(rt_scene *scene);
 const char *rt_last_error(const rt_scene *scene);
 int  rt_abi_version(void);

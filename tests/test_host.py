@@ -1,11 +1,12 @@
 """CPU: the C++ host mirror (host/state.cpp, host/gpu_worker.cpp) against the independent Python loader and
 the reference's partition() semantics (master/main.go:54-91)."""
 import json
+import os
 
 import numpy as np
 import pytest
 
-from conftest import EXAMPLE_SCENE
+from conftest import EXAMPLE_SCENE, GOLDEN
 from oracle import oracle as orc
 from oracle import scene_loader as sl
 
@@ -125,3 +126,17 @@ def test_partition_balanced_tiles_the_screen_and_balances_cost():
     # without history it IS partition()
     black = np.zeros((W, H, 3), dtype=np.uint8)
     assert host.partition_balanced(W, H, 8, black, 30.0) == host.partition(W, H, 8)
+
+
+def test_obj_text_host_half(tmp_path):
+    """SURVEY s8 f3, host half of the OBJ ingest: bytes of the file, the material table (default material first, then first-use
+    order, de-duplicated by value: mesh.go:151-163) and one usemtl entry per `usemtl` line.  (The parse itself runs on the GPU.)"""
+    from distributed_raytracer_b200 import host
+    n, n_mat, n_use = host.obj_text_probe(os.path.join(GOLDEN, "example", "suzanne.obj"))
+    assert n == os.path.getsize(os.path.join(GOLDEN, "example", "suzanne.obj")) and n_mat == 2 and n_use == 1
+    (tmp_path / "m.mtl").write_text("newmtl a\nKd 1 0 0\nnewmtl b\nKd 1 0 0\nnewmtl c\nKd 0 1 0\n")
+    (tmp_path / "m.obj").write_text("mtllib m.mtl\nv 0 0 0\nusemtl a\nusemtl b\n  usemtl c\nusemtl missing\n")
+    n, n_mat, n_use = host.obj_text_probe(str(tmp_path / "m.obj"))
+    assert n_use == 4 and n_mat == 3          # default (also what `missing` maps to), a == b by value, c
+    with pytest.raises(RuntimeError):
+        host.obj_text_probe(str(tmp_path / "nope.obj"))

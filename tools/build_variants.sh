@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/../distributed-raytracer_b200/csrc"
 mkdir -p ../../build_variants
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off -shared -cudart static"
-SRC="rt_api.cu rt_group.cu render.cu bvh_build.cu wire.cu"
+SRC="rt_api.cu rt_group.cu render.cu bvh_build.cu obj_ingest.cu wire.cu"
 $NV -DRT_LD256=0 -o ../../build_variants/librt_b200_ld128.so $SRC &
 $NV -DRT_LD256=0 -DRT_OCTANT=0 -o ../../build_variants/librt_b200_nooct.so $SRC &
 wait
