@@ -294,7 +294,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
             CK(cudaMemcpyAsync(d_state, init_state, sizeof init_state, cudaMemcpyHostToDevice, st));
             CK(cudaMemsetAsync(d_front[0], 0, sizeof(int), st));
             const unsigned int fb = (ni + TB - 1) / TB;
-            const int max_levels = (RT_STACK_SIZE - 2) / (RT_W - 1);
+            const int max_levels = (RT_STACK_NODES - 2) / (RT_W - 1);
             int h_state[4] = { 1, 0, 0, 0 };
             int cur = 0;
             while (h_state[0] > 0) {
@@ -313,7 +313,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
                 CK(cudaStreamSynchronize(st));
             }
             const int base = h_state[1], depth = h_state[2];
-            if ((RT_W - 1) * depth + 2 > RT_STACK_SIZE) { err = "BVH deeper than the traversal stack"; return false; }
+            if ((RT_W - 1) * depth + 2 > RT_STACK_NODES) { err = "BVH deeper than the traversal stack"; return false; }
             *out_n_nodes = (uint32_t)base;
             if ((size_t)base < (size_t)ni) {
                 // the wide tree has far fewer nodes than the binary one it was collapsed from: shrink the allocation

@@ -339,6 +339,86 @@ RT_HD void node_test32(const RtNode *nd, const RayF &r, float tbest, NodeHits &h
 #endif
 }
 
+// fp32 test of the triangles of one leaf of an any-hit ray: true at the first triangle with t <= tmax
+RT_HD bool leaf_any_hit32(const MeshView &m, int ref, const RayF &r, float tmax, int &face, float &thit, Counters *cnt) {
+    const uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
+    RT_COUNT(cnt, tris, count);
+    for (uint32_t k = first; k < first + count; k++) {
+        const rt_f4 *p = m.tri32 + RT_TRI32_F4 * (size_t)k;
+#if RT_TRI_LD256
+        const rt_f8 t01 = ld_f8(p), t2x = ld_f8(p + 2);
+        const rt_f4 v0 = t01.a, v1 = t01.b, v2 = t2x.a;
+#else
+        const rt_f4 v0 = ld_f4(p), v1 = ld_f4(p + 1), v2 = ld_f4(p + 2);
+#endif
+        float t, u, v;
+        if (tri_test32(v0, v1, v2, r, t, u, v) && t <= tmax) {
+            face = (int)rt_float_bits(v0.w);
+            thit = t;
+            return true;
+        }
+    }
+    return false;
+}
+
+// Any-hit traversal with EVERY LEAF POSTPONED (RT_ANY_DEFER, the default for shadow rays).
+// Why: 93 % of the shadow rays of config 3 are lit, i.e. the ray must visit every node and leaf its segment meets and the
+// order is irrelevant.  In the plain "if node ... else leaf" loop the lanes of a warp sit at nodes and leaves at different
+// times, so a warp issued 25 node bodies (22 active lanes) PLUS 15.5 leaf bodies with 6 active lanes per shadow ray (ncu source
+// page, profiles/r02_ncu_c3_summary.txt) -- each a dependent load + arithmetic chain the whole warp waits for.  Here a ray first
+// walks the internal nodes only (leaf children go to the far end of the same local array), then tests its postponed leaves
+// back to back: the warp runs max-over-lanes(leaves per ray) leaf bodies instead of one per lane-and-time.  The answer
+// (is anything closer than the light?) does not depend on the order, so frames are bit-identical to the plain loop.
+// An occluded ray finds its occluder later than before (7 % of the rays).  If the array ever fills up (it does not on the
+// BASELINE scenes: <= 3 * depth nodes + the leaves one ray meets) the postponed leaves are drained early.
+#ifndef RT_ANY_DEFER
+#define RT_ANY_DEFER 1
+#endif
+// experiment: a lit ray visits every node it pushes, so the line of a pushed child can be requested at push time
+#ifndef RT_PUSH_PREFETCH
+#define RT_PUSH_PREFETCH 0
+#endif
+#if defined(__CUDA_ARCH__) && RT_PUSH_PREFETCH == 1
+#define RT_PREFETCH_NODE(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
+#elif defined(__CUDA_ARCH__) && RT_PUSH_PREFETCH == 2
+#define RT_PREFETCH_NODE(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
+#else
+#define RT_PREFETCH_NODE(p) do { } while (0)
+#endif
+RT_HD bool mesh_any_hit_deferred(const MeshView &m, const RayF &r, float &tmax, int &face, Counters *cnt) {
+    int stack[RT_STACK_SIZE];            // internal nodes: [0, sp) growing up; postponed leaves: [lp, RT_STACK_SIZE) growing down
+    int sp = 0, lp = RT_STACK_SIZE;
+    int ref = m.root_ref_any;
+    bool more = true;
+    if (ref < 0) { stack[--lp] = ref; more = false; }
+    do {
+        while (more) {
+            NodeHits n;
+            node_test32(m.nodes_any + ref, r, tmax, n);
+            RT_COUNT(cnt, nodes, 1);
+            int next = RT_EMPTY;
+#pragma unroll
+            for (int k = 0; k < RT_W; k++) {
+                if (n.hit[k]) {
+                    const int c = n.ref[k];
+                    if (c < 0) stack[--lp] = c;
+                    else if (next == RT_EMPTY) next = c;
+                    else { stack[sp++] = c; RT_PREFETCH_NODE(m.nodes_any + c); }
+                }
+            }
+            if (next != RT_EMPTY) ref = next;
+            else if (sp > 0) ref = stack[--sp];
+            else more = false;
+            if (lp - sp < 2 * RT_W) break;          // no room for another node's children: test the postponed leaves first
+        }
+        while (lp < RT_STACK_SIZE) {
+            float thit;
+            if (leaf_any_hit32(m, stack[lp++], r, tmax, face, thit, cnt)) { tmax = thit; return true; }
+        }
+    } while (more);
+    return false;
+}
+
 // Simple per-ray traversal of one mesh (object space).  ANY: stop at the first hit with t <= tbest.
 // Nearest: winner = min t, ties -> lowest face index.  Returns true if something was accepted.
 // ANY rays walk the mesh's any-hit hierarchy (nodes_any: same triangles, its own leaf size).
@@ -347,6 +427,9 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
     if (m.n_faces == 0) return false;
     float tin;
     if (!slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, tbest, tin)) return false;
+#if RT_ANY_DEFER
+    if (ANY) return mesh_any_hit_deferred(m, r, tbest, face, cnt);
+#endif
     bool found = false;
     int stack[RT_STACK_SIZE];
     float stack_t[ANY ? 1 : RT_STACK_SIZE];

@@ -19,7 +19,9 @@
 #ifndef RT_W
 #define RT_W 4                    // children per BVH node (compile-time; 4 measured best)
 #endif
-#define RT_STACK_SIZE 128         // the builder rejects trees with (RT_W-1)*depth + 1 > RT_STACK_SIZE
+#define RT_STACK_SIZE 128         // entries of a ray's traversal stack (local memory; only the touched part costs anything)
+#define RT_STACK_NODES (RT_STACK_SIZE - 3 * RT_W)   // the builder rejects trees with (RT_W-1)*depth + 2 > RT_STACK_NODES: the top
+                                  // 3*RT_W entries are the least room the postponed leaves of an any-hit ray get (rt_traverse.cuh)
 #define RT_LEAF_FIRST_BITS 27     // child ref < 0: ~ref = first | (count-1) << 27
 #define RT_LEAF_FIRST_MASK ((1u << RT_LEAF_FIRST_BITS) - 1u)
 #define RT_MAX_LEAF 16

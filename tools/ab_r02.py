@@ -29,6 +29,13 @@ VARIANTS = {
     "fused_minb8": ({"RT_B200_SHADE_MINB": "8"}, []),
     "fused_minb10": ({"RT_B200_SHADE_MINB": "10"}, []),
     "fused_any4": ({"RT_B200_MAX_LEAF_SHADE": "4"}, []),
+    # leaves of any-hit rays postponed (RT_ANY_DEFER, now the default) against the plain loop, and the knobs that may move with it
+    "fused_nodefer": ({"RT_B200_LIB": "build_variants/librt_b200_nodefer.so"}, []),
+    "pipeline_nodefer": ({"RT_B200_LIB": "build_variants/librt_b200_nodefer.so"}, ["PIPELINE"]),
+    "fused_pf1": ({"RT_B200_LIB": "build_variants/librt_b200_pf1.so"}, []),
+    "fused_pf2": ({"RT_B200_LIB": "build_variants/librt_b200_pf2.so"}, []),
+    "fused_any1": ({"RT_B200_MAX_LEAF_SHADE": "1"}, []),
+    "fused_any8": ({"RT_B200_MAX_LEAF_SHADE": "8"}, []),
 }
 
 
