@@ -105,6 +105,34 @@ __global__ void k_gather_tris(const double *__restrict__ fverts, const uint32_t 
     if (i < n) gather_tri_thread(i, fverts, vals, tri32, tri64);
 }
 
+// min / max of all vertex coordinates of a mesh in float64 (Object.Bounds, object.go:38-49), through an order-preserving map to
+// unsigned integers (-0 sorts below +0, as Go's math.Min / math.Max have it)
+__device__ __forceinline__ unsigned long long d2ord(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+static double ord2d(unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    double v; memcpy(&v, &u, 8); return v;
+}
+__global__ void k_vertex_bounds(const double *__restrict__ verts, uint32_t n_verts, unsigned long long *bounds) {
+    unsigned long long lo[3] = { ~0ull, ~0ull, ~0ull }, hi[3] = { 0ull, 0ull, 0ull };
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_verts; v += gridDim.x * blockDim.x)
+        for (int k = 0; k < 3; k++) {
+            const unsigned long long o = d2ord(verts[3 * (size_t)v + k]);
+            lo[k] = o < lo[k] ? o : lo[k];
+            hi[k] = o > hi[k] ? o : hi[k];
+        }
+    for (int k = 0; k < 3; k++) {
+        for (int s = 16; s > 0; s >>= 1) {
+            const unsigned long long a = __shfl_down_sync(0xffffffffu, lo[k], s), b = __shfl_down_sync(0xffffffffu, hi[k], s);
+            lo[k] = a < lo[k] ? a : lo[k];
+            hi[k] = b > hi[k] ? b : hi[k];
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(&bounds[k], lo[k]); atomicMax(&bounds[3 + k], hi[k]); }
+    }
+}
+
 // scratch allocations of one build, released on scope exit
 struct Scratch {
     std::vector<void *> ptrs;
@@ -173,14 +201,19 @@ cudaError_t rt_flatten_faces(MeshDevice &m, const double *d_verts, uint32_t n_ve
     if ((e = cudaMalloc((void **)&m.fmat, sizeof(uint32_t) * (nf ? nf : 1))) != cudaSuccess) return e;
     if (!nf) return cudaSuccess;
     unsigned int *d_err = nullptr;
-    if ((e = cudaMalloc((void **)&d_err, sizeof(unsigned int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&d_err, 8 + 6 * sizeof(unsigned long long))) != cudaSuccess) return e;
     cudaMemsetAsync(d_err, 0, sizeof(unsigned int), st);
+    unsigned long long *d_vb = (unsigned long long *)(d_err + 2), h_vb[6] = { ~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull };
+    cudaMemcpyAsync(d_vb, h_vb, sizeof h_vb, cudaMemcpyHostToDevice, st);
+    if (n_verts) k_vertex_bounds<<<(unsigned)std::min<size_t>(((size_t)n_verts + 255) / 256, 1024), 256, 0, st>>>(d_verts, n_verts, d_vb);
     k_flatten_faces<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(d_verts, d_normals, d_faces, (uint32_t)nf, n_verts, n_normals, m.n_materials,
                                                                   m.fverts, m.fnormals, m.fmat, d_err);
     unsigned int h_err = 0;
     e = cudaMemcpyAsync(&h_err, d_err, sizeof h_err, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_vb, d_vb, sizeof h_vb, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d_err);
+    for (int k = 0; k < 3; k++) { m.vlo[k] = n_verts ? ord2d(h_vb[k]) : HUGE_VAL; m.vhi[k] = n_verts ? ord2d(h_vb[3 + k]) : -HUGE_VAL; }
     if (e == cudaSuccess && h_err) *bad = 4 - (int)h_err;
     return e;
 }

@@ -57,6 +57,48 @@ RT_HD double go_min(double x, double y) {
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The reference's object-level candidate test (tracer.go:32): a ray is tried against an object only if box.go's predicate
+// holds for the object's bounds (object.go:31-59).  The predicate is NOT conservative: it looks for a side whose plane the ray
+// meets inside the side's rectangle, and a ray that leaves the box exactly through an edge can fail that test on both
+// adjacent sides by one rounding -- the reference then never looks at the object (seen for shadow rays in grid-aligned stress
+// scenes, tools/fuzz_degenerate_faces_cpu.py; never in a BASELINE config).  FP64_EXACT applies the same predicate to the
+// same rectangle, operation for operation.  (The rectangles INSIDE rtreego's face tree, object.go:76, depend on that
+// library's insertion order and cannot be mirrored: DESIGN.md s4.)
+// ------------------------------------------------------------------------------------------------
+#define RT_BOUND_EPSILON 1e-4      // boundEpsilon, shared/state/object.go / mesh.go
+
+// box.go:29-69, operation for operation (the dot products with the axis normals keep their multiplications by 0 and +-1)
+RT_HD bool box_intersect_exact(dv bmin, dv bmax, dv o, dv d) {
+    for (int k = 0; k < 6; k++) {                                                       // boxNormals, box.go:7-11
+        const dv n = dv_make(k == 0 ? 1.0 : (k == 1 ? -1.0 : 0.0), k == 2 ? 1.0 : (k == 3 ? -1.0 : 0.0), k == 4 ? 1.0 : (k == 5 ? -1.0 : 0.0));
+        const double dn = dv_dot(d, n);                                                 // :32
+        if (dn != 0.0) {
+            const dv sp = (dv_dot(n, dv_make(1.0, 1.0, 1.0)) < 0) ? bmin : bmax;        // :35-39
+            const double dirScale = DDIV(dv_dot(dv_sub(sp, o), n), dn);                 // :42
+            if (dirScale >= 0.0) {                                                      // :45
+                const dv p = dv_add(o, dv_scale(d, dirScale));                          // :47
+                if (n.x != 0.0) { if ((bmin.y <= p.y && p.y <= bmax.y) && (bmin.z <= p.z && p.z <= bmax.z)) return true; }          // :50-53
+                else if (n.y != 0.0) { if ((bmin.x <= p.x && p.x <= bmax.x) && (bmin.z <= p.z && p.z <= bmax.z)) return true; }     // :54-57
+                else if (n.z != 0.0) { if ((bmin.x <= p.x && p.x <= bmax.x) && (bmin.y <= p.y && p.y <= bmax.y)) return true; }     // :58-61
+            }
+        }
+    }
+    return false;
+}
+
+// Object.Bounds() (object.go:31-59) + geom.NewBox (box.go:21-26) from the bounds of ALL vertices of the mesh: fl(P + v) is
+// monotone in v, so the min / max over the vertices of fl(P.x + v.x) is fl(P.x + min / max v.x).  rtreego.NewRect(p, len) keeps
+// q = p + len; NewBox returns MinCorner = p, MaxCorner = p + (q - p).  No vertices: vlo = +Inf, vhi = -Inf => the box is P.
+RT_HD void object_box_exact(dv pos, dv vlo, dv vhi, dv &bmin, dv &bmax) {
+    const dv lo = dv_make(go_min(pos.x, DADD(pos.x, vlo.x)), go_min(pos.y, DADD(pos.y, vlo.y)), go_min(pos.z, DADD(pos.z, vlo.z)));
+    const dv hi = dv_make(go_max(pos.x, DADD(pos.x, vhi.x)), go_max(pos.y, DADD(pos.y, vhi.y)), go_max(pos.z, DADD(pos.z, vhi.z)));
+    const dv len = dv_make(go_max(DSUB(hi.x, lo.x), RT_BOUND_EPSILON), go_max(DSUB(hi.y, lo.y), RT_BOUND_EPSILON), go_max(DSUB(hi.z, lo.z), RT_BOUND_EPSILON));
+    const dv q = dv_add(lo, len);
+    bmin = lo;
+    bmax = dv_add(lo, dv_sub(q, lo));
+}
+
 RT_HD bool go_is_odd_int(double x) {
     double xi;
     double xf = modf(x, &xi);

@@ -207,8 +207,14 @@ RT_HD bool trace_exact(const SceneView &sc, const FrameParams &fp, dv o, dv d, b
         const ObjRec &ob = sc.objs[k];
         if (!(ob.pos[0] == ob.pos[0])) continue;          // NaN position: the object is absent from this order (rt_b200.h)
         dv pos = dv_ld(ob.pos);
+        const MeshView &mv = sc.meshes[ob.mesh];
+        if (!brute) {                                                                    // tracer.go:32: box.go's predicate on the object's bounds
+            dv bmin, bmax;
+            object_box_exact(pos, dv_ld(mv.vlo), dv_ld(mv.vhi), bmin, bmax);
+            if (!box_intersect_exact(bmin, bmax, o, d)) continue;
+        }
         BestExact b; b.has = false; b.dist = 0.0; b.face = -1;
-        mesh_nearest_exact(sc.meshes[ob.mesh], dv_sub(o, pos), d, b, brute, cnt);       // object.go:71
+        mesh_nearest_exact(mv, dv_sub(o, pos), d, b, brute, cnt);                        // object.go:71
         if (b.has) {
             dv ipw = dv_add(b.h.ip, pos);                                                // object.go:109
             double dist = dv_len(dv_sub(ipw, cam));                                      // tracer.go:38

@@ -87,6 +87,8 @@ struct MeshView {
     const RtNode  *nodes_any;
     int      root_ref_any;
     uint32_t n_nodes_any;
+    uint32_t pad_;
+    double   vlo[3], vhi[3];   // float64 bounds of ALL vertices of the mesh: Object.Bounds (object.go:38-49) for tracer.go:32's test
 };
 
 struct ObjRec { double pos[3]; uint32_t mesh; uint32_t pad; };

@@ -149,6 +149,17 @@ class Scene:
     def build_rtrees(self):
         lib().orc_build_rtrees(self.h)
 
+    def rtree_path_check(self, mesh, face, o, d):
+        """(rectangles on the R-tree path to `face`, index of the first one box.go's predicate rejects or -1, that rectangle)"""
+        o = np.ascontiguousarray(o, dtype=np.float64)
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        first = C.c_int(-1)
+        bmin, bmax = np.zeros(3), np.zeros(3)
+        lib().orc_rtree_path_check.restype = C.c_int
+        lib().orc_rtree_path_check.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        n = lib().orc_rtree_path_check(self.h, mesh, face, _p(o), _p(d), C.byref(first), _p(bmin), _p(bmax))
+        return n, first.value, bmin, bmax
+
     def trace(self, o, d, mode=CULLED):
         o = np.ascontiguousarray(o, dtype=np.float64)
         d = np.ascontiguousarray(d, dtype=np.float64)

@@ -633,6 +633,31 @@ static void rt_search(const omesh *m, const rnode *n, vec o, vec d, nearest_t *n
     }
 }
 
+/* Diagnostic (tests / tools only): follows the R-tree path from the root to `face` of mesh `mesh` and evaluates box.go's
+ * predicate on every entry rectangle of that path for the OBJECT-SPACE ray (o, d).  Returns the number of rectangles on the
+ * path (0: face not found / no tree); *first_rejected = index of the first rectangle the predicate rejects (-1: none), and
+ * that rectangle in bmin / bmax.  Used to show WHY the reference-shaped walk can miss a real hit. */
+static int rt_path(const rnode *n, int32_t face, const rnode **nodes, int *slots, int depth) {
+    for (int k = 0; k < n->n; k++) {
+        nodes[depth] = n; slots[depth] = k;
+        if (n->leaf) { if (n->face[k] == face) return depth + 1; }
+        else { int r = rt_path(n->child[k], face, nodes, slots, depth + 1); if (r) return r; }
+    }
+    return 0;
+}
+int orc_rtree_path_check(const orc_scene *s, uint32_t mesh, int32_t face, const double *o, const double *d, int *first_rejected,
+                         double *bmin, double *bmax) {
+    *first_rejected = -1;
+    if (mesh >= s->n_meshes || !s->meshes[mesh].rroot) return 0;
+    const rnode *nodes[64]; int slots[64];
+    int len = rt_path(s->meshes[mesh].rroot, face, nodes, slots, 0);
+    for (int k = 0; k < len; k++) {
+        vec lo = nodes[k]->emin[slots[k]], hi = nodes[k]->emax[slots[k]];
+        if (!box_intersect(lo, hi, v_ld(o), v_ld(d))) { *first_rejected = k; v_st(bmin, lo); v_st(bmax, hi); break; }
+    }
+    return len;
+}
+
 /* Returns hit; ip_world, normal, face index, material index */
 static int object_intersection(const orc_scene *s, int mode, uint32_t k, vec o, vec d, vec *ipw, vec *normal,
                                int32_t *face, int32_t *mat, orc_stats *st) {

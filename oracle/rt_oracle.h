@@ -79,6 +79,8 @@ orc_scene *orc_scene_create(const orc_mesh_desc *meshes, uint32_t n_meshes,
 void orc_scene_destroy(orc_scene *);
 /* build the reference-shaped R-trees (mesh.go:139,208) now instead of lazily */
 void orc_build_rtrees(orc_scene *);
+int orc_rtree_path_check(const orc_scene *s, uint32_t mesh, int32_t face, const double *o, const double *d, int *first_rejected,
+                         double *bmin, double *bmax);
 
 /* per-frame mutable state (environment.go:65-69) */
 void orc_frame_set(orc_scene *, const double *cam13, double tan_half_fov,

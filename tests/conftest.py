@@ -106,3 +106,15 @@ def degenerate_scenes():
         "edge_on_triangle": scene([mesh([[0.0, -1.0, 1.0], [0.0, 1.0, 1.0], [0.0, 0.0, -1.0]] + tri, [[0, 1, 2], [3, 4, 5]])],
                                   [[0, 0, 0], [0.0, 0.0, -2.0]], [0, 0]),
     }
+
+
+def box_predicate_scene():
+    """tests/golden/box_predicate_object_level.npz: a 50-triangle grid-aligned stress scene (found by
+    tools/fuzz_degenerate_faces_cpu.py) in which one shadow ray leaves the object's bounds exactly through an edge: box.go's
+    predicate (box.go:29-69) rejects the bounds on both adjacent sides by one rounding, so the reference never searches the
+    object for that ray (tracer.go:32) and the pixel stays lit although a triangle lies between it and the light."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "box_predicate_object_level.npz"))
+    sc = {"meshes": [{k: z[k] for k in ("verts", "normals", "faces", "materials")}], "obj_pos": z["obj_pos"], "obj_mesh": z["obj_mesh"],
+          "camera": z["camera"], "lights": z["lights"]}
+    return sc, int(z["W"]), int(z["H"])

@@ -172,6 +172,12 @@ void *emul_scene_create2(const rt_scene_desc *desc, int max_leaf, int max_leaf_a
         }
         m.materials.assign(d.materials, d.materials + 10 * (size_t)d.n_materials);
         build_mesh(m, max_leaf, max_leaf_any);
+        for (int c = 0; c < 3; c++) { m.view.vlo[c] = HUGE_VAL; m.view.vhi[c] = -HUGE_VAL; }
+        for (size_t v = 0; v < d.n_verts; v++)                   // Object.Bounds walks ALL vertices of the mesh (object.go:38-49)
+            for (int c = 0; c < 3; c++) {
+                m.view.vlo[c] = go_min(m.view.vlo[c], d.verts[3 * v + c]);
+                m.view.vhi[c] = go_max(m.view.vhi[c], d.verts[3 * v + c]);
+            }
         m.view.fverts = m.fverts.data();
         m.view.fnormals = d.n_normals ? m.fnormals.data() : nullptr;
         m.view.fmat = m.fmat.data();

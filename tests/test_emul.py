@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import emul_build as eb
-from conftest import degenerate_scenes, random_soup_scene
+from conftest import box_predicate_scene, degenerate_scenes, random_soup_scene
 from oracle import oracle as orc
 
 import distributed_raytracer_b200 as rt
@@ -348,3 +348,20 @@ def test_object_with_nan_position_is_absent(precision):
         assert np.array_equal(face, face_o) and np.array_equal(col.view(np.uint64), col_o.view(np.uint64)) and np.array_equal(rgb, rgb_o)
     else:
         assert (face == face_o).mean() >= 0.995 and (np.abs(rgb.astype(np.int32) - rgb_o.astype(np.int32)).max(axis=1) <= 1).mean() >= 0.995
+
+
+def test_exact_replay_applies_the_reference_object_level_predicate():
+    """tracer.go:32 + box.go:29-69: the reference searches an object only if its NON-conservative box predicate accepts the
+    object's bounds.  In this stress scene the predicate rejects the bounds for one shadow ray that really crosses them; the
+    replay of the FP64_EXACT kernels follows the reference-shaped walk of the oracle bit for bit, while a conservative search
+    (the oracle's distance-pruning mode) finds the occluder the reference never looks at."""
+    sc, W, H = box_predicate_scene()
+    S = orc.Scene(sc)
+    S.build_rtrees()
+    rgb_r, col_r, face_r, _ = S.render_region(W, H, mode=orc.RTREE)
+    rgb_c, col_c, face_c, _ = S.render_region(W, H, mode=orc.CULLED)
+    E = eb.EmulScene(sc, rt.FP64_EXACT, 4)
+    rgb, col, face, obj, lit, cnt = E.render(sc["camera"], sc["lights"], W, H)
+    E.close(); S.close()
+    assert np.array_equal(face, face_r) and np.array_equal(col.view(np.uint64), col_r.view(np.uint64)) and np.array_equal(rgb, rgb_r)
+    assert not np.array_equal(col_c.view(np.uint64), col_r.view(np.uint64))      # the fixture does exercise the corner

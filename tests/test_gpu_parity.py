@@ -682,6 +682,23 @@ def test_degenerate_inputs(rt, name):
     ge.close(); gf.close(); S.close()
 
 
+def test_exact_applies_the_reference_object_level_predicate(rt):
+    """tracer.go:32 + box.go:29-69 on the GPU: FP64_EXACT == the oracle's reference-shaped walk on the stress scene in which the
+    reference's non-conservative box predicate rejects the object's bounds for a shadow ray that crosses them
+    (tests/golden/box_predicate_object_level.npz; CPU twin: test_emul.py)."""
+    from conftest import box_predicate_scene
+    sc, W, H = box_predicate_scene()
+    S = orc.Scene(sc)
+    S.build_rtrees()
+    rgb_r, col_r, face_r, _ = S.render_region(W, H, mode=orc.RTREE)
+    rgb_c, col_c, face_c, _ = S.render_region(W, H, mode=orc.CULLED)
+    g = rt.GpuScene(sc, precision=rt.FP64_EXACT)
+    rgb, col, face, obj, lit = g.render_region_debug(W, H)
+    g.close(); S.close()
+    assert np.array_equal(face, face_r) and np.array_equal(col.view(np.uint64), col_r.view(np.uint64)) and np.array_equal(rgb, rgb_r)
+    assert not np.array_equal(col_c.view(np.uint64), col_r.view(np.uint64))
+
+
 def test_host_tracer_bulk_trace_and_draw(rt, example_scene):
     """The reference-facing interface: Tracer.BulkTrace (distributed/main.go:46-91) over partition() rectangles
     (master/main.go:54-91) reassembles into the same screen as draw() (sequential/main.go:15-32)."""
