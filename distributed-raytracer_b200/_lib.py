@@ -16,7 +16,7 @@ FP64_EXACT, FP32_FAST = 0, 1
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0x0, 0x1
 QUANT_RGB255, QUANT_RGBA16_SHR8 = 0x0, 0x2
 FLAG_COUNT, FLAG_BRUTE_FORCE, FLAG_SIMPLE, FLAG_PERSISTENT = 0x4, 0x8, 0x10, 0x20
-FLAG_FUSED, FLAG_PIPELINE, FLAG_NO_CULL = 0x40, 0x80, 0x100
+FLAG_FUSED, FLAG_PIPELINE, FLAG_NO_CULL, FLAG_SM_AFFINE = 0x40, 0x80, 0x100, 0x200
 
 
 def LANE(k):

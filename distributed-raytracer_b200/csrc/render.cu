@@ -304,20 +304,12 @@ __global__ void __launch_bounds__(128) k_phong(FrameParams fp, SceneView sc_in, 
 #ifndef RT_FUSED_THREADS
 #define RT_FUSED_THREADS 128      // threads per CTA of the fused kernel (64: measured in profiles/r02_kernel_ab.txt)
 #endif
-template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(RT_FUSED_THREADS, MINB * (128 / RT_FUSED_THREADS)) k_frame_fused(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
-                                                            bool rowmajor, bool sdl, unsigned int *counters,
-                                                            uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour,
-                                                            int32_t *__restrict__ out_face, int32_t *__restrict__ out_obj,
-                                                            uint32_t *__restrict__ out_lit, Counters *gstats) {
-    RT_DECLARE_TRAV_SMEM();
-    const SceneView sc = bind_frame(sc_in, fr, trav_smem);
-    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nrays = ray_count(fp);
+// one 8x4 pixel block of a frame, all 32 lanes of a warp: `ray` = 32 * block + lane in the numbering of map_ray
+template <bool COUNT>
+__device__ __forceinline__ void fused_block(const FrameParams &fp, const SceneView &sc, uint32_t ray, bool rowmajor, bool sdl, unsigned int *counters,
+                                            uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour, int32_t *__restrict__ out_face,
+                                            int32_t *__restrict__ out_obj, uint32_t *__restrict__ out_lit, Counters &c0, Counters &c1) {
     const unsigned lane = threadIdx.x & 31;
-    if ((ray & ~31u) >= nrays) return;                        // warp-uniform
-    if (warp_cancelled(counters, fp)) return;
-    Counters c0, c1; c0.nodes = c0.tris = c1.nodes = c1.tris = 0;
     const PixMap pm = map_ray(ray, fp, rowmajor);
     if (fp.tile_w > 0 && block_culled(fp, pm.i - (int)(ray & 7u), pm.j - (int)((ray >> 3) & 3u))) return;      // warp-uniform: a warp is one 8x4 block
     bool hit = false;
@@ -348,6 +340,113 @@ __global__ void __launch_bounds__(RT_FUSED_THREADS, MINB * (128 / RT_FUSED_THREA
             if (out_obj) out_obj[o] = tr.obj;
             if (out_lit) out_lit[o] = lit;
         }
+    }
+}
+
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(RT_FUSED_THREADS, MINB * (128 / RT_FUSED_THREADS)) k_frame_fused(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
+                                                            bool rowmajor, bool sdl, unsigned int *counters,
+                                                            uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour,
+                                                            int32_t *__restrict__ out_face, int32_t *__restrict__ out_obj,
+                                                            uint32_t *__restrict__ out_lit, Counters *gstats) {
+    RT_DECLARE_TRAV_SMEM();
+    const SceneView sc = bind_frame(sc_in, fr, trav_smem);
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nrays = ray_count(fp);
+    if ((ray & ~31u) >= nrays) return;                        // warp-uniform
+    if (warp_cancelled(counters, fp)) return;
+    Counters c0, c1; c0.nodes = c0.tris = c1.nodes = c1.tris = 0;
+    fused_block<COUNT>(fp, sc, ray, rowmajor, sdl, counters, out_rgb, out_colour, out_face, out_obj, out_lit, c0, c1);
+    if (COUNT) { flush_counters(gstats, c0); flush_counters(gstats ? gstats + 1 : nullptr, c1); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same frame with PERSISTENT, SM-AFFINE warps (RT_FLAG_SM_AFFINE / RT_B200_SM_AFFINE; north_star part 2: persistent threads
+// that refill their work with one atomic per warp).  The hardware block scheduler hands the CTAs of the plain kernel to whichever
+// SM has room, so the 36 warps resident on one SM work on ~9 unrelated places of the screen and every SM pulls the same BVH
+// lines through its own L1.  Here the grid is SMs x resident CTAs; the frame is cut into CHUNKS of RT_CHUNK_BLOCKS 8x4 blocks that
+// are neighbours on the screen (tile mode: consecutive blocks of the rank's tiles; region mode: 4 x RT_CHUNK_BLOCKS/4 blocks = 32 x 32 pixels),
+// every SM owns one chunk at a time (its id sits in a per-SM word of the lane's chunk state) and ALL its warps take their next
+// block from that chunk with one atomicAdd -- so the warps that share an L1 walk the same part of the tree at the same time.
+// When a chunk runs out, the warp that notices locks the word, takes the next chunk of the frame from a global counter and
+// publishes it; when the frame has no chunks left a warp helps the other SMs finish theirs before it retires.
+// chunk state (uint32 words, zeroed per frame): [0] next chunk, [1] spare, [2 .. 2+RT_MAX_SM) per-SM word, then one
+// next-block counter per chunk.  Per-SM word: 0 = nothing yet, 1 = locked (being refilled), 2 = frame exhausted, c + 3 = chunk c.
+// ---------------------------------------------------------------------------------------------
+struct ChunkGrid { uint32_t n_chunks, n_blocks, nbx, nby, cgx; };     // region mode: cgx chunks per row of chunks; tile mode: cgx = 0
+
+__host__ __device__ inline ChunkGrid chunk_grid(const FrameParams &fp) {
+    ChunkGrid g;
+    g.n_blocks = ray_count(fp) / 32u;
+    if (fp.tile_w > 0) { g.nbx = g.nby = g.cgx = 0; g.n_chunks = (g.n_blocks + RT_CHUNK_BLOCKS - 1) / RT_CHUNK_BLOCKS; return g; }
+    g.nbx = fp.rnbx > 0 ? (uint32_t)fp.rnbx : (uint32_t)(fp.w + 7) / 8;
+    g.nby = g.nbx ? g.n_blocks / g.nbx : 0;
+    g.cgx = (g.nbx + 3) / 4;
+    g.n_chunks = g.cgx * ((g.nby + RT_CHUNK_BLOCKS / 4 - 1) / (RT_CHUNK_BLOCKS / 4));
+    return g;
+}
+// block `idx` of chunk `c` -> linear block number of map_ray, or 0xffffffff if that slot lies outside the frame
+__device__ __forceinline__ uint32_t chunk_block(const ChunkGrid &g, uint32_t c, uint32_t idx) {
+    if (g.cgx == 0) { const uint32_t b = c * RT_CHUNK_BLOCKS + idx; return b < g.n_blocks ? b : 0xffffffffu; }
+    const uint32_t bx = (c % g.cgx) * 4 + (idx & 3u), by = (c / g.cgx) * (RT_CHUNK_BLOCKS / 4) + (idx >> 2);
+    return (bx < g.nbx && by < g.nby) ? by * g.nbx + bx : 0xffffffffu;
+}
+__device__ __forceinline__ unsigned int ld_volatile(const unsigned int *p) { return *(const volatile unsigned int *)p; }
+
+// lane 0 of a warp: the next block of this SM's chunk (0xfffffffe = the frame is finished).  `slots` = blocks per chunk.
+__device__ __forceinline__ uint32_t claim_block(unsigned int *state, const ChunkGrid &g, unsigned smid, unsigned n_sm) {
+    unsigned int *word = state + 2 + smid, *next = state + 2 + RT_MAX_SM;
+    for (;;) {
+        const unsigned int w = ld_volatile(word);
+        if (w >= 3u) {
+            const uint32_t c = w - 3u, idx = atomicAdd(&next[c], 1u);
+            if (idx < RT_CHUNK_BLOCKS) { const uint32_t b = chunk_block(g, c, idx); if (b != 0xffffffffu) return b; continue; }
+            if (atomicCAS(word, w, 1u) != w) continue;                         // somebody else refills
+        } else if (w == 1u) {
+            __nanosleep(40);
+            continue;
+        } else if (w == 2u) {
+            break;
+        } else if (atomicCAS(word, 0u, 1u) != 0u) continue;
+        // this warp holds the lock: take the next chunk of the frame
+        const uint32_t c = atomicAdd(&state[0], 1u);
+        __threadfence();
+        *(volatile unsigned int *)word = c < g.n_chunks ? c + 3u : 2u;
+    }
+    // no chunks left: help the SMs that are still inside one
+    for (unsigned k = 1; k < n_sm; k++) {
+        const unsigned int w = ld_volatile(state + 2 + (smid + k) % n_sm);
+        if (w < 3u) continue;
+        const uint32_t c = w - 3u;
+        while (ld_volatile(&next[c]) < RT_CHUNK_BLOCKS) {
+            const uint32_t idx = atomicAdd(&next[c], 1u);
+            if (idx >= RT_CHUNK_BLOCKS) break;
+            const uint32_t b = chunk_block(g, c, idx);
+            if (b != 0xffffffffu) return b;
+        }
+    }
+    return 0xfffffffeu;
+}
+
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_frame_fused_sm(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr, bool rowmajor, bool sdl,
+                                                               unsigned int *counters, unsigned int *chunk_state, unsigned n_sm,
+                                                               uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour,
+                                                               int32_t *__restrict__ out_face, int32_t *__restrict__ out_obj,
+                                                               uint32_t *__restrict__ out_lit, Counters *gstats) {
+    const SceneView sc = bind_frame(sc_in, fr, nullptr);
+    const ChunkGrid g = chunk_grid(fp);
+    const unsigned lane = threadIdx.x & 31;
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    Counters c0, c1; c0.nodes = c0.tris = c1.nodes = c1.tris = 0;
+    for (;;) {
+        uint32_t blk = 0;
+        if (lane == 0) blk = frame_cancelled(counters, fp) ? 0xfffffffeu : claim_block(chunk_state, g, smid % RT_MAX_SM, n_sm);
+        blk = __shfl_sync(FULL, blk, 0);
+        if (blk == 0xfffffffeu) break;
+        fused_block<COUNT>(fp, sc, blk * 32u + lane, rowmajor, sdl, counters, out_rgb, out_colour, out_face, out_obj, out_lit, c0, c1);
+        __syncwarp();
     }
     if (COUNT) { flush_counters(gstats, c0); flush_counters(gstats ? gstats + 1 : nullptr, c1); }
 }
@@ -733,6 +832,21 @@ cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
     if (nrays == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool rowmajor = (job.flags & RT_LAYOUT_ROWMAJOR) != 0, sdl = (job.flags & RT_QUANT_RGBA16_SHR8) != 0;
+    if (job.sm_affine && job.d_chunk_state) {
+        // persistent SM-affine form: SMs x resident CTAs, work handed out in screen-local chunks (see k_frame_fused_sm)
+        const ChunkGrid g = chunk_grid(fp);
+        if ((size_t)2 + RT_MAX_SM + g.n_chunks > job.chunk_state_words || job.sm_count > RT_MAX_SM) return cudaErrorInvalidValue;
+        cudaError_t e = cudaMemsetAsync(job.d_chunk_state, 0, sizeof(unsigned int) * ((size_t)2 + RT_MAX_SM + g.n_chunks), st);
+        if (e != cudaSuccess) return e;
+#define LAUNCH_FUSED_SM(CN, MB) do { prefer_l1(k_frame_fused_sm<CN, MB>);                                                             \
+        k_frame_fused_sm<CN, MB><<<(unsigned)job.sm_count * (unsigned)(MB), 128, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_chunk_state, \
+                                                    (unsigned)job.sm_count, job.d_out_rgb, job.d_out_colour, job.d_out_face, job.d_out_obj, job.d_out_lit, job.d_stats); } while (0)
+        if (count) LAUNCH_FUSED_SM(true, 4);
+        else if (job.shade_minb >= 9) LAUNCH_FUSED_SM(false, 9);
+        else LAUNCH_FUSED_SM(false, 8);
+#undef LAUNCH_FUSED_SM
+        return cudaGetLastError();
+    }
     const unsigned nblk = (nrays + RT_FUSED_THREADS - 1) / RT_FUSED_THREADS;
     // the traversal kernels use no shared memory: ask for the whole unified L1 / shared array as L1 (once per kernel and device)
 #define LAUNCH_FUSED(CN, MB) do { prefer_l1(k_frame_fused<CN, MB>);                                                                   \

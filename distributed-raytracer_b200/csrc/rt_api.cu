@@ -40,6 +40,7 @@ struct Lane {
     HitRec *d_hits = nullptr; double *d_hit_colour = nullptr; uint32_t *d_hit_lit = nullptr; double *d_hit_geom = nullptr;
     size_t cap_rays = 0;
     unsigned int *d_counters = nullptr; Counters *d_stats = nullptr;
+    unsigned int *d_chunk_state = nullptr; size_t cap_chunk_state = 0;   // k_frame_fused_sm
     uint8_t *d_rgb = nullptr; size_t cap_rgb = 0;
     double *d_dbg_colour = nullptr; int32_t *d_dbg_face = nullptr, *d_dbg_obj = nullptr; uint32_t *d_dbg_lit = nullptr;
     size_t cap_dbg = 0;
@@ -67,6 +68,7 @@ struct rt_scene {
     bool cull = true;                  // projected-root-box culling of primary rays (RT_B200_CULL)
     int shade_minb = 8;
     bool primary_persistent = false;
+    bool sm_affine = false;
     bool split_shade = false;
     bool shade32 = false;              // RT_B200_SHADE32=1: FP32_FAST shades in fp32 too (opt-in)
     uint32_t sync_timeout_ms = 2000;   // device-side wait on a peer's hand-off flag gives up after this (master/main.go:35: 2 s per order)
@@ -125,6 +127,7 @@ void destroy_lane(Lane &L) {
     if (L.stream) cudaStreamSynchronize(L.stream);
     cudaFree(L.d_objs); cudaFree(L.d_lights);
     cudaFree(L.d_hits); cudaFree(L.d_hit_colour); cudaFree(L.d_hit_lit); cudaFree(L.d_hit_geom); cudaFree(L.d_counters); cudaFree(L.d_stats);
+    cudaFree(L.d_chunk_state);
     cudaFree(L.d_rgb); cudaFree(L.d_dbg_colour); cudaFree(L.d_dbg_face); cudaFree(L.d_dbg_obj); cudaFree(L.d_dbg_lit);
     if (L.h_pinned) cudaFreeHost(L.h_pinned);
     cudaFree(L.d_wire); cudaFree(L.d_wire_scratch); cudaFree(L.d_wire_len);
@@ -306,6 +309,17 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
                                      : (size_t)((fp.w + 7) / 8) * (size_t)((fp.h + 3) / 4) * 32u;
     int rc = ensure_scratch(s, L, fused ? 0 : full_rays, out_bytes, internal_rgb, dbg, npix_out);
     if (rc != RT_OK) return rc;
+    const bool sm_affine = fused && (s->sm_affine || (flags & RT_FLAG_SM_AFFINE)) && s->sm_count <= RT_MAX_SM;
+    if (sm_affine) {
+        // chunk state of the persistent kernel, sized for the un-culled frame (same reason as above)
+        const size_t nb = full_rays / 32u, nbx = fp.tile_w > 0 ? 0 : (size_t)(fp.w + 7) / 8, nby = fp.tile_w > 0 ? 0 : (size_t)(fp.h + 3) / 4;
+        const size_t words = 2 + RT_MAX_SM + nb / RT_CHUNK_BLOCKS + nbx + nby + 8;
+        if (words > L.cap_chunk_state) {
+            cudaFree(L.d_chunk_state); L.d_chunk_state = nullptr; L.cap_chunk_state = 0;
+            CU(s, cudaMalloc((void **)&L.d_chunk_state, words * sizeof(unsigned int)));
+            L.cap_chunk_state = words;
+        }
+    }
     cudaStream_t st = out.ext_stream ? out.ext_stream : L.stream;
     uint8_t *d_rgb = internal_rgb ? L.d_rgb : out.d_rgb;
 
@@ -332,6 +346,7 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     job.shade_minb = s->shade_minb;
     job.primary_persistent = s->primary_persistent;
     job.fused = fused;
+    job.sm_affine = sm_affine; job.d_chunk_state = L.d_chunk_state; job.chunk_state_words = L.cap_chunk_state;
 
     CU(s, cudaMemsetAsync(L.d_counters, 0, 4 * sizeof(unsigned int), st));
     if (flags & RT_FLAG_COUNT) CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), st));
@@ -547,6 +562,7 @@ static int create_scene_common(uint32_t precision, int32_t device, uint32_t n_me
     s->shade32 = env_int("RT_B200_SHADE32", 0) != 0 && precision == RT_FP32_FAST;
     s->max_leaf_any = env_int("RT_B200_MAX_LEAF_SHADE", RT_DEFAULT_MAX_LEAF_SHADE);
     s->fused = env_int("RT_B200_FUSED", RT_DEFAULT_FUSED) != 0;
+    s->sm_affine = env_int("RT_B200_SM_AFFINE", 0) != 0;
     s->cull = env_int("RT_B200_CULL", 1) != 0;
     s->sync_timeout_ms = (uint32_t)std::max(1, env_int("RT_B200_SYNC_TIMEOUT_MS", 2000));
     int n_lanes = env_int("RT_B200_LANES", 9);      // lane 0 + a pool of 8 for concurrent BulkTrace calls / frames in flight

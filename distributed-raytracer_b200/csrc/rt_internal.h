@@ -68,6 +68,8 @@ struct RenderJob {
     bool      primary_persistent;  // default primary kernel of FP32_FAST (RT_B200_PERSISTENT=1), overridable per call
     int       shade_minb;     // K4 occupancy experiment: min resident CTAs per SM (register cap)
     bool      fused;          // FP32_FAST: one fused kernel per frame instead of K2 -> K4 -> K5
+    bool      sm_affine;      // ... in its persistent SM-affine form (RT_FLAG_SM_AFFINE)
+    unsigned int *d_chunk_state; size_t chunk_state_words;
 };
 
 // render.cu : enqueue K2 (primary) / K4 (shadow+shade) / K5 (framebuffer) on `st`

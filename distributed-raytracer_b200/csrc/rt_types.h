@@ -49,6 +49,11 @@
 #ifndef RT_DEFAULT_MAX_LEAF_SHADE
 #define RT_DEFAULT_MAX_LEAF_SHADE 2
 #endif
+// persistent SM-affine frame kernel (render.cu: k_frame_fused_sm): 8x4 blocks per chunk, per-SM words of the chunk state
+#ifndef RT_CHUNK_BLOCKS
+#define RT_CHUNK_BLOCKS 32
+#endif
+#define RT_MAX_SM 256
 #ifndef RT_DEFAULT_FUSED
 #define RT_DEFAULT_FUSED 1
 #endif

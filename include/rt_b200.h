@@ -61,6 +61,9 @@ typedef enum {
 #define RT_FLAG_FUSED        0x40u /* FP32_FAST only: ONE kernel per frame -- a warp traces its 8x4 pixel block, shades the
                                       hits (shadow rays + Phong) and writes the pixels; no hit list, no K4/K5 launches */
 #define RT_FLAG_PIPELINE     0x80u /* the three-kernel pipeline K2 -> K4 -> K5 even if the scene's default is the fused kernel */
+#define RT_FLAG_SM_AFFINE    0x200u /* FP32_FAST, fused frame kernel only: persistent warps, every SM works through screen-local chunks of
+                                      the frame (one atomic per warp refill) so that the warps sharing an L1 walk the same part of the
+                                      tree; RT_B200_SM_AFFINE=1 makes it the scene's default */
 #define RT_FLAG_NO_CULL      0x100u /* trace every pixel block of the region: no projected-root-box culling (A/B, tests) */
 
 /* Lanes.  A scene handle owns one immutable copy of the geometry (+ BVH) and several LANES -- per-call resources: stream,

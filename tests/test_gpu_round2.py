@@ -102,6 +102,49 @@ def test_cull_rectangle_in_tile_mode(rt, example_scene):
     g.close()
 
 
+@pytest.mark.parametrize("scene_kind", ["example", "subdiv3", "three_objects"])
+def test_sm_affine_persistent_kernel_equals_the_plain_fused_kernel(rt, example_scene, scene_kind):
+    """RT_FLAG_SM_AFFINE (k_frame_fused_sm: persistent warps, screen-local chunks per SM, one atomic per refill) hands the same
+    8x4 blocks to the same device code in another order: every output is bit-identical -- whole frames, odd sizes whose chunk grid
+    overhangs the frame, sub-regions, both layouts and quantisers, with and without the cull rectangle, tile mode for 1 and 3 ranks."""
+    import torch
+    sc = {"example": lambda: example_scene, "subdiv3": lambda: subdivided(example_scene, 3),
+          "three_objects": lambda: random_soup_scene(n_tris=150, seed=13, n_obj=3, n_lights=4)}[scene_kind]()
+    g = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    for (W, H) in [(480, 270), (333, 187), (40, 12), (8, 4), (1, 1)]:
+        for extra in (0, rt.FLAG_NO_CULL):
+            a = g.render_region_debug(W, H, flags=rt.FLAG_FUSED | extra)
+            na = g.stats()["hit_pixels"]
+            b = g.render_region_debug(W, H, flags=rt.FLAG_FUSED | rt.FLAG_SM_AFFINE | extra)
+            nb = g.stats()["hit_pixels"]
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+            assert na == nb
+    W, H = 480, 270
+    x0, y0, w, h = W // 5, H // 7, W // 2 + 3, H // 2 + 1
+    for flags in (0, rt.LAYOUT_ROWMAJOR, rt.QUANT_RGBA16_SHR8):
+        assert np.array_equal(g.render_region(W, H, x0, y0, w, h, flags=flags | rt.FLAG_FUSED),
+                              g.render_region(W, H, x0, y0, w, h, flags=flags | rt.FLAG_FUSED | rt.FLAG_SM_AFFINE))
+    tw, th = 32, 16
+    for n in (1, 3):
+        per = rt.tiles_per_rank(W, H, tw, th, n)
+        for rank in range(n):
+            outs = []
+            for flags in (rt.FLAG_FUSED, rt.FLAG_FUSED | rt.FLAG_SM_AFFINE):
+                t = torch.zeros(per * tw * th * 3, dtype=torch.uint8, device="cuda")
+                g.render_tiles_device(W, H, tw, th, rank, n, t.data_ptr(), None, flags)
+                outs.append(t.cpu().numpy())
+            assert np.array_equal(outs[0], outs[1])
+    # counting build: the same traversal work is reported
+    g.render_region_debug(W, H, flags=rt.FLAG_FUSED | rt.FLAG_COUNT)
+    c0 = g.stats()
+    g.render_region_debug(W, H, flags=rt.FLAG_FUSED | rt.FLAG_SM_AFFINE | rt.FLAG_COUNT)
+    c1 = g.stats()
+    for k in ("nodes_primary", "tris_primary", "nodes_shade", "tris_shade", "hit_pixels", "shadow_rays"):
+        assert c0[k] == c1[k], k
+    g.close()
+
+
 @pytest.mark.parametrize("leaf_any", [1, 2])
 def test_any_hit_hierarchy_leaf_size(rt, example_scene, monkeypatch, leaf_any):
     sc = subdivided(example_scene, 3)

@@ -34,6 +34,12 @@ VARIANTS = {
     "pipeline_nodefer": ({"RT_B200_LIB": "build_variants/librt_b200_nodefer.so"}, ["PIPELINE"]),
     "fused_pf1": ({"RT_B200_LIB": "build_variants/librt_b200_pf1.so"}, []),
     "fused_pf2": ({"RT_B200_LIB": "build_variants/librt_b200_pf2.so"}, []),
+    # persistent SM-affine frame kernel (k_frame_fused_sm); chunk = 32 8x4 blocks unless the build says otherwise
+    "fused_sm": ({"RT_B200_SM_AFFINE": "1"}, []),
+    "fused_sm_minb8": ({"RT_B200_SM_AFFINE": "1", "RT_B200_SHADE_MINB": "8"}, []),
+    "fused_sm_c16": ({"RT_B200_SM_AFFINE": "1", "RT_B200_LIB": "build_variants/librt_b200_chunk16.so"}, []),
+    "fused_sm_c64": ({"RT_B200_SM_AFFINE": "1", "RT_B200_LIB": "build_variants/librt_b200_chunk64.so"}, []),
+    "fused_sm_c128": ({"RT_B200_SM_AFFINE": "1", "RT_B200_LIB": "build_variants/librt_b200_chunk128.so"}, []),
     "fused_any1": ({"RT_B200_MAX_LEAF_SHADE": "1"}, []),
     "fused_any8": ({"RT_B200_MAX_LEAF_SHADE": "8"}, []),
 }

@@ -16,4 +16,8 @@ $NV -DRT_ANY_DEFER=0 -o ../../build_variants/librt_b200_nodefer.so $SRC &
 $NV -DRT_PUSH_PREFETCH=1 -o ../../build_variants/librt_b200_pf1.so $SRC &
 $NV -DRT_PUSH_PREFETCH=2 -o ../../build_variants/librt_b200_pf2.so $SRC &
 wait
+$NV -DRT_CHUNK_BLOCKS=16 -o ../../build_variants/librt_b200_chunk16.so $SRC &
+$NV -DRT_CHUNK_BLOCKS=64 -o ../../build_variants/librt_b200_chunk64.so $SRC &
+$NV -DRT_CHUNK_BLOCKS=128 -o ../../build_variants/librt_b200_chunk128.so $SRC &
+wait
 # $NV -DRT_W=8 -o ../../build_variants/librt_b200_w8.so $SRC      # 8 children per node: measured 35-70 % slower (profiles/r02_kernel_ab.txt)
