@@ -133,6 +133,13 @@ __global__ void k_vertex_bounds(const double *__restrict__ verts, uint32_t n_ver
     }
 }
 
+__global__ void k_quantise_nodes(const RtNode *__restrict__ nodes, uint32_t n, RtNodeQ *__restrict__ out, float ox, float oy, float oz,
+                                 float sx, float sy, float sz) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float qorg[3] = { ox, oy, oz }, qstep[3] = { sx, sy, sz };
+    if (i < n) quantise_node_thread(i, nodes, out, qorg, qstep);
+}
+
 // scratch allocations of one build, released on scope exit
 struct Scratch {
     std::vector<void *> ptrs;
@@ -150,8 +157,10 @@ struct Scratch {
         if (ev1) cudaEventDestroy(ev1);
         if (!ok && m) {
             if (m->nodes_any != m->nodes) cudaFree(m->nodes_any);
+            if (m->qnodes_any != m->qnodes) cudaFree(m->qnodes_any);
+            cudaFree(m->qnodes);
             cudaFree(m->nodes); cudaFree(m->tri32); cudaFree(m->tri64);
-            m->nodes = nullptr; m->nodes_any = nullptr; m->tri32 = nullptr; m->tri64 = nullptr;
+            m->nodes = nullptr; m->nodes_any = nullptr; m->tri32 = nullptr; m->tri64 = nullptr; m->qnodes = nullptr; m->qnodes_any = nullptr;
         }
     }
 };
@@ -221,6 +230,7 @@ cudaError_t rt_flatten_faces(MeshDevice &m, const double *d_verts, uint32_t n_ve
 bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max_leaf_any, int sm_count, cudaStream_t st, std::string &err) {
     const uint32_t n = m.n_faces;
     m.nodes = nullptr; m.nodes_any = nullptr; m.tri32 = nullptr; m.tri64 = nullptr; m.n_nodes = 0; m.n_nodes_any = 0; m.root_ref = 0; m.root_ref_any = 0;
+    m.qnodes = nullptr; m.qnodes_any = nullptr;
     memset(&m.info, 0, sizeof m.info);
     m.info.n_faces = n; m.info.max_leaf = (uint32_t)max_leaf;
     for (int k = 0; k < 3; k++) { m.lo[k] = 0.f; m.hi[k] = 0.f; }
@@ -377,6 +387,21 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
     }
     m.info.n_nodes = m.n_nodes;
     m.info.n_nodes_any = m.n_nodes_any;
+#if RT_NODEQ
+    if (want32) {
+        // the 64-byte nodes the FP32_FAST rays fetch (rt_types.h: RtNodeQ), quantised from the float hierarchies just built
+        qgrid_from_bounds(m.lo, m.hi, m.qorg, m.qstep);
+        auto quantise = [&](const RtNode *src, uint32_t cnt, RtNodeQ **dst) -> bool {
+            CK(cudaMalloc(dst, sizeof(RtNodeQ) * (size_t)(cnt ? cnt : 1)));
+            if (cnt) k_quantise_nodes<<<(cnt + TB - 1) / TB, TB, 0, st>>>(src, cnt, *dst, m.qorg[0], m.qorg[1], m.qorg[2], m.qstep[0], m.qstep[1], m.qstep[2]);
+            CK(cudaGetLastError());
+            return true;
+        };
+        if (!quantise(m.nodes, m.n_nodes, &m.qnodes)) return false;
+        if (m.nodes_any != m.nodes) { if (!quantise(m.nodes_any, m.n_nodes_any, &m.qnodes_any)) return false; }
+        else m.qnodes_any = m.qnodes;
+    }
+#endif
     CK(cudaEventRecord(sc.ev1, st));
     CK(cudaEventSynchronize(sc.ev1));
     CK(cudaEventElapsedTime(&m.info.ms_build, sc.ev0, sc.ev1));

@@ -118,6 +118,8 @@ template <class T> cudaError_t upload(T **d, const T *h, size_t n, cudaStream_t 
 
 void free_mesh(MeshDevice &m) {
     if (m.nodes_any != m.nodes) cudaFree(m.nodes_any);
+    if (m.qnodes_any != m.qnodes) cudaFree(m.qnodes_any);
+    cudaFree(m.qnodes);
     cudaFree(m.nodes); cudaFree(m.tri32); cudaFree(m.tri64); cudaFree(m.fverts); cudaFree(m.fnormals); cudaFree(m.fmat);
     cudaFree(m.materials);
     m = MeshDevice();
@@ -614,7 +616,8 @@ static int create_scene_common(uint32_t precision, int32_t device, uint32_t n_me
         v.nodes = m.nodes; v.tri32 = m.tri32; v.tri64 = m.tri64; v.fverts = m.fverts; v.fnormals = m.fnormals; v.fmat = m.fmat;
         v.materials = m.materials; v.n_faces = m.n_faces; v.n_nodes = m.n_nodes; v.root_ref = m.root_ref;
         v.nodes_any = m.nodes_any; v.root_ref_any = m.root_ref_any; v.n_nodes_any = m.n_nodes_any;
-        for (int c = 0; c < 3; c++) { v.lo[c] = m.lo[c]; v.hi[c] = m.hi[c]; v.vlo[c] = m.vlo[c]; v.vhi[c] = m.vhi[c]; }
+        v.qnodes = m.qnodes; v.qnodes_any = m.qnodes_any;
+        for (int c = 0; c < 3; c++) { v.lo[c] = m.lo[c]; v.hi[c] = m.hi[c]; v.vlo[c] = m.vlo[c]; v.vhi[c] = m.vhi[c]; v.qorg[c] = m.qorg[c]; v.qstep[c] = m.qstep[c]; }
     }
     CUB_(upload(&s->d_meshes, s->h_views.data(), s->h_views.size(), st0));
     CUB_(cudaStreamSynchronize(st0));

@@ -286,6 +286,36 @@ RT_HD unsigned int emit_write_thread(int p, const int *frontier, int fsize, int 
     return nleaf;
 }
 
+// grid of the quantised nodes from the padded mesh bounds (rt_types.h: RtNodeQ): two cells of margin on either side
+RT_HD void qgrid_from_bounds(const float lo[3], const float hi[3], float qorg[3], float qstep[3]) {
+    for (int k = 0; k < 3; k++) {
+        float st = (hi[k] - lo[k]) / RT_QGRID_CELLS;
+        if (!(st > 1e-30f)) st = 1e-30f;
+        qstep[k] = st;
+        qorg[k] = lo[k] - 2.0f * st;
+    }
+}
+RT_HD uint16_t qgrid_down(float v, float org, float st) {
+    double q = floor(((double)v - (double)org) / (double)st) - 1.0;
+    return (uint16_t)(q < 0.0 ? 0.0 : (q > 65535.0 ? 65535.0 : q));
+}
+RT_HD uint16_t qgrid_up(float v, float org, float st) {
+    double q = ceil(((double)v - (double)org) / (double)st) + 1.0;
+    return (uint16_t)(q < 0.0 ? 0.0 : (q > 65535.0 ? 65535.0 : q));
+}
+// node i of a float hierarchy -> its 64-byte quantised form (every box grows by at least one cell on every side)
+RT_HD void quantise_node_thread(uint32_t i, const RtNode *nodes, RtNodeQ *out, const float qorg[3], const float qstep[3]) {
+    const RtNode nd = nodes[i];
+    RtNodeQ q;
+    for (int s = 0; s < 4; s++) {
+        q.x[s] = qgrid_down(nd.lox[s], qorg[0], qstep[0]); q.x[4 + s] = qgrid_up(nd.hix[s], qorg[0], qstep[0]);
+        q.y[s] = qgrid_down(nd.loy[s], qorg[1], qstep[1]); q.y[4 + s] = qgrid_up(nd.hiy[s], qorg[1], qstep[1]);
+        q.z[s] = qgrid_down(nd.loz[s], qorg[2], qstep[2]); q.z[4 + s] = qgrid_up(nd.hiz[s], qorg[2], qstep[2]);
+        q.ref[s] = nd.ref[s];
+    }
+    out[i] = q;
+}
+
 RT_HD float rt_int_as_float(int v) {
 #if defined(__CUDA_ARCH__)
     return __int_as_float(v);

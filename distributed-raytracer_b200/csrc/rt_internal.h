@@ -24,6 +24,8 @@ struct MeshDevice {
     uint32_t  n_faces = 0, n_nodes = 0, n_nodes_any = 0, n_materials = 0;
     int       root_ref = 0, root_ref_any = 0;
     float     lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+    RtNodeQ  *qnodes = nullptr, *qnodes_any = nullptr;      // FP32_FAST: quantised 64-byte nodes (qnodes_any == qnodes when the hierarchies agree)
+    float     qorg[3] = { 0, 0, 0 }, qstep[3] = { 1, 1, 1 };
     double    vlo[3] = { 0, 0, 0 }, vhi[3] = { 0, 0, 0 };   // float64 bounds of all vertices of the mesh (rt_flatten_faces)
     rt_bvh_info info;
 };

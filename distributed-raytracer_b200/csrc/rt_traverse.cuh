@@ -397,10 +397,17 @@ RT_HD bool mesh_any_hit_deferred(const MeshView &m, const RayF &r, float &tmax, 
     int ref = m.root_ref_any;
     bool more = true;
     if (ref < 0) { stack[--lp] = ref; more = false; }
+#if RT_USE_NODEQ
+    const RayQ rq = make_rayq(m, r);
+#endif
     do {
         while (more) {
             NodeHits n;
+#if RT_USE_NODEQ
+            node_test32q(m.qnodes_any + ref, rq, tmax, n);
+#else
             node_test32(m.nodes_any + ref, r, tmax, n);
+#endif
             RT_COUNT(cnt, nodes, 1);
             int next = RT_EMPTY;
 #pragma unroll
@@ -424,6 +431,57 @@ RT_HD bool mesh_any_hit_deferred(const MeshView &m, const RayF &r, float &tmax, 
     } while (more);
     return false;
 }
+
+// ---- quantised 64-byte nodes (rt_types.h: RtNodeQ) ----
+struct alignas(32) rt_u8 { uint32_t w[8]; };
+RT_HD rt_u8 ld_u8(const void *p) {
+#if defined(__CUDA_ARCH__)
+    rt_u8 r;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+    return r;
+#else
+    rt_u8 r; memcpy(&r, p, 32); return r;
+#endif
+}
+// 2^23 + (low or high 16-bit field of w) as a float: the field becomes the low mantissa bits of 0x4B000000 (one PRMT)
+RT_HD float q16f(uint32_t w, bool high) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, high ? 0x7632u : 0x7610u));
+#else
+    return rt_bits_float(0x4B000000u | (high ? (w >> 16) : (w & 0xffffu)));
+#endif
+}
+// the ray in the grid of a mesh's quantised nodes: plane q of an axis is met at t = (2^23 + q) * s + c
+struct RayQ { float sx, sy, sz, cx, cy, cz; };
+RT_HD RayQ make_rayq(const MeshView &m, const RayF &r) {
+    RayQ q;
+    q.sx = m.qstep[0] * r.ix; q.sy = m.qstep[1] * r.iy; q.sz = m.qstep[2] * r.iz;
+    q.cx = fmaf(-8388608.0f, q.sx, (m.qorg[0] - r.ox) * r.ix);
+    q.cy = fmaf(-8388608.0f, q.sy, (m.qorg[1] - r.oy) * r.iy);
+    q.cz = fmaf(-8388608.0f, q.sz, (m.qorg[2] - r.oz) * r.iz);
+    return q;
+}
+RT_HD void node_test32q(const RtNodeQ *nd, const RayQ &q, float tbest, NodeHits &h) {
+    const rt_u8 a = ld_u8(nd), b = ld_u8(reinterpret_cast<const char *>(nd) + 32);     // a: x, y planes; b: z planes, refs
+#define RT_CHILDQ(k)                                                                                                       \
+    {                                                                                                                      \
+        const float x0 = fmaf(q16f(a.w[(k) >> 1], (k) & 1), q.sx, q.cx), x1 = fmaf(q16f(a.w[2 + ((k) >> 1)], (k) & 1), q.sx, q.cx);   \
+        const float y0 = fmaf(q16f(a.w[4 + ((k) >> 1)], (k) & 1), q.sy, q.cy), y1 = fmaf(q16f(a.w[6 + ((k) >> 1)], (k) & 1), q.sy, q.cy); \
+        const float z0 = fmaf(q16f(b.w[(k) >> 1], (k) & 1), q.sz, q.cz), z1 = fmaf(q16f(b.w[2 + ((k) >> 1)], (k) & 1), q.sz, q.cz);   \
+        const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));                           \
+        const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tbest));                          \
+        const int rf = (int)b.w[4 + (k)];                                                                                  \
+        h.t[k] = tn; h.ref[k] = rf; h.hit[k] = tn <= tf && rf != RT_EMPTY;                                                 \
+    }
+    RT_CHILDQ(0) RT_CHILDQ(1) RT_CHILDQ(2) RT_CHILDQ(3)
+#undef RT_CHILDQ
+}
+#if RT_NODEQ && RT_W == 4
+#define RT_USE_NODEQ 1
+#else
+#define RT_USE_NODEQ 0
+#endif
 
 // Simple per-ray traversal of one mesh (object space).  ANY: stop at the first hit with t <= tbest.
 // Nearest: winner = min t, ties -> lowest face index.  Returns true if something was accepted.
@@ -458,12 +516,21 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
         }                                                                                                                  \
         sp++;                                                                                                              \
     } while (0)
+#if RT_USE_NODEQ
+    const RtNodeQ *nodes = ANY ? m.qnodes_any : m.qnodes;
+    const RayQ rq = make_rayq(m, r);
+#else
     const RtNode *nodes = ANY ? m.nodes_any : m.nodes;
+#endif
     int ref = ANY ? m.root_ref_any : m.root_ref;
     for (;;) {
         if (ref >= 0) {
             NodeHits n;
+#if RT_USE_NODEQ
+            node_test32q(nodes + ref, rq, tbest, n);
+#else
             node_test32(nodes + ref, r, tbest, n);
+#endif
             RT_COUNT(cnt, nodes, 1);
             int next = RT_EMPTY;
             float tnext = 0.0f;

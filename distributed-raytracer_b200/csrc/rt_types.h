@@ -72,6 +72,24 @@ struct alignas(32) RtNode {
     int pad[RT_W];
 };
 
+// EXPERIMENT, MEASURED SLOWER, off by default (-DRT_NODEQ=1; profiles/r02_kernel_ab.txt): the same RT_W = 4 children with their boxes
+// on a 16-bit grid that spans the mesh (origin qorg, cell qstep per axis; MeshView), 64 bytes = 2 x LDG.E.256 instead of 112 bytes
+// in 4 loads.  Motivation: ncu on the fused frame kernel shows the L1 data pipe as the busiest unit (69.6 % of peak) with 3.7
+// data-pipe wavefronts per tag wavefront, while issue slots are 58 % used.  A plane is decoded with one PRMT (the 16-bit field
+// becomes the mantissa of 2^23 + q) and folded into the slab test's FFMA: t = (2^23 + q) * (qstep / d) + ((qorg - o) / d -
+// 2^23 * qstep / d).  Rounding: the folded constant costs at most half a cell, and every lower / upper plane is stored one whole
+// cell further out (floor - 1 / ceil + 1 on a grid that starts two cells outside the mesh), so the quantised box always contains
+// the float box it was made from: the hierarchy still only culls (identical frames, identical node counts per shadow ray).
+// Result on C3: K4 0.555 -> 0.548 ms, K2 0.283 -> 0.323 ms, fused frame 0.603 -> 0.625 ms pipelined.  Halving the node bytes buys
+// nothing and the 24 extra PRMT per visit cost the primary rays 14 %: the traversal is bound by neither L1 bytes nor DRAM but by
+// the dependent latency of a visit at the occupancy 56 registers allow.
+// word layout: x[0..3] = lo of children 0..3, x[4..7] = hi; likewise y, z; then the 4 child refs.
+#ifndef RT_NODEQ
+#define RT_NODEQ 0
+#endif
+struct alignas(32) RtNodeQ { uint16_t x[8], y[8], z[8]; int ref[4]; };
+#define RT_QGRID_CELLS 65531.0f   // cells across the padded mesh extent; + 2 cells of margin on either side < 65536
+
 RT_HD int rt_leaf_ref(uint32_t first, uint32_t count) { return ~(int)(first | ((count - 1u) << RT_LEAF_FIRST_BITS)); }
 RT_HD uint32_t rt_leaf_first(int ref) { return ((uint32_t)~ref) & RT_LEAF_FIRST_MASK; }
 RT_HD uint32_t rt_leaf_count(int ref) { return (((uint32_t)~ref) >> RT_LEAF_FIRST_BITS) + 1u; }
@@ -93,6 +111,8 @@ struct MeshView {
     int      root_ref_any;
     uint32_t n_nodes_any;
     uint32_t pad_;
+    const RtNodeQ *qnodes, *qnodes_any;   // FP32_FAST: the 64-byte quantised form of nodes / nodes_any (null in FP64_EXACT scenes)
+    float    qorg[3], qstep[3];           // its grid: plane = qorg + q * qstep
     double   vlo[3], vhi[3];   // float64 bounds of ALL vertices of the mesh: Object.Bounds (object.go:38-49) for tracer.go:32's test
 };
 

@@ -32,6 +32,7 @@ enum { EV_nodes = 0, EV_tris = 1 };
 
 struct EmulMesh {
     std::vector<RtNode> nodes, nodes_any;
+    std::vector<RtNodeQ> qnodes, qnodes_any;
     std::vector<rt_f4> tri32;
     std::vector<double> tri64, fverts, fnormals, materials;
     std::vector<uint32_t> fmat;
@@ -143,6 +144,17 @@ static void build_mesh(EmulMesh &m, int max_leaf, int max_leaf_any) {
     if (max_leaf_any == max_leaf || n == 1) { v.root_ref_any = v.root_ref; v.n_nodes_any = v.n_nodes; }
     v.nodes = m.nodes.data(); v.tri32 = m.tri32.data(); v.tri64 = m.tri64.data();
     v.nodes_any = (max_leaf_any == max_leaf || n == 1) ? m.nodes.data() : m.nodes_any.data();
+    // bvh_build.cu: k_quantise_nodes
+    qgrid_from_bounds(v.lo, v.hi, v.qorg, v.qstep);
+    m.qnodes.resize(m.nodes.size() ? m.nodes.size() : 1);
+    for (uint32_t i = 0; i < m.nodes.size(); i++) quantise_node_thread(i, m.nodes.data(), m.qnodes.data(), v.qorg, v.qstep);
+    v.qnodes = m.qnodes.data();
+    if (v.nodes_any == v.nodes) v.qnodes_any = v.qnodes;
+    else {
+        m.qnodes_any.resize(m.nodes_any.size() ? m.nodes_any.size() : 1);
+        for (uint32_t i = 0; i < m.nodes_any.size(); i++) quantise_node_thread(i, m.nodes_any.data(), m.qnodes_any.data(), v.qorg, v.qstep);
+        v.qnodes_any = m.qnodes_any.data();
+    }
 }
 
 extern "C" {
@@ -241,6 +253,25 @@ int emul_bvh_check(void *h, uint32_t mesh, uint32_t *out_nodes, uint32_t *out_de
         }
     }
     for (uint32_t f = 0; f < n; f++) if (seen[f] != 1) return 6;
+    // quantised nodes (RtNodeQ): same refs, and every plane at least half a cell outside the float box it replaces (the decode
+    // of the traversal, t = (2^23 + q) * s + c, is off by at most half a cell: rt_types.h)
+    auto qcheck = [&](const std::vector<RtNode> &fn, const std::vector<RtNodeQ> &qn) -> int {
+        for (size_t i = 0; i < fn.size(); i++)
+            for (int c = 0; c < RT_W; c++) {
+                if (qn[i].ref[c] != fn[i].ref[c]) return 8;
+                if (fn[i].ref[c] == RT_EMPTY) continue;
+                const float lo[3] = { fn[i].lox[c], fn[i].loy[c], fn[i].loz[c] }, hi[3] = { fn[i].hix[c], fn[i].hiy[c], fn[i].hiz[c] };
+                const uint16_t ql[3] = { qn[i].x[c], qn[i].y[c], qn[i].z[c] }, qh[3] = { qn[i].x[4 + c], qn[i].y[4 + c], qn[i].z[4 + c] };
+                for (int k = 0; k < 3; k++) {
+                    const double o = m.view.qorg[k], st = m.view.qstep[k];
+                    if (!(o + ((double)ql[k] + 0.5) * st <= (double)lo[k]) || !(o + ((double)qh[k] - 0.5) * st >= (double)hi[k])) return 9;
+                    if (ql[k] == 0 || qh[k] == 65535) return 10;           // the grid has room: nothing is ever clamped
+                }
+            }
+        return 0;
+    };
+    if (int rc = qcheck(m.nodes, m.qnodes)) return rc;
+    if (!m.nodes_any.empty()) if (int rc = qcheck(m.nodes_any, m.qnodes_any)) return rc;
     return 0;
 }
 

@@ -365,3 +365,19 @@ def test_exact_replay_applies_the_reference_object_level_predicate():
     E.close(); S.close()
     assert np.array_equal(face, face_r) and np.array_equal(col.view(np.uint64), col_r.view(np.uint64)) and np.array_equal(rgb, rgb_r)
     assert not np.array_equal(col_c.view(np.uint64), col_r.view(np.uint64))      # the fixture does exercise the corner
+
+
+def test_quantised_node_experiment_renders_the_identical_frame(example_scene):
+    """-DRT_NODEQ=1 (64-byte nodes on a 16-bit grid, measured slower on B200 and off by default): the quantised boxes contain
+    the float boxes (emul_bvh_check codes 8-10), so the hierarchy still only culls and every output is identical."""
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 2)]
+    outs = []
+    for defs in ((), ("-DRT_NODEQ=1",)):
+        E = eb.EmulScene(sc, rt.FP32_FAST, 4, 2, defs=defs)
+        assert E.bvh_check()[0] == 0
+        outs.append(E.render(sc["camera"], sc["lights"], 160, 120))
+        E.close()
+    for a, b in zip(outs[0][:5], outs[1][:5]):
+        assert np.array_equal(a, b)
+    assert outs[0][5][2] == outs[1][5][2] and outs[0][5][2] > 0       # hit pixels

@@ -34,6 +34,10 @@ VARIANTS = {
     "pipeline_nodefer": ({"RT_B200_LIB": "build_variants/librt_b200_nodefer.so"}, ["PIPELINE"]),
     "fused_pf1": ({"RT_B200_LIB": "build_variants/librt_b200_pf1.so"}, []),
     "fused_pf2": ({"RT_B200_LIB": "build_variants/librt_b200_pf2.so"}, []),
+    # 64-byte quantised nodes (RT_NODEQ, now the default) against the 112-byte float nodes
+    "fused_noq": ({"RT_B200_LIB": "build_variants/librt_b200_noq.so"}, []),
+    "pipeline_noq": ({"RT_B200_LIB": "build_variants/librt_b200_noq.so"}, ["PIPELINE"]),
+    "fused_minb10": ({"RT_B200_SHADE_MINB": "10"}, []),
     # persistent SM-affine frame kernel (k_frame_fused_sm); chunk = 32 8x4 blocks unless the build says otherwise
     "fused_sm": ({"RT_B200_SM_AFFINE": "1"}, []),
     "fused_sm_minb8": ({"RT_B200_SM_AFFINE": "1", "RT_B200_SHADE_MINB": "8"}, []),

@@ -20,4 +20,5 @@ $NV -DRT_CHUNK_BLOCKS=16 -o ../../build_variants/librt_b200_chunk16.so $SRC &
 $NV -DRT_CHUNK_BLOCKS=64 -o ../../build_variants/librt_b200_chunk64.so $SRC &
 $NV -DRT_CHUNK_BLOCKS=128 -o ../../build_variants/librt_b200_chunk128.so $SRC &
 wait
+$NV -DRT_NODEQ=0 -o ../../build_variants/librt_b200_noq.so $SRC
 # $NV -DRT_W=8 -o ../../build_variants/librt_b200_w8.so $SRC      # 8 children per node: measured 35-70 % slower (profiles/r02_kernel_ab.txt)
