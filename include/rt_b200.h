@@ -54,8 +54,8 @@ typedef enum {
 #define RT_QUANT_RGB255      0x0u  /* uint8(255*c)          -- colour.RGB.RGB(), colour.go:59-61            */
 #define RT_QUANT_RGBA16_SHR8 0x2u  /* uint32(0xFFFF*c) >> 8 -- colour.RGB.RGBA() + go-sdl2 Surface.Set      */
 #define RT_FLAG_COUNT        0x4u  /* accumulate traversal counters (slower; for roofline accounting)       */
-#define RT_FLAG_BRUTE_FORCE  0x8u  /* FP64_EXACT only: ignore the BVH, test every face (debug; NOT the reference's
-                                      semantics for meshes with zero-area faces)               */
+#define RT_FLAG_BRUTE_FORCE  0x8u  /* FP64_EXACT only: ignore the BVH and the object-level candidate test of tracer.go:32, test every
+                                      face of every object (debug; see DESIGN.md s4 for where that differs)   */
 #define RT_FLAG_SIMPLE       0x10u /* FP32_FAST only: one-thread-per-ray primary kernel (the default: fastest measured) */
 #define RT_FLAG_PERSISTENT   0x20u /* FP32_FAST only: persistent warp-cooperative primary kernel (ballot/shuffle refill) */
 #define RT_FLAG_FUSED        0x40u /* FP32_FAST only: ONE kernel per frame -- a warp traces its 8x4 pixel block, shades the
