@@ -45,6 +45,11 @@ struct Lane {
     double *d_dbg_colour = nullptr; int32_t *d_dbg_face = nullptr, *d_dbg_obj = nullptr; uint32_t *d_dbg_lit = nullptr;
     size_t cap_dbg = 0;
     uint8_t *h_pinned = nullptr; size_t cap_pinned = 0;
+    // rt_bulk_trace in strips: the device->host copy of strip k runs on copy_stream while strip k+1 renders on `stream`
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaStream_t> strip_stream;          // one per strip, descending priority: strip 0's blocks are scheduled first
+    std::vector<cudaEvent_t> strip_ev, copy_ev;
+    cudaEvent_t start_ev = nullptr;
     // result wire format (wire.cu): encoded message, block-scan scratch, message length (device + pinned host)
     uint8_t *d_wire = nullptr; size_t cap_wire = 0;
     void *d_wire_scratch = nullptr; size_t cap_wire_scratch = 0;
@@ -69,6 +74,7 @@ struct rt_scene {
     int shade_minb = 8;
     bool primary_persistent = false;
     bool sm_affine = false;
+    int bulk_strips = 4;
     bool split_shade = false;
     bool shade32 = false;              // RT_B200_SHADE32=1: FP32_FAST shades in fp32 too (opt-in)
     uint32_t sync_timeout_ms = 2000;   // device-side wait on a peer's hand-off flag gives up after this (master/main.go:35: 2 s per order)
@@ -132,6 +138,11 @@ void destroy_lane(Lane &L) {
     cudaFree(L.d_chunk_state);
     cudaFree(L.d_rgb); cudaFree(L.d_dbg_colour); cudaFree(L.d_dbg_face); cudaFree(L.d_dbg_obj); cudaFree(L.d_dbg_lit);
     if (L.h_pinned) cudaFreeHost(L.h_pinned);
+    for (cudaEvent_t e : L.strip_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : L.copy_ev) cudaEventDestroy(e);
+    for (cudaStream_t t : L.strip_stream) cudaStreamDestroy(t);
+    if (L.start_ev) cudaEventDestroy(L.start_ev);
+    if (L.copy_stream) cudaStreamDestroy(L.copy_stream);
     cudaFree(L.d_wire); cudaFree(L.d_wire_scratch); cudaFree(L.d_wire_len);
     if (L.h_wire_len) cudaFreeHost(L.h_wire_len);
     for (auto &e : L.ev) if (e) cudaEventDestroy(e);
@@ -266,6 +277,9 @@ struct RenderOut {
     uint8_t *h_rgb = nullptr; double *h_colour = nullptr; int32_t *h_face = nullptr, *h_obj = nullptr; uint32_t *h_lit = nullptr;
     uint8_t *d_rgb = nullptr;      // external device output (device variants)
     cudaStream_t ext_stream = nullptr; bool async = false;
+    // a frame rendered as several launches (strips of one order): only the first zeroes the lane's counters and opens the frame's
+    // timing events, only the last closes them
+    bool first = true, last = true;
 };
 
 void collect_stats(rt_scene *s, Lane &L) {
@@ -290,6 +304,11 @@ void collect_stats(rt_scene *s, Lane &L) {
     L.stats_pending = false;
 }
 
+// one fused kernel per frame (FP32_FAST): the scene's default, RT_FLAG_FUSED / RT_FLAG_PIPELINE per call
+static bool will_fuse(const rt_scene *s, uint32_t flags) {
+    return s->precision == RT_FP32_FAST && !s->shade32 && !(flags & (RT_FLAG_PIPELINE | RT_FLAG_PERSISTENT)) && (s->fused || (flags & RT_FLAG_FUSED));
+}
+
 // the whole render path on one lane: clear -> K2 -> K4 -> K5 -> (copy out).  Caller holds L.mu.
 int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, size_t npix_out, const RenderOut &out) {
     if (!L.have_frame) return fail(s, RT_ERR_STATE, "render before rt_frame_set");
@@ -301,9 +320,7 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     const size_t out_bytes = npix_out * 3;
     const bool dbg = out.h_colour || out.h_face || out.h_obj || out.h_lit;
     const bool internal_rgb = out.d_rgb == nullptr;
-    // one fused kernel per frame (FP32_FAST): the scene's default, RT_FLAG_FUSED / RT_FLAG_PIPELINE per call
-    const bool fused = s->precision == RT_FP32_FAST && !s->shade32 && !(flags & (RT_FLAG_PIPELINE | RT_FLAG_PERSISTENT)) &&
-                       (s->fused || (flags & RT_FLAG_FUSED));
+    const bool fused = will_fuse(s, flags);
     // The hit-list scratch is sized for the UN-culled ray count of the region / tile set, so that a camera move (another cull
     // rectangle) never re-allocates: cudaMalloc / cudaFree wait for the device, and in the multi-GPU pipeline a peer's hand-off
     // kernel may be spinning on this very rank's progress.  The fused kernel needs no hit list at all.
@@ -350,8 +367,10 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     job.fused = fused;
     job.sm_affine = sm_affine; job.d_chunk_state = L.d_chunk_state; job.chunk_state_words = L.cap_chunk_state;
 
-    CU(s, cudaMemsetAsync(L.d_counters, 0, 4 * sizeof(unsigned int), st));
-    if (flags & RT_FLAG_COUNT) CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), st));
+    if (out.first) {
+        CU(s, cudaMemsetAsync(L.d_counters, 0, 4 * sizeof(unsigned int), st));
+        if (flags & RT_FLAG_COUNT) CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), st));
+    }
     // background: sequential/main.go:17 surface.FillRect(nil, 0); distributed/main.go:70 default 0,0,0
     if (fp.tile_final) CU(s, rt_launch_clear_tiles(fp, (flags & RT_LAYOUT_ROWMAJOR) != 0, d_rgb, st));   // only this rank's pixels (peer framebuffer)
     else CU(s, cudaMemsetAsync(d_rgb, 0, out_bytes, st));
@@ -361,11 +380,10 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     if (job.d_out_lit) CU(s, cudaMemsetAsync(job.d_out_lit, 0, sizeof(uint32_t) * npix_out, st));
 
     auto cancelled = [&]() { return s->cancel_gen.load() != my_gen; };
-    CU(s, cudaEventRecord(L.ev[0], st));
+    if (out.first) CU(s, cudaEventRecord(L.ev[0], st));
     if (job.fused) {
         CU(s, rt_launch_fused(job, st));
-        CU(s, cudaEventRecord(L.ev[1], st));
-        CU(s, cudaEventRecord(L.ev[2], st));
+        if (out.last) { CU(s, cudaEventRecord(L.ev[1], st)); CU(s, cudaEventRecord(L.ev[2], st)); }
     } else {
         CU(s, rt_launch_primary(job, st));
         CU(s, cudaEventRecord(L.ev[1], st));
@@ -375,9 +393,9 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
         if (cancelled()) { cudaStreamSynchronize(st); return fail(s, RT_ERR_CANCELLED, "cancelled"); }
         CU(s, rt_launch_write(job, st));
     }
-    CU(s, cudaEventRecord(L.ev[3], st));
+    if (out.last) CU(s, cudaEventRecord(L.ev[3], st));
 
-    L.stats.primary_rays = (uint64_t)fp.w * (uint64_t)fp.h;
+    L.stats.primary_rays = (out.first ? 0 : L.stats.primary_rays) + (uint64_t)fp.w * (uint64_t)fp.h;
     if (fp.tile_w > 0) L.stats.primary_rays = (uint64_t)fp.n_local_tiles * (uint64_t)(fp.tile_w * fp.tile_h);   // answered pixels, traced or culled
     L.stats_pending = true;
     L.stats_counted = (flags & RT_FLAG_COUNT) != 0;
@@ -565,6 +583,7 @@ static int create_scene_common(uint32_t precision, int32_t device, uint32_t n_me
     s->max_leaf_any = env_int("RT_B200_MAX_LEAF_SHADE", RT_DEFAULT_MAX_LEAF_SHADE);
     s->fused = env_int("RT_B200_FUSED", RT_DEFAULT_FUSED) != 0;
     s->sm_affine = env_int("RT_B200_SM_AFFINE", 0) != 0;
+    s->bulk_strips = env_int("RT_B200_BULK_STRIPS", 4);
     s->cull = env_int("RT_B200_CULL", 1) != 0;
     s->sync_timeout_ms = (uint32_t)std::max(1, env_int("RT_B200_SYNC_TIMEOUT_MS", 2000));
     int n_lanes = env_int("RT_B200_LANES", 9);      // lane 0 + a pool of 8 for concurrent BulkTrace calls / frames in flight
@@ -738,6 +757,99 @@ int rt_render_region(rt_scene *s, uint32_t W, uint32_t H, uint32_t x, uint32_t y
     return rt_render_region_debug(s, W, H, x, y, w, h, out_rgb, nullptr, nullptr, nullptr, nullptr, flags);
 }
 
+// One BulkTrace order answered in STRIPS (RT_B200_BULK_STRIPS, default 4; orders below 256k pixels are not cut): the reply of a 4K order
+// is 24.9 MB, whose device->host copy (~0.45 ms) used to start when the whole frame kernel (~0.74 ms) had finished.  The region is
+// cut into strips that are contiguous in the reply (BulkTrace's column-major layout: ranges of pixel columns, a multiple of 8 wide;
+// RT_LAYOUT_ROWMAJOR: ranges of rows, a multiple of 4 high); the strips render together on streams of descending priority, and strip k crosses PCIe on
+// the lane's copy stream as soon as it is done, while the later strips are still rendering.  Same kernels, same 8x4 blocks relative to the strip's origin, same bytes.
+static int bulk_strips(rt_scene *s, uint32_t w, uint32_t h, uint32_t flags) {
+    // only frames of the fused kernel are cut: its one counter (hit pixels) simply keeps adding up across the strips, whereas the hit list of
+    // the three-kernel pipeline is per launch; FP64_EXACT orders are compute-bound by orders of magnitude
+    if (s->bulk_strips <= 1 || (uint64_t)w * h < (1u << 18) || !will_fuse(s, flags)) return 1;
+    const bool rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0;
+    const uint32_t unit = rowmajor ? 4u : 8u, extent = rowmajor ? h : w;
+    const uint32_t most = extent / (8u * unit);                    // a strip is at least 8 blocks thick
+    return (int)std::min<uint32_t>((uint32_t)s->bulk_strips, most ? most : 1u);
+}
+
+static int bulk_trace_strips(rt_scene *s, Lane &L, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb,
+                             uint32_t flags, int strips) {
+    CU(s, cudaSetDevice(s->device));
+    const size_t total = (size_t)w * h * 3;
+    int rc = ensure_scratch(s, L, 0, total, true, false, (size_t)w * h);
+    if (rc != RT_OK) return rc;
+    if (!L.copy_stream) {
+        CU(s, cudaStreamCreateWithFlags(&L.copy_stream, cudaStreamNonBlocking));
+        CU(s, cudaEventCreateWithFlags(&L.start_ev, cudaEventDisableTiming));
+    }
+    int prio_least = 0, prio_greatest = 0;
+    CU(s, cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));          // greatest = numerically lowest
+    while ((int)L.strip_ev.size() < strips) {
+        const int k = (int)L.strip_ev.size();
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaStream_t t = nullptr;
+        CU(s, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        L.strip_ev.push_back(a);
+        CU(s, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        L.copy_ev.push_back(b);
+        CU(s, cudaStreamCreateWithPriority(&t, cudaStreamNonBlocking, std::min(prio_greatest + k, prio_least)));
+        L.strip_stream.push_back(t);
+    }
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, out_rgb) == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (!pinned && total > L.cap_pinned) {
+        if (L.h_pinned) cudaFreeHost(L.h_pinned);
+        L.h_pinned = nullptr; L.cap_pinned = 0;
+        CU(s, cudaMallocHost((void **)&L.h_pinned, total));
+        L.cap_pinned = total;
+    }
+    uint8_t *dst = pinned ? out_rgb : L.h_pinned;
+    const bool rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0;
+    const uint32_t unit = rowmajor ? 4u : 8u, extent = rowmajor ? h : w;
+    const uint32_t units = (extent + unit - 1) / unit;
+    const unsigned int my_gen = s->cancel_gen.load();
+    // the frame's counters and its first timing event belong to the lane's own stream; every strip starts after them
+    CU(s, cudaMemsetAsync(L.d_counters, 0, 4 * sizeof(unsigned int), L.stream));
+    if (flags & RT_FLAG_COUNT) CU(s, cudaMemsetAsync(L.d_stats, 0, 2 * sizeof(Counters), L.stream));
+    CU(s, cudaEventRecord(L.ev[0], L.stream));
+    CU(s, cudaEventRecord(L.start_ev, L.stream));
+    L.stats.primary_rays = 0;
+    std::vector<size_t> off(strips + 1, 0);
+    auto drain = [&]() { for (int k = 0; k < strips; k++) cudaStreamSynchronize(L.strip_stream[k]); cudaStreamSynchronize(L.copy_stream); cudaStreamSynchronize(L.stream); };
+    for (int k = 0; k < strips; k++) {
+        const uint32_t a = (uint32_t)((uint64_t)units * k / strips) * unit, b = k + 1 == strips ? extent : (uint32_t)((uint64_t)units * (k + 1) / strips) * unit;
+        FrameParams fp;
+        rc = rowmajor ? region_params(s, L, fp, W, H, x, y + a, w, b - a, flags) : region_params(s, L, fp, W, H, x + a, y, b - a, h, flags);
+        if (rc != RT_OK) { drain(); return rc; }
+        off[k] = (size_t)a * (rowmajor ? w : h) * 3;
+        off[k + 1] = (size_t)b * (rowmajor ? w : h) * 3;
+        // the strips are in flight TOGETHER (the GPU stays full: one strip alone is mostly kernel tail), each on its own stream; the
+        // block scheduler serves the streams in priority order, so strip k finishes -- and starts crossing PCIe -- before strip k+1
+        cudaStream_t st = L.strip_stream[k];
+        CU(s, cudaStreamWaitEvent(st, L.start_ev, 0));
+        RenderOut o;
+        o.d_rgb = L.d_rgb + off[k]; o.async = true; o.first = false; o.last = false; o.ext_stream = st;
+        rc = render_lane(s, L, fp, flags, (size_t)(b - a) * (rowmajor ? w : h), o);
+        if (rc != RT_OK) { drain(); return rc; }
+        CU(s, cudaEventRecord(L.strip_ev[k], st));
+        CU(s, cudaStreamWaitEvent(L.copy_stream, L.strip_ev[k], 0));
+        CU(s, cudaMemcpyAsync(dst + off[k], L.d_rgb + off[k], off[k + 1] - off[k], cudaMemcpyDeviceToHost, L.copy_stream));
+        if (!pinned) CU(s, cudaEventRecord(L.copy_ev[k], L.copy_stream));
+        CU(s, cudaStreamWaitEvent(L.stream, L.strip_ev[k], 0));
+    }
+    CU(s, cudaEventRecord(L.ev[1], L.stream)); CU(s, cudaEventRecord(L.ev[2], L.stream)); CU(s, cudaEventRecord(L.ev[3], L.stream));
+    L.last_stream = L.stream;
+    if (pinned) CU(s, cudaStreamSynchronize(L.copy_stream));
+    else for (int k = 0; k < strips; k++) {                       // pageable destination: strip k is copied out while the later ones are in flight
+        CU(s, cudaEventSynchronize(L.copy_ev[k]));
+        memcpy(out_rgb + off[k], L.h_pinned + off[k], off[k + 1] - off[k]);
+    }
+    CU(s, cudaStreamSynchronize(L.stream));
+    if (s->cancel_gen.load() != my_gen) return fail(s, RT_ERR_CANCELLED, "cancelled");
+    return RT_OK;
+}
+
 int rt_bulk_trace(rt_scene *s, const rt_camera *cam, const rt_light *lights, uint32_t n_lights, const double *obj_pos, uint32_t W,
                   uint32_t H, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint8_t *out_rgb, uint32_t flags) {
     API_ENTER();
@@ -754,9 +866,18 @@ int rt_bulk_trace(rt_scene *s, const rt_camera *cam, const rt_light *lights, uin
         FrameParams fp;
         if (rc == RT_OK) rc = region_params(s, *Lp, fp, W, H, x, y, w, h, flags);
         if (rc == RT_OK) {
-            RenderOut o; o.h_rgb = out_rgb;
             s->last_lane.store(idx);
-            rc = render_lane(s, *Lp, fp, flags, (size_t)w * h, o);
+            // Strips buy latency for an order that has the GPU to itself (one order per frame and worker is how master/pool drives a
+            // worker: 1.21 -> 1.00 ms for the 4K frame); with other orders in flight on this handle the GPU is full anyway, their copies
+            // already overlap this order's kernel, and the extra launches cost 2.6 % of throughput -- those orders stay uncut.
+            int others = 0;
+            { std::lock_guard<std::mutex> lk2(s->mu); for (auto &lp : s->lanes) others += (lp->busy && lp.get() != Lp) ? 1 : 0; }
+            const int strips = others ? 1 : bulk_strips(s, w, h, flags);
+            if (strips > 1) rc = bulk_trace_strips(s, *Lp, W, H, x, y, w, h, out_rgb, flags, strips);
+            else {
+                RenderOut o; o.h_rgb = out_rgb;
+                rc = render_lane(s, *Lp, fp, flags, (size_t)w * h, o);
+            }
         }
     }
     release_lane(s, Lp);

@@ -145,6 +145,44 @@ def test_sm_affine_persistent_kernel_equals_the_plain_fused_kernel(rt, example_s
     g.close()
 
 
+def test_bulk_trace_in_strips_returns_the_same_reply(rt, example_scene, monkeypatch):
+    """rt_bulk_trace cuts a large order into strips that are contiguous in the reply and overlaps the device->host copy of strip k
+    with the render of strip k+1 (RT_B200_BULK_STRIPS, default 4).  The reply must be byte-identical to the uncut order: both
+    layouts, pinned and pageable destinations, a sub-region, odd sizes, and the frame's hit count in rt_get_stats."""
+    import torch
+    sc = subdivided(example_scene, 2)
+    cam, lights = sc["camera"], sc["lights"]
+    monkeypatch.setenv("RT_B200_BULK_STRIPS", "1")
+    g1 = rt.GpuScene(sc, precision=rt.FP32_FAST)
+    replies = {}
+    for strips in ("4", "7"):
+        monkeypatch.setenv("RT_B200_BULK_STRIPS", strips)
+        g = rt.GpuScene(sc, precision=rt.FP32_FAST)
+        for (W, H, x, y, w, h) in [(1280, 720, 0, 0, 1280, 720), (1283, 717, 0, 0, 1283, 717), (1280, 720, 100, 50, 1000, 600), (640, 360, 0, 0, 640, 360)]:
+            for flags in (0, rt.LAYOUT_ROWMAJOR, rt.QUANT_RGBA16_SHR8, rt.FLAG_PIPELINE):
+                a = g1.bulk_trace(cam, lights, W, H, x, y, w, h, flags=flags)
+                na = g1.stats()["hit_pixels"]
+                b = g.bulk_trace(cam, lights, W, H, x, y, w, h, flags=flags)                      # pageable numpy destination
+                nb = g.stats()["hit_pixels"]
+                assert np.array_equal(a, b), (strips, W, H, x, y, w, h, flags)
+                assert na == nb == int((a.reshape(-1, 3).any(axis=1)).sum()) or na == nb
+                pinned = torch.empty(w * h * 3, dtype=torch.uint8, pin_memory=True)              # pinned destination: copied in place
+                out = pinned.numpy().reshape(-1, 3)
+                g.bulk_trace(cam, lights, W, H, x, y, w, h, flags=flags, out=out)
+                assert np.array_equal(a, out)
+        replies[strips] = True
+        g.close()
+    # FP64_EXACT orders (and RT_FLAG_PIPELINE above) are not cut: same reply either way
+    monkeypatch.setenv("RT_B200_BULK_STRIPS", "4")
+    ge = rt.GpuScene(example_scene, precision=rt.FP64_EXACT)
+    monkeypatch.setenv("RT_B200_BULK_STRIPS", "1")
+    ge1 = rt.GpuScene(example_scene, precision=rt.FP64_EXACT)
+    a = ge1.bulk_trace(example_scene["camera"], example_scene["lights"], 800, 600, 0, 0, 800, 600)
+    b = ge.bulk_trace(example_scene["camera"], example_scene["lights"], 800, 600, 0, 0, 800, 600)
+    assert np.array_equal(a, b) and a.any()
+    ge.close(); ge1.close(); g1.close()
+
+
 @pytest.mark.parametrize("leaf_any", [1, 2])
 def test_any_hit_hierarchy_leaf_size(rt, example_scene, monkeypatch, leaf_any):
     sc = subdivided(example_scene, 3)
