@@ -45,6 +45,69 @@ func NewScene(env state.Environment, device int, fast bool) (*Scene, error) {
 	return s, nil
 }
 
+// ObjModel is one model handed over as the TEXT of its OBJ file (rt_obj_mesh_desc): the GPU parses the geometry (v / vn / f lines,
+// gwob's semantics, mesh.go:109-133,166-204); the worker only supplies what the small MTL file says -- the material table in
+// first-use order (mesh.go:151-163) and, for every `usemtl` line of the text, its byte offset and the material it selects.
+type ObjModel struct {
+	Text            []byte
+	Materials       []float64 // 10 per material: Ka Kd Ks Ns
+	UsemtlOffset    []uint64  // ascending byte offsets of the `usemtl` lines
+	UsemtlMaterial  []uint32
+	DefaultMaterial uint32 // material of the faces above the first usemtl line
+}
+
+// NewSceneFromOBJ is NewScene for a worker that has the model FILES (or their bytes from the master) instead of decoded meshes:
+// nothing but the files' bytes crosses PCIe, and neither gwob's tokenizer nor MeshFromFile's value-keyed de-duplication maps
+// (mesh.go:146-203) nor the per-face R-tree Insert (mesh.go:208) runs on the host.  objPos: 3 per object; objModel: index into models.
+func NewSceneFromOBJ(models []ObjModel, objPos []float64, objModel []uint32, ids []uint, device int, fast bool) (*Scene, error) {
+	if len(objPos) != 3*len(objModel) {
+		return nil, fmt.Errorf("rtb200: %d positions for %d objects", len(objPos)/3, len(objModel))
+	}
+	pin := new(runtime.Pinner)
+	defer pin.Unpin()
+	descs := (*C.rt_obj_mesh_desc)(C.calloc(C.size_t(maxInt(len(models), 1)), C.sizeof_rt_obj_mesh_desc))
+	defer C.free(unsafe.Pointer(descs))
+	dv := unsafe.Slice(descs, maxInt(len(models), 1))
+	for i := range models {
+		m := &models[i]
+		if len(m.Text) > 0 {
+			pin.Pin(&m.Text[0])
+			dv[i].obj_text = (*C.char)(unsafe.Pointer(&m.Text[0]))
+		}
+		dv[i].obj_bytes = C.uint64_t(len(m.Text))
+		if len(m.Materials) > 0 {
+			pin.Pin(&m.Materials[0])
+			dv[i].materials = (*C.double)(&m.Materials[0])
+		}
+		dv[i].n_materials = C.uint32_t(len(m.Materials) / 10)
+		if len(m.UsemtlOffset) > 0 {
+			pin.Pin(&m.UsemtlOffset[0])
+			pin.Pin(&m.UsemtlMaterial[0])
+			dv[i].usemtl_offset = (*C.uint64_t)(&m.UsemtlOffset[0])
+			dv[i].usemtl_material = (*C.uint32_t)(&m.UsemtlMaterial[0])
+		}
+		dv[i].n_usemtl = C.uint32_t(len(m.UsemtlOffset))
+		dv[i].default_material = C.uint32_t(m.DefaultMaterial)
+	}
+	var pp *C.double
+	var pm *C.uint32_t
+	if len(objModel) > 0 {
+		pin.Pin(&objPos[0])
+		pin.Pin(&objModel[0])
+		pp, pm = (*C.double)(&objPos[0]), (*C.uint32_t)(&objModel[0])
+	}
+	precision := C.uint32_t(C.RT_FP64_EXACT)
+	if fast {
+		precision = C.uint32_t(C.RT_FP32_FAST)
+	}
+	s := &Scene{ids: ids}
+	if rc := C.rt_scene_create_obj(descs, C.uint32_t(len(models)), pp, pm, C.uint32_t(len(objModel)), C.int32_t(device), precision, &s.h); rc != 0 {
+		return nil, fmt.Errorf("rt_scene_create_obj: %d %s", int(rc), C.GoString(C.rt_last_error(nil)))
+	}
+	runtime.SetFinalizer(s, func(s *Scene) { s.Close() })
+	return s, nil
+}
+
 // fillSceneDesc flattens env into an rt_scene_desc.  rt_mesh_desc holds C pointers into Go memory: allowed for the duration
 // of the create call because the slices contain no Go pointers; the descriptor array itself lives in C memory, and the
 // slices stay pinned until release() is called (after rt_scene_create / rt_group_create has copied everything).
