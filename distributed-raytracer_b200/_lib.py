@@ -70,7 +70,7 @@ class Stats(C.Structure):
                 ("nodes_fetched", C.c_uint64), ("tris_fetched", C.c_uint64), ("nodes_primary", C.c_uint64),
                 ("tris_primary", C.c_uint64), ("nodes_shade", C.c_uint64), ("tris_shade", C.c_uint64), ("node_bytes", C.c_uint64),
                 ("tri_bytes", C.c_uint64), ("ms_primary", C.c_float), ("ms_shade", C.c_float), ("ms_write", C.c_float),
-                ("ms_total", C.c_float)]
+                ("ms_total", C.c_float), ("occluded_fraction", C.c_float), ("any_defer", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

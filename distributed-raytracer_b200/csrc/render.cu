@@ -28,6 +28,7 @@ __device__ __forceinline__ SceneView bind_frame(SceneView sc, const InlineFrame 
     if (fr.use_lights) sc.lights = fr.lights;
     if (fr.use_objs) sc.objs = fr.objs;
     sc.trav_smem = trav_smem;
+    sc.defer = sc.tune ? *(const volatile unsigned int *)(sc.tune + 2) : 0u;      // once per CTA
     return sc;
 }
 // the shared-memory part of the traversal stacks of a 128-thread CTA (SceneView::trav_smem): 8 KB
@@ -61,6 +62,24 @@ __device__ __forceinline__ void append_hit(bool hit, uint32_t ray, int obj, int 
     if (hit) {
         HitRec h; h.pix = ray; h.obj = obj; h.face = face; h.t = t;
         hits[base + __popc(m & ((1u << lane) - 1u))] = h;
+    }
+}
+
+// Self-tuning of the any-hit postponement bound (SceneView::tune): every warp that shaded hits adds its shadow rays and how many of
+// them were occluded; whenever the (sampled) count crosses a multiple of 16 384 the warp that crossed it re-derives the bound from the running
+// ratio.  One CTA in four takes part (a sample is all a tuning knob needs).  All 32 lanes call; lanes without a hit are ignored.
+__device__ __forceinline__ void tune_any_defer(unsigned int *tune, bool valid, uint32_t lit, int n_lights) {
+    if (!tune || (blockIdx.x & 3u)) return;
+    unsigned tot = valid ? (unsigned)n_lights : 0u, occ = valid ? (unsigned)(n_lights - __popc(lit)) : 0u;
+    tot = __reduce_add_sync(FULL, tot);
+    occ = __reduce_add_sync(FULL, occ);
+    if ((threadIdx.x & 31) == 0 && tot) {
+        const unsigned old = atomicAdd(&tune[0], tot), oc = atomicAdd(&tune[1], occ) + occ, now = old + tot;
+        if ((now >> 14) != (old >> 14)) {
+            const float f = (float)oc / (float)now;
+            *(volatile unsigned int *)(tune + 2) = f < 0.15f ? 16u : (f < 0.40f ? 8u : 4u);
+            if (now > (1u << 30)) { *(volatile unsigned int *)tune = 0u; *(volatile unsigned int *)(tune + 1) = 0u; }   // a fresh window; racing adds only blur a ratio
+        }
     }
 }
 
@@ -218,6 +237,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView s
         double col[3];
         uint32_t lit = SHADE32 ? shade_hit_fast32(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, col, (COUNT && valid) ? &c : nullptr)
                                : shade_hit<EXACT>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, (COUNT && valid) ? &c : nullptr);
+        if (!EXACT) tune_any_defer(sc.tune, valid, lit, fp.n_lights);
         if (valid) {
             hit_colour[3 * (size_t)h] = col[0]; hit_colour[3 * (size_t)h + 1] = col[1]; hit_colour[3 * (size_t)h + 2] = col[2];
             hit_lit[h] = lit;
@@ -328,6 +348,7 @@ __device__ __forceinline__ void fused_block(const FrameParams &fp, const SceneVi
         const float st = __shfl_sync(FULL, tr.t, src);
         double col[3];
         const uint32_t lit = shade_hit<false>(sc, fp, si, sj, sobj, sface, st, false, col, (COUNT && hit) ? &c1 : nullptr);
+        tune_any_defer(sc.tune, hit, lit, fp.n_lights);
         if (hit) {
             const size_t o = pm.out;
             if (out_rgb) {
@@ -747,7 +768,7 @@ template <class K> static void prefer_l1(K kern) {
 
 cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.defer = 0;
     const uint32_t nrays = ray_count(fp);
     if (nrays == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
@@ -789,7 +810,7 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
 
 cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.defer = 0;
     if (ray_count(fp) == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
@@ -827,7 +848,7 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
 
 cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.defer = 0;
     const uint32_t nrays = ray_count(fp);
     if (nrays == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;

@@ -75,6 +75,7 @@ struct rt_scene {
     bool primary_persistent = false;
     bool sm_affine = false;
     int bulk_strips = 4;
+    unsigned int *d_tune = nullptr;    // SceneView::tune: {shadow rays, occluded, postponement bound, spare}; nullptr = fixed bound (RT_B200_ANY_DEFER)
     bool split_shade = false;
     bool shade32 = false;              // RT_B200_SHADE32=1: FP32_FAST shades in fp32 too (opt-in)
     uint32_t sync_timeout_ms = 2000;   // device-side wait on a peer's hand-off flag gives up after this (master/main.go:35: 2 s per order)
@@ -155,6 +156,7 @@ void destroy_all(rt_scene *s) {
     s->lanes.clear();
     for (auto &m : s->meshes) free_mesh(m);
     cudaFree(s->d_meshes);
+    cudaFree(s->d_tune); s->d_tune = nullptr;
     s->d_meshes = nullptr;
     if (s->cancel_stream) { cudaStreamDestroy(s->cancel_stream); s->cancel_stream = nullptr; }
     if (s->h_cancel_word) { cudaFreeHost(s->h_cancel_word); s->h_cancel_word = nullptr; }
@@ -301,6 +303,13 @@ void collect_stats(rt_scene *s, Lane &L) {
     cudaEventElapsedTime(&L.stats.ms_shade, L.ev[1], L.ev[2]);
     cudaEventElapsedTime(&L.stats.ms_write, L.ev[2], L.ev[3]);
     cudaEventElapsedTime(&L.stats.ms_total, L.ev[0], L.ev[3]);
+    L.stats.occluded_fraction = 0.f; L.stats.any_defer = s->h_views.empty() ? 0u : s->h_views[0].any_defer;
+    if (s->d_tune) {
+        unsigned int t[4] = { 0, 0, 0, 0 };
+        cudaMemcpy(t, s->d_tune, sizeof t, cudaMemcpyDeviceToHost);
+        L.stats.occluded_fraction = t[0] ? (float)t[1] / (float)t[0] : 0.f;
+        L.stats.any_defer = t[2];
+    }
     L.stats_pending = false;
 }
 
@@ -365,6 +374,7 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     job.shade_minb = s->shade_minb;
     job.primary_persistent = s->primary_persistent;
     job.fused = fused;
+    job.d_tune = s->d_tune;
     job.sm_affine = sm_affine; job.d_chunk_state = L.d_chunk_state; job.chunk_state_words = L.cap_chunk_state;
 
     if (out.first) {
@@ -616,6 +626,11 @@ static int create_scene_common(uint32_t precision, int32_t device, uint32_t n_me
     }
     CUB_(cudaStreamCreateWithFlags(&s->cancel_stream, cudaStreamNonBlocking));
     CUB_(cudaMallocHost((void **)&s->h_cancel_word, sizeof(unsigned int)));
+    if (!getenv("RT_B200_ANY_DEFER") && s->precision == RT_FP32_FAST) {       // self-tuned unless the caller fixes the bound
+        CUB_(cudaMalloc((void **)&s->d_tune, 4 * sizeof(unsigned int)));
+        const unsigned int init[4] = { 0u, 0u, 8u, 0u };
+        CUB_(cudaMemcpy(s->d_tune, init, sizeof init, cudaMemcpyHostToDevice));
+    }
     cudaStream_t st0 = s->lanes[0]->stream;
     s->meshes.resize(n_meshes);
     s->h_views.resize(n_meshes);
@@ -636,6 +651,7 @@ static int create_scene_common(uint32_t precision, int32_t device, uint32_t n_me
         v.materials = m.materials; v.n_faces = m.n_faces; v.n_nodes = m.n_nodes; v.root_ref = m.root_ref;
         v.nodes_any = m.nodes_any; v.root_ref_any = m.root_ref_any; v.n_nodes_any = m.n_nodes_any;
         v.qnodes = m.qnodes; v.qnodes_any = m.qnodes_any;
+        v.any_defer = (uint32_t)std::max(1, std::min(env_int("RT_B200_ANY_DEFER", 8), RT_STACK_SIZE));
         for (int c = 0; c < 3; c++) { v.lo[c] = m.lo[c]; v.hi[c] = m.hi[c]; v.vlo[c] = m.vlo[c]; v.vhi[c] = m.vhi[c]; v.qorg[c] = m.qorg[c]; v.qstep[c] = m.qstep[c]; }
     }
     CUB_(upload(&s->d_meshes, s->h_views.data(), s->h_views.size(), st0));

@@ -72,6 +72,7 @@ struct RenderJob {
     bool      fused;          // FP32_FAST: one fused kernel per frame instead of K2 -> K4 -> K5
     bool      sm_affine;      // ... in its persistent SM-affine form (RT_FLAG_SM_AFFINE)
     unsigned int *d_chunk_state; size_t chunk_state_words;
+    unsigned int *d_tune;     // SceneView::tune (scene-level, shared by all lanes) or nullptr
 };
 
 // render.cu : enqueue K2 (primary) / K4 (shadow+shade) / K5 (framebuffer) on `st`

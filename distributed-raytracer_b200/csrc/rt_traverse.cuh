@@ -26,6 +26,12 @@ struct SceneView {
     // banks, so a push / pop is ONE shared-memory wavefront per warp instead of up to 32 local-memory wavefronts through L1
     // (ncu, fused kernel: local loads + stores were 28 % of the LSU wavefronts and 40 % of the L1 sectors).
     uint32_t *trav_smem;
+    // Scene-level tuning words in device memory (null in the CPU replay): [0] shadow rays counted, [1] of which occluded,
+    // [2] leaves an any-hit ray postpones before it tests them.  The render kernels keep [0] / [1] (one CTA in four samples its
+    // rays) and re-derive [2] every 16 384 sampled rays (render.cu: tune_any_defer): the answer of an any-hit ray does not depend on the order of its tests, so the knob can
+    // move under running frames without changing a bit of the output.
+    unsigned int *tune;
+    uint32_t defer;            // the bound the current warp works with (read from tune[2] once per pixel block; 0 = the mesh's own)
 };
 
 // MEASURED SLOWER (profiles/r02_kernel_ab.txt: fused frame 0.627 -> 0.726 ms pipelined, K2 +15 %, K4 +9 %): the depth test and the
@@ -375,8 +381,12 @@ RT_HD bool leaf_any_hit32(const MeshView &m, int ref, const RayF &r, float tmax,
 // walks the internal nodes only (leaf children go to the far end of the same local array), then tests its postponed leaves
 // back to back: the warp runs max-over-lanes(leaves per ray) leaf bodies instead of one per lane-and-time.  The answer
 // (is anything closer than the light?) does not depend on the order, so frames are bit-identical to the plain loop.
-// An occluded ray finds its occluder later than before (7 % of the rays).  If the array ever fills up (it does not on the
-// BASELINE scenes: <= 3 * depth nodes + the leaves one ray meets) the postponed leaves are drained early.
+// An occluded ray finds its occluder later than before, so the postponement is BOUNDED: once `defer` leaves are waiting they are
+// tested before the walk goes on.  Measured (profiles/r02_kernel_ab.txt, ms per pipelined frame; bound 1 / 2 / 4 / 8 / 16 / none):
+//   C3 (7 % of the shadow rays occluded):   0.708 / 0.664 / 0.627 / 0.612 / 0.610 / 0.611     (plain loop: 0.626)
+//   C4 (10 M-triangle soup, mostly occluded): 27.1 / 25.2 / 24.2 / 24.9 / 27.6 / 33.2          (plain loop: 22.8)
+// No single bound suits both, so the kernels measure the occluded share of their own shadow rays and pick 16, 8 or 4 for the rays
+// that follow (SceneView::tune); RT_B200_ANY_DEFER fixes it instead.
 #ifndef RT_ANY_DEFER
 #define RT_ANY_DEFER 1
 #endif
@@ -391,9 +401,10 @@ RT_HD bool leaf_any_hit32(const MeshView &m, int ref, const RayF &r, float tmax,
 #else
 #define RT_PREFETCH_NODE(p) do { } while (0)
 #endif
-RT_HD bool mesh_any_hit_deferred(const MeshView &m, const RayF &r, float &tmax, int &face, Counters *cnt) {
+RT_HD bool mesh_any_hit_deferred(const MeshView &m, const RayF &r, float &tmax, int &face, Counters *cnt, uint32_t defer = 0) {
     int stack[RT_STACK_SIZE];            // internal nodes: [0, sp) growing up; postponed leaves: [lp, RT_STACK_SIZE) growing down
     int sp = 0, lp = RT_STACK_SIZE;
+    const int lp_drain = RT_STACK_SIZE - (int)(defer ? defer : m.any_defer);
     int ref = m.root_ref_any;
     bool more = true;
     if (ref < 0) { stack[--lp] = ref; more = false; }
@@ -422,7 +433,9 @@ RT_HD bool mesh_any_hit_deferred(const MeshView &m, const RayF &r, float &tmax, 
             if (next != RT_EMPTY) ref = next;
             else if (sp > 0) ref = stack[--sp];
             else more = false;
-            if (lp - sp < 2 * RT_W) break;          // no room for another node's children: test the postponed leaves first
+            // enough leaves are waiting (or the array is nearly full): test them before walking on, so that an OCCLUDED ray meets its
+            // occluder after at most any_defer + RT_W - 1 postponed leaves instead of after its whole node walk
+            if (lp <= lp_drain || lp - sp < 2 * RT_W) break;
         }
         while (lp < RT_STACK_SIZE) {
             float thit;
@@ -487,12 +500,12 @@ RT_HD void node_test32q(const RtNodeQ *nd, const RayQ &q, float tbest, NodeHits 
 // Nearest: winner = min t, ties -> lowest face index.  Returns true if something was accepted.
 // ANY rays walk the mesh's any-hit hierarchy (nodes_any: same triangles, its own leaf size).
 template <bool ANY>
-RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &face, Counters *cnt, uint32_t *smem = nullptr) {
+RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &face, Counters *cnt, uint32_t *smem = nullptr, uint32_t defer = 0) {
     if (m.n_faces == 0) return false;
     float tin;
     if (!slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, tbest, tin)) return false;
 #if RT_ANY_DEFER
-    if (ANY) return mesh_any_hit_deferred(m, r, tbest, face, cnt);
+    if (ANY) return mesh_any_hit_deferred(m, r, tbest, face, cnt, defer);
 #endif
     bool found = false;
     int stack[RT_STACK_SIZE];
@@ -658,7 +671,7 @@ RT_HD bool light_visible(const SceneView &sc, const FrameParams &fp, dv P, int o
                            (float)Ld.y, (float)Ld.z);
         float tmax = (float)(lightLen - RT_SHADOW_BIAS);
         int f = -1;
-        return !mesh_trace_fast<true>(sc.meshes[ob.mesh], r, tmax, f, cnt, sc.trav_smem);
+        return !mesh_trace_fast<true>(sc.meshes[ob.mesh], r, tmax, f, cnt, sc.trav_smem, sc.defer);
     } else {
         TraceFast s;
         bool shaded = trace_fast_nearest(sc, fp, so, Ld, false, s, cnt);

@@ -110,7 +110,7 @@ struct MeshView {
     const RtNode  *nodes_any;
     int      root_ref_any;
     uint32_t n_nodes_any;
-    uint32_t pad_;
+    uint32_t any_defer;                   // any-hit rays test their postponed leaves once this many are waiting (rt_traverse.cuh); >= 1
     const RtNodeQ *qnodes, *qnodes_any;   // FP32_FAST: the 64-byte quantised form of nodes / nodes_any (null in FP64_EXACT scenes)
     float    qorg[3], qstep[3];           // its grid: plane = qorg + q * qstep
     double   vlo[3], vhi[3];   // float64 bounds of ALL vertices of the mesh: Object.Bounds (object.go:38-49) for tracer.go:32's test

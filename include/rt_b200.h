@@ -133,6 +133,10 @@ typedef struct {
     float    ms_shade;         /* library's stream (valid after a synchronous render call)         */
     float    ms_write;
     float    ms_total;
+    /* self-tuned by the kernels (FP32_FAST): the share of this handle's recent shadow rays that were OCCLUDED and the number of
+     * leaves an any-hit ray currently postpones before it tests them (rt_traverse.cuh; lit scenes batch many, occluded scenes few) */
+    float    occluded_fraction;
+    uint32_t any_defer;
 } rt_stats;
 
 typedef struct {

@@ -183,6 +183,38 @@ def test_bulk_trace_in_strips_returns_the_same_reply(rt, example_scene, monkeypa
     ge.close(); ge1.close(); g1.close()
 
 
+def test_any_hit_postponement_tunes_itself_and_never_changes_a_pixel(rt, example_scene, monkeypatch):
+    """The kernels count the occluded share of their own shadow rays and pick how many leaves an any-hit ray postpones (16 / 8 / 4:
+    rt_stats.any_defer, occluded_fraction).  The count must equal what the lit masks of the frame say, the bound must follow the
+    thresholds, and a fixed bound (RT_B200_ANY_DEFER) must give the identical frame."""
+    W, H = 1280, 720
+    scenes = {"suzanne": example_scene, "soup": random_soup_scene(n_tris=4000, seed=5, n_lights=4, extent=1.0, half=0.25)}
+    for name, sc in scenes.items():
+        monkeypatch.delenv("RT_B200_ANY_DEFER", raising=False)
+        g = rt.GpuScene(sc, precision=rt.FP32_FAST)
+        rgb, col, face, obj, lit = g.render_region_debug(W, H)
+        st = g.stats()
+        hit = face >= 0
+        n_l = np.asarray(sc["lights"]).reshape(-1, 6).shape[0]
+        popc = np.array([bin(int(v)).count("1") for v in np.unique(lit)])
+        lut = dict(zip(np.unique(lit).tolist(), popc.tolist()))
+        occluded = int(sum((n_l - lut[int(v)]) * int(c) for v, c in zip(*np.unique(lit[hit], return_counts=True))))
+        total = int(hit.sum()) * n_l
+        assert total >= 4 * 65536, "the scene must produce enough shadow rays for a few tuning steps"
+        f = occluded / total
+        assert abs(st["occluded_fraction"] - f) < 0.05          # one CTA in four is sampled
+        assert st["any_defer"] in (4, 8, 16)
+        ref = g.render_region(W, H)
+        g.close()
+        for fixed in ("1", "4", "128"):
+            monkeypatch.setenv("RT_B200_ANY_DEFER", fixed)
+            gf = rt.GpuScene(sc, precision=rt.FP32_FAST)
+            assert np.array_equal(gf.render_region(W, H), ref)
+            assert gf.stats()["any_defer"] == int(fixed)
+            gf.close()
+        print(name, "occluded fraction %.3f -> bound %d" % (f, st["any_defer"]))
+
+
 @pytest.mark.parametrize("leaf_any", [1, 2])
 def test_any_hit_hierarchy_leaf_size(rt, example_scene, monkeypatch, leaf_any):
     sc = subdivided(example_scene, 3)
