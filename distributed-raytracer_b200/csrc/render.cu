@@ -68,7 +68,7 @@ __device__ __forceinline__ void append_hit(bool hit, uint32_t ray, int obj, int 
 // Self-tuning of the any-hit postponement bound (SceneView::tune): every warp that shaded hits adds its shadow rays and how many of
 // them were occluded; whenever the (sampled) count crosses a multiple of 16 384 the warp that crossed it re-derives the bound from the running
 // ratio.  One CTA in four takes part (a sample is all a tuning knob needs).  All 32 lanes call; lanes without a hit are ignored.
-__device__ __forceinline__ void tune_any_defer(unsigned int *tune, bool valid, uint32_t lit, int n_lights) {
+__device__ __forceinline__ void tune_any_defer(unsigned int *tune, unsigned int *tune_host, bool valid, uint32_t lit, int n_lights) {
     if (!tune || (blockIdx.x & 3u)) return;
     unsigned tot = valid ? (unsigned)n_lights : 0u, occ = valid ? (unsigned)(n_lights - __popc(lit)) : 0u;
     tot = __reduce_add_sync(FULL, tot);
@@ -77,7 +77,9 @@ __device__ __forceinline__ void tune_any_defer(unsigned int *tune, bool valid, u
         const unsigned old = atomicAdd(&tune[0], tot), oc = atomicAdd(&tune[1], occ) + occ, now = old + tot;
         if ((now >> 14) != (old >> 14)) {
             const float f = (float)oc / (float)now;
-            *(volatile unsigned int *)(tune + 2) = f < 0.15f ? 16u : (f < 0.40f ? 8u : 4u);
+            const unsigned int bound = f < 0.15f ? 16u : (f < 0.40f ? 8u : 1u);
+            *(volatile unsigned int *)(tune + 2) = bound;
+            if (tune_host) *(volatile unsigned int *)tune_host = bound;
             if (now > (1u << 30)) { *(volatile unsigned int *)tune = 0u; *(volatile unsigned int *)(tune + 1) = 0u; }   // a fresh window; racing adds only blur a ratio
         }
     }
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(FrameParams fp, SceneView s
         double col[3];
         uint32_t lit = SHADE32 ? shade_hit_fast32(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, col, (COUNT && valid) ? &c : nullptr)
                                : shade_hit<EXACT>(sc, fp, pm.i, pm.j, hr.obj, hr.face, hr.t, brute, col, (COUNT && valid) ? &c : nullptr);
-        if (!EXACT) tune_any_defer(sc.tune, valid, lit, fp.n_lights);
+        if (!EXACT) tune_any_defer(sc.tune, sc.tune_host, valid, lit, fp.n_lights);
         if (valid) {
             hit_colour[3 * (size_t)h] = col[0]; hit_colour[3 * (size_t)h + 1] = col[1]; hit_colour[3 * (size_t)h + 2] = col[2];
             hit_lit[h] = lit;
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(128) k_phong(FrameParams fp, SceneView sc_in, 
 #define RT_FUSED_THREADS 128      // threads per CTA of the fused kernel (64: measured in profiles/r02_kernel_ab.txt)
 #endif
 // one 8x4 pixel block of a frame, all 32 lanes of a warp: `ray` = 32 * block + lane in the numbering of map_ray
-template <bool COUNT>
+template <bool COUNT, bool DEFER>
 __device__ __forceinline__ void fused_block(const FrameParams &fp, const SceneView &sc, uint32_t ray, bool rowmajor, bool sdl, unsigned int *counters,
                                             uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour, int32_t *__restrict__ out_face,
                                             int32_t *__restrict__ out_obj, uint32_t *__restrict__ out_lit, Counters &c0, Counters &c1) {
@@ -347,8 +349,8 @@ __device__ __forceinline__ void fused_block(const FrameParams &fp, const SceneVi
         const int sobj = __shfl_sync(FULL, tr.obj, src), sface = __shfl_sync(FULL, tr.face, src);
         const float st = __shfl_sync(FULL, tr.t, src);
         double col[3];
-        const uint32_t lit = shade_hit<false>(sc, fp, si, sj, sobj, sface, st, false, col, (COUNT && hit) ? &c1 : nullptr);
-        tune_any_defer(sc.tune, hit, lit, fp.n_lights);
+        const uint32_t lit = shade_hit<false, DEFER>(sc, fp, si, sj, sobj, sface, st, false, col, (COUNT && hit) ? &c1 : nullptr);
+        tune_any_defer(sc.tune, sc.tune_host, hit, lit, fp.n_lights);
         if (hit) {
             const size_t o = pm.out;
             if (out_rgb) {
@@ -364,7 +366,7 @@ __device__ __forceinline__ void fused_block(const FrameParams &fp, const SceneVi
     }
 }
 
-template <bool COUNT, int MINB>
+template <bool COUNT, int MINB, bool DEFER>
 __global__ void __launch_bounds__(RT_FUSED_THREADS, MINB * (128 / RT_FUSED_THREADS)) k_frame_fused(FrameParams fp, SceneView sc_in, const __grid_constant__ InlineFrame fr,
                                                             bool rowmajor, bool sdl, unsigned int *counters,
                                                             uint8_t *__restrict__ out_rgb, double *__restrict__ out_colour,
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(RT_FUSED_THREADS, MINB * (128 / RT_FUSED_THREA
     if ((ray & ~31u) >= nrays) return;                        // warp-uniform
     if (warp_cancelled(counters, fp)) return;
     Counters c0, c1; c0.nodes = c0.tris = c1.nodes = c1.tris = 0;
-    fused_block<COUNT>(fp, sc, ray, rowmajor, sdl, counters, out_rgb, out_colour, out_face, out_obj, out_lit, c0, c1);
+    fused_block<COUNT, DEFER>(fp, sc, ray, rowmajor, sdl, counters, out_rgb, out_colour, out_face, out_obj, out_lit, c0, c1);
     if (COUNT) { flush_counters(gstats, c0); flush_counters(gstats ? gstats + 1 : nullptr, c1); }
 }
 
@@ -466,7 +468,7 @@ __global__ void __launch_bounds__(128, MINB) k_frame_fused_sm(FrameParams fp, Sc
         if (lane == 0) blk = frame_cancelled(counters, fp) ? 0xfffffffeu : claim_block(chunk_state, g, smid % RT_MAX_SM, n_sm);
         blk = __shfl_sync(FULL, blk, 0);
         if (blk == 0xfffffffeu) break;
-        fused_block<COUNT>(fp, sc, blk * 32u + lane, rowmajor, sdl, counters, out_rgb, out_colour, out_face, out_obj, out_lit, c0, c1);
+        fused_block<COUNT, true>(fp, sc, blk * 32u + lane, rowmajor, sdl, counters, out_rgb, out_colour, out_face, out_obj, out_lit, c0, c1);
         __syncwarp();
     }
     if (COUNT) { flush_counters(gstats, c0); flush_counters(gstats ? gstats + 1 : nullptr, c1); }
@@ -768,7 +770,7 @@ template <class K> static void prefer_l1(K kern) {
 
 cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.defer = 0;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.tune_host = job.d_tune_host; sc.defer = 0;
     const uint32_t nrays = ray_count(fp);
     if (nrays == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
@@ -810,7 +812,7 @@ cudaError_t rt_launch_primary(const RenderJob &job, cudaStream_t st) {
 
 cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.defer = 0;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.tune_host = job.d_tune_host; sc.defer = 0;
     if (ray_count(fp) == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
     const bool brute = (job.flags & RT_FLAG_BRUTE_FORCE) != 0;
@@ -848,7 +850,7 @@ cudaError_t rt_launch_shade(const RenderJob &job, cudaStream_t st) {
 
 cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
     const FrameParams &fp = job.fp;
-    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.defer = 0;
+    SceneView sc; sc.meshes = job.d_meshes; sc.objs = job.d_objs; sc.lights = job.d_lights; sc.trav_smem = nullptr; sc.tune = job.d_tune; sc.tune_host = job.d_tune_host; sc.defer = 0;
     const uint32_t nrays = ray_count(fp);
     if (nrays == 0) return cudaSuccess;
     const bool count = (job.flags & RT_FLAG_COUNT) != 0;
@@ -870,9 +872,11 @@ cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
     }
     const unsigned nblk = (nrays + RT_FUSED_THREADS - 1) / RT_FUSED_THREADS;
     // the traversal kernels use no shared memory: ask for the whole unified L1 / shared array as L1 (once per kernel and device)
-#define LAUNCH_FUSED(CN, MB) do { prefer_l1(k_frame_fused<CN, MB>);                                                                   \
-        k_frame_fused<CN, MB><<<nblk, RT_FUSED_THREADS, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_out_rgb, job.d_out_colour, \
+    // the any-hit loop is a compile-time property of the variant: the plain loop when the (self-tuned or fixed) bound says 1
+#define LAUNCH_FUSED_D(CN, MB, DF) do { prefer_l1(k_frame_fused<CN, MB, DF>);                                                          \
+        k_frame_fused<CN, MB, DF><<<nblk, RT_FUSED_THREADS, 0, st>>>(fp, sc, job.fr, rowmajor, sdl, job.d_counters, job.d_out_rgb, job.d_out_colour, \
                                                     job.d_out_face, job.d_out_obj, job.d_out_lit, job.d_stats); } while (0)
+#define LAUNCH_FUSED(CN, MB) do { if (job.any_plain) LAUNCH_FUSED_D(CN, MB, false); else LAUNCH_FUSED_D(CN, MB, true); } while (0)
     if (count) LAUNCH_FUSED(true, 1);
     else if (job.shade_minb >= 10) LAUNCH_FUSED(false, 10);
     else if (job.shade_minb >= 9) LAUNCH_FUSED(false, 9);
@@ -881,6 +885,7 @@ cudaError_t rt_launch_fused(const RenderJob &job, cudaStream_t st) {
     else if (job.shade_minb >= 6) LAUNCH_FUSED(false, 6);
     else LAUNCH_FUSED(false, 1);
 #undef LAUNCH_FUSED
+#undef LAUNCH_FUSED_D
     return cudaGetLastError();
 }
 

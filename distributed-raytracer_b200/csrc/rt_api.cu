@@ -75,6 +75,8 @@ struct rt_scene {
     bool primary_persistent = false;
     bool sm_affine = false;
     int bulk_strips = 4;
+    unsigned int *h_tune = nullptr, *d_tune_host = nullptr;   // host-mapped copy of the bound (pinned; the kernels write it, the launcher reads it)
+    int any_defer_fixed = 0;           // RT_B200_ANY_DEFER (0 = self-tuned)
     unsigned int *d_tune = nullptr;    // SceneView::tune: {shadow rays, occluded, postponement bound, spare}; nullptr = fixed bound (RT_B200_ANY_DEFER)
     bool split_shade = false;
     bool shade32 = false;              // RT_B200_SHADE32=1: FP32_FAST shades in fp32 too (opt-in)
@@ -157,6 +159,7 @@ void destroy_all(rt_scene *s) {
     for (auto &m : s->meshes) free_mesh(m);
     cudaFree(s->d_meshes);
     cudaFree(s->d_tune); s->d_tune = nullptr;
+    if (s->h_tune) { cudaFreeHost(s->h_tune); s->h_tune = nullptr; s->d_tune_host = nullptr; }
     s->d_meshes = nullptr;
     if (s->cancel_stream) { cudaStreamDestroy(s->cancel_stream); s->cancel_stream = nullptr; }
     if (s->h_cancel_word) { cudaFreeHost(s->h_cancel_word); s->h_cancel_word = nullptr; }
@@ -374,7 +377,8 @@ int render_lane(rt_scene *s, Lane &L, const FrameParams &fp_in, uint32_t flags, 
     job.shade_minb = s->shade_minb;
     job.primary_persistent = s->primary_persistent;
     job.fused = fused;
-    job.d_tune = s->d_tune;
+    job.d_tune = s->d_tune; job.d_tune_host = s->d_tune_host;
+    job.any_plain = (s->h_tune ? *(volatile unsigned int *)s->h_tune : (unsigned int)s->any_defer_fixed) == 1u;
     job.sm_affine = sm_affine; job.d_chunk_state = L.d_chunk_state; job.chunk_state_words = L.cap_chunk_state;
 
     if (out.first) {
@@ -630,7 +634,10 @@ static int create_scene_common(uint32_t precision, int32_t device, uint32_t n_me
         CUB_(cudaMalloc((void **)&s->d_tune, 4 * sizeof(unsigned int)));
         const unsigned int init[4] = { 0u, 0u, 8u, 0u };
         CUB_(cudaMemcpy(s->d_tune, init, sizeof init, cudaMemcpyHostToDevice));
-    }
+        CUB_(cudaHostAlloc((void **)&s->h_tune, sizeof(unsigned int), cudaHostAllocMapped));
+        *s->h_tune = 8u;
+        CUB_(cudaHostGetDevicePointer((void **)&s->d_tune_host, s->h_tune, 0));
+    } else s->any_defer_fixed = std::max(1, std::min(env_int("RT_B200_ANY_DEFER", 8), RT_STACK_SIZE));
     cudaStream_t st0 = s->lanes[0]->stream;
     s->meshes.resize(n_meshes);
     s->h_views.resize(n_meshes);

@@ -73,6 +73,8 @@ struct RenderJob {
     bool      sm_affine;      // ... in its persistent SM-affine form (RT_FLAG_SM_AFFINE)
     unsigned int *d_chunk_state; size_t chunk_state_words;
     unsigned int *d_tune;     // SceneView::tune (scene-level, shared by all lanes) or nullptr
+    unsigned int *d_tune_host; // device address of the host-mapped copy of the bound
+    bool      any_plain;      // launch the kernel variant with the plain any-hit loop (bound 1)
 };
 
 // render.cu : enqueue K2 (primary) / K4 (shadow+shade) / K5 (framebuffer) on `st`

@@ -31,6 +31,7 @@ struct SceneView {
     // rays) and re-derive [2] every 16 384 sampled rays (render.cu: tune_any_defer): the answer of an any-hit ray does not depend on the order of its tests, so the knob can
     // move under running frames without changing a bit of the output.
     unsigned int *tune;
+    unsigned int *tune_host;   // host-mapped copy of word [2]: lets the HOST pick the kernel variant without a synchronisation
     uint32_t defer;            // the bound the current warp works with (read from tune[2] once per pixel block; 0 = the mesh's own)
 };
 
@@ -385,8 +386,8 @@ RT_HD bool leaf_any_hit32(const MeshView &m, int ref, const RayF &r, float tmax,
 // tested before the walk goes on.  Measured (profiles/r02_kernel_ab.txt, ms per pipelined frame; bound 1 / 2 / 4 / 8 / 16 / none):
 //   C3 (7 % of the shadow rays occluded):   0.708 / 0.664 / 0.627 / 0.612 / 0.610 / 0.611     (plain loop: 0.626)
 //   C4 (10 M-triangle soup, mostly occluded): 27.1 / 25.2 / 24.2 / 24.9 / 27.6 / 33.2          (plain loop: 22.8)
-// No single bound suits both, so the kernels measure the occluded share of their own shadow rays and pick 16, 8 or 4 for the rays
-// that follow (SceneView::tune); RT_B200_ANY_DEFER fixes it instead.
+// No single bound suits both, so the kernels measure the occluded share of their own shadow rays and pick 16, 8 or 1 for the rays that follow (SceneView::tune; 1 = the plain loop: the host launches the kernel variant compiled
+// with it); RT_B200_ANY_DEFER fixes it instead.
 #ifndef RT_ANY_DEFER
 #define RT_ANY_DEFER 1
 #endif
@@ -404,7 +405,8 @@ RT_HD bool leaf_any_hit32(const MeshView &m, int ref, const RayF &r, float tmax,
 RT_HD bool mesh_any_hit_deferred(const MeshView &m, const RayF &r, float &tmax, int &face, Counters *cnt, uint32_t defer = 0) {
     int stack[RT_STACK_SIZE];            // internal nodes: [0, sp) growing up; postponed leaves: [lp, RT_STACK_SIZE) growing down
     int sp = 0, lp = RT_STACK_SIZE;
-    const int lp_drain = RT_STACK_SIZE - (int)(defer ? defer : m.any_defer);
+    const uint32_t bound = defer ? defer : m.any_defer;
+    const int lp_drain = RT_STACK_SIZE - (int)(bound < 4u ? 4u : bound);      // a kernel variant without the plain loop treats 1 .. 3 as 4
     int ref = m.root_ref_any;
     bool more = true;
     if (ref < 0) { stack[--lp] = ref; more = false; }
@@ -499,14 +501,15 @@ RT_HD void node_test32q(const RtNodeQ *nd, const RayQ &q, float tbest, NodeHits 
 // Simple per-ray traversal of one mesh (object space).  ANY: stop at the first hit with t <= tbest.
 // Nearest: winner = min t, ties -> lowest face index.  Returns true if something was accepted.
 // ANY rays walk the mesh's any-hit hierarchy (nodes_any: same triangles, its own leaf size).
-template <bool ANY>
+template <bool ANY, bool DEFER = (RT_ANY_DEFER != 0)>
 RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &face, Counters *cnt, uint32_t *smem = nullptr, uint32_t defer = 0) {
     if (m.n_faces == 0) return false;
     float tin;
     if (!slab32(m.lo[0], m.hi[0], m.lo[1], m.hi[1], m.lo[2], m.hi[2], r, tbest, tin)) return false;
-#if RT_ANY_DEFER
-    if (ANY) return mesh_any_hit_deferred(m, r, tbest, face, cnt, defer);
-#endif
+    // DEFER = false is the plain loop below: the right one for scenes whose shadow rays are mostly occluded (a bound of 1).  It is a
+    // COMPILE-TIME choice per kernel variant, picked by the host from the self-tuned bound: both loops in one kernel cost the fused
+    // frame of C3 2.7 % (registers), profiles/r02_kernel_ab.txt
+    if (ANY && DEFER) return mesh_any_hit_deferred(m, r, tbest, face, cnt, defer);
     bool found = false;
     int stack[RT_STACK_SIZE];
     float stack_t[ANY ? 1 : RT_STACK_SIZE];
@@ -652,7 +655,7 @@ RT_HD HitGeom hit_geometry(const SceneView &sc, const FrameParams &fp, int i, in
 }
 
 // tracer.go:61-64 : is light l visible from hit point P of object `obj`?  Ld = unit vector towards the light.
-template <bool EXACT>
+template <bool EXACT, bool DEFER = (RT_ANY_DEFER != 0)>
 RT_HD bool light_visible(const SceneView &sc, const FrameParams &fp, dv P, int obj, int l, bool brute, dv &Ld, Counters *cnt) {
     const LightRec &L = sc.lights[l];
     dv Lv = dv_sub(dv_ld(L.pos), P);
@@ -671,7 +674,7 @@ RT_HD bool light_visible(const SceneView &sc, const FrameParams &fp, dv P, int o
                            (float)Ld.y, (float)Ld.z);
         float tmax = (float)(lightLen - RT_SHADOW_BIAS);
         int f = -1;
-        return !mesh_trace_fast<true>(sc.meshes[ob.mesh], r, tmax, f, cnt, sc.trav_smem, sc.defer);
+        return !mesh_trace_fast<true, DEFER>(sc.meshes[ob.mesh], r, tmax, f, cnt, sc.trav_smem, sc.defer);
     } else {
         TraceFast s;
         bool shaded = trace_fast_nearest(sc, fp, so, Ld, false, s, cnt);
@@ -803,7 +806,7 @@ RT_HD uint32_t shade_hit_fast32(const SceneView &sc, const FrameParams &fp, int 
 }
 
 // fused form: geometry, one shadow query per light, Phong accumulation (both modes).  Returns the lit mask.
-template <bool EXACT>
+template <bool EXACT, bool DEFER = (RT_ANY_DEFER != 0)>
 RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int j, int obj, int face, float t32,
                          bool brute, double col[3], Counters *cnt) {
     dv cam = dv_ld(fp.cam_pos);
@@ -814,7 +817,7 @@ RT_HD uint32_t shade_hit(const SceneView &sc, const FrameParams &fp, int i, int 
     for (int l = 0; l < fp.n_lights; l++) {
         RT_SYNCWARP();                       // every lane of the warp runs this loop (k_shade): reconverge per light
         dv Ld;
-        bool lit = light_visible<EXACT>(sc, fp, g.P, obj, l, brute, Ld, cnt);
+        bool lit = light_visible<EXACT, DEFER>(sc, fp, g.P, obj, l, brute, Ld, cnt);
         RT_SYNCWARP();
         if (lit) {
             lit_mask |= 1u << (l & 31);

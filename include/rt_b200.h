@@ -134,7 +134,8 @@ typedef struct {
     float    ms_write;
     float    ms_total;
     /* self-tuned by the kernels (FP32_FAST): the share of this handle's recent shadow rays that were OCCLUDED and the number of
-     * leaves an any-hit ray currently postpones before it tests them (rt_traverse.cuh; lit scenes batch many, occluded scenes few) */
+     * leaves an any-hit ray currently postpones before it tests them (rt_traverse.cuh; lit scenes batch 16 or 8, 1 = the plain loop
+     * for scenes whose shadow rays are mostly occluded) */
     float    occluded_fraction;
     uint32_t any_defer;
 } rt_stats;

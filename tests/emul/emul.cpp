@@ -322,7 +322,7 @@ static int render_core(EmulScene *s, FrameParams fp, const rt_light *lights, uin
     // hybrid shared / local stack of mesh_trace_fast (incl. the overflow into the local part) is exercised on the CPU as well
     static uint32_t s_trav[RT_SMEM_STACK_WORDS * RT_SMEM_STACK_STRIDE];
     sc.trav_smem = getenv("RT_EMUL_NO_SMEM_STACK") ? nullptr : s_trav;
-    sc.tune = nullptr; sc.defer = 0;
+    sc.tune = nullptr; sc.tune_host = nullptr; sc.defer = 0;
     const bool brute = (flags & RT_FLAG_BRUTE_FORCE) != 0, rowmajor = (flags & RT_LAYOUT_ROWMAJOR) != 0,
                sdl = (flags & RT_QUANT_RGBA16_SHR8) != 0;
     if (out_rgb) memset(out_rgb, 0, 3 * npix);
@@ -403,7 +403,7 @@ long long emul_shade_events(void *h, const rt_camera *cam, const rt_light *light
     // hybrid shared / local stack of mesh_trace_fast (incl. the overflow into the local part) is exercised on the CPU as well
     static uint32_t s_trav[RT_SMEM_STACK_WORDS * RT_SMEM_STACK_STRIDE];
     sc.trav_smem = getenv("RT_EMUL_NO_SMEM_STACK") ? nullptr : s_trav;
-    sc.tune = nullptr; sc.defer = 0;
+    sc.tune = nullptr; sc.tune_host = nullptr; sc.defer = 0;
     std::vector<HitRec> hits;
     Counters c; c.nodes = 0; c.tris = 0;
     const uint32_t nrays = ray_count(fp);

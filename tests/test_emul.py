@@ -381,3 +381,20 @@ def test_quantised_node_experiment_renders_the_identical_frame(example_scene):
     for a, b in zip(outs[0][:5], outs[1][:5]):
         assert np.array_equal(a, b)
     assert outs[0][5][2] == outs[1][5][2] and outs[0][5][2] > 0       # hit pixels
+
+
+def test_plain_and_postponing_any_hit_loops_render_the_identical_frame(example_scene, monkeypatch):
+    """The two any-hit loops (leaves tested where they are met / postponed in batches of a bounded size) answer every shadow ray
+    alike, whatever the bound: replay built with -DRT_ANY_DEFER=0 against the default build with bounds 4, 16 and 128."""
+    sc = dict(example_scene)
+    sc["meshes"] = [workloads.subdivide(example_scene["meshes"][0], 2)]
+    E = eb.EmulScene(sc, rt.FP32_FAST, 4, 2, defs=("-DRT_ANY_DEFER=0",))
+    ref = E.render(sc["camera"], sc["lights"], 160, 120)
+    E.close()
+    for bound in ("4", "16", "128"):
+        monkeypatch.setenv("RT_B200_ANY_DEFER", bound)
+        E = eb.EmulScene(sc, rt.FP32_FAST, 4, 2)
+        out = E.render(sc["camera"], sc["lights"], 160, 120)
+        E.close()
+        for a, b in zip(ref[:5], out[:5]):
+            assert np.array_equal(a, b)

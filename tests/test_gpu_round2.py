@@ -203,7 +203,7 @@ def test_any_hit_postponement_tunes_itself_and_never_changes_a_pixel(rt, example
         assert total >= 4 * 65536, "the scene must produce enough shadow rays for a few tuning steps"
         f = occluded / total
         assert abs(st["occluded_fraction"] - f) < 0.05          # one CTA in four is sampled
-        assert st["any_defer"] in (4, 8, 16)
+        assert st["any_defer"] in (1, 8, 16)
         ref = g.render_region(W, H)
         g.close()
         for fixed in ("1", "4", "128"):
