@@ -146,8 +146,18 @@ struct Scratch {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     MeshDevice *m = nullptr;
     bool ok = false;
+    // one arena for the ~25 temporary arrays of a build: cudaMalloc / cudaFree each synchronise the device and cost more than the
+    // kernels they serve (the build kernels of a 1 M-face mesh run ~3 ms; 25 allocations + frees made it ~40 ms)
+    char *arena = nullptr; size_t arena_size = 0, arena_used = 0;
+    void reserve(size_t bytes) {
+        if (cudaMalloc((void **)&arena, bytes) == cudaSuccess) { arena_size = bytes; ptrs.push_back(arena); }
+        else { arena = nullptr; cudaGetLastError(); }                   // no room for the arena: fall back to one allocation per array
+    }
     template <class T> cudaError_t alloc(T **p, size_t bytes) {
-        cudaError_t e = cudaMalloc((void **)p, bytes ? bytes : 16);
+        bytes = (bytes ? bytes : 16);
+        const size_t at = (arena_used + 255) & ~(size_t)255;
+        if (arena && at + bytes <= arena_size) { *p = (T *)(arena + at); arena_used = at + bytes; return cudaSuccess; }
+        cudaError_t e = cudaMalloc((void **)p, bytes);
         if (e == cudaSuccess) ptrs.push_back((void *)*p);
         return e;
     }
@@ -258,6 +268,7 @@ bool rt_build_bvh(MeshDevice &m, bool want32, bool want64, int max_leaf, int max
 
     CK(cudaEventCreate(&sc.ev0)); CK(cudaEventCreate(&sc.ev1));
     CK(cudaEventRecord(sc.ev0, st));
+    sc.reserve((size_t)n * 176 + ((size_t)48 << 20));       // ~150 bytes of temporaries per face + the CUB work space; overflow falls back
     CK(sc.alloc(&d_bounds, 6 * sizeof(unsigned int)));
     {
         unsigned int init[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
