@@ -139,10 +139,19 @@ def run_c5(args):
     rects = host.partition(W, H, n)                                   # master/main.go:101 -> :54-91
     assert len(rects) == n, (len(rects), n)
     scenes = [rt.GpuScene(sc, device=d, precision=rt.FP32_FAST) for d in range(n)]       # register(): once per worker
-    outs = []
-    for (x, y, w, h) in rects:
-        p = L.rt_host_alloc(w * h * 3)
-        outs.append(np.ctypeslib.as_array((ctypes.c_uint8 * (w * h * 3)).from_address(p)))
+    bufs = []
+    for _ in range(n):                                                 # --balanced moves the rectangles every frame: full-size buffers
+        p = L.rt_host_alloc(W * H * 3)
+        bufs.append(np.ctypeslib.as_array((ctypes.c_uint8 * (W * H * 3)).from_address(p)))
+    outs = [bufs[k][:w * h * 3] for k, (x, y, w, h) in enumerate(rects)]
+    DS = 8                                                             # the master's cost table is built from every 8th pixel of the last frame
+
+    small = np.zeros((W // DS, H // DS, 3), dtype=np.uint8)           # every 8th pixel of the frame just drawn, filled by the workers
+
+    def next_rects():
+        """partition() with the cuts placed by the cost of the frame just drawn (integration/go/master/partition_balanced.go)"""
+        r8 = host.partition_balanced(W // DS, H // DS, n, small, args.hit_weight)
+        return [(x * DS, y * DS, w * DS, h * DS) for (x, y, w, h) in r8]
     screen = np.zeros((W, H, 3), dtype=np.uint8)                       # column-major like the wire layout (i*H + j)
     centre = np.array([1.0, 1.0, -1.0])
     fov = float(sc["camera"][12])
@@ -150,32 +159,48 @@ def run_c5(args):
     cams = [workloads.orbit_camera(centre, 6.0, np.deg2rad(3.0 * f), 0.0, fov) for f in range(args.frames)]   # 3 deg / frame
     hits = [0] * n
 
+    cur = {"rects": rects}
+
     def worker(k, cam):
-        x, y, w, h = rects[k]
-        scenes[k].bulk_trace(cam, sc["lights"], W, H, x, y, w, h, out=outs[k], tan_half_fov=tan_half)   # Tracer.BulkTrace
-        screen[x:x + w, y:y + h] = outs[k].reshape(w, h, 3)            # master/main.go:166-176 (frame assembly)
+        x, y, w, h = cur["rects"][k]
+        out = bufs[k][:w * h * 3]
+        scenes[k].bulk_trace(cam, sc["lights"], W, H, x, y, w, h, out=out, tan_half_fov=tan_half)   # Tracer.BulkTrace
+        o3 = out.reshape(w, h, 3)
+        screen[x:x + w, y:y + h] = o3                                  # master/main.go:166-176 (frame assembly)
+        if args.balanced:
+            small[x // DS:(x + w) // DS, y // DS:(y + h) // DS] = o3[::DS, ::DS]
         return k
+
+    def frame(cam):
+        list(pool.map(lambda k: worker(k, cam), range(n)))             # one frame: all orders in flight, wait for all (coordinator)
+        if args.balanced:
+            cur["rects"] = next_rects()
 
     pool = ThreadPoolExecutor(n)
     for cam in cams[:3]:
-        list(pool.map(lambda k: worker(k, cam), range(n)))
+        frame(cam)
     t_frames = []
     t0 = time.perf_counter()
     for cam in cams:
         tf = time.perf_counter()
-        list(pool.map(lambda k: worker(k, cam), range(n)))             # one frame: all orders in flight, wait for all (coordinator)
+        frame(cam)
         t_frames.append(time.perf_counter() - tf)
     wall = time.perf_counter() - t0
     total_hits = 0                                                     # ray accounting: an untimed second pass over the frames
+    worst = 0.0
     for cam in cams:
-        list(pool.map(lambda k: worker(k, cam), range(n)))
-        total_hits += sum(s.stats()["hit_pixels"] for s in scenes)
+        frame(cam)
+        per = [s.stats()["hit_pixels"] for s in scenes]
+        total_hits += sum(per)
+        worst += max(per) / max(1.0, sum(per) / n)
+    rects = cur["rects"]
     rays = W * H * len(cams) + total_hits * len(sc["lights"])
     out = {"config": "C5: %d-frame orbit (3 deg/frame, r=6) of Suzanne x5 subdivided, 3840x2160, 2 lights, FP32_FAST, "
                      "partition() rectangles, one BulkTrace stream per GPU, HOST result buffers + frame assembly" % len(cams),
            "n_gpus": n, "frames": len(cams), "wall_s": wall, "frames_per_s": len(cams) / wall, "mrays_per_s": rays / wall / 1e6,
            "ms_per_frame_median": 1e3 * float(np.median(t_frames)), "ms_per_frame_max": 1e3 * float(np.max(t_frames)),
-           "rectangles": rects, "mean_hit_pixels": total_hits / len(cams),
+           "rectangles": rects, "mean_hit_pixels": total_hits / len(cams), "balanced": bool(args.balanced), "hit_weight": args.hit_weight,
+           "mean_busiest_worker_hits_over_mean": worst / len(cams),
            "note": "Go master/pool + gRPC not executed (no Go toolchain); threads stand in for pool.Assign goroutines"}
     if args.check:
         sc_last = dict(sc, camera=cams[-1])
@@ -191,6 +216,8 @@ if __name__ == "__main__":
     ap.add_argument("--replicas", type=int, default=4)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--frames", type=int, default=120)
+    ap.add_argument("--balanced", action="store_true", help="c5: cuts placed by the cost of the previous frame (SURVEY s8 f4) instead of partition()'s halves")
+    ap.add_argument("--hit-weight", type=float, default=30.0, help="c5 --balanced: cost of a hit pixel in units of a miss pixel")
     ap.add_argument("--check", type=int, default=0, help="oracle check on every check-th pixel (0 = off)")
     a = ap.parse_args()
     import __graft_entry__ as ge
