@@ -27,6 +27,18 @@ struct dv { double x, y, z; };
 
 RT_HD dv dv_make(double x, double y, double z) { dv r; r.x = x; r.y = y; r.z = z; return r; }
 RT_HD dv dv_ld(const double *p) { return dv_make(p[0], p[1], p[2]); }
+// per-hit records (float64 vertices / normals of the winning face) are read once per pixel: streaming loads keep them from evicting
+// BVH nodes out of L1 (RT_HIT_STREAM, compile-time experiment)
+#ifndef RT_HIT_STREAM
+#define RT_HIT_STREAM 0
+#endif
+RT_HD dv dv_ld_once(const double *p) {
+#if defined(__CUDA_ARCH__) && RT_HIT_STREAM
+    return dv_make(__ldcs(p), __ldcs(p + 1), __ldcs(p + 2));
+#else
+    return dv_make(p[0], p[1], p[2]);
+#endif
+}
 RT_HD dv dv_add(dv a, dv b) { return dv_make(DADD(a.x, b.x), DADD(a.y, b.y), DADD(a.z, b.z)); }              // vector.go:14
 RT_HD dv dv_sub(dv a, dv b) { return dv_make(DSUB(a.x, b.x), DSUB(a.y, b.y), DSUB(a.z, b.z)); }              // vector.go:19
 RT_HD dv dv_scale(dv a, double s) { return dv_make(DMUL(s, a.x), DMUL(s, a.y), DMUL(s, a.z)); }              // vector.go:24
@@ -204,11 +216,11 @@ RT_HD dv primary_dir_exact(int i, int j, const FrameParams &fp) {
 RT_HD dv hit_normal_exact(const MeshView &m, int face, double r1, double r2, double r3) {
     if (m.fnormals) {
         const double *n = m.fnormals + 9 * (size_t)face;
-        return dv_norm(dv_add(dv_add(dv_scale(dv_ld(n), r1), dv_scale(dv_ld(n + 3), r2)), dv_scale(dv_ld(n + 6), r3)));
+        return dv_norm(dv_add(dv_add(dv_scale(dv_ld_once(n), r1), dv_scale(dv_ld_once(n + 3), r2)), dv_scale(dv_ld_once(n + 6), r3)));
     }
     const double *p = m.fverts + 9 * (size_t)face;
-    dv P1 = dv_ld(p);
-    return dv_norm(dv_cross(dv_sub(dv_ld(p + 3), P1), dv_sub(dv_ld(p + 6), P1)));
+    dv P1 = dv_ld_once(p);
+    return dv_norm(dv_cross(dv_sub(dv_ld_once(p + 3), P1), dv_sub(dv_ld_once(p + 6), P1)));
 }
 
 // colour.go:38-50

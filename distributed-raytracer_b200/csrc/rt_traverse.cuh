@@ -78,6 +78,35 @@ RT_HD rt_f8 ld_f8(const rt_f4 *p) {
     rt_f8 r; r.a = ld_f4(p); r.b = ld_f4(p + 1); return r;
 #endif
 }
+// Cache policy (profiles/r02_kernel_ab.txt): RT_TRI_NOALLOC (default) loads the triangle records of a leaf with L1::no_allocate -- they are
+// used once per ray, and the lines they would evict hold BVH nodes: -0.7 % on the pipelined C3 frame, small but repeatable to 0.01 %.
+// RT_NODE_EVICT_LAST (marking the node lines evict_last in L1) changes nothing and stays off.
+#ifndef RT_TRI_NOALLOC
+#define RT_TRI_NOALLOC 1
+#endif
+#ifndef RT_NODE_EVICT_LAST
+#define RT_NODE_EVICT_LAST 0
+#endif
+RT_HD rt_f8 ld_f8_tri(const rt_f4 *p) {
+#if defined(__CUDA_ARCH__) && RT_LD256 && RT_TRI_NOALLOC
+    rt_f8 r;
+    asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+#else
+    return ld_f8(p);
+#endif
+}
+RT_HD rt_f8 ld_f8_node(const rt_f4 *p) {
+#if defined(__CUDA_ARCH__) && RT_LD256 && RT_NODE_EVICT_LAST
+    rt_f8 r;
+    asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+    return r;
+#else
+    return ld_f8(p);
+#endif
+}
 RT_HD rt_i4 ld_i4(const rt_i4 *p) {
 #if defined(__CUDA_ARCH__)
     int4 v = __ldg(reinterpret_cast<const int4 *>(p));
@@ -313,7 +342,7 @@ RT_HD void node_test32(const RtNode *nd, const RayF &r, float tbest, NodeHits &h
 #if RT_LD256 && RT_W == 4
     // lo[4] and hi[4] of an axis are one 32-byte vector: 3 x LDG.256 + the refs = 4 load instructions per visit
     const rt_f4 *q = reinterpret_cast<const rt_f4 *>(nd);
-    const rt_f8 bx = ld_f8(q), by = ld_f8(q + 2), bz = ld_f8(q + 4);
+    const rt_f8 bx = ld_f8_node(q), by = ld_f8_node(q + 2), bz = ld_f8_node(q + 4);
     const rt_i4 rf = ld_i4(reinterpret_cast<const rt_i4 *>(q + 6));
 #define RT_CHILD(k, c)                                                                                                     \
     {                                                                                                                      \
@@ -359,7 +388,7 @@ RT_HD bool leaf_any_hit32(const MeshView &m, int ref, const RayF &r, float tmax,
     for (uint32_t k = first; k < first + count; k++) {
         const rt_f4 *p = m.tri32 + RT_TRI32_F4 * (size_t)k;
 #if RT_TRI_LD256
-        const rt_f8 t01 = ld_f8(p), t2x = ld_f8(p + 2);
+        const rt_f8 t01 = ld_f8_tri(p), t2x = ld_f8_tri(p + 2);
         const rt_f4 v0 = t01.a, v1 = t01.b, v2 = t2x.a;
 #else
         const rt_f4 v0 = ld_f4(p), v1 = ld_f4(p + 1), v2 = ld_f4(p + 2);
@@ -566,7 +595,7 @@ RT_HD bool mesh_trace_fast(const MeshView &m, const RayF &r, float &tbest, int &
             for (uint32_t k = first; k < first + count; k++) {
                 const rt_f4 *p = m.tri32 + RT_TRI32_F4 * (size_t)k;
 #if RT_TRI_LD256
-                const rt_f8 t01 = ld_f8(p), t2x = ld_f8(p + 2);
+                const rt_f8 t01 = ld_f8_tri(p), t2x = ld_f8_tri(p + 2);
                 const rt_f4 v0 = t01.a, v1 = t01.b, v2 = t2x.a;
 #else
                 rt_f4 v0 = ld_f4(p), v1 = ld_f4(p + 1), v2 = ld_f4(p + 2);
@@ -642,9 +671,10 @@ RT_HD HitGeom hit_geometry(const SceneView &sc, const FrameParams &fp, int i, in
     const double *pv = m.fverts + 9 * (size_t)face;
     dv ol = dv_sub(cam, pos);                                                    // object.go:71
     TriHit h;
-    if (!tri_intersection_exact(dv_ld(pv), dv_ld(pv + 3), dv_ld(pv + 6), ol, d, h)) {
+    const dv V1 = dv_ld_once(pv), V2 = dv_ld_once(pv + 3), V3 = dv_ld_once(pv + 6);
+    if (!tri_intersection_exact(V1, V2, V3, ol, d, h)) {
         // FP32_FAST only: the fp32 winner is rejected by the fp64 test by a hair -> evaluate it anyway
-        if (!tri_intersection_exact(dv_ld(pv), dv_ld(pv + 3), dv_ld(pv + 6), ol, d, h, true)) {
+        if (!tri_intersection_exact(V1, V2, V3, ol, d, h, true)) {
             h.t = (double)t32; h.ip = dv_add(ol, dv_scale(d, h.t)); h.r1 = 1.0; h.r2 = 0.0; h.r3 = 0.0;
         }
     }

@@ -21,4 +21,8 @@ $NV -DRT_CHUNK_BLOCKS=64 -o ../../build_variants/librt_b200_chunk64.so $SRC &
 $NV -DRT_CHUNK_BLOCKS=128 -o ../../build_variants/librt_b200_chunk128.so $SRC &
 wait
 $NV -DRT_NODEQ=0 -o ../../build_variants/librt_b200_noq.so $SRC
+$NV -DRT_TRI_NOALLOC=0 -o ../../build_variants/librt_b200_trialloc.so $SRC &
+$NV -DRT_NODE_EVICT_LAST=1 -o ../../build_variants/librt_b200_nodeel.so $SRC &
+$NV -DRT_HIT_STREAM=1 -o ../../build_variants/librt_b200_hitstream.so $SRC &
+wait
 # $NV -DRT_W=8 -o ../../build_variants/librt_b200_w8.so $SRC      # 8 children per node: measured 35-70 % slower (profiles/r02_kernel_ab.txt)
