@@ -381,11 +381,31 @@ RT_HD void node_test32(const RtNode *nd, const RayF &r, float tbest, NodeHits &h
 #endif
 }
 
-// fp32 test of the triangles of one leaf of an any-hit ray: true at the first triangle with t <= tmax
+// fp32 test of the triangles of one leaf of an any-hit ray: true at the first triangle with t <= tmax.
+// RT_LEAF_PAIR (compile-time experiment, off): the records of the first TWO triangles are requested together (any-hit leaves hold <= 2
+// by default), so a two-triangle leaf costs one load latency instead of two.  Measured (profiles/r02_kernel_ab.txt): K4 of the
+// three-kernel pipeline 0.559 -> 0.550 ms, but the fused frame kernel -- which sits at its register limit (56) -- 0.605 -> 0.633 ms.
+#ifndef RT_LEAF_PAIR
+#define RT_LEAF_PAIR 0
+#endif
 RT_HD bool leaf_any_hit32(const MeshView &m, int ref, const RayF &r, float tmax, int &face, float &thit, Counters *cnt) {
     const uint32_t first = rt_leaf_first(ref), count = rt_leaf_count(ref);
     RT_COUNT(cnt, tris, count);
-    for (uint32_t k = first; k < first + count; k++) {
+    uint32_t k = first;
+#if RT_LEAF_PAIR && RT_TRI_LD256
+    {
+        const rt_f4 *p = m.tri32 + RT_TRI32_F4 * (size_t)first;
+        const bool two = count >= 2u;
+        const rt_f8 a01 = ld_f8_tri(p), a2x = ld_f8_tri(p + 2);
+        rt_f8 b01 = a01, b2x = a2x;
+        if (two) { b01 = ld_f8_tri(p + 4); b2x = ld_f8_tri(p + 6); }
+        float t, u, v;
+        if (tri_test32(a01.a, a01.b, a2x.a, r, t, u, v) && t <= tmax) { face = (int)rt_float_bits(a01.a.w); thit = t; return true; }
+        if (two && tri_test32(b01.a, b01.b, b2x.a, r, t, u, v) && t <= tmax) { face = (int)rt_float_bits(b01.a.w); thit = t; return true; }
+        k = first + 2u;
+    }
+#endif
+    for (; k < first + count; k++) {
         const rt_f4 *p = m.tri32 + RT_TRI32_F4 * (size_t)k;
 #if RT_TRI_LD256
         const rt_f8 t01 = ld_f8_tri(p), t2x = ld_f8_tri(p + 2);

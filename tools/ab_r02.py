@@ -39,6 +39,8 @@ VARIANTS = {
     "pipeline_noq": ({"RT_B200_LIB": "build_variants/librt_b200_noq.so"}, ["PIPELINE"]),
     "fused_minb10": ({"RT_B200_SHADE_MINB": "10"}, []),
     # L1 cache-policy hints: triangle records L1::no_allocate, node lines L1::evict_last
+    "fused_nopair": ({"RT_B200_LIB": "build_variants/librt_b200_nopair.so"}, []),          # -DRT_LEAF_PAIR=0: triangles of a leaf loaded one after the other
+    "pipeline_nopair": ({"RT_B200_LIB": "build_variants/librt_b200_nopair.so"}, ["PIPELINE"]),
     "fused_trialloc": ({"RT_B200_LIB": "build_variants/librt_b200_trialloc.so"}, []),      # -DRT_TRI_NOALLOC=0: triangle records allocate in L1
     "fused_nodeel": ({"RT_B200_LIB": "build_variants/librt_b200_nodeel.so"}, []),          # -DRT_NODE_EVICT_LAST=1
     "fused_hitstream": ({"RT_B200_LIB": "build_variants/librt_b200_hitstream.so"}, []),    # -DRT_HIT_STREAM=1: per-hit fp64 records with ld.global.cs
