@@ -39,6 +39,8 @@ VARIANTS = {
     "pipeline_noq": ({"RT_B200_LIB": "build_variants/librt_b200_noq.so"}, ["PIPELINE"]),
     "fused_minb10": ({"RT_B200_SHADE_MINB": "10"}, []),
     # L1 cache-policy hints: triangle records L1::no_allocate, node lines L1::evict_last
+    "fused_pair_minb8": ({"RT_B200_LIB": "build_variants/librt_b200_pair.so", "RT_B200_SHADE_MINB": "8"}, []),
+    "fused_pair_minb7": ({"RT_B200_LIB": "build_variants/librt_b200_pair.so", "RT_B200_SHADE_MINB": "7"}, []),
     "fused_nopair": ({"RT_B200_LIB": "build_variants/librt_b200_nopair.so"}, []),          # -DRT_LEAF_PAIR=0: triangles of a leaf loaded one after the other
     "pipeline_nopair": ({"RT_B200_LIB": "build_variants/librt_b200_nopair.so"}, ["PIPELINE"]),
     "fused_trialloc": ({"RT_B200_LIB": "build_variants/librt_b200_trialloc.so"}, []),      # -DRT_TRI_NOALLOC=0: triangle records allocate in L1
