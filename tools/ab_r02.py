@@ -52,6 +52,13 @@ VARIANTS = {
     "fused_sm_c16": ({"RT_B200_SM_AFFINE": "1", "RT_B200_LIB": "build_variants/librt_b200_chunk16.so"}, []),
     "fused_sm_c64": ({"RT_B200_SM_AFFINE": "1", "RT_B200_LIB": "build_variants/librt_b200_chunk64.so"}, []),
     "fused_sm_c128": ({"RT_B200_SM_AFFINE": "1", "RT_B200_LIB": "build_variants/librt_b200_chunk128.so"}, []),
+    "fused_any3": ({"RT_B200_MAX_LEAF_SHADE": "3"}, []),
+    "fused_leaf2": ({"RT_B200_MAX_LEAF": "2"}, []),
+    "fused_leaf3": ({"RT_B200_MAX_LEAF": "3"}, []),
+    "fused_leaf6": ({"RT_B200_MAX_LEAF": "6"}, []),
+    "fused_leaf8": ({"RT_B200_MAX_LEAF": "8"}, []),
+    "fused_defer32": ({"RT_B200_ANY_DEFER": "32"}, []),
+    "fused_defer12": ({"RT_B200_ANY_DEFER": "12"}, []),
     "fused_any1": ({"RT_B200_MAX_LEAF_SHADE": "1"}, []),
     "fused_any8": ({"RT_B200_MAX_LEAF_SHADE": "8"}, []),
 }
